@@ -1,0 +1,87 @@
+"""ctypes binding of libCudaRasterizer.so (the flat C ABI of include/gm_rasterizer.h).
+
+There is NO fallback: if the library is missing or does not export a symbol the header declares,
+importing this module raises.  Build it with `python -m gaussianmesh_b200.build`.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+PKG = Path(__file__).resolve().parent
+LIB_PATH = PKG / "diff_gaussian_rasterizater" / "libCudaRasterizer.so"
+
+GM_OK = 0
+GM_ERR_CUDA = -1
+GM_ERR_BAD_ARGUMENT = -2
+GM_ERR_TOO_MANY_TILES = -3
+GM_ERR_BINNING_OVERFLOW = -4
+
+_ERR_NAMES = {
+    GM_ERR_CUDA: "GM_ERR_CUDA",
+    GM_ERR_BAD_ARGUMENT: "GM_ERR_BAD_ARGUMENT",
+    GM_ERR_TOO_MANY_TILES: "GM_ERR_TOO_MANY_TILES",
+    GM_ERR_BINNING_OVERFLOW: "GM_ERR_BINNING_OVERFLOW",
+}
+
+_p = C.c_void_p
+_i = C.c_int
+_f = C.c_float
+_z = C.c_size_t
+
+# name -> (restype, argtypes); the order of arguments is that of include/gm_rasterizer.h
+_VIEW_ARGS = [_p, _p, _p, _p, _p, _f, _p, _p, _p, _p, _p, _f, _f]  # means3D .. tan_fovy
+SIGNATURES = {
+    "gm_version": (C.c_char_p, []),
+    "gm_last_error": (C.c_char_p, []),
+    "gm_required_geom": (_z, [_z]),
+    "gm_required_image": (_z, [_z]),
+    "gm_required_binning": (_z, [_z]),
+    "gm_mark_visible": (_i, [_i, _p, _p, _p, _p, _p]),
+    "gm_forward_0": (_i, [_p, _i, _i, _i, _p, _i, _i, *_VIEW_ARGS, _i, _p, _i, _p]),
+    "gm_forward_1": (_i, [_p, _p, _p, _i, _i, _i, _i, _p, _i, _i, *_VIEW_ARGS, _i, _p, _p, _i, _p]),
+    "gm_forward": (_i, [_p, _p, _z, _p, _i, _i, _i, _p, _i, _i, *_VIEW_ARGS, _i, _p, _p, _i, _p, _p]),
+    "gm_forward_status": (_i, [_p, _p, _p, _p]),
+    "gm_backward": (_i, [_i, _i, _i, _i, _p, _i, _i, _p, _p, _p, _p, _f, _p, _p, _p, _p, _p, _f, _f, _p,
+                         _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _p]),
+    "gm_mesh_bind_forward": (_i, [_i, _p, _p, _p, _p, _p, _p, _p, _f, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "gm_mesh_bind_backward": (_i, [_i, _p, _p, _p, _p, _p, _p, _p, _f, _p, _p, _p, _p, _p, _p, _p,
+                                   _p, _p, _p, _p, _p, _p]),
+    "gm_deform_gaussians": (_i, [_i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _i, _p, _p, _p, _p]),
+    "gm_sh_to_rgb_rotated": (_i, [_i, _i, _i, _p, _p, _p, _p, _p, _p]),
+    "gm_l1_loss": (_i, [_z, _p, _p, _p, _p, _p]),
+}
+
+
+class RasterizerError(RuntimeError):
+    def __init__(self, where: str, code: int, detail: str = ""):
+        self.code = code
+        name = _ERR_NAMES.get(code, str(code))
+        super().__init__(f"{where} failed: {name}" + (f" ({detail})" if detail else ""))
+
+
+def _load() -> C.CDLL:
+    if not LIB_PATH.exists():
+        raise ImportError(
+            f"{LIB_PATH} is missing: the CUDA library is the product and there is no fallback. "
+            "Build it with `python -m gaussianmesh_b200.build`.")
+    lib = C.CDLL(str(LIB_PATH))
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the .so is stale
+        fn.restype = res
+        fn.argtypes = args
+    return lib
+
+
+lib = _load()
+
+
+def check(rc: int, where: str) -> int:
+    if rc < 0:
+        detail = lib.gm_last_error().decode() if rc == GM_ERR_CUDA else ""
+        raise RasterizerError(where, rc, detail)
+    return rc
+
+
+def version() -> str:
+    return lib.gm_version().decode()

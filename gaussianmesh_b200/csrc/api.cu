@@ -1,0 +1,480 @@
+// Host-side entry points of libCudaRasterizer.so:
+//   * the flat C ABI declared in include/gm_rasterizer.h, and
+//   * the C++ symbols of namespace CudaRasterizer that the reference's Jittor glue links against
+//     (declared in csrc/cuda_rasterizer/rasterizer.h, mirroring dgr/cuda_rasterizer/rasterizer.h).
+// No device memory is allocated here; all scratch lives in the caller's three chunks.
+#include <cstdio>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+
+#include "common.cuh"
+#include "kernels.h"
+#include "cuda_rasterizer/rasterizer_impl.h"
+
+namespace gm {
+
+static thread_local std::string g_last_error;
+
+void set_last_error(const char* what, cudaError_t err)
+{
+	g_last_error = std::string(what) + ": " + cudaGetErrorString(err);
+}
+
+// The reference's CHECK_CUDA (auxiliary.h:165-172): synchronise + check only in debug mode.  Launch
+// configuration errors are cheap to see, so they are reported in both modes.
+int check_stage(const char* what, bool debug, cudaStream_t stream)
+{
+	cudaError_t err = cudaGetLastError();
+	if (err == cudaSuccess && debug)
+		err = cudaStreamSynchronize(stream);
+	if (err == cudaSuccess && debug)
+		err = cudaGetLastError();
+	if (err != cudaSuccess) {
+		set_last_error(what, err);
+		if (debug)
+			fprintf(stderr, "\n[CUDA ERROR] in stage %s: %s\n", what, cudaGetErrorString(err));
+		return GM_ERR_CUDA;
+	}
+	return GM_OK;
+}
+
+static bool make_view(ViewParams& vp, int D, int M, const float* background, int width, int height,
+                      float scale_modifier, const float* viewmatrix, const float* projmatrix, const float* cam_pos,
+                      float tan_fovx, float tan_fovy)
+{
+	vp.view = viewmatrix;
+	vp.proj = projmatrix;
+	vp.campos = cam_pos;
+	vp.bg = background;
+	vp.tan_fovx = tan_fovx;
+	vp.tan_fovy = tan_fovy;
+	// rasterizer_impl.cu:359-360
+	vp.focal_y = height / (2.0f * tan_fovy);
+	vp.focal_x = width / (2.0f * tan_fovx);
+	vp.scale_modifier = scale_modifier;
+	vp.W = width;
+	vp.H = height;
+	vp.tiles_x = (width + kTile - 1) / kTile;
+	vp.tiles_y = (height + kTile - 1) / kTile;
+	vp.D = D;
+	vp.M = M;
+	return width > 0 && height > 0;
+}
+
+// Largest instance count whose BinningState fits in `bytes`.
+static uint32_t binning_capacity_instances(size_t bytes)
+{
+	if (bytes < 1024)
+		return 0;
+	size_t r = ((bytes - 640) / 48) & ~(size_t)7;
+	while (r > 0 && required<BinningState>(r) > bytes)
+		r -= 8;
+	if (r > 0xfffffff0u)
+		r = 0xfffffff0u;
+	return (uint32_t)r;
+}
+
+static int forward_stage0(char* geom_buffer, int P, const ViewParams& vp, const float* means3D, const float* shs,
+                          const float* colors_precomp, const float* opacities, const float* scales,
+                          const float* rotations, const float* cov3D_precomp, bool prefiltered, int* radii,
+                          uint32_t capacity, bool debug, cudaStream_t stream, GeometryState& geom)
+{
+	if (P < 0 || means3D == nullptr || opacities == nullptr)
+		return GM_ERR_BAD_ARGUMENT;
+	if (colors_precomp == nullptr && shs == nullptr)
+		return GM_ERR_BAD_ARGUMENT;
+	if (cov3D_precomp == nullptr && (scales == nullptr || rotations == nullptr))
+		return GM_ERR_BAD_ARGUMENT;
+	const int num_tiles = vp.tiles_x * vp.tiles_y;
+	if (num_tiles > GM_MAX_TILES)
+		return GM_ERR_TOO_MANY_TILES;
+
+	geom = GeometryState::fromChunk(geom_buffer, (size_t)P);
+	if (radii == nullptr)
+		radii = geom.internal_radii;
+
+	launch_preprocess(P, means3D, scales, rotations, opacities, shs, cov3D_precomp, colors_precomp, vp, radii, geom,
+	                  prefiltered, stream);
+	if (int rc = check_stage("preprocess", debug, stream)) return rc;
+	launch_tile_scan(num_tiles, geom, capacity, stream);
+	if (int rc = check_stage("tile_scan", debug, stream)) return rc;
+	return GM_OK;
+}
+
+static int forward_stage1(const GeometryState& geom, char* binning_buffer, char* image_buffer, int P,
+                          const ViewParams& vp, uint32_t capacity, const int* radii, float* out_color, bool debug,
+                          cudaStream_t stream)
+{
+	if (out_color == nullptr || image_buffer == nullptr || (capacity > 0 && binning_buffer == nullptr))
+		return GM_ERR_BAD_ARGUMENT;
+	const int num_tiles = vp.tiles_x * vp.tiles_y;
+	BinningState binning = BinningState::fromChunk(binning_buffer, (size_t)capacity);
+	ImageState img = ImageState::fromChunk(image_buffer, (size_t)vp.W * vp.H);
+	if (radii == nullptr)
+		radii = geom.internal_radii;
+
+	launch_emit(P, radii, geom, binning, capacity, vp, stream);
+	if (int rc = check_stage("emit", debug, stream)) return rc;
+	launch_sort_pack(num_tiles, geom, binning, capacity, stream);
+	if (int rc = check_stage("sort_pack", debug, stream)) return rc;
+	launch_blend_forward(geom, binning, img, capacity, vp, out_color, stream);
+	if (int rc = check_stage("blend_forward", debug, stream)) return rc;
+	return GM_OK;
+}
+
+} // namespace gm
+
+using namespace gm;
+
+extern "C" {
+
+const char* gm_version(void) { return "gaussianmesh-b200 0.1.0 sm_100a"; }
+const char* gm_last_error(void) { return g_last_error.c_str(); }
+
+size_t gm_required_geom(size_t P) { return required<GeometryState>(P); }
+size_t gm_required_image(size_t N) { return required<ImageState>(N); }
+size_t gm_required_binning(size_t R) { return required<BinningState>(R); }
+
+int gm_mark_visible(int P, const float* means3D, const float* viewmatrix, const float* projmatrix,
+                    uint8_t* present, gm_stream_t stream)
+{
+	(void)projmatrix;   // the reference computes p_proj but only tests view-space z (auxiliary.h:153)
+	if (P < 0 || (P > 0 && (means3D == nullptr || viewmatrix == nullptr || present == nullptr)))
+		return GM_ERR_BAD_ARGUMENT;
+	launch_mark_visible(P, means3D, viewmatrix, present, (cudaStream_t)stream);
+	return check_stage("mark_visible", false, (cudaStream_t)stream);
+}
+
+int gm_forward_0(char* geom_buffer, int P, int D, int M, const float* background, int width, int height,
+                 const float* means3D, const float* shs, const float* colors_precomp, const float* opacities,
+                 const float* scales, float scale_modifier, const float* rotations, const float* cov3D_precomp,
+                 const float* viewmatrix, const float* projmatrix, const float* cam_pos, float tan_fovx,
+                 float tan_fovy, int prefiltered, int* radii, int debug, gm_stream_t stream_)
+{
+	cudaStream_t stream = (cudaStream_t)stream_;
+	ViewParams vp;
+	if (!make_view(vp, D, M, background, width, height, scale_modifier, viewmatrix, projmatrix, cam_pos, tan_fovx, tan_fovy))
+		return GM_ERR_BAD_ARGUMENT;
+	if (geom_buffer == nullptr)
+		return GM_ERR_BAD_ARGUMENT;
+	GeometryState geom;
+	if (int rc = forward_stage0(geom_buffer, P, vp, means3D, shs, colors_precomp, opacities, scales, rotations,
+	                            cov3D_precomp, prefiltered != 0, radii, 0xfffffff0u, debug != 0, stream, geom))
+		return rc;
+	// rasterizer_impl.cu:409-411: the instance total goes back to the host (blocking)
+	uint32_t num_rendered = 0;
+	cudaError_t err = cudaMemcpyAsync(&num_rendered, &geom.header->num_rendered, sizeof(uint32_t),
+	                                  cudaMemcpyDeviceToHost, stream);
+	if (err == cudaSuccess)
+		err = cudaStreamSynchronize(stream);
+	if (err != cudaSuccess) {
+		set_last_error("forward_0 readback", err);
+		return GM_ERR_CUDA;
+	}
+	return (int)num_rendered;
+}
+
+int gm_forward_1(char* geom_buffer, char* binning_buffer, char* image_buffer, int P, int D, int M,
+                 int num_rendered, const float* background, int width, int height, const float* means3D,
+                 const float* shs, const float* colors_precomp, const float* opacities, const float* scales,
+                 float scale_modifier, const float* rotations, const float* cov3D_precomp,
+                 const float* viewmatrix, const float* projmatrix, const float* cam_pos, float tan_fovx,
+                 float tan_fovy, int prefiltered, float* out_color, int* radii, int debug, gm_stream_t stream_)
+{
+	(void)means3D; (void)shs; (void)colors_precomp; (void)opacities; (void)scales; (void)rotations;
+	(void)cov3D_precomp; (void)prefiltered;
+	cudaStream_t stream = (cudaStream_t)stream_;
+	ViewParams vp;
+	if (!make_view(vp, D, M, background, width, height, scale_modifier, viewmatrix, projmatrix, cam_pos, tan_fovx, tan_fovy))
+		return GM_ERR_BAD_ARGUMENT;
+	if (geom_buffer == nullptr || num_rendered < 0 || P < 0)
+		return GM_ERR_BAD_ARGUMENT;
+	if (vp.tiles_x * vp.tiles_y > GM_MAX_TILES)
+		return GM_ERR_TOO_MANY_TILES;
+	GeometryState geom = GeometryState::fromChunk(geom_buffer, (size_t)P);
+	return forward_stage1(geom, binning_buffer, image_buffer, P, vp, (uint32_t)num_rendered, radii, out_color,
+	                      debug != 0, stream);
+}
+
+int gm_forward(char* geom_buffer, char* binning_buffer, size_t binning_capacity, char* image_buffer, int P,
+               int D, int M, const float* background, int width, int height, const float* means3D,
+               const float* shs, const float* colors_precomp, const float* opacities, const float* scales,
+               float scale_modifier, const float* rotations, const float* cov3D_precomp,
+               const float* viewmatrix, const float* projmatrix, const float* cam_pos, float tan_fovx,
+               float tan_fovy, int prefiltered, float* out_color, int* radii, int debug,
+               int* num_rendered_host, gm_stream_t stream_)
+{
+	cudaStream_t stream = (cudaStream_t)stream_;
+	ViewParams vp;
+	if (!make_view(vp, D, M, background, width, height, scale_modifier, viewmatrix, projmatrix, cam_pos, tan_fovx, tan_fovy))
+		return GM_ERR_BAD_ARGUMENT;
+	if (geom_buffer == nullptr)
+		return GM_ERR_BAD_ARGUMENT;
+	const uint32_t capacity = binning_capacity_instances(binning_capacity);
+	GeometryState geom;
+	if (int rc = forward_stage0(geom_buffer, P, vp, means3D, shs, colors_precomp, opacities, scales, rotations,
+	                            cov3D_precomp, prefiltered != 0, radii, capacity, debug != 0, stream, geom))
+		return rc;
+	if (num_rendered_host != nullptr) {
+		cudaError_t err = cudaMemcpyAsync(num_rendered_host, &geom.header->num_rendered, sizeof(uint32_t),
+		                                  cudaMemcpyDeviceToHost, stream);
+		if (err != cudaSuccess) {
+			set_last_error("forward count readback", err);
+			return GM_ERR_CUDA;
+		}
+	}
+	return forward_stage1(geom, binning_buffer, image_buffer, P, vp, capacity, radii, out_color, debug != 0, stream);
+}
+
+int gm_forward_status(const char* geom_buffer, int* num_rendered, int* num_visible, gm_stream_t stream_)
+{
+	cudaStream_t stream = (cudaStream_t)stream_;
+	if (geom_buffer == nullptr)
+		return GM_ERR_BAD_ARGUMENT;
+	char* p = const_cast<char*>(geom_buffer);
+	GeometryState geom = GeometryState::fromChunk(p, 0);
+	FrameHeader h;
+	cudaError_t err = cudaMemcpyAsync(&h, geom.header, sizeof(FrameHeader), cudaMemcpyDeviceToHost, stream);
+	if (err == cudaSuccess)
+		err = cudaStreamSynchronize(stream);
+	if (err != cudaSuccess) {
+		set_last_error("forward_status", err);
+		return GM_ERR_CUDA;
+	}
+	if (num_rendered) *num_rendered = (int)h.num_rendered;
+	if (num_visible) *num_visible = (int)h.num_visible;
+	return h.overflow ? GM_ERR_BINNING_OVERFLOW : GM_OK;
+}
+
+int gm_backward(int P, int D, int M, int R, const float* background, int width, int height,
+                const float* means3D, const float* shs, const float* colors_precomp, const float* scales,
+                float scale_modifier, const float* rotations, const float* cov3D_precomp,
+                const float* viewmatrix, const float* projmatrix, const float* campos, float tan_fovx,
+                float tan_fovy, const int* radii, char* geom_buffer, char* binning_buffer, char* image_buffer,
+                const float* dL_dpix, float* dL_dmean2D, float* dL_dconic, float* dL_dopacity,
+                float* dL_dcolor, float* dL_dmean3D, float* dL_dcov3D, float* dL_dsh, float* dL_dscale,
+                float* dL_drot, int debug, gm_stream_t stream_)
+{
+	cudaStream_t stream = (cudaStream_t)stream_;
+	ViewParams vp;
+	if (!make_view(vp, D, M, background, width, height, scale_modifier, viewmatrix, projmatrix, campos, tan_fovx, tan_fovy))
+		return GM_ERR_BAD_ARGUMENT;
+	if (P < 0 || R < 0 || geom_buffer == nullptr || image_buffer == nullptr || dL_dpix == nullptr ||
+	    dL_dmean2D == nullptr || dL_dconic == nullptr || dL_dopacity == nullptr || dL_dcolor == nullptr ||
+	    dL_dmean3D == nullptr || dL_dcov3D == nullptr)
+		return GM_ERR_BAD_ARGUMENT;
+	// rasterizer_impl.cu:576-596: SH / scale-rot gradients only exist on those paths
+	const bool sh_path = (colors_precomp == nullptr);
+	const bool sr_path = (cov3D_precomp == nullptr);
+	if ((sh_path && (shs == nullptr || dL_dsh == nullptr)) ||
+	    (sr_path && (scales == nullptr || rotations == nullptr || dL_dscale == nullptr || dL_drot == nullptr)))
+		return GM_ERR_BAD_ARGUMENT;
+	if (vp.tiles_x * vp.tiles_y > GM_MAX_TILES)
+		return GM_ERR_TOO_MANY_TILES;
+	if (P == 0)
+		return GM_OK;
+
+	GeometryState geom = GeometryState::fromChunk(geom_buffer, (size_t)P);
+	BinningState binning = BinningState::fromChunk(binning_buffer, (size_t)R);
+	ImageState img = ImageState::fromChunk(image_buffer, (size_t)width * height);
+	if (radii == nullptr)
+		radii = geom.internal_radii;
+
+	launch_blend_backward(geom, binning, img, (uint32_t)R, vp, dL_dpix, dL_dmean2D, dL_dconic, dL_dopacity,
+	                      dL_dcolor, stream);
+	if (int rc = check_stage("blend_backward", debug != 0, stream)) return rc;
+
+	const float* cov3D_ptr = sr_path ? geom.cov3D : cov3D_precomp;
+	launch_geometry_backward(P, means3D, radii, sh_path ? shs : nullptr, sr_path ? scales : nullptr,
+	                         sr_path ? rotations : nullptr, cov3D_ptr, vp, geom, dL_dmean2D, dL_dconic, dL_dcolor,
+	                         dL_dmean3D, dL_dcov3D, dL_dsh, dL_dscale, dL_drot, stream);
+	return check_stage("geometry_backward", debug != 0, stream);
+}
+
+int gm_mesh_bind_forward(int P, const float* bc_logits, const float* distance, const float* vertex1,
+                         const float* vertex2, const float* vertex3, const float* normal, const float* r,
+                         float alpha_distance, const float* log_scale, const float* rot_raw,
+                         const float* opacity_logit, float* xyz, float* scale, float* rot, float* opacity,
+                         gm_stream_t stream)
+{
+	if (P < 0)
+		return GM_ERR_BAD_ARGUMENT;
+	if (xyz != nullptr && (!bc_logits || !distance || !vertex1 || !vertex2 || !vertex3 || !normal || !r))
+		return GM_ERR_BAD_ARGUMENT;
+	if ((scale != nullptr && !log_scale) || (rot != nullptr && !rot_raw) || (opacity != nullptr && !opacity_logit))
+		return GM_ERR_BAD_ARGUMENT;
+	launch_mesh_bind_forward(P, bc_logits, distance, vertex1, vertex2, vertex3, normal, r, alpha_distance, log_scale,
+	                         rot_raw, opacity_logit, xyz, scale, rot, opacity, (cudaStream_t)stream);
+	return check_stage("mesh_bind_forward", false, (cudaStream_t)stream);
+}
+
+int gm_mesh_bind_backward(int P, const float* bc_logits, const float* distance, const float* vertex1,
+                          const float* vertex2, const float* vertex3, const float* normal, const float* r,
+                          float alpha_distance, const float* log_scale, const float* rot_raw,
+                          const float* opacity_logit, const float* dL_dxyz, const float* dL_dscale,
+                          const float* dL_drot, const float* dL_dopacity, float* dL_dbc_logits,
+                          float* dL_ddistance, float* dL_dlog_scale, float* dL_drot_raw,
+                          float* dL_dopacity_logit, gm_stream_t stream)
+{
+	if (P < 0)
+		return GM_ERR_BAD_ARGUMENT;
+	if (dL_dxyz != nullptr && dL_dbc_logits != nullptr &&
+	    (!bc_logits || !distance || !vertex1 || !vertex2 || !vertex3 || !normal || !r))
+		return GM_ERR_BAD_ARGUMENT;
+	if ((dL_dscale && dL_dlog_scale && !log_scale) || (dL_drot && dL_drot_raw && !rot_raw) ||
+	    (dL_dopacity && dL_dopacity_logit && !opacity_logit))
+		return GM_ERR_BAD_ARGUMENT;
+	launch_mesh_bind_backward(P, bc_logits, distance, vertex1, vertex2, vertex3, normal, r, alpha_distance, log_scale,
+	                          rot_raw, opacity_logit, dL_dxyz, dL_dscale, dL_drot, dL_dopacity, dL_dbc_logits,
+	                          dL_ddistance, dL_dlog_scale, dL_drot_raw, dL_dopacity_logit, (cudaStream_t)stream);
+	return check_stage("mesh_bind_backward", false, (cudaStream_t)stream);
+}
+
+int gm_deform_gaussians(int P, int num_vertices, const float* vertex_rest, const float* vertex_deformed,
+                        const float* vertex_R, const float* vertex_S, const int* gaussian_triangles,
+                        const float* weights, const float* pos_in, const float* cov_in, int cov_in_is_full,
+                        float* pos_out, float* cov6_out, float* rot_out, gm_stream_t stream)
+{
+	if (P < 0 || num_vertices < 0)
+		return GM_ERR_BAD_ARGUMENT;
+	if (P > 0 && (!vertex_rest || !vertex_deformed || !vertex_R || !vertex_S || !gaussian_triangles || !weights ||
+	              !pos_in || !cov_in || !pos_out || !cov6_out))
+		return GM_ERR_BAD_ARGUMENT;
+	launch_deform(P, vertex_rest, vertex_deformed, vertex_R, vertex_S, gaussian_triangles, weights, pos_in, cov_in,
+	              cov_in_is_full, pos_out, cov6_out, rot_out, (cudaStream_t)stream);
+	return check_stage("deform", false, (cudaStream_t)stream);
+}
+
+int gm_sh_to_rgb_rotated(int P, int D, int M, const float* pos, const float* campos, const float* rot,
+                         const float* shs, float* rgb, gm_stream_t stream)
+{
+	if (P < 0 || D < 0 || D > 3 || M < (D + 1) * (D + 1))
+		return GM_ERR_BAD_ARGUMENT;
+	if (P > 0 && (!pos || !campos || !shs || !rgb))
+		return GM_ERR_BAD_ARGUMENT;
+	launch_sh_rotated(P, D, M, pos, campos, rot, shs, rgb, (cudaStream_t)stream);
+	return check_stage("sh_to_rgb_rotated", false, (cudaStream_t)stream);
+}
+
+int gm_l1_loss(size_t numel, const float* img, const float* target, float* loss, float* dL_dimg, gm_stream_t stream)
+{
+	if (loss == nullptr || (numel > 0 && (!img || !target)))
+		return GM_ERR_BAD_ARGUMENT;
+	launch_l1(numel, img, target, loss, dL_dimg, (cudaStream_t)stream);
+	return check_stage("l1_loss", false, (cudaStream_t)stream);
+}
+
+} // extern "C"
+
+// ------------------------------------------------------------------------------------------------
+// C++ ABI of the reference (legacy default stream, exceptions instead of error codes).
+// ------------------------------------------------------------------------------------------------
+namespace CudaRasterizer {
+
+static void raise_on_error(int rc, const char* where)
+{
+	if (rc >= 0)
+		return;
+	std::string msg = std::string(where) + " failed (" + std::to_string(rc) + ")";
+	if (rc == GM_ERR_CUDA)
+		msg += std::string(": ") + gm_last_error();
+	throw std::runtime_error(msg);
+}
+
+GeometryState GeometryState::fromChunk(char*& chunk, size_t P)
+{
+	GeometryState s;
+	s.begin = chunk;
+	gm::GeometryState::fromChunk(chunk, P);
+	s.end = chunk;
+	return s;
+}
+
+ImageState ImageState::fromChunk(char*& chunk, size_t N)
+{
+	ImageState s;
+	s.begin = chunk;
+	gm::ImageState::fromChunk(chunk, N);
+	s.end = chunk;
+	return s;
+}
+
+BinningState BinningState::fromChunk(char*& chunk, size_t R)
+{
+	BinningState s;
+	s.begin = chunk;
+	gm::BinningState::fromChunk(chunk, R);
+	s.end = chunk;
+	return s;
+}
+
+void Rasterizer::markVisible(int P, float* means3D, float* viewmatrix, float* projmatrix, bool* present)
+{
+	raise_on_error(gm_mark_visible(P, means3D, viewmatrix, projmatrix, reinterpret_cast<uint8_t*>(present), nullptr),
+	               "markVisible");
+}
+
+int Rasterizer::forward_0(char* geometryBuffer, const int P, int D, int M, const float* background,
+	const int width, int height, const float* means3D, const float* shs, const float* colors_precomp,
+	const float* opacities, const float* scales, const float scale_modifier, const float* rotations,
+	const float* cov3D_precomp, const float* viewmatrix, const float* projmatrix, const float* cam_pos,
+	const float tan_fovx, float tan_fovy, const bool prefiltered, int* radii, bool debug)
+{
+	int rc = gm_forward_0(geometryBuffer, P, D, M, background, width, height, means3D, shs, colors_precomp, opacities,
+	                      scales, scale_modifier, rotations, cov3D_precomp, viewmatrix, projmatrix, cam_pos, tan_fovx,
+	                      tan_fovy, prefiltered, radii, debug, nullptr);
+	raise_on_error(rc, "forward_0");
+	return rc;
+}
+
+void Rasterizer::forward_1(char* geometryBuffer, char* binningBuffer, char* imageBuffer, const int P, int D, int M,
+	int num_rendered, const float* background, const int width, int height, const float* means3D,
+	const float* shs, const float* colors_precomp, const float* opacities, const float* scales,
+	const float scale_modifier, const float* rotations, const float* cov3D_precomp, const float* viewmatrix,
+	const float* projmatrix, const float* cam_pos, const float tan_fovx, float tan_fovy, const bool prefiltered,
+	float* out_color, int* radii, bool debug)
+{
+	raise_on_error(gm_forward_1(geometryBuffer, binningBuffer, imageBuffer, P, D, M, num_rendered, background, width,
+	                            height, means3D, shs, colors_precomp, opacities, scales, scale_modifier, rotations,
+	                            cov3D_precomp, viewmatrix, projmatrix, cam_pos, tan_fovx, tan_fovy, prefiltered,
+	                            out_color, radii, debug, nullptr),
+	               "forward_1");
+}
+
+int Rasterizer::forward(std::function<char* (size_t)> geometryBuffer, std::function<char* (size_t)> binningBuffer,
+	std::function<char* (size_t)> imageBuffer, const int P, int D, int M, const float* background,
+	const int width, int height, const float* means3D, const float* shs, const float* colors_precomp,
+	const float* opacities, const float* scales, const float scale_modifier, const float* rotations,
+	const float* cov3D_precomp, const float* viewmatrix, const float* projmatrix, const float* cam_pos,
+	const float tan_fovx, float tan_fovy, const bool prefiltered, float* out_color, int* radii, bool debug)
+{
+	char* geom = geometryBuffer(required<GeometryState>(P));
+	char* img = imageBuffer(required<ImageState>((size_t)width * height));
+	int R = forward_0(geom, P, D, M, background, width, height, means3D, shs, colors_precomp, opacities, scales,
+	                  scale_modifier, rotations, cov3D_precomp, viewmatrix, projmatrix, cam_pos, tan_fovx, tan_fovy,
+	                  prefiltered, radii, debug);
+	char* binning = binningBuffer(required<BinningState>(R));
+	forward_1(geom, binning, img, P, D, M, R, background, width, height, means3D, shs, colors_precomp, opacities,
+	          scales, scale_modifier, rotations, cov3D_precomp, viewmatrix, projmatrix, cam_pos, tan_fovx, tan_fovy,
+	          prefiltered, out_color, radii, debug);
+	return R;
+}
+
+void Rasterizer::backward(const int P, int D, int M, int R, const float* background, const int width, int height,
+	const float* means3D, const float* shs, const float* colors_precomp, const float* scales,
+	const float scale_modifier, const float* rotations, const float* cov3D_precomp, const float* viewmatrix,
+	const float* projmatrix, const float* campos, const float tan_fovx, float tan_fovy, const int* radii,
+	char* geom_buffer, char* binning_buffer, char* image_buffer, const float* dL_dpix, float* dL_dmean2D,
+	float* dL_dconic, float* dL_dopacity, float* dL_dcolor, float* dL_dmean3D, float* dL_dcov3D, float* dL_dsh,
+	float* dL_dscale, float* dL_drot, bool debug)
+{
+	raise_on_error(gm_backward(P, D, M, R, background, width, height, means3D, shs, colors_precomp, scales,
+	                           scale_modifier, rotations, cov3D_precomp, viewmatrix, projmatrix, campos, tan_fovx,
+	                           tan_fovy, radii, geom_buffer, binning_buffer, image_buffer, dL_dpix, dL_dmean2D,
+	                           dL_dconic, dL_dopacity, dL_dcolor, dL_dmean3D, dL_dcov3D, dL_dsh, dL_dscale, dL_drot,
+	                           debug, nullptr),
+	               "backward");
+}
+
+} // namespace CudaRasterizer

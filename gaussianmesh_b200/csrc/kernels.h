@@ -1,0 +1,57 @@
+// Host-side launch prototypes of the sm_100a kernels (one .cu per pipeline stage).
+#pragma once
+#include <cuda_runtime_api.h>
+#include "state.h"
+
+namespace gm {
+
+int launch_mark_visible(int P, const float* means3D, const float* viewmatrix, uint8_t* present, cudaStream_t stream);
+
+int launch_preprocess(int P, const float* means3D, const float* scales, const float* rotations,
+                      const float* opacities, const float* shs, const float* cov3D_precomp,
+                      const float* colors_precomp, const ViewParams& vp, int* radii,
+                      const GeometryState& g, bool prefiltered, cudaStream_t stream);
+
+int launch_tile_scan(int num_tiles, const GeometryState& g, uint32_t capacity, cudaStream_t stream);
+
+int launch_emit(int P, const int* radii, const GeometryState& g, const BinningState& b, uint32_t capacity,
+                const ViewParams& vp, cudaStream_t stream);
+
+int launch_sort_pack(int num_tiles, const GeometryState& g, const BinningState& b, uint32_t capacity,
+                     cudaStream_t stream);
+
+int launch_blend_forward(const GeometryState& g, const BinningState& b, const ImageState& img, uint32_t capacity,
+                         const ViewParams& vp, float* out_color, cudaStream_t stream);
+
+int launch_blend_backward(const GeometryState& g, const BinningState& b, const ImageState& img, uint32_t capacity,
+                          const ViewParams& vp, const float* dL_dpix, float* dL_dmean2D, float* dL_dconic,
+                          float* dL_dopacity, float* dL_dcolor, cudaStream_t stream);
+
+int launch_geometry_backward(int P, const float* means3D, const int* radii, const float* shs, const float* scales,
+                             const float* rotations, const float* cov3Ds, const ViewParams& vp,
+                             const GeometryState& g, const float* dL_dmean2D, const float* dL_dconic,
+                             const float* dL_dcolor, float* dL_dmean3D, float* dL_dcov3D, float* dL_dsh,
+                             float* dL_dscale, float* dL_drot, cudaStream_t stream);
+
+int launch_mesh_bind_forward(int P, const float* bc_logits, const float* distance, const float* v1, const float* v2,
+                             const float* v3, const float* normal, const float* r, float alpha_distance,
+                             const float* log_scale, const float* rot_raw, const float* opacity_logit, float* xyz,
+                             float* scale, float* rot, float* opacity, cudaStream_t stream);
+
+int launch_mesh_bind_backward(int P, const float* bc_logits, const float* distance, const float* v1, const float* v2,
+                              const float* v3, const float* normal, const float* r, float alpha_distance,
+                              const float* log_scale, const float* rot_raw, const float* opacity_logit,
+                              const float* dL_dxyz, const float* dL_dscale, const float* dL_drot,
+                              const float* dL_dopacity, float* dL_dbc, float* dL_ddist, float* dL_dlog_scale,
+                              float* dL_drot_raw, float* dL_dopacity_logit, cudaStream_t stream);
+
+int launch_deform(int P, const float* V, const float* Vd, const float* VR, const float* VS, const int* tri,
+                  const float* w, const float* pos_in, const float* cov_in, int cov_full, float* pos_out,
+                  float* cov6_out, float* rot_out, cudaStream_t stream);
+
+int launch_sh_rotated(int P, int D, int M, const float* pos, const float* campos, const float* rot, const float* shs,
+                      float* rgb, cudaStream_t stream);
+
+int launch_l1(size_t numel, const float* img, const float* target, float* loss, float* dL_dimg, cudaStream_t stream);
+
+} // namespace gm

@@ -1,0 +1,203 @@
+// Per-Gaussian forward stage: near cull, projection, 3D->2D covariance, conic, radius, tile
+// rectangle, SH->RGB, and -- new in this design -- the per-tile instance COUNT with exact
+// rectangle culling, so that no prefix sum over Gaussians and no global key sort is needed
+// afterwards (DESIGN.md "binning").
+//
+// Replaces preprocessCUDA<3> (dgr/cuda_rasterizer/forward.cu:155-256), checkFrustum
+// (rasterizer_impl.cu:54-66) and the tiles_touched/InclusiveSum pair (forward.cu:255,
+// rasterizer_impl.cu:407).
+#include <cstdio>
+#include "common.cuh"
+#include "kernels.h"
+
+namespace gm {
+
+namespace {
+
+constexpr int kThreads = 256;
+
+// auxiliary.h:138-163 -- only the near plane is tested (the +-1.3 NDC test is commented out in the
+// reference).  prefiltered == true turns a culled point into a device trap, as in the reference.
+__device__ __forceinline__ bool near_cull_passes(const float3& p_orig, const float* view, bool prefiltered,
+                                                 float3& p_view)
+{
+	p_view = transform_point_4x3(p_orig, view);
+	if (p_view.z <= 0.2f) {
+		if (prefiltered) {
+			printf("Point is filtered although prefiltered is set. This shouldn't happen!");
+			__trap();
+		}
+		return false;
+	}
+	return true;
+}
+
+__global__ void __launch_bounds__(kThreads)
+mark_visible_kernel(int P, const float* __restrict__ means3D, const float* __restrict__ view, uint8_t* __restrict__ present)
+{
+	int idx = blockIdx.x * kThreads + threadIdx.x;
+	if (idx >= P)
+		return;
+	float3 p = make_float3(means3D[3 * idx], means3D[3 * idx + 1], means3D[3 * idx + 2]);
+	float3 pv;
+	present[idx] = near_cull_passes(p, view, false, pv) ? 1 : 0;
+}
+
+__global__ void __launch_bounds__(kThreads)
+preprocess_kernel(int P,
+                  const float* __restrict__ means3D,
+                  const float* __restrict__ scales,
+                  const float* __restrict__ rotations,
+                  const float* __restrict__ opacities,
+                  const float* __restrict__ shs,
+                  const float* __restrict__ cov3D_precomp,
+                  const float* __restrict__ colors_precomp,
+                  ViewParams vp,
+                  int* __restrict__ radii,
+                  GeometryState g,
+                  bool prefiltered)
+{
+	__shared__ float s_view[16];
+	__shared__ float s_proj[16];
+	__shared__ float s_cam[3];
+	if (threadIdx.x < 16) {
+		s_view[threadIdx.x] = vp.view[threadIdx.x];
+		s_proj[threadIdx.x] = vp.proj[threadIdx.x];
+	}
+	if (threadIdx.x < 3)
+		s_cam[threadIdx.x] = vp.campos[threadIdx.x];
+	__syncthreads();
+
+	const int idx = blockIdx.x * kThreads + threadIdx.x;
+	bool visible = false;
+
+	if (idx < P) {
+		// forward.cu:186-187: a Gaussian that exits early keeps radius 0 (and touches no tile).
+		int my_radius_i = 0;
+
+		do {
+			const float3 p_orig = make_float3(means3D[3 * idx], means3D[3 * idx + 1], means3D[3 * idx + 2]);
+			float3 p_view;
+			if (!near_cull_passes(p_orig, s_view, prefiltered, p_view))
+				break;
+
+			// forward.cu:195-198
+			const float4 p_hom = transform_point_4x4(p_orig, s_proj);
+			const float p_w = 1.0f / (p_hom.w + 0.0000001f);
+			const float3 p_proj = make_float3(p_hom.x * p_w, p_hom.y * p_w, p_hom.z * p_w);
+
+			// forward.cu:200-211
+			float cov6[6];
+			if (cov3D_precomp != nullptr) {
+#pragma unroll
+				for (int i = 0; i < 6; i++)
+					cov6[i] = cov3D_precomp[6 * idx + i];
+			} else {
+				const float3 sc = make_float3(scales[3 * idx], scales[3 * idx + 1], scales[3 * idx + 2]);
+				const float4 q = reinterpret_cast<const float4*>(rotations)[idx];
+				cov3d_from_scale_rot(sc, vp.scale_modifier, q, cov6);
+#pragma unroll
+				for (int i = 0; i < 6; i++)
+					g.cov3D[6 * idx + i] = cov6[i];
+			}
+
+			// forward.cu:213-223
+			const float3 cov = cov2d(p_orig, vp.focal_x, vp.focal_y, vp.tan_fovx, vp.tan_fovy, cov6, s_view);
+			const float det = (cov.x * cov.z - cov.y * cov.y);
+			if (det == 0.0f)
+				break;
+			const float det_inv = 1.f / det;
+			const float3 conic = make_float3(cov.z * det_inv, -cov.y * det_inv, cov.x * det_inv);
+
+			// forward.cu:225-237
+			const float mid = 0.5f * (cov.x + cov.z);
+			const float lambda1 = mid + sqrtf(max(0.1f, mid * mid - det));
+			const float lambda2 = mid - sqrtf(max(0.1f, mid * mid - det));
+			const float my_radius = ceilf(3.f * sqrtf(max(lambda1, lambda2)));
+			const float2 point_image = make_float2(ndc_to_pix(p_proj.x, vp.W), ndc_to_pix(p_proj.y, vp.H));
+			int x0, y0, x1, y1;
+			tile_rect(point_image, (int)my_radius, vp.tiles_x, vp.tiles_y, x0, y0, x1, y1);
+			if ((x1 - x0) * (y1 - y0) == 0)
+				break;
+
+			// forward.cu:239-247 (SH -> RGB with clamp mask) or precomputed colours
+			float4 rgbc;
+			if (colors_precomp == nullptr) {
+				// forward.cu:25-27: dir = (pos - campos) / length
+				float dx = p_orig.x - s_cam[0], dy = p_orig.y - s_cam[1], dz = p_orig.z - s_cam[2];
+				const float len = sqrtf(dx * dx + dy * dy + dz * dz);
+				dx = dx / len; dy = dy / len; dz = dz / len;
+				const ShDir d = sh_dir(dx, dy, dz);
+				const float* sh = shs + (size_t)idx * vp.M * 3;
+				float r = sh_channel(vp.D, d, [sh](int k) { return sh[3 * k + 0]; });
+				float gch = sh_channel(vp.D, d, [sh](int k) { return sh[3 * k + 1]; });
+				float b = sh_channel(vp.D, d, [sh](int k) { return sh[3 * k + 2]; });
+				r += 0.5f; gch += 0.5f; b += 0.5f;
+				const uint32_t bits = (r < 0 ? 1u : 0u) | (gch < 0 ? 2u : 0u) | (b < 0 ? 4u : 0u);
+				rgbc = make_float4(max(r, 0.0f), max(gch, 0.0f), max(b, 0.0f), __uint_as_float(bits));
+			} else {
+				rgbc = make_float4(colors_precomp[3 * idx], colors_precomp[3 * idx + 1], colors_precomp[3 * idx + 2],
+				                   __uint_as_float(0u));
+			}
+
+			// forward.cu:249-255
+			const float opacity = opacities[idx];
+			g.depths[idx] = p_view.z;
+			g.means2D[idx] = point_image;
+			g.conic_opacity[idx] = make_float4(conic.x, conic.y, conic.z, opacity);
+			g.rgb_clamp[idx] = rgbc;
+			my_radius_i = (int)my_radius;
+			visible = true;
+
+			// Per-tile instance count.  Tiles whose 16x16 pixel block cannot receive any alpha
+			// >= 1/255 from this Gaussian are skipped (rect_cannot_contribute is output-preserving).
+			const float thr = cull_threshold(opacity);
+			if (thr >= 0.0f) {
+				for (int ty = y0; ty < y1; ty++) {
+					const float py0 = (float)(ty * kTile);
+					const float py1 = fminf(py0 + (kTile - 1), (float)(vp.H - 1));
+					for (int tx = x0; tx < x1; tx++) {
+						const float px0 = (float)(tx * kTile);
+						const float px1 = fminf(px0 + (kTile - 1), (float)(vp.W - 1));
+						if (!rect_cannot_contribute(point_image.x, point_image.y, conic.x, conic.y, conic.z, thr,
+						                            px0, py0, px1, py1))
+							atomicAdd(&g.tile_count[ty * vp.tiles_x + tx], 1u);
+					}
+				}
+			}
+		} while (false);
+
+		radii[idx] = my_radius_i;
+	}
+
+	const int n_vis = __syncthreads_count(visible);
+	if (threadIdx.x == 0 && n_vis > 0)
+		atomicAdd(&g.header->num_visible, (uint32_t)n_vis);
+}
+
+} // namespace
+
+int launch_mark_visible(int P, const float* means3D, const float* viewmatrix, uint8_t* present, cudaStream_t stream)
+{
+	if (P <= 0)
+		return GM_OK;
+	mark_visible_kernel<<<(P + kThreads - 1) / kThreads, kThreads, 0, stream>>>(P, means3D, viewmatrix, present);
+	return GM_OK;
+}
+
+int launch_preprocess(int P, const float* means3D, const float* scales, const float* rotations,
+                      const float* opacities, const float* shs, const float* cov3D_precomp,
+                      const float* colors_precomp, const ViewParams& vp, int* radii,
+                      const GeometryState& g, bool prefiltered, cudaStream_t stream)
+{
+	const int num_tiles = vp.tiles_x * vp.tiles_y;
+	cudaMemsetAsync(g.header, 0, sizeof(FrameHeader), stream);
+	cudaMemsetAsync(g.tile_count, 0, sizeof(uint32_t) * (size_t)num_tiles, stream);
+	if (P <= 0)
+		return GM_OK;
+	preprocess_kernel<<<(P + kThreads - 1) / kThreads, kThreads, 0, stream>>>(
+		P, means3D, scales, rotations, opacities, shs, cov3D_precomp, colors_precomp, vp, radii, g, prefiltered);
+	return GM_OK;
+}
+
+} // namespace gm

@@ -1,0 +1,136 @@
+// Layout of the three caller-owned scratch chunks (geometry / image / binning).
+//
+// These replace the reference's GeometryState / ImageState / BinningState
+// (dgr/cuda_rasterizer/rasterizer_impl.h:21-73, rasterizer_impl.cu:155-194).  The chunks are
+// opaque to callers, so only the *protocol* is kept (caller sizes them with required<T>(), the
+// library carves 128-byte aligned sub-arrays, forward -> backward must see them unchanged); the
+// contents are laid out for the B200 pipeline described in DESIGN.md:
+//
+//   geometry : frame header, per-Gaussian SoA state, per-tile counters (count / start / fill)
+//   image    : per-pixel final transmittance and last-contributor index
+//   binning  : per-instance (depth,id) keys bucketed by tile, then three packed, tile-contiguous
+//              record arrays that the blend kernels stage with cp.async.bulk (TMA)
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <cuda_runtime_api.h>
+#include "../../include/gm_rasterizer.h"
+
+namespace gm {
+
+constexpr int kTile = GM_TILE;                 // 16x16 pixel tiles (config.h:16-17)
+constexpr int kTilePixels = kTile * kTile;
+constexpr int kSegAlign = 4;                   // tile segments start on a multiple of 4 instances
+                                               // => every record array offset is 32-byte aligned
+constexpr size_t kChunkAlign = 128;
+
+// Written by the tile-scan kernel, read by later stages and by gm_forward_status().
+struct FrameHeader {
+	uint32_t num_rendered;   // padded instance total of this view (sum of aligned tile counts)
+	uint32_t num_visible;    // Gaussians with radii > 0
+	uint32_t overflow;       // 1 if num_rendered exceeded the binning capacity handed to gm_forward
+	uint32_t capacity;       // binning capacity in instances used for this frame
+	uint32_t num_tiles;
+	uint32_t pad[27];
+};
+static_assert(sizeof(FrameHeader) == 128, "FrameHeader must be one 128-byte line");
+
+struct GeometryState {
+	FrameHeader* header;
+	float* depths;            // [P]   view-space z                                (forward.cu:249)
+	int* internal_radii;      // [P]   used when the caller passes radii == NULL   (rasterizer_impl.cu:364)
+	float2* means2D;          // [P]   pixel-space centre                          (forward.cu:251)
+	float* cov3D;             // [6P]  world covariance, scale/rot path only       (forward.cu:146-151)
+	float4* conic_opacity;    // [P]   (a, b, c, opacity)                          (forward.cu:253)
+	float4* rgb_clamp;        // [P]   (r, g, b, clamp bits as uint)               (forward.cu:63-70)
+	uint32_t* tile_count;     // [GM_MAX_TILES] instances per tile after exact tile culling
+	uint32_t* tile_start;     // [GM_MAX_TILES] first instance of the tile (multiple of kSegAlign)
+	uint32_t* tile_fill;      // [GM_MAX_TILES] emit cursor
+
+	static GeometryState fromChunk(char*& chunk, size_t P);
+};
+
+struct ImageState {
+	float* accum_alpha;       // [N] final transmittance T                         (forward.cu:369)
+	uint32_t* n_contrib;      // [N] 1-based list position of the last contributor (forward.cu:370)
+
+	static ImageState fromChunk(char*& chunk, size_t N);
+};
+
+struct BinningState {
+	uint64_t* keys;           // [R] (depth bits << 32) | gaussian id, bucketed by tile, unsorted
+	float4* rec_conic;        // [R] (a, b, c, opacity)            sorted front-to-back within a tile
+	float4* rec_xyrg;         // [R] (x, y, r, g)
+	float2* rec_bid;          // [R] (b, gaussian id as bits)
+
+	static BinningState fromChunk(char*& chunk, size_t R);
+};
+
+template <typename T>
+inline void obtain(char*& chunk, T*& ptr, size_t count, size_t alignment = kChunkAlign)
+{
+	uintptr_t at = (reinterpret_cast<uintptr_t>(chunk) + alignment - 1) & ~(uintptr_t)(alignment - 1);
+	ptr = reinterpret_cast<T*>(at);
+	chunk = reinterpret_cast<char*>(ptr + count);
+}
+
+template <typename T>
+inline size_t required(size_t n)
+{
+	char* end = nullptr;
+	T::fromChunk(end, n);
+	return reinterpret_cast<size_t>(end) + kChunkAlign;
+}
+
+inline GeometryState GeometryState::fromChunk(char*& chunk, size_t P)
+{
+	GeometryState g;
+	obtain(chunk, g.header, 1);
+	obtain(chunk, g.depths, P);
+	obtain(chunk, g.internal_radii, P);
+	obtain(chunk, g.means2D, P);
+	obtain(chunk, g.cov3D, 6 * P);
+	obtain(chunk, g.conic_opacity, P);
+	obtain(chunk, g.rgb_clamp, P);
+	obtain(chunk, g.tile_count, (size_t)GM_MAX_TILES);
+	obtain(chunk, g.tile_start, (size_t)GM_MAX_TILES);
+	obtain(chunk, g.tile_fill, (size_t)GM_MAX_TILES);
+	return g;
+}
+
+inline ImageState ImageState::fromChunk(char*& chunk, size_t N)
+{
+	ImageState s;
+	obtain(chunk, s.accum_alpha, N);
+	obtain(chunk, s.n_contrib, N);
+	return s;
+}
+
+inline BinningState BinningState::fromChunk(char*& chunk, size_t R)
+{
+	// Round up so that a full-width bulk copy of the last (padded) batch never leaves the chunk.
+	size_t Rp = (R + 7) & ~(size_t)7;
+	BinningState b;
+	obtain(chunk, b.keys, Rp);
+	obtain(chunk, b.rec_conic, Rp);
+	obtain(chunk, b.rec_xyrg, Rp);
+	obtain(chunk, b.rec_bid, Rp);
+	return b;
+}
+
+// Per-view constants.  The four small arrays stay DEVICE pointers (the reference API hands
+// them over as device tensors, rasterizer.h:24-132); kernels load them once per thread block.
+struct ViewParams {
+	const float* view;    // [16] column-major W2C as stored by scene/cameras.py:48 (auxiliary.h:57-65)
+	const float* proj;    // [16] full projection (scene/cameras.py:49-50)
+	const float* campos;  // [3]
+	const float* bg;      // [3]
+	float tan_fovx, tan_fovy;
+	float focal_x, focal_y;
+	float scale_modifier;
+	int W, H;
+	int tiles_x, tiles_y;
+	int D, M;
+};
+
+} // namespace gm

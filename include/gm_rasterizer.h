@@ -1,0 +1,180 @@
+/*
+ * gm_rasterizer.h -- flat C ABI of libCudaRasterizer.so (B200 / sm_100a build).
+ *
+ * This is the drop-in boundary for the one hot path this repository replaces:
+ *   mesh-face bind/deform -> per-Gaussian preprocess -> tile binning/sort -> per-tile alpha blend
+ *   (forward and backward).
+ * Every entry takes plain device pointers, sizes and a CUDA stream; none allocates or frees
+ * device memory (the caller owns every byte, exactly as with the reference library).
+ * All pointers are DEVICE pointers unless the parameter name ends in _host.
+ *
+ * Citations are relative to the reference checkout
+ * (gaussian_renderer/diff_gaussian_rasterizater/ abbreviated as dgr/).
+ *
+ * Return value of every int-returning entry: GM_OK (0) or a negative GM_ERR_* code.  With
+ * debug != 0 each stage is followed by a stream synchronise + error check (the reference's
+ * CHECK_CUDA, dgr/cuda_rasterizer/auxiliary.h:165-172); with debug == 0 only launch-time
+ * errors are reported, as in the reference.
+ */
+#ifndef GM_RASTERIZER_H_INCLUDED
+#define GM_RASTERIZER_H_INCLUDED
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GM_OK 0
+#define GM_ERR_CUDA (-1)            /* a CUDA runtime call or kernel failed (see gm_last_error)      */
+#define GM_ERR_BAD_ARGUMENT (-2)    /* inconsistent pointers / sizes (e.g. neither SH nor colours)    */
+#define GM_ERR_TOO_MANY_TILES (-3)  /* ceil(W/16)*ceil(H/16) exceeds GM_MAX_TILES                     */
+#define GM_ERR_BINNING_OVERFLOW (-4)/* binning chunk smaller than the instance count of this view     */
+
+#define GM_TILE 16                  /* BLOCK_X == BLOCK_Y, dgr/cuda_rasterizer/config.h:16-17         */
+#define GM_MAX_TILES (1 << 18)      /* per-tile counters live in the geometry chunk       */
+
+typedef void* gm_stream_t;          /* a cudaStream_t; NULL = the legacy default stream               */
+
+/* ---- library info ------------------------------------------------------------------------ */
+const char* gm_version(void);       /* "gaussianmesh-b200 <semver> sm_100a"                           */
+const char* gm_last_error(void);    /* text of the last GM_ERR_CUDA on this host thread               */
+
+/* ---- opaque chunk sizing; replaces CudaRasterizer::required<T>()
+ *      (dgr/cuda_rasterizer/rasterizer_impl.h:67-73, used at dgr/rasterize_points.py:74-76,186) --- */
+size_t gm_required_geom(size_t P);          /* GeometryState for P Gaussians                        */
+size_t gm_required_image(size_t N);         /* ImageState for N = W*H pixels                        */
+size_t gm_required_binning(size_t R);       /* BinningState for R (Gaussian, tile) instances        */
+
+/* ---- markVisible; replaces Rasterizer::markVisible (dgr/cuda_rasterizer/rasterizer.h:24-29,
+ *      rasterizer_impl.cu:54-66,141-153).  present[P] is a byte mask (C++ bool). ---------------- */
+int gm_mark_visible(int P, const float* means3D, const float* viewmatrix, const float* projmatrix,
+                    uint8_t* present, gm_stream_t stream);
+
+/* ---- two-phase forward; replaces Rasterizer::forward_0 / forward_1
+ *      (dgr/cuda_rasterizer/rasterizer.h:31-76, rasterizer_impl.cu:338-513), the pair the
+ *      reference's glue calls (dgr/rasterize_points.py:164-266).
+ *
+ *  gm_forward_0: preprocess + per-tile instance count + tile offsets.  Returns the number of
+ *  (Gaussian, tile) instances the caller must size the binning chunk for (>= 0), or GM_ERR_*.
+ *  Like the reference it ends with a blocking 4-byte device->host read.
+ *  Null-pointer variants as in the reference (rasterizer_impl.cu:364-367, rasterize_points.py:
+ *  162-163): colors_precomp == NULL -> SH path (shs [P,M,3], degree D); cov3D_precomp == NULL ->
+ *  scales [P,3] / rotations [P,4] path (quaternion used UN-normalised, forward.cu:127);
+ *  radii == NULL -> radii kept only inside the geometry chunk. */
+int gm_forward_0(char* geom_buffer, int P, int D, int M, const float* background, int width,
+                 int height, const float* means3D, const float* shs, const float* colors_precomp,
+                 const float* opacities, const float* scales, float scale_modifier,
+                 const float* rotations, const float* cov3D_precomp, const float* viewmatrix,
+                 const float* projmatrix, const float* cam_pos, float tan_fovx, float tan_fovy,
+                 int prefiltered, int* radii, int debug, gm_stream_t stream);
+
+/*  gm_forward_1: instance emit + per-tile depth sort + record packing + front-to-back blend.
+ *  num_rendered is the value gm_forward_0 returned; binning_buffer must hold
+ *  gm_required_binning(num_rendered) bytes, image_buffer gm_required_image(W*H).
+ *  out_color is planar [3,H,W] (forward.cu:368-373). */
+int gm_forward_1(char* geom_buffer, char* binning_buffer, char* image_buffer, int P, int D, int M,
+                 int num_rendered, const float* background, int width, int height,
+                 const float* means3D, const float* shs, const float* colors_precomp,
+                 const float* opacities, const float* scales, float scale_modifier,
+                 const float* rotations, const float* cov3D_precomp, const float* viewmatrix,
+                 const float* projmatrix, const float* cam_pos, float tan_fovx, float tan_fovy,
+                 int prefiltered, float* out_color, int* radii, int debug, gm_stream_t stream);
+
+/* ---- single-call forward; replaces Rasterizer::forward (rasterizer.h:79-100,
+ *      rasterizer_impl.cu:198-336) WITHOUT its host synchronisation: the caller hands in a
+ *      binning chunk of binning_capacity bytes sized from a high-water mark; the instance count
+ *      is written asynchronously to *num_rendered_host (pinned host memory, may be NULL).  If the
+ *      view needs more than the chunk holds the frame is rendered from the instances that fit,
+ *      *num_rendered_host still receives the full requirement, and the next
+ *      gm_forward_status() on this geometry chunk returns GM_ERR_BINNING_OVERFLOW. */
+int gm_forward(char* geom_buffer, char* binning_buffer, size_t binning_capacity,
+               char* image_buffer, int P, int D, int M, const float* background, int width,
+               int height, const float* means3D, const float* shs, const float* colors_precomp,
+               const float* opacities, const float* scales, float scale_modifier,
+               const float* rotations, const float* cov3D_precomp, const float* viewmatrix,
+               const float* projmatrix, const float* cam_pos, float tan_fovx, float tan_fovy,
+               int prefiltered, float* out_color, int* radii, int debug,
+               int* num_rendered_host, gm_stream_t stream);
+
+/*  Blocking: synchronises `stream`, reads the frame header of a geometry chunk and reports
+ *  GM_OK / GM_ERR_BINNING_OVERFLOW; *num_rendered / *num_visible may be NULL. */
+int gm_forward_status(const char* geom_buffer, int* num_rendered, int* num_visible,
+                      gm_stream_t stream);
+
+/* ---- backward; replaces Rasterizer::backward (rasterizer.h:102-132,
+ *      rasterizer_impl.cu:515-608).  The three chunks must be those of the matching forward,
+ *      unmodified.  All nine gradient buffers MUST be zero-initialised by the caller
+ *      (dgr/rasterize_points.py:302-310): dL_dmean2D [P,3] (NDC units, .z unused),
+ *      dL_dconic [P,4] (.x=a, .y=b, .w=c, .z unused; backward.cu:549-551), dL_dopacity [P],
+ *      dL_dcolor [P,3], dL_dmean3D [P,3], dL_dcov3D [P,6], dL_dsh [P,M,3], dL_dscale [P,3],
+ *      dL_drot [P,4] (gradient w.r.t. the UN-normalised quaternion, backward.cu:340). */
+int gm_backward(int P, int D, int M, int R, const float* background, int width, int height,
+                const float* means3D, const float* shs, const float* colors_precomp,
+                const float* scales, float scale_modifier, const float* rotations,
+                const float* cov3D_precomp, const float* viewmatrix, const float* projmatrix,
+                const float* campos, float tan_fovx, float tan_fovy, const int* radii,
+                char* geom_buffer, char* binning_buffer, char* image_buffer,
+                const float* dL_dpix, float* dL_dmean2D, float* dL_dconic, float* dL_dopacity,
+                float* dL_dcolor, float* dL_dmean3D, float* dL_dcov3D, float* dL_dsh,
+                float* dL_dscale, float* dL_drot, int debug, gm_stream_t stream);
+
+/* ---- mesh-bound Gaussian parametrisation (training side); replaces the Jittor op chains of
+ *      MeshBasedGaussianModel.get_xyz / get_scaling / get_rotation / get_opacity
+ *      (scene/mesh_based_gaussian_model.py:34-43,122-152):
+ *        xyz     = softmax(bc) . (v1,v2,v3) + alpha_distance * r * (sigmoid(distance) - 0.5) * normal
+ *        scale   = exp(log_scale);  rot = q / max(|q|, 1e-12);  opacity = sigmoid(opacity_logit)
+ *      Any of the activation input/output pairs may be NULL to skip that activation. --------- */
+int gm_mesh_bind_forward(int P, const float* bc_logits /*[P,3]*/, const float* distance /*[P,1]*/,
+                         const float* vertex1, const float* vertex2, const float* vertex3 /*[P,3]*/,
+                         const float* normal /*[P,3]*/, const float* r /*[P,1]*/,
+                         float alpha_distance,
+                         const float* log_scale /*[P,3]*/, const float* rot_raw /*[P,4]*/,
+                         const float* opacity_logit /*[P,1]*/,
+                         float* xyz /*[P,3]*/, float* scale /*[P,3]*/, float* rot /*[P,4]*/,
+                         float* opacity /*[P,1]*/, gm_stream_t stream);
+
+/*  Vector-Jacobian product of the above: given dL/dxyz, dL/dscale, dL/drot, dL/dopacity (any may
+ *  be NULL) writes (not accumulates) dL/dbc_logits, dL/ddistance, dL/dlog_scale, dL/drot_raw,
+ *  dL/dopacity_logit. */
+int gm_mesh_bind_backward(int P, const float* bc_logits, const float* distance,
+                          const float* vertex1, const float* vertex2, const float* vertex3,
+                          const float* normal, const float* r, float alpha_distance,
+                          const float* log_scale, const float* rot_raw, const float* opacity_logit,
+                          const float* dL_dxyz, const float* dL_dscale, const float* dL_drot,
+                          const float* dL_dopacity,
+                          float* dL_dbc_logits, float* dL_ddistance, float* dL_dlog_scale,
+                          float* dL_drot_raw, float* dL_dopacity_logit, gm_stream_t stream);
+
+/* ---- edit-time per-face local-frame transform; replaces SingleObjectDeform.deform_gaussian
+ *      (edittool/__init__.py:103-131) and the per-frame strip_symmetric
+ *      (edittool/general_utils.py:26-37):
+ *        dpos_g = sum_k w_k (V' - V)[tri_k];  R_g = (sum_k w_k R[tri_k])^T;  S_g = sum_k w_k S[tri_k]
+ *        A = R_g S_g;  Sigma' = A Sigma A^T;  pos' = pos + dpos_g
+ *      cov_in is either packed [P,6] (cov_in_is_full == 0) or full [P,3,3] (== 1).
+ *      Outputs: pos_out [P,3], cov6_out [P,6] (packed xx,xy,xz,yy,yz,zz), rot_out [P,3,3] (= R_g). */
+int gm_deform_gaussians(int P, int num_vertices, const float* vertex_rest /*[Vn,3]*/,
+                        const float* vertex_deformed /*[Vn,3]*/, const float* vertex_R /*[Vn,3,3]*/,
+                        const float* vertex_S /*[Vn,3,3]*/, const int* gaussian_triangles /*[P,3]*/,
+                        const float* weights /*[P,3]*/, const float* pos_in /*[P,3]*/,
+                        const float* cov_in, int cov_in_is_full,
+                        float* pos_out, float* cov6_out, float* rot_out, gm_stream_t stream);
+
+/* ---- edit-time per-frame colour; replaces the Jittor chain of
+ *      ObjectVisualTool.render_gaussian (edittool/__init__.py:442-448) + eval_sh
+ *      (edittool/sh_utils.py:34-89):  dir = normalize(pos - campos); dir' = R_g^T dir;
+ *      rgb = max(eval_sh(D, shs, dir') + 0.5, 0).   shs is [P,M,3]; rot may be NULL (identity). */
+int gm_sh_to_rgb_rotated(int P, int D, int M, const float* pos /*[P,3]*/, const float* campos /*[3]*/,
+                         const float* rot /*[P,3,3] or NULL*/, const float* shs,
+                         float* rgb /*[P,3]*/, gm_stream_t stream);
+
+/* ---- L1 loss of config 4 (utils/loss_utils.py:17-18): writes mean|img-target| to *loss and
+ *      dL/dimg = sign(img-target)/numel to dL_dimg (may be NULL).  numel = 3*W*H. ------------- */
+int gm_l1_loss(size_t numel, const float* img, const float* target, float* loss /*[1]*/,
+               float* dL_dimg, gm_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GM_RASTERIZER_H_INCLUDED */
