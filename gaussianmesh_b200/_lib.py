@@ -34,14 +34,20 @@ _VIEW_ARGS = [_p, _p, _p, _p, _p, _f, _p, _p, _p, _p, _p, _f, _f]  # means3D .. 
 SIGNATURES = {
     "gm_version": (C.c_char_p, []),
     "gm_last_error": (C.c_char_p, []),
+    "gm_profile_num_stages": (_i, []),
+    "gm_profile_stage_name": (C.c_char_p, [_i]),
+    "gm_profile_begin": (None, []),
+    "gm_profile_end": (_i, [_p, _p]),
     "gm_required_geom": (_z, [_z]),
     "gm_required_image": (_z, [_z]),
     "gm_required_binning": (_z, [_z]),
+    "gm_binning_capacity": (_z, [_z]),
     "gm_mark_visible": (_i, [_i, _p, _p, _p, _p, _p]),
     "gm_forward_0": (_i, [_p, _i, _i, _i, _p, _i, _i, *_VIEW_ARGS, _i, _p, _i, _p]),
     "gm_forward_1": (_i, [_p, _p, _p, _i, _i, _i, _i, _p, _i, _i, *_VIEW_ARGS, _i, _p, _p, _i, _p]),
     "gm_forward": (_i, [_p, _p, _z, _p, _i, _i, _i, _p, _i, _i, *_VIEW_ARGS, _i, _p, _p, _i, _p, _p]),
     "gm_forward_status": (_i, [_p, _p, _p, _p]),
+    "gm_geom_view": (None, [_p, _z, _p]),
     "gm_backward": (_i, [_i, _i, _i, _i, _p, _i, _i, _p, _p, _p, _p, _f, _p, _p, _p, _p, _p, _f, _f, _p,
                          _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _p]),
     "gm_mesh_bind_forward": (_i, [_i, _p, _p, _p, _p, _p, _p, _p, _f, _p, _p, _p, _p, _p, _p, _p, _p]),
@@ -85,3 +91,16 @@ def check(rc: int, where: str) -> int:
 
 def version() -> str:
     return lib.gm_version().decode()
+
+
+def profile_begin() -> None:
+    lib.gm_profile_begin()
+
+
+def profile_end() -> dict:
+    """{stage name: (total ms, launches)} for every stage launched since profile_begin()."""
+    n = lib.gm_profile_num_stages()
+    ms = (C.c_float * n)()
+    cnt = (C.c_uint64 * n)()
+    check(lib.gm_profile_end(ms, cnt), "gm_profile_end")
+    return {lib.gm_profile_stage_name(i).decode(): (float(ms[i]), int(cnt[i])) for i in range(n) if cnt[i]}

@@ -5,8 +5,10 @@
 // No device memory is allocated here; all scratch lives in the caller's three chunks.
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <stdexcept>
 #include <string>
+#include <vector>
 
 #include "common.cuh"
 #include "kernels.h"
@@ -39,6 +41,46 @@ int check_stage(const char* what, bool debug, cudaStream_t stream)
 	return GM_OK;
 }
 
+// ---- optional per-stage timing (gm_profile_begin / gm_profile_end) -----------------------------
+// When enabled, every stage launch is bracketed by two events recorded on the launch stream; the
+// elapsed times are summed per stage in gm_profile_end.  Used by bench.py for the roofline of the
+// dominant kernel; off by default (no events, no overhead).
+enum Stage { kStPreprocess, kStTileScan, kStEmit, kStSortPack, kStBlendFwd, kStBlendBwd, kStGeomBwd, kStL1,
+             kStMeshBindFwd, kStMeshBindBwd, kStDeform, kStShRotated, kStMarkVisible, kNumStages };
+static const char* const kStageNames[kNumStages] = {
+	"preprocess", "tile_scan", "emit", "sort_pack", "blend_forward", "blend_backward", "geometry_backward",
+	"l1_loss", "mesh_bind_forward", "mesh_bind_backward", "deform", "sh_to_rgb_rotated", "mark_visible"};
+
+struct StageRecord { int stage; cudaEvent_t start, stop; };
+static std::mutex g_profile_mutex;
+static bool g_profile_on = false;
+static std::vector<StageRecord> g_profile_records;
+static uint64_t g_launch_counts[kNumStages];
+
+struct StageScope {
+	cudaStream_t stream;
+	cudaEvent_t stop = nullptr;
+	StageScope(int stage, cudaStream_t s) : stream(s)
+	{
+		if (!g_profile_on)
+			return;
+		std::lock_guard<std::mutex> lock(g_profile_mutex);
+		g_launch_counts[stage]++;
+		StageRecord r;
+		r.stage = stage;
+		if (cudaEventCreate(&r.start) != cudaSuccess || cudaEventCreate(&r.stop) != cudaSuccess)
+			return;
+		cudaEventRecord(r.start, stream);
+		stop = r.stop;
+		g_profile_records.push_back(r);
+	}
+	~StageScope()
+	{
+		if (stop != nullptr)
+			cudaEventRecord(stop, stream);
+	}
+};
+
 static bool make_view(ViewParams& vp, int D, int M, const float* background, int width, int height,
                       float scale_modifier, const float* viewmatrix, const float* projmatrix, const float* cam_pos,
                       float tan_fovx, float tan_fovy)
@@ -65,13 +107,13 @@ static bool make_view(ViewParams& vp, int D, int M, const float* background, int
 // Largest instance count whose BinningState fits in `bytes`.
 static uint32_t binning_capacity_instances(size_t bytes)
 {
-	if (bytes < 1024)
-		return 0;
-	size_t r = ((bytes - 640) / 48) & ~(size_t)7;
-	while (r > 0 && required<BinningState>(r) > bytes)
-		r -= 8;
+	// 48 bytes per instance (8 key + 16 + 16 + 8 record) plus alignment slack: start from the upper bound
+	// and step down to the largest multiple of 8 whose carved chunk fits.
+	size_t r = (bytes / 48) & ~(size_t)7;
 	if (r > 0xfffffff0u)
 		r = 0xfffffff0u;
+	while (r > 0 && required<BinningState>(r) > bytes)
+		r -= 8;
 	return (uint32_t)r;
 }
 
@@ -94,10 +136,10 @@ static int forward_stage0(char* geom_buffer, int P, const ViewParams& vp, const 
 	if (radii == nullptr)
 		radii = geom.internal_radii;
 
-	launch_preprocess(P, means3D, scales, rotations, opacities, shs, cov3D_precomp, colors_precomp, vp, radii, geom,
-	                  prefiltered, stream);
+	{ StageScope scope_(kStPreprocess, stream); launch_preprocess(P, means3D, scales, rotations, opacities, shs, cov3D_precomp, colors_precomp, vp, radii, geom,
+	                  prefiltered, stream); }
 	if (int rc = check_stage("preprocess", debug, stream)) return rc;
-	launch_tile_scan(num_tiles, geom, capacity, stream);
+	{ StageScope scope_(kStTileScan, stream); launch_tile_scan(num_tiles, geom, capacity, stream); }
 	if (int rc = check_stage("tile_scan", debug, stream)) return rc;
 	return GM_OK;
 }
@@ -114,11 +156,11 @@ static int forward_stage1(const GeometryState& geom, char* binning_buffer, char*
 	if (radii == nullptr)
 		radii = geom.internal_radii;
 
-	launch_emit(P, radii, geom, binning, capacity, vp, stream);
+	{ StageScope scope_(kStEmit, stream); launch_emit(P, radii, geom, binning, capacity, vp, stream); }
 	if (int rc = check_stage("emit", debug, stream)) return rc;
-	launch_sort_pack(num_tiles, geom, binning, capacity, stream);
+	{ StageScope scope_(kStSortPack, stream); launch_sort_pack(num_tiles, geom, binning, capacity, stream); }
 	if (int rc = check_stage("sort_pack", debug, stream)) return rc;
-	launch_blend_forward(geom, binning, img, capacity, vp, out_color, stream);
+	{ StageScope scope_(kStBlendFwd, stream); launch_blend_forward(geom, binning, img, capacity, vp, out_color, stream); }
 	if (int rc = check_stage("blend_forward", debug, stream)) return rc;
 	return GM_OK;
 }
@@ -132,9 +174,45 @@ extern "C" {
 const char* gm_version(void) { return "gaussianmesh-b200 0.1.0 sm_100a"; }
 const char* gm_last_error(void) { return g_last_error.c_str(); }
 
+int gm_profile_num_stages(void) { return kNumStages; }
+const char* gm_profile_stage_name(int stage) { return (stage >= 0 && stage < kNumStages) ? kStageNames[stage] : ""; }
+
+void gm_profile_begin(void)
+{
+	std::lock_guard<std::mutex> lock(g_profile_mutex);
+	for (auto& r : g_profile_records) { cudaEventDestroy(r.start); cudaEventDestroy(r.stop); }
+	g_profile_records.clear();
+	memset(g_launch_counts, 0, sizeof(g_launch_counts));
+	g_profile_on = true;
+}
+
+int gm_profile_end(float* ms_per_stage, uint64_t* launches_per_stage)
+{
+	std::lock_guard<std::mutex> lock(g_profile_mutex);
+	g_profile_on = false;
+	int rc = GM_OK;
+	for (int i = 0; i < kNumStages; i++) {
+		if (ms_per_stage) ms_per_stage[i] = 0.0f;
+		if (launches_per_stage) launches_per_stage[i] = g_launch_counts[i];
+	}
+	for (auto& r : g_profile_records) {
+		float ms = 0.0f;
+		cudaError_t err = cudaEventSynchronize(r.stop);
+		if (err == cudaSuccess)
+			err = cudaEventElapsedTime(&ms, r.start, r.stop);
+		if (err != cudaSuccess) { set_last_error("profile_end", err); rc = GM_ERR_CUDA; }
+		else if (ms_per_stage) ms_per_stage[r.stage] += ms;
+		cudaEventDestroy(r.start);
+		cudaEventDestroy(r.stop);
+	}
+	g_profile_records.clear();
+	return rc;
+}
+
 size_t gm_required_geom(size_t P) { return required<GeometryState>(P); }
 size_t gm_required_image(size_t N) { return required<ImageState>(N); }
 size_t gm_required_binning(size_t R) { return required<BinningState>(R); }
+size_t gm_binning_capacity(size_t bytes) { return binning_capacity_instances(bytes); }
 
 int gm_mark_visible(int P, const float* means3D, const float* viewmatrix, const float* projmatrix,
                     uint8_t* present, gm_stream_t stream)
@@ -142,7 +220,7 @@ int gm_mark_visible(int P, const float* means3D, const float* viewmatrix, const 
 	(void)projmatrix;   // the reference computes p_proj but only tests view-space z (auxiliary.h:153)
 	if (P < 0 || (P > 0 && (means3D == nullptr || viewmatrix == nullptr || present == nullptr)))
 		return GM_ERR_BAD_ARGUMENT;
-	launch_mark_visible(P, means3D, viewmatrix, present, (cudaStream_t)stream);
+	{ StageScope scope_(kStMarkVisible, (cudaStream_t)stream); launch_mark_visible(P, means3D, viewmatrix, present, (cudaStream_t)stream); }
 	return check_stage("mark_visible", false, (cudaStream_t)stream);
 }
 
@@ -203,7 +281,7 @@ int gm_forward(char* geom_buffer, char* binning_buffer, size_t binning_capacity,
                float scale_modifier, const float* rotations, const float* cov3D_precomp,
                const float* viewmatrix, const float* projmatrix, const float* cam_pos, float tan_fovx,
                float tan_fovy, int prefiltered, float* out_color, int* radii, int debug,
-               int* num_rendered_host, gm_stream_t stream_)
+               uint32_t* frame_info_host, gm_stream_t stream_)
 {
 	cudaStream_t stream = (cudaStream_t)stream_;
 	ViewParams vp;
@@ -216,8 +294,9 @@ int gm_forward(char* geom_buffer, char* binning_buffer, size_t binning_capacity,
 	if (int rc = forward_stage0(geom_buffer, P, vp, means3D, shs, colors_precomp, opacities, scales, rotations,
 	                            cov3D_precomp, prefiltered != 0, radii, capacity, debug != 0, stream, geom))
 		return rc;
-	if (num_rendered_host != nullptr) {
-		cudaError_t err = cudaMemcpyAsync(num_rendered_host, &geom.header->num_rendered, sizeof(uint32_t),
+	if (frame_info_host != nullptr) {
+		// FrameHeader starts with {num_rendered, num_visible, overflow, capacity}
+		cudaError_t err = cudaMemcpyAsync(frame_info_host, geom.header, 4 * sizeof(uint32_t),
 		                                  cudaMemcpyDeviceToHost, stream);
 		if (err != cudaSuccess) {
 			set_last_error("forward count readback", err);
@@ -245,6 +324,13 @@ int gm_forward_status(const char* geom_buffer, int* num_rendered, int* num_visib
 	if (num_rendered) *num_rendered = (int)h.num_rendered;
 	if (num_visible) *num_visible = (int)h.num_visible;
 	return h.overflow ? GM_ERR_BINNING_OVERFLOW : GM_OK;
+}
+
+void gm_geom_view(char* geom_buffer, size_t P, void** out6)
+{
+	GeometryState g = GeometryState::fromChunk(geom_buffer, P);
+	out6[0] = g.depths; out6[1] = g.means2D; out6[2] = g.cov3D; out6[3] = g.conic_opacity;
+	out6[4] = g.rgb_clamp; out6[5] = g.tile_count;
 }
 
 int gm_backward(int P, int D, int M, int R, const float* background, int width, int height,
@@ -281,14 +367,14 @@ int gm_backward(int P, int D, int M, int R, const float* background, int width, 
 	if (radii == nullptr)
 		radii = geom.internal_radii;
 
-	launch_blend_backward(geom, binning, img, (uint32_t)R, vp, dL_dpix, dL_dmean2D, dL_dconic, dL_dopacity,
-	                      dL_dcolor, stream);
+	{ StageScope scope_(kStBlendBwd, stream); launch_blend_backward(geom, binning, img, (uint32_t)R, vp, dL_dpix, dL_dmean2D, dL_dconic, dL_dopacity,
+	                      dL_dcolor, stream); }
 	if (int rc = check_stage("blend_backward", debug != 0, stream)) return rc;
 
 	const float* cov3D_ptr = sr_path ? geom.cov3D : cov3D_precomp;
-	launch_geometry_backward(P, means3D, radii, sh_path ? shs : nullptr, sr_path ? scales : nullptr,
+	{ StageScope scope_(kStGeomBwd, stream); launch_geometry_backward(P, means3D, radii, sh_path ? shs : nullptr, sr_path ? scales : nullptr,
 	                         sr_path ? rotations : nullptr, cov3D_ptr, vp, geom, dL_dmean2D, dL_dconic, dL_dcolor,
-	                         dL_dmean3D, dL_dcov3D, dL_dsh, dL_dscale, dL_drot, stream);
+	                         dL_dmean3D, dL_dcov3D, dL_dsh, dL_dscale, dL_drot, stream); }
 	return check_stage("geometry_backward", debug != 0, stream);
 }
 
@@ -304,8 +390,8 @@ int gm_mesh_bind_forward(int P, const float* bc_logits, const float* distance, c
 		return GM_ERR_BAD_ARGUMENT;
 	if ((scale != nullptr && !log_scale) || (rot != nullptr && !rot_raw) || (opacity != nullptr && !opacity_logit))
 		return GM_ERR_BAD_ARGUMENT;
-	launch_mesh_bind_forward(P, bc_logits, distance, vertex1, vertex2, vertex3, normal, r, alpha_distance, log_scale,
-	                         rot_raw, opacity_logit, xyz, scale, rot, opacity, (cudaStream_t)stream);
+	{ StageScope scope_(kStMeshBindFwd, (cudaStream_t)stream); launch_mesh_bind_forward(P, bc_logits, distance, vertex1, vertex2, vertex3, normal, r, alpha_distance, log_scale,
+	                         rot_raw, opacity_logit, xyz, scale, rot, opacity, (cudaStream_t)stream); }
 	return check_stage("mesh_bind_forward", false, (cudaStream_t)stream);
 }
 
@@ -325,9 +411,9 @@ int gm_mesh_bind_backward(int P, const float* bc_logits, const float* distance, 
 	if ((dL_dscale && dL_dlog_scale && !log_scale) || (dL_drot && dL_drot_raw && !rot_raw) ||
 	    (dL_dopacity && dL_dopacity_logit && !opacity_logit))
 		return GM_ERR_BAD_ARGUMENT;
-	launch_mesh_bind_backward(P, bc_logits, distance, vertex1, vertex2, vertex3, normal, r, alpha_distance, log_scale,
+	{ StageScope scope_(kStMeshBindBwd, (cudaStream_t)stream); launch_mesh_bind_backward(P, bc_logits, distance, vertex1, vertex2, vertex3, normal, r, alpha_distance, log_scale,
 	                          rot_raw, opacity_logit, dL_dxyz, dL_dscale, dL_drot, dL_dopacity, dL_dbc_logits,
-	                          dL_ddistance, dL_dlog_scale, dL_drot_raw, dL_dopacity_logit, (cudaStream_t)stream);
+	                          dL_ddistance, dL_dlog_scale, dL_drot_raw, dL_dopacity_logit, (cudaStream_t)stream); }
 	return check_stage("mesh_bind_backward", false, (cudaStream_t)stream);
 }
 
@@ -341,8 +427,8 @@ int gm_deform_gaussians(int P, int num_vertices, const float* vertex_rest, const
 	if (P > 0 && (!vertex_rest || !vertex_deformed || !vertex_R || !vertex_S || !gaussian_triangles || !weights ||
 	              !pos_in || !cov_in || !pos_out || !cov6_out))
 		return GM_ERR_BAD_ARGUMENT;
-	launch_deform(P, vertex_rest, vertex_deformed, vertex_R, vertex_S, gaussian_triangles, weights, pos_in, cov_in,
-	              cov_in_is_full, pos_out, cov6_out, rot_out, (cudaStream_t)stream);
+	{ StageScope scope_(kStDeform, (cudaStream_t)stream); launch_deform(P, vertex_rest, vertex_deformed, vertex_R, vertex_S, gaussian_triangles, weights, pos_in, cov_in,
+	              cov_in_is_full, pos_out, cov6_out, rot_out, (cudaStream_t)stream); }
 	return check_stage("deform", false, (cudaStream_t)stream);
 }
 
@@ -353,7 +439,7 @@ int gm_sh_to_rgb_rotated(int P, int D, int M, const float* pos, const float* cam
 		return GM_ERR_BAD_ARGUMENT;
 	if (P > 0 && (!pos || !campos || !shs || !rgb))
 		return GM_ERR_BAD_ARGUMENT;
-	launch_sh_rotated(P, D, M, pos, campos, rot, shs, rgb, (cudaStream_t)stream);
+	{ StageScope scope_(kStShRotated, (cudaStream_t)stream); launch_sh_rotated(P, D, M, pos, campos, rot, shs, rgb, (cudaStream_t)stream); }
 	return check_stage("sh_to_rgb_rotated", false, (cudaStream_t)stream);
 }
 
@@ -361,7 +447,7 @@ int gm_l1_loss(size_t numel, const float* img, const float* target, float* loss,
 {
 	if (loss == nullptr || (numel > 0 && (!img || !target)))
 		return GM_ERR_BAD_ARGUMENT;
-	launch_l1(numel, img, target, loss, dL_dimg, (cudaStream_t)stream);
+	{ StageScope scope_(kStL1, (cudaStream_t)stream); launch_l1(numel, img, target, loss, dL_dimg, (cudaStream_t)stream); }
 	return check_stage("l1_loss", false, (cudaStream_t)stream);
 }
 

@@ -1,0 +1,132 @@
+"""Host side of the mesh-bound Gaussian kernels (torch + ctypes over libCudaRasterizer.so).
+
+  mesh_bind            training-time per-face bind + activations, differentiable
+                       (scene/mesh_based_gaussian_model.py:34-43,122-152)
+  deform_gaussians     edit-time per-face local-frame transform (edittool/__init__.py:103-131)
+  sh_to_rgb_rotated    edit-time per-frame colour in the rotated frame (edittool/__init__.py:442-448)
+  l1_loss              utils/loss_utils.py:17-18, differentiable
+
+No CPU path: CUDA tensors only.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+
+from ._lib import lib, check, RasterizerError, GM_ERR_BAD_ARGUMENT
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _c(t: Optional[torch.Tensor], dtype=torch.float32) -> Optional[torch.Tensor]:
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RasterizerError("mesh_gaussians", GM_ERR_BAD_ARGUMENT, "tensor is not on a CUDA device (there is no CPU path)")
+    if t.dtype != dtype or not t.is_contiguous():
+        t = t.to(dtype).contiguous()
+    return t
+
+
+def _p(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+class _MeshBind(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, bc_logits, distance, log_scale, rot_raw, opacity_logit, vertex1, vertex2, vertex3, normal, r,
+                alpha_distance):
+        bc_logits, distance, log_scale, rot_raw, opacity_logit = map(_c, (bc_logits, distance, log_scale, rot_raw, opacity_logit))
+        vertex1, vertex2, vertex3, normal, r = map(_c, (vertex1, vertex2, vertex3, normal, r))
+        P = bc_logits.shape[0]
+        dev = bc_logits.device
+        xyz = torch.empty(P, 3, dtype=torch.float32, device=dev)
+        scale = torch.empty(P, 3, dtype=torch.float32, device=dev)
+        rot = torch.empty(P, 4, dtype=torch.float32, device=dev)
+        opacity = torch.empty(P, 1, dtype=torch.float32, device=dev)
+        check(lib.gm_mesh_bind_forward(P, _p(bc_logits), _p(distance), _p(vertex1), _p(vertex2), _p(vertex3), _p(normal),
+                                       _p(r), float(alpha_distance), _p(log_scale), _p(rot_raw), _p(opacity_logit),
+                                       _p(xyz), _p(scale), _p(rot), _p(opacity), _stream()), "gm_mesh_bind_forward")
+        ctx.save_for_backward(bc_logits, distance, log_scale, rot_raw, opacity_logit, vertex1, vertex2, vertex3, normal, r)
+        ctx.alpha_distance = float(alpha_distance)
+        return xyz, scale, rot, opacity
+
+    @staticmethod
+    def backward(ctx, g_xyz, g_scale, g_rot, g_opacity):
+        bc_logits, distance, log_scale, rot_raw, opacity_logit, vertex1, vertex2, vertex3, normal, r = ctx.saved_tensors
+        P = bc_logits.shape[0]
+        dev = bc_logits.device
+        g_xyz, g_scale, g_rot, g_opacity = map(_c, (g_xyz, g_scale, g_rot, g_opacity))
+        d_bc = torch.zeros(P, 3, dtype=torch.float32, device=dev) if g_xyz is None else torch.empty(P, 3, dtype=torch.float32, device=dev)
+        d_dist = torch.zeros(P, 1, dtype=torch.float32, device=dev) if g_xyz is None else torch.empty(P, 1, dtype=torch.float32, device=dev)
+        d_ls = torch.zeros(P, 3, dtype=torch.float32, device=dev) if g_scale is None else torch.empty(P, 3, dtype=torch.float32, device=dev)
+        d_rr = torch.zeros(P, 4, dtype=torch.float32, device=dev) if g_rot is None else torch.empty(P, 4, dtype=torch.float32, device=dev)
+        d_ol = torch.zeros(P, 1, dtype=torch.float32, device=dev) if g_opacity is None else torch.empty(P, 1, dtype=torch.float32, device=dev)
+        check(lib.gm_mesh_bind_backward(P, _p(bc_logits), _p(distance), _p(vertex1), _p(vertex2), _p(vertex3), _p(normal),
+                                        _p(r), ctx.alpha_distance, _p(log_scale), _p(rot_raw), _p(opacity_logit),
+                                        _p(g_xyz), _p(g_scale), _p(g_rot), _p(g_opacity),
+                                        _p(d_bc), _p(d_dist), _p(d_ls), _p(d_rr), _p(d_ol), _stream()),
+              "gm_mesh_bind_backward")
+        return d_bc, d_dist, d_ls, d_rr, d_ol, None, None, None, None, None, None
+
+
+def mesh_bind(bc_logits, distance, log_scale, rot_raw, opacity_logit, vertex1, vertex2, vertex3, normal, r,
+              alpha_distance: float = 4.0) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
+    """(get_xyz, get_scaling, get_rotation, get_opacity) of MeshBasedGaussianModel in one kernel:
+        xyz = softmax(bc) . (v1,v2,v3) + alpha_distance * r * (sigmoid(distance) - 0.5) * normal
+    Differentiable w.r.t. the five parameter tensors."""
+    return _MeshBind.apply(bc_logits, distance, log_scale, rot_raw, opacity_logit, vertex1, vertex2, vertex3, normal,
+                           r, alpha_distance)
+
+
+def deform_gaussians(vertex_rest, vertex_deformed, vertex_R, vertex_S, gaussian_triangles, weights, pos, cov,
+                     want_rot: bool = True):
+    """SingleObjectDeform.deform_gaussian.  `cov` is [P,6] packed or [P,3,3] full.
+    Returns (pos' [P,3], cov' [P,6] packed = strip_symmetric(A Sigma A^T), R_g [P,3,3] or None)."""
+    vertex_rest, vertex_deformed, vertex_R, vertex_S, weights, pos, cov = map(
+        _c, (vertex_rest, vertex_deformed, vertex_R, vertex_S, weights, pos, cov))
+    tri = _c(gaussian_triangles, torch.int32)
+    P = pos.shape[0]
+    dev = pos.device
+    full = 1 if cov.dim() == 3 else 0
+    pos_out = torch.empty(P, 3, dtype=torch.float32, device=dev)
+    cov_out = torch.empty(P, 6, dtype=torch.float32, device=dev)
+    rot_out = torch.empty(P, 3, 3, dtype=torch.float32, device=dev) if want_rot else None
+    check(lib.gm_deform_gaussians(P, vertex_rest.shape[0], _p(vertex_rest), _p(vertex_deformed), _p(vertex_R),
+                                  _p(vertex_S), _p(tri), _p(weights), _p(pos), _p(cov), full, _p(pos_out),
+                                  _p(cov_out), _p(rot_out), _stream()), "gm_deform_gaussians")
+    return pos_out, cov_out, rot_out
+
+
+def sh_to_rgb_rotated(pos, campos, rot, shs, degree: int = 3) -> torch.Tensor:
+    """clamp(eval_sh(degree, shs, R_g^T normalize(pos - campos)) + 0.5, 0); rot may be None."""
+    pos, campos, rot, shs = map(_c, (pos, campos, rot, shs))
+    P = pos.shape[0]
+    rgb = torch.empty(P, 3, dtype=torch.float32, device=pos.device)
+    check(lib.gm_sh_to_rgb_rotated(P, int(degree), int(shs.shape[1]), _p(pos), _p(campos), _p(rot), _p(shs), _p(rgb),
+                                   _stream()), "gm_sh_to_rgb_rotated")
+    return rgb
+
+
+class _L1(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, img, target):
+        img, target = _c(img), _c(target)
+        loss = torch.empty(1, dtype=torch.float32, device=img.device)
+        grad = torch.empty_like(img)
+        check(lib.gm_l1_loss(img.numel(), _p(img), _p(target), _p(loss), _p(grad), _stream()), "gm_l1_loss")
+        ctx.save_for_backward(grad)
+        return loss.view(())
+
+    @staticmethod
+    def backward(ctx, g):
+        (grad,) = ctx.saved_tensors
+        return grad * g, None
+
+
+def l1_loss(network_output: torch.Tensor, gt: torch.Tensor) -> torch.Tensor:
+    """mean(abs(network_output - gt)) (utils/loss_utils.py:17-18), fused with its gradient."""
+    return _L1.apply(network_output, gt)

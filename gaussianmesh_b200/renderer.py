@@ -1,0 +1,299 @@
+"""Render functions above the rasterizer op -- the callers of the hot path.
+
+  render()              mirror of gaussian_renderer.render (reference gaussian_renderer/__init__.py:26-143)
+                        for the mesh-bound model, CUDA SH / CUDA covariance branch
+  MeshGaussianModel     the accessors of scene/mesh_based_gaussian_model.py:122-174 that feed render(),
+                        computed by the fused bind kernel
+  DeformedObject        edit-time object: SingleObjectDeform.deform_gaussian + ObjectVisualTool.render_gaussian
+                        (edittool/__init__.py:103-131, 400-475)
+  ViewBatchRenderer     sync-free forward rendering of a list of views on one GPU
+  train_step()          config-4 step: forward + L1 + full backward through the C ABI without autograd overhead
+  shard_views()         contiguous-block partition of independent views over ranks (no collective)
+
+torch is plumbing here (device memory, streams); all arithmetic is in libCudaRasterizer.so.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import mesh_gaussians as mg
+from ._lib import lib, check
+from .arena import RenderArena
+from .diff_gaussian_rasterizater import (GaussianRasterizationSettings, GaussianRasterizer, NewGaussianRasterizer)
+from .synthetic import Camera
+from .view_shard import shard_views, ShardContext  # noqa: F401  (re-exported)
+
+
+# ---------------------------------------------------------------------------------------------
+# views
+# ---------------------------------------------------------------------------------------------
+@dataclass
+class DeviceCamera:
+    """A view with its three small matrices resident on the device."""
+    image_width: int
+    image_height: int
+    FoVx: float
+    FoVy: float
+    world_view_transform: torch.Tensor
+    full_proj_transform: torch.Tensor
+    camera_center: torch.Tensor
+
+    @staticmethod
+    def from_packed(cam: Camera, packed: torch.Tensor) -> "DeviceCamera":
+        """`packed` is a [35] device tensor: viewmatrix | projmatrix | campos (Camera.packed())."""
+        return DeviceCamera(cam.image_width, cam.image_height, cam.FoVx, cam.FoVy,
+                            packed[0:16].view(4, 4), packed[16:32].view(4, 4), packed[32:35])
+
+    @staticmethod
+    def upload(cam: Camera, device) -> "DeviceCamera":
+        return DeviceCamera.from_packed(cam, torch.from_numpy(cam.packed()).to(device))
+
+
+def upload_cameras(cams: Sequence[Camera], device) -> List[DeviceCamera]:
+    """One H2D copy for the whole camera set."""
+    if not cams:
+        return []
+    packed = torch.from_numpy(np.stack([c.packed() for c in cams])).to(device)
+    return [DeviceCamera.from_packed(c, packed[i]) for i, c in enumerate(cams)]
+
+
+def make_settings(cam, bg: torch.Tensor, sh_degree: int, scaling_modifier: float = 1.0, debug: bool = False
+                  ) -> GaussianRasterizationSettings:
+    """reference gaussian_renderer/__init__.py:46-62"""
+    return GaussianRasterizationSettings(
+        image_height=int(cam.image_height), image_width=int(cam.image_width),
+        tanfovx=math.tan(cam.FoVx * 0.5), tanfovy=math.tan(cam.FoVy * 0.5), bg=bg,
+        scale_modifier=scaling_modifier, viewmatrix=cam.world_view_transform, projmatrix=cam.full_proj_transform,
+        sh_degree=sh_degree, campos=cam.camera_center, prefiltered=False, debug=debug)
+
+
+# ---------------------------------------------------------------------------------------------
+# training-time model accessors + render()
+# ---------------------------------------------------------------------------------------------
+class MeshGaussianModel:
+    """Parameters and per-Gaussian face data of MeshBasedGaussianModel, with the activations of
+    scene/mesh_based_gaussian_model.py:34-43,122-174 evaluated by ONE fused kernel per frame
+    (`mesh_bind`) instead of ~10 elementwise kernels; SH features are kept as a single [P,16,3]
+    tensor so that get_features needs no per-frame concat (reference :167-170)."""
+
+    def __init__(self, arrays: Dict[str, np.ndarray], device, sh_degree: int = 3, alpha_distance: float = 4.0,
+                 requires_grad: bool = True):
+        t = lambda k: torch.from_numpy(np.ascontiguousarray(arrays[k])).to(device)
+        self._bc = t("bc_logits").requires_grad_(requires_grad)
+        self._distance = t("distance").requires_grad_(requires_grad)
+        self._scaling = t("log_scales").requires_grad_(requires_grad)
+        self._rotation = t("rot_raw" if "rot_raw" in arrays else "rotations").requires_grad_(requires_grad)
+        self._opacity = t("opacity_logit").requires_grad_(requires_grad)
+        self._features = t("shs").requires_grad_(requires_grad)
+        self.vertex1, self.vertex2, self.vertex3 = t("vertex1"), t("vertex2"), t("vertex3")
+        self.normal, self.r = t("normal"), t("r")
+        self.alpha_distance = alpha_distance
+        self.active_sh_degree = sh_degree
+        self.max_sh_degree = 3
+        self.screenspace_points = torch.zeros(self._bc.shape[0], 3, device=device, requires_grad=requires_grad)
+        self._cache = None
+
+    def parameters(self) -> List[torch.Tensor]:
+        return [self._bc, self._distance, self._scaling, self._rotation, self._opacity, self._features]
+
+    def activate(self):
+        """(xyz, scaling, rotation, opacity) -- one kernel, one autograd node."""
+        return mg.mesh_bind(self._bc, self._distance, self._scaling, self._rotation, self._opacity, self.vertex1,
+                            self.vertex2, self.vertex3, self.normal, self.r, self.alpha_distance)
+
+    @property
+    def get_xyz(self): return self.activate()[0]
+    @property
+    def get_scaling(self): return self.activate()[1]
+    @property
+    def get_rotation(self): return self.activate()[2]
+    @property
+    def get_opacity(self): return self.activate()[3]
+    @property
+    def get_features(self): return self._features
+    @property
+    def get_number(self): return self._bc.shape[0]
+
+
+@dataclass
+class PipelineParams:
+    """arguments/__init__.py:64-69; only the CUDA branches are implemented on this path."""
+    convert_SHs_python: bool = False
+    compute_cov3D_python: bool = False
+    debug: bool = False
+
+
+def render(viewpoint_camera, pc: MeshGaussianModel, pipe: PipelineParams, bg_color: torch.Tensor,
+           scaling_modifier: float = 1.0, override_color: Optional[torch.Tensor] = None,
+           arena: Optional[RenderArena] = None) -> Dict[str, torch.Tensor]:
+    """reference gaussian_renderer/__init__.py:26-143 (without the optional bg_gaussian concat)."""
+    if pipe.convert_SHs_python or pipe.compute_cov3D_python:
+        raise NotImplementedError("the Python SH / covariance fallbacks are the reference's slow path; "
+                                  "this renderer always uses the CUDA branches")
+    screenspace_points = pc.screenspace_points
+    raster_settings = make_settings(viewpoint_camera, bg_color, pc.active_sh_degree, scaling_modifier, pipe.debug)
+    rasterizer = GaussianRasterizer(raster_settings=raster_settings, arena=arena)
+    means3D, scales, rotations, opacity = pc.activate()
+    shs, colors_precomp = (pc.get_features, None) if override_color is None else (None, override_color)
+    rendered_image, radii = rasterizer(means3D=means3D, means2D=screenspace_points, shs=shs,
+                                       colors_precomp=colors_precomp, opacities=opacity, scales=scales,
+                                       rotations=rotations, cov3D_precomp=None)
+    return {"render": rendered_image, "viewspace_points": screenspace_points, "visibility_filter": radii > 0,
+            "radii": radii, "vertex1": pc.vertex1, "vertex2": pc.vertex2, "vertex3": pc.vertex3, "scale": scales}
+
+
+# ---------------------------------------------------------------------------------------------
+# edit-time object
+# ---------------------------------------------------------------------------------------------
+class DeformedObject:
+    """SingleObjectDeform + ObjectVisualTool.render_gaussian for one mesh-bound object.
+
+    load:    pos [P,3], cov [P,6] or [P,3,3], opacity [P,1], shs [P,16,3], triangles [P,3] (vertex ids of each
+             Gaussian's face), weights [P,3] (barycentric, edittool/__init__.py:95-99), rest vertices [Vn,3]
+    deform:  once per deformed mesh (edittool/__init__.py:103-131), one kernel
+    render:  per frame: rotated-direction SH colour (one kernel) -> NewGaussianRasterizer with
+             colors_precomp + cov3D_precomp (edittool/__init__.py:442-472)
+    """
+
+    def __init__(self, pos, cov, opacity, shs, triangles, weights, vertex_rest, device):
+        dev = torch.device(device)
+        f = lambda a: torch.as_tensor(a, dtype=torch.float32).contiguous().to(dev)
+        self.pos, self.cov, self.opacity, self.shs = f(pos), f(cov), f(opacity), f(shs)
+        self.weights, self.vertex = f(weights), f(vertex_rest)
+        self.triangles = torch.as_tensor(triangles, dtype=torch.int32).contiguous().to(dev)
+        P = self.pos.shape[0]
+        # identity deformation until deform() is called (edittool/__init__.py:57-60)
+        self.deform_pos = self.pos
+        c = self.cov
+        self.deform_cov6 = c if c.dim() == 2 else torch.stack(
+            [c[:, 0, 0], c[:, 0, 1], c[:, 0, 2], c[:, 1, 1], c[:, 1, 2], c[:, 2, 2]], dim=1).contiguous()
+        self.deform_rot = torch.eye(3, device=dev).expand(P, 3, 3).contiguous()
+        self.device = dev
+
+    def deform(self, vertex_deformed, vertex_R, vertex_S) -> None:
+        f = lambda a: torch.as_tensor(a, dtype=torch.float32).contiguous().to(self.device)
+        self.deform_pos, self.deform_cov6, self.deform_rot = mg.deform_gaussians(
+            self.vertex, f(vertex_deformed), f(vertex_R), f(vertex_S), self.triangles, self.weights, self.pos, self.cov)
+
+    def render_gaussian(self, cam, bg: torch.Tensor, arena: Optional[RenderArena] = None) -> torch.Tensor:
+        colors = mg.sh_to_rgb_rotated(self.deform_pos, cam.camera_center, self.deform_rot, self.shs, 3)
+        rasterizer = NewGaussianRasterizer(make_settings(cam, bg, 3), arena=arena)
+        means2D = torch.zeros_like(self.deform_pos)
+        with torch.no_grad():
+            image, _ = rasterizer(means3D=self.deform_pos, means2D=means2D, shs=None, colors_precomp=colors,
+                                  opacities=self.opacity, scales=None, rotations=None, cov3D_precomp=self.deform_cov6)
+        return image
+
+
+# ---------------------------------------------------------------------------------------------
+# sync-free batch rendering of independent views
+# ---------------------------------------------------------------------------------------------
+class ViewBatchRenderer:
+    """Forward-render many views of one static Gaussian set on one GPU with no host synchronisation
+    inside the loop.  Overflowed frames (arena high-water mark too low) are re-rendered after the
+    batch, so results never depend on the arena size."""
+
+    def __init__(self, device, means3D, opacities, shs=None, colors_precomp=None, scales=None, rotations=None,
+                 cov3D_precomp=None, sh_degree: int = 3, scale_modifier: float = 1.0, force_m: Optional[int] = None):
+        self.device = torch.device(device)
+        c = lambda t: None if t is None else t.detach().to(self.device, torch.float32).contiguous()
+        self.means3D, self.opacities, self.shs = c(means3D), c(opacities), c(shs)
+        self.colors, self.scales, self.rotations, self.cov = c(colors_precomp), c(scales), c(rotations), c(cov3D_precomp)
+        if (self.shs is None) == (self.colors is None):
+            raise Exception('Please provide excatly one of either SHs or precomputed colors!')
+        if ((self.scales is None or self.rotations is None) == (self.cov is None)):
+            raise Exception('Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!')
+        self.P = self.means3D.shape[0]
+        self.D = sh_degree
+        self.M = force_m if force_m is not None else (self.shs.shape[1] if self.shs is not None else 0)
+        self.scale_modifier = scale_modifier
+        self.arena = RenderArena(self.device, strict=False)
+        self.radii = torch.empty(self.P, dtype=torch.int32, device=self.device)
+
+    def _view_args(self, cam) -> tuple:
+        p = lambda t: None if t is None else t.data_ptr()
+        return (p(self.means3D), p(self.shs), p(self.colors), p(self.opacities), p(self.scales),
+                float(self.scale_modifier), p(self.rotations), p(self.cov), cam.world_view_transform.data_ptr(),
+                cam.full_proj_transform.data_ptr(), cam.camera_center.data_ptr(),
+                math.tan(cam.FoVx * 0.5), math.tan(cam.FoVy * 0.5))
+
+    def render_into(self, cam, bg: torch.Tensor, out: torch.Tensor) -> None:
+        """Enqueue one view; `out` is a [3,H,W] float32 device tensor."""
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        self.arena.forward(self.P, self.D, self.M, bg, cam.image_width, cam.image_height, self._view_args(cam),
+                           False, False, stream, out_color=out, radii=self.radii)
+
+    def render_views(self, cams: Sequence, bg: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Render all `cams` (DeviceCamera) into out [n,3,H,W]; returns it.  One sync at the end."""
+        n = len(cams)
+        if out is None:
+            out = torch.empty(n, 3, cams[0].image_height, cams[0].image_width, dtype=torch.float32, device=self.device)
+        first = self.arena.frames
+        for i, cam in enumerate(cams):
+            self.render_into(cam, bg, out[i])
+        for frame in self.arena.verify():          # grown arena; re-render the frames that did not fit
+            i = frame - first
+            if 0 <= i < n:
+                self.render_into(cams[i], bg, out[i])
+        if self.arena.verify():
+            raise RuntimeError("arena overflow persisted after growth")   # cannot happen: grown to the high-water mark
+        return out
+
+
+# ---------------------------------------------------------------------------------------------
+# config-4 training step without autograd bookkeeping
+# ---------------------------------------------------------------------------------------------
+class TrainStep:
+    """forward + L1(target) + full backward to (means3D, shs, opacities, scales, rotations) through the
+    C ABI, reusing every buffer across steps (train_mesh_gaussian.py:85-96 with the L1 term only;
+    the optimizer step is excluded).  Gradients are left in `self.grads`."""
+
+    def __init__(self, device, means3D, opacities, shs, scales, rotations, W: int, H: int, sh_degree: int = 3):
+        self.device = torch.device(device)
+        c = lambda t: t.detach().to(self.device, torch.float32).contiguous()
+        self.means3D, self.opacities, self.shs, self.scales, self.rotations = map(c, (means3D, opacities, shs, scales, rotations))
+        self.P, self.W, self.H, self.D, self.M = self.means3D.shape[0], W, H, sh_degree, self.shs.shape[1]
+        P, M = self.P, self.M
+        self.arena = RenderArena(self.device, strict=False)
+        self.image = torch.empty(3, H, W, dtype=torch.float32, device=self.device)
+        self.dL_dimg = torch.empty_like(self.image)
+        self.loss = torch.zeros(1, dtype=torch.float32, device=self.device)
+        self.radii = torch.empty(P, dtype=torch.int32, device=self.device)
+        sizes = {"means3D": 3 * P, "means2D": 3 * P, "colors": 3 * P, "opacity": P, "cov3D": 6 * P, "sh": 3 * M * P,
+                 "scales": 3 * P, "rotations": 4 * P, "conic": 4 * P}
+        offs, total = {}, 0
+        for k, s in sizes.items():
+            offs[k] = total
+            total += ((s + 31) // 32) * 32
+        self._slab = torch.empty(total, dtype=torch.float32, device=self.device)
+        self.grads = {k: self._slab[offs[k]:offs[k] + sizes[k]] for k in sizes}
+
+    def _view_args(self, cam) -> tuple:
+        p = lambda t: t.data_ptr()
+        return (p(self.means3D), p(self.shs), None, p(self.opacities), p(self.scales), 1.0, p(self.rotations), None,
+                p(cam.world_view_transform), p(cam.full_proj_transform), p(cam.camera_center),
+                math.tan(cam.FoVx * 0.5), math.tan(cam.FoVy * 0.5))
+
+    def step(self, cam, bg: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
+        """Enqueue one training step; returns the (device) loss tensor.  No host synchronisation."""
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        va = self._view_args(cam)
+        cap, _, _, geom, binning, image_state = self.arena.forward(
+            self.P, self.D, self.M, bg, self.W, self.H, va, False, False, stream, out_color=self.image, radii=self.radii)
+        check(lib.gm_l1_loss(self.image.numel(), self.image.data_ptr(), target.data_ptr(), self.loss.data_ptr(),
+                             self.dL_dimg.data_ptr(), stream), "gm_l1_loss")
+        self._slab.zero_()
+        g = self.grads
+        check(lib.gm_backward(self.P, self.D, self.M, cap, bg.data_ptr(), self.W, self.H, va[0], va[1], None, va[4], 1.0,
+                              va[6], None, va[8], va[9], va[10], va[11], va[12], self.radii.data_ptr(),
+                              geom.data_ptr(), binning.data_ptr(), image_state.data_ptr(), self.dL_dimg.data_ptr(),
+                              g["means2D"].data_ptr(), g["conic"].data_ptr(), g["opacity"].data_ptr(),
+                              g["colors"].data_ptr(), g["means3D"].data_ptr(), g["cov3D"].data_ptr(),
+                              g["sh"].data_ptr(), g["scales"].data_ptr(), g["rotations"].data_ptr(), 0, stream),
+              "gm_backward")
+        return self.loss

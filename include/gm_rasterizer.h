@@ -41,11 +41,24 @@ typedef void* gm_stream_t;          /* a cudaStream_t; NULL = the legacy default
 const char* gm_version(void);       /* "gaussianmesh-b200 <semver> sm_100a"                           */
 const char* gm_last_error(void);    /* text of the last GM_ERR_CUDA on this host thread               */
 
+/* ---- optional per-stage timing.  Between gm_profile_begin() and gm_profile_end() every kernel stage
+ *      launched through this library is bracketed by two CUDA events on its launch stream;
+ *      gm_profile_end() waits for them and returns, per stage, the summed elapsed milliseconds and
+ *      the number of launches (arrays of gm_profile_num_stages() entries; either may be NULL).
+ *      Off by default: no events are recorded and nothing is added to the stream. ----------------- */
+int gm_profile_num_stages(void);
+const char* gm_profile_stage_name(int stage);
+void gm_profile_begin(void);
+int gm_profile_end(float* ms_per_stage, uint64_t* launches_per_stage);
+
 /* ---- opaque chunk sizing; replaces CudaRasterizer::required<T>()
  *      (dgr/cuda_rasterizer/rasterizer_impl.h:67-73, used at dgr/rasterize_points.py:74-76,186) --- */
 size_t gm_required_geom(size_t P);          /* GeometryState for P Gaussians                        */
 size_t gm_required_image(size_t N);         /* ImageState for N = W*H pixels                        */
 size_t gm_required_binning(size_t R);       /* BinningState for R (Gaussian, tile) instances        */
+/*  Inverse of gm_required_binning: the instance capacity gm_forward derives from a binning chunk of
+ *  `bytes` bytes.  This is the R to hand to gm_backward after a gm_forward over that chunk. */
+size_t gm_binning_capacity(size_t bytes);
 
 /* ---- markVisible; replaces Rasterizer::markVisible (dgr/cuda_rasterizer/rasterizer.h:24-29,
  *      rasterizer_impl.cu:54-66,141-153).  present[P] is a byte mask (C++ bool). ---------------- */
@@ -84,11 +97,13 @@ int gm_forward_1(char* geom_buffer, char* binning_buffer, char* image_buffer, in
 
 /* ---- single-call forward; replaces Rasterizer::forward (rasterizer.h:79-100,
  *      rasterizer_impl.cu:198-336) WITHOUT its host synchronisation: the caller hands in a
- *      binning chunk of binning_capacity bytes sized from a high-water mark; the instance count
- *      is written asynchronously to *num_rendered_host (pinned host memory, may be NULL).  If the
- *      view needs more than the chunk holds the frame is rendered from the instances that fit,
- *      *num_rendered_host still receives the full requirement, and the next
- *      gm_forward_status() on this geometry chunk returns GM_ERR_BINNING_OVERFLOW. */
+ *      binning chunk of binning_capacity bytes sized from a high-water mark; the frame's
+ *      counters are written asynchronously to frame_info_host[4] (pinned host memory, may be
+ *      NULL): [0] instances this view needs, [1] visible Gaussians, [2] overflow flag,
+ *      [3] capacity in instances.  If the view needs more than the chunk holds, the frame is
+ *      rendered from the instances that fit (tiles past the capacity come out as background),
+ *      [0] still receives the full requirement and [2] is 1; gm_forward_status() on the geometry
+ *      chunk then returns GM_ERR_BINNING_OVERFLOW. */
 int gm_forward(char* geom_buffer, char* binning_buffer, size_t binning_capacity,
                char* image_buffer, int P, int D, int M, const float* background, int width,
                int height, const float* means3D, const float* shs, const float* colors_precomp,
@@ -96,12 +111,18 @@ int gm_forward(char* geom_buffer, char* binning_buffer, size_t binning_capacity,
                const float* rotations, const float* cov3D_precomp, const float* viewmatrix,
                const float* projmatrix, const float* cam_pos, float tan_fovx, float tan_fovy,
                int prefiltered, float* out_color, int* radii, int debug,
-               int* num_rendered_host, gm_stream_t stream);
+               uint32_t* frame_info_host, gm_stream_t stream);
 
 /*  Blocking: synchronises `stream`, reads the frame header of a geometry chunk and reports
  *  GM_OK / GM_ERR_BINNING_OVERFLOW; *num_rendered / *num_visible may be NULL. */
 int gm_forward_status(const char* geom_buffer, int* num_rendered, int* num_visible,
                       gm_stream_t stream);
+
+/*  Diagnostic: device pointers into a geometry chunk carved for P Gaussians, for tests that compare
+ *  per-Gaussian state with the reference's GeometryState (rasterizer_impl.h:21-39).  out[0] depths
+ *  f32[P], out[1] means2D f32[P,2], out[2] cov3D f32[P,6], out[3] conic_opacity f32[P,4],
+ *  out[4] rgb+clamp-bits f32[P,4], out[5] per-tile instance counts u32[tiles]. */
+void gm_geom_view(char* geom_buffer, size_t P, void** out6);
 
 /* ---- backward; replaces Rasterizer::backward (rasterizer.h:102-132,
  *      rasterizer_impl.cu:515-608).  The three chunks must be those of the matching forward,

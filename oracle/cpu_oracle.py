@@ -1,0 +1,159 @@
+"""TEST INFRASTRUCTURE ONLY -- numpy/ctypes front end of the CPU oracle (oracle/cpu_rasterizer.c).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg may import this module; nothing under
+gaussianmesh_b200/ does.  Build the libraries with `make -C oracle cpu`.
+
+Pinning status: the reference has no tests or golden vectors for this path; the oracle is
+pinned against outputs of the reference's own CUDA code recorded on a B200 (tests/golden/*.npz, see
+tests/golden/make_golden.py) and against finite differences (tests/test_oracle.py).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import os
+import time
+from typing import Dict, Optional
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+_LIBS = {}
+
+
+def _lib(dtype):
+    name = "libgmo_f32.so" if dtype == np.float32 else "libgmo_f64.so"
+    if name not in _LIBS:
+        path = os.path.join(HERE, "_build", name)
+        if not os.path.exists(path):
+            raise FileNotFoundError(f"{path} missing: run `make -C oracle cpu`")
+        l = C.CDLL(path)
+        l.gmo_preprocess.restype = C.c_int64
+        assert l.gmo_sizeof_real() == np.dtype(dtype).itemsize
+        _LIBS[name] = l
+    return _LIBS[name]
+
+
+def _p(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _a(x, dtype) -> Optional[np.ndarray]:
+    return None if x is None else np.ascontiguousarray(x, dtype=dtype)
+
+
+def _view_scalars(cam, dtype):
+    real = C.c_float if dtype == np.float32 else C.c_double
+    return real(cam.tanfovx), real(cam.tanfovy)
+
+
+def forward(arrays: Dict[str, np.ndarray], cam, bg, degree: int, colors: Optional[np.ndarray] = None,
+            cov3D: Optional[np.ndarray] = None, scale_modifier: float = 1.0, dtype=np.float32, M: Optional[int] = None
+            ) -> Dict[str, np.ndarray]:
+    """The reference forward on the CPU.  `arrays` holds means3D, opacities and (shs | colors=...) and
+    (scales, rotations | cov3D=...); `cam` is a gaussianmesh_b200.synthetic.Camera."""
+    l = _lib(dtype)
+    real = C.c_float if dtype == np.float32 else C.c_double
+    means = _a(arrays["means3D"], dtype)
+    P = means.shape[0]
+    W, H = cam.image_width, cam.image_height
+    shs = None if colors is not None else _a(arrays["shs"], dtype)
+    colors = _a(colors, dtype)
+    scales = None if cov3D is not None else _a(arrays["scales"], dtype)
+    rots = None if cov3D is not None else _a(arrays["rotations"], dtype)
+    cov3D = _a(cov3D, dtype)
+    opac = _a(arrays["opacities"], dtype).reshape(-1)
+    view = _a(cam.world_view_transform.reshape(-1), dtype)
+    proj = _a(cam.full_proj_transform.reshape(-1), dtype)
+    campos = _a(cam.camera_center, dtype)
+    bg = _a(bg, dtype)
+    if M is None:
+        M = shs.shape[1] if shs is not None else 0
+    st = {
+        "radii": np.zeros(P, np.int32), "depths": np.zeros(P, dtype), "means2D": np.zeros((P, 2), dtype),
+        "cov3D": np.zeros((P, 6), dtype), "conic_opacity": np.zeros((P, 4), dtype), "rgb": np.zeros((P, 3), dtype),
+        "clamped": np.zeros((P, 3), np.uint8), "tiles_touched": np.zeros(P, np.int32),
+    }
+    tx, ty = _view_scalars(cam, dtype)
+    R = l.gmo_preprocess(P, degree, M, W, H, tx, ty, real(scale_modifier), _p(view), _p(proj), _p(campos), _p(means),
+                         _p(shs), _p(colors), _p(opac), _p(scales), _p(rots), _p(cov3D), _p(st["radii"]), _p(st["depths"]),
+                         _p(st["means2D"]), _p(st["cov3D"]), _p(st["conic_opacity"]), _p(st["rgb"]), _p(st["clamped"]),
+                         _p(st["tiles_touched"]))
+    tiles = ((W + 15) // 16) * ((H + 15) // 16)
+    keys = np.zeros(max(R, 1), np.uint64)
+    ids = np.zeros(max(R, 1), np.uint32)
+    ranges = np.zeros((tiles, 2), np.uint32)
+    l.gmo_bin(P, W, H, _p(st["radii"]), _p(st["means2D"]), _p(st["depths"]), _p(st["tiles_touched"]), C.c_int64(R),
+              _p(keys), _p(ids), _p(ranges))
+    color = np.zeros((3, H, W), dtype)
+    final_T = np.zeros((H, W), dtype)
+    n_contrib = np.zeros((H, W), np.uint32)
+    l.gmo_blend_forward(W, H, _p(ranges), _p(ids), _p(st["means2D"]), _p(st["conic_opacity"]), _p(st["rgb"]), _p(bg),
+                        _p(color), _p(final_T), _p(n_contrib))
+    if cov3D is not None:
+        st["cov3D"] = cov3D
+    st.update({"color": color, "final_T": final_T, "n_contrib": n_contrib, "num_rendered": int(R), "keys": keys[:R],
+               "point_list": ids[:R], "ranges": ranges, "M": M, "dtype": dtype,
+               "inputs": dict(means=means, shs=shs, colors=colors, scales=scales, rots=rots, cov3D=cov3D, opac=opac,
+                              view=view, proj=proj, campos=campos, bg=bg, scale_modifier=scale_modifier)})
+    return st
+
+
+def backward(arrays, cam, bg, degree: int, fwd: Dict[str, np.ndarray], dL_dpix: np.ndarray) -> Dict[str, np.ndarray]:
+    """The reference backward on the CPU, from the state `forward` returned.  Gradient layouts are the
+    reference's (rasterize_points.py:302-310)."""
+    dtype = fwd["dtype"]
+    l = _lib(dtype)
+    real = C.c_float if dtype == np.float32 else C.c_double
+    i = fwd["inputs"]
+    P = i["means"].shape[0]
+    W, H = cam.image_width, cam.image_height
+    M = fwd["M"]
+    dL = _a(dL_dpix, dtype)
+    g = {"means2D": np.zeros((P, 3), dtype), "conic": np.zeros((P, 4), dtype), "opacities": np.zeros((P, 1), dtype),
+         "colors": np.zeros((P, 3), dtype), "means3D": np.zeros((P, 3), dtype), "cov3D": np.zeros((P, 6), dtype),
+         "shs": np.zeros((P, max(M, 1), 3), dtype), "scales": np.zeros((P, 3), dtype), "rotations": np.zeros((P, 4), dtype)}
+    R = fwd["num_rendered"]
+    ids = np.ascontiguousarray(fwd["point_list"]) if R else np.zeros(1, np.uint32)
+    l.gmo_blend_backward(P, W, H, _p(fwd["ranges"]), _p(ids), C.c_int64(R), _p(fwd["means2D"]), _p(fwd["conic_opacity"]),
+                         _p(fwd["rgb"]), _p(i["bg"]), _p(fwd["final_T"]), _p(fwd["n_contrib"]), _p(dL), _p(g["means2D"]),
+                         _p(g["conic"]), _p(g["opacities"]), _p(g["colors"]))
+    tx, ty = _view_scalars(cam, dtype)
+    cov_all = _a(fwd["cov3D"], dtype)
+    l.gmo_geometry_backward(P, degree, M, W, H, tx, ty, real(i["scale_modifier"]), _p(i["view"]), _p(i["proj"]),
+                            _p(i["campos"]), _p(i["means"]), _p(fwd["radii"]), _p(i["shs"]), _p(fwd["clamped"]),
+                            _p(i["scales"]), _p(i["rots"]), _p(cov_all), _p(g["means2D"]), _p(g["conic"]), _p(g["colors"]),
+                            _p(g["means3D"]), _p(g["cov3D"]), _p(g["shs"]), _p(g["scales"]), _p(g["rotations"]))
+    if M == 0:
+        g["shs"] = g["shs"][:, :0]
+    return g
+
+
+def mark_visible(means3D: np.ndarray, cam, dtype=np.float32) -> np.ndarray:
+    means = _a(means3D, dtype)
+    out = np.zeros(means.shape[0], np.uint8)
+    _lib(dtype).gmo_mark_visible(means.shape[0], _p(means), _p(_a(cam.world_view_transform.reshape(-1), dtype)), _p(out))
+    return out.astype(bool)
+
+
+def timed_sample(P: int, W: int, H: int, frames: int = 1) -> dict:
+    """bench.py's cpu_baseline: forward + L1 + backward of the benchmark workload on the host cores."""
+    import sys
+    sys.path.insert(0, os.path.dirname(HERE))
+    from gaussianmesh_b200 import synthetic
+    arrays = synthetic.gaussian_scene(P, seed=0)
+    cams = synthetic.orbit_cameras(100, W, H)
+    target = np.random.default_rng(1).uniform(0.0, 1.0, size=(3, H, W)).astype(np.float32)
+    bg = np.zeros(3, np.float32)
+    t0 = time.perf_counter()
+    for f in range(frames):
+        fwd = forward(arrays, cams[f % len(cams)], bg, 3)
+        diff = fwd["color"] - target
+        loss = float(np.abs(diff).mean())
+        dL = (np.sign(diff) / diff.size).astype(np.float32)
+        backward(arrays, cams[f % len(cams)], bg, 3, fwd, dL)
+    dt = time.perf_counter() - t0
+    cores = int(os.environ.get("OMP_NUM_THREADS", os.cpu_count() or 1))
+    return {"value": frames / dt, "unit": "frames/s", "cores": cores, "kind": "port",
+            "sample": f"{frames} training frame(s) (forward + L1 + backward) of the same {P}-Gaussian {W}x{H} workload "
+                      f"through oracle/cpu_rasterizer.c (C + OpenMP restatement of the reference), {dt:.2f} s, loss {loss:.6f}"}

@@ -1,0 +1,135 @@
+"""TEST INFRASTRUCTURE: ctypes binding of oracle/_ref/libRefCudaRasterizer.so -- the UNMODIFIED reference
+CUDA rasterizer compiled for sm_100a by oracle/Makefile plus the flat shim oracle/ref_shim.cu.
+Only tests/, __graft_entry__.smoke() and bench.py's reference legs may import this."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Dict, Optional
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF_LIB = os.path.join(ROOT, "oracle", "_ref", "libRefCudaRasterizer.so")
+
+_p, _i, _f, _z = C.c_void_p, C.c_int, C.c_float, C.c_size_t
+_VIEW = [_p, _p, _p, _p, _p, _f, _p, _p, _p, _p, _p, _f, _f]
+_lib = None
+
+
+def available() -> bool:
+    return os.path.exists(REF_LIB)
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        l = C.CDLL(REF_LIB)
+        l.ref_required_geom.restype = _z; l.ref_required_geom.argtypes = [_z]
+        l.ref_required_image.restype = _z; l.ref_required_image.argtypes = [_z]
+        l.ref_required_binning.restype = _z; l.ref_required_binning.argtypes = [_z]
+        l.ref_mark_visible.restype = None; l.ref_mark_visible.argtypes = [_i, _p, _p, _p, _p]
+        l.ref_forward_0.restype = _i
+        l.ref_forward_0.argtypes = [_p, _i, _i, _i, _p, _i, _i, *_VIEW, _i, _p, _i]
+        l.ref_forward_1.restype = _i
+        l.ref_forward_1.argtypes = [_p, _p, _p, _i, _i, _i, _i, _p, _i, _i, *_VIEW, _i, _p, _p, _i]
+        l.ref_forward.restype = _i
+        l.ref_forward.argtypes = [_p, _z, _p, _z, _p, _z, _i, _i, _i, _p, _i, _i, *_VIEW, _i, _p, _p, _i, _p]
+        l.ref_backward.restype = _i
+        l.ref_backward.argtypes = [_i, _i, _i, _i, _p, _i, _i, _p, _p, _p, _p, _f, _p, _p, _p, _p, _p, _f, _f, _p,
+                                   _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i]
+        l.ref_geom_view.restype = None; l.ref_geom_view.argtypes = [_p, _z, _p]
+        l.ref_image_view.restype = None; l.ref_image_view.argtypes = [_p, _z, _p]
+        l.ref_binning_view.restype = None; l.ref_binning_view.argtypes = [_p, _z, _p]
+        _lib = l
+    return _lib
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None or t.numel() == 0 else t.data_ptr()
+
+
+class RefFrame:
+    """One forward of the reference (two-phase, as its Jittor glue drives it) and, optionally, its backward."""
+
+    def __init__(self, bg, means3D, opacities, viewmatrix, projmatrix, campos, tanfovx, tanfovy, H, W, degree,
+                 shs=None, colors=None, scales=None, rotations=None, cov3D=None, scale_modifier=1.0, M=None, sync=True):
+        l = lib()
+        dev = means3D.device
+        self.P = P = means3D.shape[0]
+        self.H, self.W, self.D = H, W, degree
+        self.M = M if M is not None else (shs.shape[1] if shs is not None else 0)
+        self.inputs = dict(bg=bg, means3D=means3D, opacities=opacities, viewmatrix=viewmatrix, projmatrix=projmatrix,
+                           campos=campos, shs=shs, colors=colors, scales=scales, rotations=rotations, cov3D=cov3D)
+        self.tan = (float(tanfovx), float(tanfovy))
+        self.scale_modifier = float(scale_modifier)
+        self.view_args = (_ptr(means3D), _ptr(shs), _ptr(colors), _ptr(opacities), _ptr(scales), self.scale_modifier,
+                          _ptr(rotations), _ptr(cov3D), _ptr(viewmatrix), _ptr(projmatrix), _ptr(campos), *self.tan)
+        self.geom = torch.zeros(l.ref_required_geom(P), dtype=torch.uint8, device=dev)
+        self.image = torch.zeros(l.ref_required_image(H * W), dtype=torch.uint8, device=dev)
+        self.radii = torch.zeros(P, dtype=torch.int32, device=dev)
+        self.color = torch.zeros(3, H, W, dtype=torch.float32, device=dev)
+        if sync:
+            torch.cuda.synchronize()
+        R = l.ref_forward_0(self.geom.data_ptr(), P, degree, self.M, _ptr(bg), W, H, *self.view_args, 0,
+                            self.radii.data_ptr(), 0)
+        assert R >= 0, "reference forward_0 failed"
+        self.R = R
+        self.binning = torch.zeros(l.ref_required_binning(R), dtype=torch.uint8, device=dev)
+        rc = l.ref_forward_1(self.geom.data_ptr(), self.binning.data_ptr(), self.image.data_ptr(), P, degree, self.M, R,
+                             _ptr(bg), W, H, *self.view_args, 0, self.color.data_ptr(), self.radii.data_ptr(), 0)
+        assert rc == 0, "reference forward_1 failed"
+        if sync:
+            torch.cuda.synchronize()
+
+    def geom_state(self) -> Dict[str, torch.Tensor]:
+        """Copies of the reference's per-Gaussian intermediate state."""
+        P = self.P
+        ptrs = (C.c_void_p * 9)()
+        lib().ref_geom_view(self.geom.data_ptr(), P, ptrs)
+        base = self.geom.data_ptr()
+
+        def view(k, dtype, shape):
+            off = ptrs[k] - base
+            n = int(torch.tensor([], dtype=dtype).element_size())
+            cnt = 1
+            for s in shape:
+                cnt *= s
+            return self.geom[off:off + cnt * n].view(dtype).view(*shape).clone()
+
+        return {"depths": view(0, torch.float32, (P,)), "clamped": view(1, torch.bool, (P, 3)),
+                "means2D": view(3, torch.float32, (P, 2)), "cov3D": view(4, torch.float32, (P, 6)),
+                "conic_opacity": view(5, torch.float32, (P, 4)), "rgb": view(6, torch.float32, (P, 3)),
+                "tiles_touched": view(7, torch.int32, (P,))}
+
+    def image_state(self) -> Dict[str, torch.Tensor]:
+        N = self.H * self.W
+        ptrs = (C.c_void_p * 3)()
+        lib().ref_image_view(self.image.data_ptr(), N, ptrs)
+        base = self.image.data_ptr()
+        o0, o1 = ptrs[0] - base, ptrs[1] - base
+        return {"final_T": self.image[o0:o0 + 4 * N].view(torch.float32).view(self.H, self.W).clone(),
+                "n_contrib": self.image[o1:o1 + 4 * N].view(torch.int32).view(self.H, self.W).clone()}
+
+    def backward(self, dL_dpix: torch.Tensor, sync=True) -> Dict[str, torch.Tensor]:
+        P, M = self.P, self.M
+        dev = dL_dpix.device
+        i = self.inputs
+        z = lambda *s: torch.zeros(*s, dtype=torch.float32, device=dev)
+        g = {"means2D": z(P, 3), "conic": z(P, 4), "opacity": z(P, 1), "colors": z(P, 3), "means3D": z(P, 3),
+             "cov3D": z(P, 6), "sh": z(P, max(M, 1), 3), "scales": z(P, 3), "rotations": z(P, 4)}
+        dL = dL_dpix.contiguous()
+        rc = lib().ref_backward(P, self.D, M, self.R, _ptr(i["bg"]), self.W, self.H, _ptr(i["means3D"]), _ptr(i["shs"]),
+                                _ptr(i["colors"]), _ptr(i["scales"]), self.scale_modifier, _ptr(i["rotations"]),
+                                _ptr(i["cov3D"]), _ptr(i["viewmatrix"]), _ptr(i["projmatrix"]), _ptr(i["campos"]),
+                                *self.tan, self.radii.data_ptr(), self.geom.data_ptr(), self.binning.data_ptr(),
+                                self.image.data_ptr(), dL.data_ptr(), g["means2D"].data_ptr(), g["conic"].data_ptr(),
+                                g["opacity"].data_ptr(), g["colors"].data_ptr(), g["means3D"].data_ptr(),
+                                g["cov3D"].data_ptr(), g["sh"].data_ptr(), g["scales"].data_ptr(),
+                                g["rotations"].data_ptr(), 0)
+        assert rc == 0, "reference backward failed"
+        if sync:
+            torch.cuda.synchronize()
+        if M == 0:
+            g["sh"] = g["sh"][:, :0]
+        return g

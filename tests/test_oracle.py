@@ -1,0 +1,267 @@
+"""CPU tests of the oracle (oracle/cpu_rasterizer.c + oracle/python_path.py).
+
+The reference ships no tests / golden vectors for this path, so the oracle is pinned against
+  (1) tests/golden/*.npz -- outputs of the reference's own CUDA code recorded on a B200
+      (tests/golden/make_golden.py through oracle/_ref), and
+  (2) finite differences of its own float64 build (the backward formulas), and
+  (3) independent formulations of the Python-side functions.
+"""
+import math
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+
+from gaussianmesh_b200 import synthetic  # noqa: E402
+
+
+@pytest.fixture(scope="session")
+def oracle():
+    subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "cpu"], check=True, capture_output=True)
+    from oracle import cpu_oracle
+    return cpu_oracle
+
+
+def _golden_cases():
+    import make_golden
+    return list(make_golden.CASES)
+
+
+# ------------------------------------------------------------------------------------------------ (1) golden
+@pytest.mark.parametrize("name", _golden_cases())
+def test_oracle_matches_reference_cuda_golden(oracle, name):
+    import make_golden
+    arrays, cam, bg, degree, variant, colors, cov, dL, want_grads = make_golden.case_inputs(name)
+    path = os.path.join(ROOT, "tests", "golden", name + ".npz")
+    gold = np.load(path)
+    if colors is not None:
+        assert np.array_equal(colors, gold["in_colors"])
+    if cov is not None:
+        assert np.array_equal(cov, gold["in_cov3D"])
+    f = oracle.forward(arrays, cam, bg, degree, colors=colors, cov3D=cov)
+    # integer / index results: exact
+    assert np.array_equal(f["radii"], gold["radii"])
+    assert f["num_rendered"] == int(gold["num_rendered"])
+    assert np.array_equal(f["tiles_touched"], gold["state_tiles_touched"].astype(np.int32))
+    assert np.array_equal(f["n_contrib"], gold["n_contrib"].astype(np.uint32))
+    vis = gold["radii"] > 0
+    if colors is None:
+        assert np.array_equal(f["clamped"][vis].astype(bool), gold["state_clamped"][vis])
+    # per-Gaussian floats: the CPU build does not contract into FMAs, so a few ulps of slack
+    assert np.abs(f["depths"][vis] - gold["state_depths"][vis]).max() <= 2e-6
+    assert np.abs(f["means2D"][vis] - gold["state_means2D"][vis]).max() <= 1e-4
+    rel = np.abs(f["conic_opacity"][vis] - gold["state_conic_opacity"][vis]) / np.maximum(np.abs(gold["state_conic_opacity"][vis]), 1e-3)
+    assert rel.max() <= 1e-2
+    # image: 1e-4 everywhere except pixels where an alpha < 1/255 or T < 1e-4 decision flipped by rounding
+    err = np.abs(f["color"] - gold["color"])
+    assert (err > 1e-4).sum() <= max(3, err.size // 20000), f"{(err > 1e-4).sum()} pixels off"
+    assert err.max() <= 1.0 / 255.0 + 1e-3
+    assert np.abs(f["final_T"] - gold["final_T"]).max() <= 4e-3
+    if want_grads:
+        g = oracle.backward(arrays, cam, bg, degree, f, dL)
+        names = {"means3D": "grad_means3D", "means2D": "grad_means2D", "opacities": "grad_opacity", "conic": "grad_conic",
+                 "cov3D": "grad_cov3D"}
+        if colors is None:
+            names["shs"] = "grad_sh"
+        else:
+            names["colors"] = "grad_colors"
+        if cov is None:
+            names.update({"scales": "grad_scales", "rotations": "grad_rotations"})
+        for k, gk in names.items():
+            b = gold[gk]
+            a = g[k].reshape(b.shape)
+            rel = np.abs(a - b).max() / max(np.abs(b).max(), 1e-30)
+            assert rel <= 1e-3, f"{k}: {rel:.3e}"
+
+
+# ------------------------------------------------------------------------------------------------ (2) finite differences
+def _fd_scene(P=24, seed=3):
+    arrays = synthetic.gaussian_scene(P, seed=seed, extent=0.8, log_scale_mean=math.log(0.25), log_scale_std=0.3)
+    arrays["opacities"] = np.clip(arrays["opacities"], 0.2, 0.9)
+    arrays = {k: v.astype(np.float64) for k, v in arrays.items()}
+    cam = synthetic.orbit_cameras(5, 48, 40, radius=5.0)[1]
+    return arrays, cam
+
+
+def _loss(oracle, arrays, cam, bg, dL, degree, **kw):
+    f = oracle.forward(arrays, cam, bg, degree, dtype=np.float64, **kw)
+    return float((f["color"] * dL).sum()), f
+
+
+@pytest.mark.parametrize("degree", [3, 1])
+def test_backward_formulas_against_finite_differences(oracle, degree):
+    arrays, cam = _fd_scene()
+    bg = np.array([0.3, 0.1, 0.7])
+    dL = np.random.default_rng(0).uniform(-1, 1, size=(3, cam.image_height, cam.image_width))
+    _, f = _loss(oracle, arrays, cam, bg, dL, degree)
+    assert (f["radii"] > 0).all()
+    g = oracle.backward(arrays, cam, bg, degree, f, dL)
+    rng = np.random.default_rng(1)
+    for key, gkey in [("means3D", "means3D"), ("scales", "scales"), ("rotations", "rotations"), ("opacities", "opacities"),
+                      ("shs", "shs")]:
+        for trial in range(3):
+            d = rng.normal(size=arrays[key].shape)
+            if key == "shs" and degree < 3:
+                d[:, (degree + 1) ** 2:, :] = 0.0
+            eps = 1e-6
+            plus = dict(arrays); plus[key] = arrays[key] + eps * d
+            minus = dict(arrays); minus[key] = arrays[key] - eps * d
+            fd = (_loss(oracle, plus, cam, bg, dL, degree)[0] - _loss(oracle, minus, cam, bg, dL, degree)[0]) / (2 * eps)
+            an = float((g[gkey].reshape(d.shape) * d).sum())
+            assert abs(fd - an) <= 2e-5 * max(1.0, abs(an)), f"{key} trial {trial}: fd {fd} vs analytic {an}"
+
+
+def test_backward_precomputed_paths_against_finite_differences(oracle):
+    arrays, cam = _fd_scene(seed=5)
+    bg = np.array([1.0, 1.0, 1.0])
+    dL = np.random.default_rng(2).uniform(-1, 1, size=(3, cam.image_height, cam.image_width))
+    colors = np.random.default_rng(3).uniform(0, 1, size=(arrays["means3D"].shape[0], 3))
+    cov = synthetic.packed_covariance(arrays["scales"], arrays["rotations"]).astype(np.float64)
+    _, f = _loss(oracle, arrays, cam, bg, dL, 3, colors=colors, cov3D=cov)
+    g = oracle.backward(arrays, cam, bg, 3, f, dL)
+    rng = np.random.default_rng(4)
+    eps = 1e-6
+    d = rng.normal(size=colors.shape)
+    fd = (_loss(oracle, arrays, cam, bg, dL, 3, colors=colors + eps * d, cov3D=cov)[0]
+          - _loss(oracle, arrays, cam, bg, dL, 3, colors=colors - eps * d, cov3D=cov)[0]) / (2 * eps)
+    an = float((g["colors"] * d).sum())
+    assert abs(fd - an) <= 2e-5 * max(1.0, abs(an))
+    d = rng.normal(size=cov.shape) * 1e-2
+    fd = (_loss(oracle, arrays, cam, bg, dL, 3, colors=colors, cov3D=cov + eps * d)[0]
+          - _loss(oracle, arrays, cam, bg, dL, 3, colors=colors, cov3D=cov - eps * d)[0]) / (2 * eps)
+    an = float((g["cov3D"] * d).sum())     # packed off-diagonals carry both symmetric entries
+    assert abs(fd - an) <= 2e-5 * max(1.0, abs(an))
+
+
+def test_scale_gradient_is_with_respect_to_modified_scale(oracle):
+    """backward.cu:298,318-320: dL_dscale is d/d(mod * s), NOT multiplied by mod -- a reference quirk kept."""
+    arrays, cam = _fd_scene(seed=7)
+    bg = np.zeros(3)
+    dL = np.random.default_rng(5).uniform(-1, 1, size=(3, cam.image_height, cam.image_width))
+    mod = 1.3
+    _, f = _loss(oracle, arrays, cam, bg, dL, 3, scale_modifier=mod)
+    g = oracle.backward(arrays, cam, bg, 3, f, dL)
+    d = np.random.default_rng(6).normal(size=arrays["scales"].shape)
+    eps = 1e-6
+    plus = dict(arrays); plus["scales"] = arrays["scales"] + eps * d
+    minus = dict(arrays); minus["scales"] = arrays["scales"] - eps * d
+    fd = (_loss(oracle, plus, cam, bg, dL, 3, scale_modifier=mod)[0] - _loss(oracle, minus, cam, bg, dL, 3, scale_modifier=mod)[0]) / (2 * eps)
+    an = float((g["scales"] * d).sum())
+    assert abs(fd - mod * an) <= 2e-5 * max(1.0, abs(fd))
+
+
+def test_float32_and_float64_builds_agree(oracle):
+    arrays = synthetic.gaussian_scene(3000, seed=11, log_scale_mean=math.log(0.03))
+    cam = synthetic.orbit_cameras(7, 160, 96)[4]
+    bg = np.array([0.2, 0.4, 0.6], np.float32)
+    f32 = oracle.forward(arrays, cam, bg, 3)
+    f64 = oracle.forward(arrays, cam, bg, 3, dtype=np.float64)
+    assert (f32["radii"] != f64["radii"]).sum() <= 2
+    err = np.abs(f32["color"] - f64["color"])
+    assert (err > 1e-4).sum() <= 5
+
+
+# ------------------------------------------------------------------------------------------------ edge cases
+def test_empty_scene_and_empty_tiles(oracle):
+    cam = synthetic.orbit_cameras(3, 64, 48)[0]
+    bg = np.array([0.25, 0.5, 0.75], np.float32)
+    arrays = synthetic.gaussian_scene(0)
+    f = oracle.forward(arrays, cam, bg, 3)
+    assert f["num_rendered"] == 0 and f["radii"].size == 0
+    assert np.array_equal(f["color"], np.broadcast_to(bg[:, None, None], (3, 48, 64)))   # ranges (0,0) -> background
+    assert (f["final_T"] == 1).all() and (f["n_contrib"] == 0).all()
+    g = oracle.backward(arrays, cam, bg, 3, f, np.ones((3, 48, 64), np.float32))
+    assert g["means3D"].shape == (0, 3)
+
+
+def test_near_plane_cull_and_mark_visible(oracle):
+    cam = synthetic.orbit_cameras(4, 64, 64)[0]             # at (0,1,6) looking at the origin
+    pts = np.array([[0, 0, 0], [0, 1, 6.5], [0, 1, 5.9], [0, 1, 5.79]], np.float32)
+    vis = oracle.mark_visible(pts, cam)
+    assert vis.tolist() == [True, False, False, True]       # view-space z must exceed 0.2 (auxiliary.h:153)
+    arrays = synthetic.gaussian_scene(4, seed=1)
+    arrays["means3D"] = pts
+    f = oracle.forward(arrays, cam, np.zeros(3, np.float32), 3)
+    assert ((f["radii"] > 0) <= vis).all() and f["radii"][1] == 0 and f["radii"][2] == 0
+
+
+def test_sort_is_stable_on_equal_depth(oracle):
+    """Two Gaussians at the same depth keep Gaussian-id order inside every tile (stable radix sort)."""
+    cam = synthetic.orbit_cameras(4, 32, 32)[0]
+    arrays = synthetic.gaussian_scene(6, seed=2, log_scale_mean=math.log(0.3))
+    arrays["means3D"][:] = arrays["means3D"][0]
+    f = oracle.forward(arrays, cam, np.zeros(3, np.float32), 3)
+    longest = 0
+    for lo, hi in f["ranges"]:
+        ids = f["point_list"][lo:hi].tolist()
+        assert ids == sorted(ids)
+        longest = max(longest, len(ids))
+    assert longest >= 4
+    assert (np.diff(f["keys"].astype(np.uint64)) >= 0).all()
+
+
+def test_ragged_image_size(oracle):
+    arrays = synthetic.gaussian_scene(500, seed=3, log_scale_mean=math.log(0.05))
+    cam = synthetic.orbit_cameras(4, 70, 37)[1]
+    f = oracle.forward(arrays, cam, np.ones(3, np.float32), 2)
+    assert f["color"].shape == (3, 37, 70) and np.isfinite(f["color"]).all()
+    assert f["ranges"].shape == (5 * 3, 2)
+
+
+# ------------------------------------------------------------------------------------------------ (3) python path
+def test_python_covariance_matches_c_oracle_for_unit_quaternions():
+    from oracle import python_path as pp
+    arrays = synthetic.gaussian_scene(2000, seed=4)
+    a = pp.build_covariance_from_scaling_rotation(arrays["scales"], 1.0, arrays["rotations"])
+    b = synthetic.packed_covariance(arrays["scales"], arrays["rotations"])          # float64 closed form
+    assert np.abs(a - b).max() <= 1e-6 * max(1.0, np.abs(b).max())
+    # and it normalises the quaternion (utils/general_utils.py:78-80), unlike the CUDA path
+    c = pp.build_covariance_from_scaling_rotation(arrays["scales"], 1.0, arrays["rotations"] * 3.0)
+    assert np.abs(a - c).max() <= 1e-6
+
+
+def test_python_sh_matches_c_oracle(oracle):
+    from oracle import python_path as pp
+    arrays = synthetic.gaussian_scene(1500, seed=6)
+    cam = synthetic.orbit_cameras(4, 64, 64)[2]
+    for deg in (0, 1, 2, 3):
+        rgb = pp.sh_to_rgb(deg, arrays["shs"], arrays["means3D"], cam.camera_center)
+        f = oracle.forward(arrays, cam, np.zeros(3, np.float32), deg)
+        vis = f["radii"] > 0
+        assert np.abs(rgb[vis] - f["rgb"][vis]).max() <= 2e-6
+
+
+def test_python_mesh_bind_and_deform_identities():
+    from oracle import python_path as pp
+    V, F = synthetic.icosphere(2)
+    arrays = synthetic.mesh_bound_scene(3000, V, F, seed=1)
+    xyz = pp.get_xyz(arrays["bc_logits"], arrays["distance"], arrays["vertex1"], arrays["vertex2"], arrays["vertex3"],
+                     arrays["normal"], arrays["r"])
+    # with distance = 0 the point lies in the face plane and its barycentric weights are the softmax
+    zero = np.zeros_like(arrays["distance"])
+    proj = pp.get_xyz(arrays["bc_logits"], zero, arrays["vertex1"], arrays["vertex2"], arrays["vertex3"], arrays["normal"], arrays["r"])
+    w = pp.get_barycentric_coordinate(proj.astype(np.float64), arrays["vertex1"].astype(np.float64),
+                                      arrays["vertex2"].astype(np.float64), arrays["vertex3"].astype(np.float64))
+    assert np.abs(w - pp.softmax(arrays["bc_logits"])).max() <= 1e-5
+    off = ((xyz - proj) * arrays["normal"]).sum(axis=1, keepdims=True)
+    assert np.abs(off - 4.0 * arrays["r"] * (pp.sigmoid(arrays["distance"]) - 0.5)).max() <= 1e-5
+    # identity deformation leaves everything unchanged; a rigid rotation rotates positions and covariances
+    Vn = V.shape[0]
+    eye = np.broadcast_to(np.eye(3, dtype=np.float32), (Vn, 3, 3))
+    cov6 = synthetic.packed_covariance(arrays["scales"], arrays["rotations"])
+    cov = np.stack([cov6[:, 0], cov6[:, 1], cov6[:, 2], cov6[:, 1], cov6[:, 3], cov6[:, 4], cov6[:, 2], cov6[:, 4], cov6[:, 5]],
+                   axis=1).reshape(-1, 3, 3)
+    p2, c2, r2 = pp.deform_gaussian(V, V, eye, eye, arrays["triangles"], w, proj, cov)
+    assert np.abs(p2 - proj).max() <= 1e-6 and np.abs(c2 - cov).max() <= 1e-7 and np.abs(r2 - eye[0]).max() <= 1e-6
+    th = 0.7
+    Q = np.array([[math.cos(th), 0, math.sin(th)], [0, 1, 0], [-math.sin(th), 0, math.cos(th)]], np.float32)
+    # ACAP hands back R such that the local frame map is R^T (the reference transposes it, edittool/__init__.py:122)
+    p3, c3, r3 = pp.deform_gaussian(V, V @ Q.T, np.broadcast_to(Q.T, (Vn, 3, 3)), eye, arrays["triangles"], w, proj, cov)
+    assert np.abs(p3 - proj @ Q.T).max() <= 1e-5
+    assert np.abs(c3 - Q @ cov @ Q.T).max() <= 1e-6 * max(1.0, np.abs(cov).max())
+    assert np.abs(r3 - Q).max() <= 1e-6
