@@ -123,30 +123,35 @@ constexpr int kSortThreads = 256;
 constexpr int kSortSmem = 4096;   // keys; 32 KB
 
 template <typename Ptr>
+__device__ __forceinline__ void compare_exchange(Ptr a, uint32_t i, uint32_t j, uint32_t n)
+{
+	if (j < n) {
+		const uint64_t x = a[i], y = a[j];
+		if (x > y) { a[i] = y; a[j] = x; }
+	}
+}
+
+// k and s are powers of two, so every index is built from shifts and masks (lk = log2 k, ls = log2 s).
+template <typename Ptr>
 __device__ __forceinline__ void bitonic_sort(Ptr a, uint32_t n)
 {
-	uint32_t m = 1;
-	while (m < n) m <<= 1;
-	for (uint32_t k = 2; k <= m; k <<= 1) {
+	uint32_t lm = 0;
+	while ((1u << lm) < n) lm++;
+	const uint32_t half = (1u << lm) >> 1;
+	for (uint32_t lk = 1; lk <= lm; lk++) {
 		// flip step: i in the lower half of each k-block pairs with its mirror image
-		for (uint32_t t = threadIdx.x; t < m / 2; t += kSortThreads) {
-			const uint32_t blk = t / (k / 2), off = t % (k / 2);
-			const uint32_t i = blk * k + off;
-			const uint32_t j = blk * k + (k - 1 - off);
-			if (j < n) {
-				const uint64_t x = a[i], y = a[j];
-				if (x > y) { a[i] = y; a[j] = x; }
-			}
+		const uint32_t hk_mask = (1u << (lk - 1)) - 1u;
+		for (uint32_t t = threadIdx.x; t < half; t += kSortThreads) {
+			const uint32_t off = t & hk_mask;
+			const uint32_t blk = (t >> (lk - 1)) << lk;
+			compare_exchange(a, blk + off, blk + ((1u << lk) - 1u - off), n);
 		}
 		__syncthreads();
-		for (uint32_t s = k / 4; s > 0; s >>= 1) {
-			for (uint32_t t = threadIdx.x; t < m / 2; t += kSortThreads) {
-				const uint32_t i = (t / s) * (2 * s) + (t % s);
-				const uint32_t j = i + s;
-				if (j < n) {
-					const uint64_t x = a[i], y = a[j];
-					if (x > y) { a[i] = y; a[j] = x; }
-				}
+		for (int ls = (int)lk - 2; ls >= 0; ls--) {
+			const uint32_t s_mask = (1u << ls) - 1u;
+			for (uint32_t t = threadIdx.x; t < half; t += kSortThreads) {
+				const uint32_t i = ((t >> ls) << (ls + 1)) + (t & s_mask);
+				compare_exchange(a, i, i + (1u << ls), n);
 			}
 			__syncthreads();
 		}

@@ -1,17 +1,21 @@
 // Backward of the per-tile alpha blend.
 //
-// Replaces renderCUDA<3> of dgr/cuda_rasterizer/backward.cu:399-557.  Per-pixel arithmetic follows
-// backward.cu:476-554 line by line; what changes is how the nine per-(pixel, splat) partial
-// gradients reach global memory.  The reference issues nine global float atomicAdds per
-// contributing pair (backward.cu:523,545-554).  Here
-//   * the tile's sorted splat records are bulk-copied (TMA) back to front, starting at the last
-//     batch any pixel of the tile actually used (the reference walks the whole list);
-//   * a warp (8x4 pixel block) culls 32 splats in parallel against its block, exactly as the
-//     forward does;
-//   * partials are summed across the warp with shuffles, then across the 8 warps of the tile in
-//     shared memory, and leave the SM as ONE atomic per (tile, splat, component).
-// Summation order differs from the reference's (which is itself non-deterministic), hence the
-// 1e-3 relative tolerance of the gradient parity tests.
+// Replaces renderCUDA<3> of dgr/cuda_rasterizer/backward.cu:399-557.  The per-pixel recurrence
+// (backward.cu:476-534: T <- T/(1-alpha), accum_rec, dL/dalpha with the background term) is kept; what
+// changes is everything around it.  The reference issues nine global float atomicAdds per contributing
+// (pixel, splat) pair (backward.cu:523,545-554).  Here
+//   * the tile's sorted splat records are bulk-copied (TMA) back to front, starting at the last batch any
+//     pixel of the tile actually used (the reference walks the whole list);
+//   * a warp owns an 8x4 pixel block and culls 32 splats in parallel against it, exactly as the forward;
+//   * per pair each lane produces nine MOMENTS (3 colour sums and sum q, q dx, q dy, q dx^2, q dx dy,
+//     q dy^2 with q = G dL/dalpha); the splat-constant factors of backward.cu:537-554 (opacity, conic
+//     entries, -1/2, W/2, H/2) are applied once per (warp, splat) when the sums leave the warp;
+//   * the nine moments are summed over the 32 pixels with a transposing butterfly (12 shuffles instead of
+//     45) and parked in a warp-private shared-memory row; after 32 splats every lane owns one splat and
+//     sends its gradients to global memory with nine atomics -- one set per (warp, splat) that actually
+//     received a contribution, instead of one per (pixel, splat).
+// Summation order differs from the reference's (which is itself non-deterministic), hence the 1e-3
+// relative tolerance of the gradient parity tests.
 #include "common.cuh"
 #include "kernels.h"
 
@@ -20,25 +24,61 @@ namespace gm {
 namespace {
 
 constexpr int kThreads = 256;
+constexpr int kWarps = kThreads / 32;
 constexpr int kBatch = 256;
-constexpr int kComp = 9;   // dcolor r,g,b | dmean2D x,y | dconic a,b,c | dopacity
+constexpr int kComp = 9;   // colour r,g,b | q | q dx | q dy | q dx^2 | q dx dy | q dy^2
 
 struct __align__(128) BwdSmem {
 	float4 conic[2][kBatch];
 	float4 xyrg[2][kBatch];
 	float2 bid[2][kBatch];
-	float acc[kComp][kBatch + 1];   // +1: component c of splat j lands in bank (c + j) % 32
-	uint32_t touched[kBatch];
+	float park[kWarps][32 * kComp];   // [warp][splat-in-chunk * 9 + component]: stride 9 is conflict free
 	uint64_t full[2];
-	uint32_t warp_max[kThreads / 32];
+	uint32_t warp_max[kWarps];
 };
 
-__device__ __forceinline__ float warp_sum(float v)
+// Sum nine per-lane values over the warp.  On return lane 4q (q = 0..7) holds the total of v[q] and lane 2
+// holds the total of v[8] (so do lanes 4q+1 resp. 4q+2, 4q+3 -- only one of each is used).
+__device__ __forceinline__ float butterfly9(const float (&v)[kComp], int lane)
 {
+	// xor 16: 8 values -> 4 per lane
+	const bool h4 = lane & 16;
+	float w[4];
 #pragma unroll
-	for (int o = 16; o > 0; o >>= 1)
-		v += __shfl_xor_sync(0xffffffffu, v, o);
-	return v;
+	for (int i = 0; i < 4; i++) {
+		const float keep = h4 ? v[i + 4] : v[i];
+		const float send = h4 ? v[i] : v[i + 4];
+		w[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+	}
+	float s = v[8] + __shfl_xor_sync(0xffffffffu, v[8], 16);
+	// xor 8: 4 -> 2
+	const bool h3 = lane & 8;
+	float u[2];
+#pragma unroll
+	for (int i = 0; i < 2; i++) {
+		const float keep = h3 ? w[i + 2] : w[i];
+		const float send = h3 ? w[i] : w[i + 2];
+		u[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+	}
+	s += __shfl_xor_sync(0xffffffffu, s, 8);
+	// xor 4: 2 -> 1
+	const bool h2 = lane & 4;
+	float t;
+	{
+		const float keep = h2 ? u[1] : u[0];
+		const float send = h2 ? u[0] : u[1];
+		t = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+	}
+	s += __shfl_xor_sync(0xffffffffu, s, 4);
+	// xor 2: lanes with bit 1 clear keep t (value index lane >> 2), the others keep s (value 8)
+	const bool h1 = lane & 2;
+	{
+		const float keep = h1 ? s : t;
+		const float send = h1 ? t : s;
+		t = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+	}
+	t += __shfl_xor_sync(0xffffffffu, t, 1);
+	return t;
 }
 
 __global__ void __launch_bounds__(kThreads)
@@ -82,9 +122,6 @@ blend_backward_kernel(GeometryState g, BinningState b, ImageState img, uint32_t 
 		warp_last = max(warp_last, __shfl_xor_sync(0xffffffffu, warp_last, o));
 	if (lane == 0)
 		s.warp_max[warp] = warp_last;
-	for (int c = 0; c < kComp; c++)
-		s.acc[c][tid] = 0.0f;
-	s.touched[tid] = 0u;
 	if (tid == 0) {
 		mbar_init(&s.full[0], 1);
 		mbar_init(&s.full[1], 1);
@@ -93,7 +130,7 @@ blend_backward_kernel(GeometryState g, BinningState b, ImageState img, uint32_t 
 	__syncthreads();
 	uint32_t tile_last = 0;
 #pragma unroll
-	for (int w = 0; w < kThreads / 32; w++)
+	for (int w = 0; w < kWarps; w++)
 		tile_last = max(tile_last, s.warp_max[w]);
 	if (tile_last == 0)
 		return;
@@ -109,10 +146,11 @@ blend_backward_kernel(GeometryState g, BinningState b, ImageState img, uint32_t 
 	float last_alpha = 0.0f;
 	float last_color0 = 0.0f, last_color1 = 0.0f, last_color2 = 0.0f;
 
-	// backward.cu:455-461, 531-533
+	// backward.cu:455-461: d(pixel offset)/d(NDC mean); applied once per (warp, splat) below
 	const float ddelx_dx = 0.5 * W;
 	const float ddely_dy = 0.5 * H;
-	const float bg0 = bg_color[0], bg1 = bg_color[1], bg2 = bg_color[2];
+	// backward.cu:531-534: dL/dalpha += (-T_final / (1 - alpha)) * (bg . dL/dpixel)
+	const float bg_term = -T_final * (bg_color[0] * dL_dpixel0 + bg_color[1] * dL_dpixel1 + bg_color[2] * dL_dpixel2);
 
 	auto issue = [&](int batch, int buf) {
 		const uint32_t off = start + (uint32_t)batch * kBatch;
@@ -124,12 +162,16 @@ blend_backward_kernel(GeometryState g, BinningState b, ImageState img, uint32_t 
 		bulk_g2s(s.bid[buf], b.rec_bid + off, cnt4 * 8u, &s.full[buf]);
 	};
 
+	float* const park = s.park[warp];
 	const int batch_hi = (int)((tile_last - 1) / kBatch);
 	if (tid == 0)
 		issue(batch_hi, 0);
 
 	for (int it = 0, batch = batch_hi; batch >= 0; it++, batch--) {
 		const int buf = it & 1;
+		// every warp has finished batch+1 (buffer buf^1) before it is overwritten
+		if (it > 0)
+			__syncthreads();
 		if (tid == 0 && batch > 0)
 			issue(batch - 1, buf ^ 1);
 		mbar_wait(&s.full[buf], (uint32_t)(it >> 1) & 1u);
@@ -140,13 +182,15 @@ blend_backward_kernel(GeometryState g, BinningState b, ImageState img, uint32_t 
 		for (int base = (cnt > 0) ? ((cnt - 1) & ~31) : -1; base >= 0; base -= 32) {
 			const int j = base + lane;
 			bool keep = false;
+			float4 my_co = make_float4(0.f, 0.f, 0.f, 0.f);
 			if (j < cnt) {
-				const float4 co = s.conic[buf][j];
+				my_co = s.conic[buf][j];
 				const float4 xr = s.xyrg[buf][j];
-				keep = !rect_cannot_contribute(xr.x, xr.y, co.x, co.y, co.z, cull_threshold(co.w),
+				keep = !rect_cannot_contribute(xr.x, xr.y, my_co.x, my_co.y, my_co.z, cull_threshold(my_co.w),
 				                               wx0, wy0, wx1, wy1);
 			}
 			uint32_t mask = __ballot_sync(0xffffffffu, keep);
+			uint32_t touched = 0;
 			while (mask) {
 				const int k = 31 - __clz(mask);
 				mask &= ~(1u << k);
@@ -155,93 +199,75 @@ blend_backward_kernel(GeometryState g, BinningState b, ImageState img, uint32_t 
 				const float4 xr = s.xyrg[buf][jj];
 
 				// backward.cu:487-501
-				bool active = (uint32_t)(batch_base + jj) < last_contributor;
 				const float dx = xr.x - pixf_x, dy = xr.y - pixf_y;
 				const float power = -0.5f * (co.x * dx * dx + co.z * dy * dy) - co.y * dx * dy;
-				active = active && !(power > 0.0f);
 				const float G = expf(power);
 				const float alpha = min(0.99f, co.w * G);
-				active = active && !(alpha < 1.0f / 255.0f);
+				const bool active = ((uint32_t)(batch_base + jj) < last_contributor) && !(power > 0.0f) &&
+				                    !(alpha < 1.0f / 255.0f);
 				if (!__any_sync(0xffffffffu, active))
 					continue;
+				touched |= 1u << k;
 
-				float g_c0 = 0.0f, g_c1 = 0.0f, g_c2 = 0.0f;
-				float g_mx = 0.0f, g_my = 0.0f, g_ca = 0.0f, g_cb = 0.0f, g_cc = 0.0f, g_op = 0.0f;
+				float v[kComp];
+#pragma unroll
+				for (int c = 0; c < kComp; c++)
+					v[c] = 0.0f;
 				if (active) {
 					const float cb = s.bid[buf][jj].x;
-					// backward.cu:503-524
-					T = T / (1.f - alpha);
+					// backward.cu:503-534
+					const float rcp = __frcp_rn(1.f - alpha);
+					T = T * rcp;
 					const float dchannel_dcolor = alpha * T;
-					float dL_dalpha = 0.0f;
-					accum_rec0 = last_alpha * last_color0 + (1.f - last_alpha) * accum_rec0;
-					last_color0 = xr.z;
-					dL_dalpha += (xr.z - accum_rec0) * dL_dpixel0;
-					g_c0 = dchannel_dcolor * dL_dpixel0;
-					accum_rec1 = last_alpha * last_color1 + (1.f - last_alpha) * accum_rec1;
-					last_color1 = xr.w;
-					dL_dalpha += (xr.w - accum_rec1) * dL_dpixel1;
-					g_c1 = dchannel_dcolor * dL_dpixel1;
-					accum_rec2 = last_alpha * last_color2 + (1.f - last_alpha) * accum_rec2;
-					last_color2 = cb;
-					dL_dalpha += (cb - accum_rec2) * dL_dpixel2;
-					g_c2 = dchannel_dcolor * dL_dpixel2;
-					// backward.cu:525-534
-					dL_dalpha *= T;
+					const float keep_prev = 1.f - last_alpha;
+					accum_rec0 = last_alpha * last_color0 + keep_prev * accum_rec0;
+					accum_rec1 = last_alpha * last_color1 + keep_prev * accum_rec1;
+					accum_rec2 = last_alpha * last_color2 + keep_prev * accum_rec2;
+					last_color0 = xr.z; last_color1 = xr.w; last_color2 = cb;
 					last_alpha = alpha;
-					float bg_dot_dpixel = 0.0f;
-					bg_dot_dpixel += bg0 * dL_dpixel0;
-					bg_dot_dpixel += bg1 * dL_dpixel1;
-					bg_dot_dpixel += bg2 * dL_dpixel2;
-					dL_dalpha += (-T_final / (1.f - alpha)) * bg_dot_dpixel;
-					// backward.cu:537-554
-					const float dL_dG = co.w * dL_dalpha;
-					const float gdx = G * dx;
-					const float gdy = G * dy;
-					const float dG_ddelx = -gdx * co.x - gdy * co.y;
-					const float dG_ddely = -gdy * co.z - gdx * co.y;
-					g_mx = dL_dG * dG_ddelx * ddelx_dx;
-					g_my = dL_dG * dG_ddely * ddely_dy;
-					g_ca = -0.5f * gdx * dx * dL_dG;
-					g_cb = -0.5f * gdx * dy * dL_dG;
-					g_cc = -0.5f * gdy * dy * dL_dG;
-					g_op = G * dL_dalpha;
+					float dL_dalpha = (xr.z - accum_rec0) * dL_dpixel0 + (xr.w - accum_rec1) * dL_dpixel1 +
+					                  (cb - accum_rec2) * dL_dpixel2;
+					dL_dalpha = dL_dalpha * T + bg_term * rcp;
+					v[0] = dchannel_dcolor * dL_dpixel0;
+					v[1] = dchannel_dcolor * dL_dpixel1;
+					v[2] = dchannel_dcolor * dL_dpixel2;
+					// moments of q = G dL/dalpha (backward.cu:537-554 with the splat constants factored out)
+					const float q = G * dL_dalpha;
+					const float qdx = q * dx, qdy = q * dy;
+					v[3] = q;
+					v[4] = qdx;
+					v[5] = qdy;
+					v[6] = qdx * dx;
+					v[7] = qdx * dy;
+					v[8] = qdy * dy;
 				}
-				g_c0 = warp_sum(g_c0); g_c1 = warp_sum(g_c1); g_c2 = warp_sum(g_c2);
-				g_mx = warp_sum(g_mx); g_my = warp_sum(g_my);
-				g_ca = warp_sum(g_ca); g_cb = warp_sum(g_cb); g_cc = warp_sum(g_cc);
-				g_op = warp_sum(g_op);
-				if (lane < kComp) {
-					float v = g_c0;
-					v = (lane == 1) ? g_c1 : v; v = (lane == 2) ? g_c2 : v;
-					v = (lane == 3) ? g_mx : v; v = (lane == 4) ? g_my : v;
-					v = (lane == 5) ? g_ca : v; v = (lane == 6) ? g_cb : v;
-					v = (lane == 7) ? g_cc : v; v = (lane == 8) ? g_op : v;
-					atomicAdd(&s.acc[lane][jj], v);
-					if (lane == 0)
-						s.touched[jj] = 1u;
-				}
+				const float total = butterfly9(v, lane);
+				if ((lane & 3) == 0)
+					park[k * kComp + (lane >> 2)] = total;
+				else if (lane == 2)
+					park[k * kComp + 8] = total;
 			}
+			__syncwarp();
+			if ((touched >> lane) & 1u) {
+				// this lane owns splat j = base + lane of the chunk
+				const float* m = park + lane * kComp;
+				const uint32_t id = __float_as_uint(s.bid[buf][j].y);
+				const float a = my_co.x, bb = my_co.y, c = my_co.z, o = my_co.w;
+				const float Sq = m[3], Sx = m[4], Sy = m[5], Sxx = m[6], Sxy = m[7], Syy = m[8];
+				atomicAdd(&dL_dcolors[3 * (size_t)id + 0], m[0]);
+				atomicAdd(&dL_dcolors[3 * (size_t)id + 1], m[1]);
+				atomicAdd(&dL_dcolors[3 * (size_t)id + 2], m[2]);
+				// dL/dG = o dL/dalpha;  dG/ddelx = -G (a dx + b dy);  dG/ddely = -G (c dy + b dx)
+				atomicAdd(&dL_dmean2D[3 * (size_t)id + 0], -o * ddelx_dx * (a * Sx + bb * Sy));
+				atomicAdd(&dL_dmean2D[3 * (size_t)id + 1], -o * ddely_dy * (c * Sy + bb * Sx));
+				const float h = -0.5f * o;
+				atomicAdd(&dL_dconic2D[4 * (size_t)id + 0], h * Sxx);
+				atomicAdd(&dL_dconic2D[4 * (size_t)id + 1], h * Sxy);
+				atomicAdd(&dL_dconic2D[4 * (size_t)id + 3], h * Syy);
+				atomicAdd(&dL_dopacity[id], Sq);
+			}
+			__syncwarp();   // the park row is rewritten by the next chunk
 		}
-		__syncthreads();   // all warps have added their partials of this batch
-
-		// flush: thread t owns splat t of the batch
-		if (s.touched[tid]) {
-			const uint32_t id = __float_as_uint(s.bid[buf][tid].y);
-			atomicAdd(&dL_dcolors[3 * (size_t)id + 0], s.acc[0][tid]);
-			atomicAdd(&dL_dcolors[3 * (size_t)id + 1], s.acc[1][tid]);
-			atomicAdd(&dL_dcolors[3 * (size_t)id + 2], s.acc[2][tid]);
-			atomicAdd(&dL_dmean2D[3 * (size_t)id + 0], s.acc[3][tid]);
-			atomicAdd(&dL_dmean2D[3 * (size_t)id + 1], s.acc[4][tid]);
-			atomicAdd(&dL_dconic2D[4 * (size_t)id + 0], s.acc[5][tid]);
-			atomicAdd(&dL_dconic2D[4 * (size_t)id + 1], s.acc[6][tid]);
-			atomicAdd(&dL_dconic2D[4 * (size_t)id + 3], s.acc[7][tid]);
-			atomicAdd(&dL_dopacity[id], s.acc[8][tid]);
-#pragma unroll
-			for (int c = 0; c < kComp; c++)
-				s.acc[c][tid] = 0.0f;
-			s.touched[tid] = 0u;
-		}
-		__syncthreads();   // accumulators clean, buffer `buf` free for the copy issued next round
 	}
 }
 

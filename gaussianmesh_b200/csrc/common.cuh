@@ -237,6 +237,32 @@ __device__ __forceinline__ float sh_channel(int deg, const ShDir& d, ShFetch sh)
 	return result;
 }
 
+// First n_floats (= 3 (deg+1)^2) SH floats of one Gaussian into registers.  kVec: 128-bit loads; needs the
+// Gaussian's row 16-byte aligned and M*3 a multiple of 4, so a partially needed float4 still lies inside the row.
+template <bool kVec>
+__device__ __forceinline__ void load_sh(const float* __restrict__ sh, int n_floats, float (&c)[48])
+{
+	if (kVec) {
+		const float4* v = reinterpret_cast<const float4*>(sh);
+#pragma unroll
+		for (int j = 0; j < 12; j++) {
+			float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+			if (4 * j < n_floats)
+				t = __ldg(v + j);
+			c[4 * j + 0] = t.x; c[4 * j + 1] = t.y; c[4 * j + 2] = t.z; c[4 * j + 3] = t.w;
+		}
+	} else {
+#pragma unroll
+		for (int i = 0; i < 48; i++)
+			c[i] = (i < n_floats) ? __ldg(sh + i) : 0.0f;
+	}
+}
+
+__host__ __device__ __forceinline__ bool sh_rows_vectorizable(const void* shs, int M)
+{
+	return shs != nullptr && (reinterpret_cast<uintptr_t>(shs) & 15u) == 0 && M > 0 && ((M * 3) & 3) == 0;
+}
+
 // ---- exact (output-preserving) rectangle culling -------------------------------------------------
 // A splat contributes to a pixel only if power <= 0 and opacity*exp(power) >= 1/255
 // (forward.cu:336-345, backward.cu:494-501).  For an axis-aligned pixel rectangle

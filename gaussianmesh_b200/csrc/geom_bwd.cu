@@ -24,6 +24,7 @@ __device__ __forceinline__ float3 dnormvdv3(float3 v, float3 dv)   // auxiliary.
 	return r;
 }
 
+template <bool kVecSH>
 __global__ void __launch_bounds__(kThreads)
 geometry_backward_kernel(int P,
                          const float* __restrict__ means3D,
@@ -158,92 +159,87 @@ geometry_backward_kernel(int P,
 	}
 
 	// ------------------------------------------------------------------ backward.cu:20-139
+	// dL/dsh[k] = basis_k(dir) * dL/dRGB (clamp-masked, :31-34), dL/ddir = sum_k grad basis_k * (sh_k . dL/dRGB),
+	// then through the normalisation of dir (dnormvdv, :128-138).  The row of SH coefficients is read and the
+	// row of gradients written with 128-bit accesses.
 	if (shs != nullptr) {
 		const int deg = vp.D;
 		const float3 dir_orig = make_float3(mean.x - s_cam[0], mean.y - s_cam[1], mean.z - s_cam[2]);
 		const float len = sqrtf(dir_orig.x * dir_orig.x + dir_orig.y * dir_orig.y + dir_orig.z * dir_orig.z);
 		const float x = dir_orig.x / len, y = dir_orig.y / len, z = dir_orig.z / len;
+		const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
 
-		const float* sh = shs + (size_t)idx * vp.M * 3;
-		float* dsh = dL_dsh + (size_t)idx * vp.M * 3;
+		const int n_floats = 3 * (deg + 1) * (deg + 1);
+		float sh[48];
+		load_sh<kVecSH>(shs + (size_t)idx * vp.M * 3, n_floats, sh);
 		const uint32_t clamp_bits = __float_as_uint(g.rgb_clamp[idx].w);
 		float dRGB[3];
 #pragma unroll
 		for (int ch = 0; ch < 3; ch++)
 			dRGB[ch] = dL_dcolor[3 * idx + ch] * (((clamp_bits >> ch) & 1u) ? 0 : 1);
 
-		float dRGBdx[3] = {0, 0, 0}, dRGBdy[3] = {0, 0, 0}, dRGBdz[3] = {0, 0, 0};
-#define GM_SH(k, ch) sh[3 * (k) + (ch)]
-#define GM_DSH(k, w) do { _Pragma("unroll") for (int ch = 0; ch < 3; ch++) dsh[3 * (k) + ch] = (w) * dRGB[ch]; } while (0)
-
-		GM_DSH(0, GM_SH_C0);
+		// basis values and their gradients w.r.t. the unit direction (zero above `deg`)
+		float B[16], Gx[16], Gy[16], Gz[16];
+#pragma unroll
+		for (int k = 0; k < 16; k++) { B[k] = 0.f; Gx[k] = 0.f; Gy[k] = 0.f; Gz[k] = 0.f; }
+		B[0] = GM_SH_C0;
 		if (deg > 0) {
-			GM_DSH(1, -GM_SH_C1 * y);
-			GM_DSH(2, GM_SH_C1 * z);
-			GM_DSH(3, -GM_SH_C1 * x);
-#pragma unroll
-			for (int ch = 0; ch < 3; ch++) {
-				dRGBdx[ch] = -GM_SH_C1 * GM_SH(3, ch);
-				dRGBdy[ch] = -GM_SH_C1 * GM_SH(1, ch);
-				dRGBdz[ch] = GM_SH_C1 * GM_SH(2, ch);
-			}
-			if (deg > 1) {
-				const float xx = x * x, yy = y * y, zz = z * z;
-				const float xy = x * y, yz = y * z, xz = x * z;
-				GM_DSH(4, GM_SH_C2_0 * xy);
-				GM_DSH(5, GM_SH_C2_1 * yz);
-				GM_DSH(6, GM_SH_C2_2 * (2.f * zz - xx - yy));
-				GM_DSH(7, GM_SH_C2_3 * xz);
-				GM_DSH(8, GM_SH_C2_4 * (xx - yy));
-#pragma unroll
-				for (int ch = 0; ch < 3; ch++) {
-					dRGBdx[ch] += GM_SH_C2_0 * y * GM_SH(4, ch) + GM_SH_C2_2 * 2.f * -x * GM_SH(6, ch) + GM_SH_C2_3 * z * GM_SH(7, ch) + GM_SH_C2_4 * 2.f * x * GM_SH(8, ch);
-					dRGBdy[ch] += GM_SH_C2_0 * x * GM_SH(4, ch) + GM_SH_C2_1 * z * GM_SH(5, ch) + GM_SH_C2_2 * 2.f * -y * GM_SH(6, ch) + GM_SH_C2_4 * 2.f * -y * GM_SH(8, ch);
-					dRGBdz[ch] += GM_SH_C2_1 * y * GM_SH(5, ch) + GM_SH_C2_2 * 2.f * 2.f * z * GM_SH(6, ch) + GM_SH_C2_3 * x * GM_SH(7, ch);
-				}
-				if (deg > 2) {
-					GM_DSH(9, GM_SH_C3_0 * y * (3.f * xx - yy));
-					GM_DSH(10, GM_SH_C3_1 * xy * z);
-					GM_DSH(11, GM_SH_C3_2 * y * (4.f * zz - xx - yy));
-					GM_DSH(12, GM_SH_C3_3 * z * (2.f * zz - 3.f * xx - 3.f * yy));
-					GM_DSH(13, GM_SH_C3_4 * x * (4.f * zz - xx - yy));
-					GM_DSH(14, GM_SH_C3_5 * z * (xx - yy));
-					GM_DSH(15, GM_SH_C3_6 * x * (xx - 3.f * yy));
-#pragma unroll
-					for (int ch = 0; ch < 3; ch++) {
-						dRGBdx[ch] += (
-							GM_SH_C3_0 * GM_SH(9, ch) * 3.f * 2.f * xy +
-							GM_SH_C3_1 * GM_SH(10, ch) * yz +
-							GM_SH_C3_2 * GM_SH(11, ch) * -2.f * xy +
-							GM_SH_C3_3 * GM_SH(12, ch) * -3.f * 2.f * xz +
-							GM_SH_C3_4 * GM_SH(13, ch) * (-3.f * xx + 4.f * zz - yy) +
-							GM_SH_C3_5 * GM_SH(14, ch) * 2.f * xz +
-							GM_SH_C3_6 * GM_SH(15, ch) * 3.f * (xx - yy));
-						dRGBdy[ch] += (
-							GM_SH_C3_0 * GM_SH(9, ch) * 3.f * (xx - yy) +
-							GM_SH_C3_1 * GM_SH(10, ch) * xz +
-							GM_SH_C3_2 * GM_SH(11, ch) * (-3.f * yy + 4.f * zz - xx) +
-							GM_SH_C3_3 * GM_SH(12, ch) * -3.f * 2.f * yz +
-							GM_SH_C3_4 * GM_SH(13, ch) * -2.f * xy +
-							GM_SH_C3_5 * GM_SH(14, ch) * -2.f * yz +
-							GM_SH_C3_6 * GM_SH(15, ch) * -3.f * 2.f * xy);
-						dRGBdz[ch] += (
-							GM_SH_C3_1 * GM_SH(10, ch) * xy +
-							GM_SH_C3_2 * GM_SH(11, ch) * 4.f * 2.f * yz +
-							GM_SH_C3_3 * GM_SH(12, ch) * 3.f * (2.f * zz - xx - yy) +
-							GM_SH_C3_4 * GM_SH(13, ch) * 4.f * 2.f * xz +
-							GM_SH_C3_5 * GM_SH(14, ch) * (xx - yy));
-					}
-				}
-			}
+			B[1] = -GM_SH_C1 * y; Gy[1] = -GM_SH_C1;
+			B[2] = GM_SH_C1 * z;  Gz[2] = GM_SH_C1;
+			B[3] = -GM_SH_C1 * x; Gx[3] = -GM_SH_C1;
 		}
-#undef GM_SH
-#undef GM_DSH
-		// backward.cu:128-138
-		const float3 dL_ddir = make_float3(
-			dRGBdx[0] * dRGB[0] + dRGBdx[1] * dRGB[1] + dRGBdx[2] * dRGB[2],
-			dRGBdy[0] * dRGB[0] + dRGBdy[1] * dRGB[1] + dRGBdy[2] * dRGB[2],
-			dRGBdz[0] * dRGB[0] + dRGBdz[1] * dRGB[1] + dRGBdz[2] * dRGB[2]);
+		if (deg > 1) {
+			B[4] = GM_SH_C2_0 * xy; Gx[4] = GM_SH_C2_0 * y; Gy[4] = GM_SH_C2_0 * x;
+			B[5] = GM_SH_C2_1 * yz; Gy[5] = GM_SH_C2_1 * z; Gz[5] = GM_SH_C2_1 * y;
+			B[6] = GM_SH_C2_2 * (2.f * zz - xx - yy);
+			Gx[6] = GM_SH_C2_2 * 2.f * -x; Gy[6] = GM_SH_C2_2 * 2.f * -y; Gz[6] = GM_SH_C2_2 * 2.f * 2.f * z;
+			B[7] = GM_SH_C2_3 * xz; Gx[7] = GM_SH_C2_3 * z; Gz[7] = GM_SH_C2_3 * x;
+			B[8] = GM_SH_C2_4 * (xx - yy); Gx[8] = GM_SH_C2_4 * 2.f * x; Gy[8] = GM_SH_C2_4 * 2.f * -y;
+		}
+		if (deg > 2) {
+			B[9] = GM_SH_C3_0 * y * (3.f * xx - yy);
+			Gx[9] = GM_SH_C3_0 * 3.f * 2.f * xy; Gy[9] = GM_SH_C3_0 * 3.f * (xx - yy);
+			B[10] = GM_SH_C3_1 * xy * z;
+			Gx[10] = GM_SH_C3_1 * yz; Gy[10] = GM_SH_C3_1 * xz; Gz[10] = GM_SH_C3_1 * xy;
+			B[11] = GM_SH_C3_2 * y * (4.f * zz - xx - yy);
+			Gx[11] = GM_SH_C3_2 * -2.f * xy; Gy[11] = GM_SH_C3_2 * (-3.f * yy + 4.f * zz - xx); Gz[11] = GM_SH_C3_2 * 4.f * 2.f * yz;
+			B[12] = GM_SH_C3_3 * z * (2.f * zz - 3.f * xx - 3.f * yy);
+			Gx[12] = GM_SH_C3_3 * -3.f * 2.f * xz; Gy[12] = GM_SH_C3_3 * -3.f * 2.f * yz; Gz[12] = GM_SH_C3_3 * 3.f * (2.f * zz - xx - yy);
+			B[13] = GM_SH_C3_4 * x * (4.f * zz - xx - yy);
+			Gx[13] = GM_SH_C3_4 * (-3.f * xx + 4.f * zz - yy); Gy[13] = GM_SH_C3_4 * -2.f * xy; Gz[13] = GM_SH_C3_4 * 4.f * 2.f * xz;
+			B[14] = GM_SH_C3_5 * z * (xx - yy);
+			Gx[14] = GM_SH_C3_5 * 2.f * xz; Gy[14] = GM_SH_C3_5 * -2.f * yz; Gz[14] = GM_SH_C3_5 * (xx - yy);
+			B[15] = GM_SH_C3_6 * x * (xx - 3.f * yy);
+			Gx[15] = GM_SH_C3_6 * 3.f * (xx - yy); Gy[15] = GM_SH_C3_6 * -3.f * 2.f * xy;
+		}
+
+		float3 dL_ddir = make_float3(0.f, 0.f, 0.f);
+		float out[48];
+#pragma unroll
+		for (int k = 0; k < 16; k++) {
+			const float w = sh[3 * k] * dRGB[0] + sh[3 * k + 1] * dRGB[1] + sh[3 * k + 2] * dRGB[2];
+			dL_ddir.x += Gx[k] * w; dL_ddir.y += Gy[k] * w; dL_ddir.z += Gz[k] * w;
+			out[3 * k] = B[k] * dRGB[0]; out[3 * k + 1] = B[k] * dRGB[1]; out[3 * k + 2] = B[k] * dRGB[2];
+		}
+		// only coefficients up to `deg` are written (the caller's zeros stay above it, as in the reference)
+		float* dsh = dL_dsh + (size_t)idx * vp.M * 3;
+		if (kVecSH) {
+			float4* dsh4 = reinterpret_cast<float4*>(dsh);
+#pragma unroll
+			for (int j4 = 0; j4 < 12; j4++) {
+				if (4 * j4 + 4 <= n_floats)
+					dsh4[j4] = make_float4(out[4 * j4], out[4 * j4 + 1], out[4 * j4 + 2], out[4 * j4 + 3]);
+				else {
+#pragma unroll
+					for (int e = 0; e < 4; e++)
+						if (4 * j4 + e < n_floats) dsh[4 * j4 + e] = out[4 * j4 + e];
+				}
+			}
+		} else {
+#pragma unroll
+			for (int i = 0; i < 48; i++)
+				if (i < n_floats) dsh[i] = out[i];
+		}
 		const float3 d = dnormvdv3(dir_orig, dL_ddir);
 		dmean.x += d.x; dmean.y += d.y; dmean.z += d.z;
 	}
@@ -311,9 +307,17 @@ int launch_geometry_backward(int P, const float* means3D, const int* radii, cons
 {
 	if (P <= 0)
 		return GM_OK;
-	geometry_backward_kernel<<<(P + kThreads - 1) / kThreads, kThreads, 0, stream>>>(
-		P, means3D, radii, shs, scales, rotations, cov3Ds, vp, g, dL_dmean2D, dL_dconic, dL_dcolor,
-		dL_dmean3D, dL_dcov3D, dL_dsh, dL_dscale, dL_drot);
+	const dim3 grid((P + kThreads - 1) / kThreads);
+	const bool vec = sh_rows_vectorizable(shs, vp.M) && sh_rows_vectorizable(dL_dsh, vp.M) &&
+	                 vp.M * 3 >= 3 * (vp.D + 1) * (vp.D + 1);
+	if (vec)
+		geometry_backward_kernel<true><<<grid, kThreads, 0, stream>>>(
+			P, means3D, radii, shs, scales, rotations, cov3Ds, vp, g, dL_dmean2D, dL_dconic, dL_dcolor,
+			dL_dmean3D, dL_dcov3D, dL_dsh, dL_dscale, dL_drot);
+	else
+		geometry_backward_kernel<false><<<grid, kThreads, 0, stream>>>(
+			P, means3D, radii, shs, scales, rotations, cov3Ds, vp, g, dL_dmean2D, dL_dconic, dL_dcolor,
+			dL_dmean3D, dL_dcov3D, dL_dsh, dL_dscale, dL_drot);
 	return GM_OK;
 }
 

@@ -43,6 +43,7 @@ mark_visible_kernel(int P, const float* __restrict__ means3D, const float* __res
 	present[idx] = near_cull_passes(p, view, false, pv) ? 1 : 0;
 }
 
+template <bool kVecSH>
 __global__ void __launch_bounds__(kThreads)
 preprocess_kernel(int P,
                   const float* __restrict__ means3D,
@@ -128,10 +129,11 @@ preprocess_kernel(int P,
 				const float len = sqrtf(dx * dx + dy * dy + dz * dz);
 				dx = dx / len; dy = dy / len; dz = dz / len;
 				const ShDir d = sh_dir(dx, dy, dz);
-				const float* sh = shs + (size_t)idx * vp.M * 3;
-				float r = sh_channel(vp.D, d, [sh](int k) { return sh[3 * k + 0]; });
-				float gch = sh_channel(vp.D, d, [sh](int k) { return sh[3 * k + 1]; });
-				float b = sh_channel(vp.D, d, [sh](int k) { return sh[3 * k + 2]; });
+				float sh[48];
+				load_sh<kVecSH>(shs + (size_t)idx * vp.M * 3, 3 * (vp.D + 1) * (vp.D + 1), sh);
+				float r = sh_channel(vp.D, d, [&sh](int k) { return sh[3 * k + 0]; });
+				float gch = sh_channel(vp.D, d, [&sh](int k) { return sh[3 * k + 1]; });
+				float b = sh_channel(vp.D, d, [&sh](int k) { return sh[3 * k + 2]; });
 				r += 0.5f; gch += 0.5f; b += 0.5f;
 				const uint32_t bits = (r < 0 ? 1u : 0u) | (gch < 0 ? 2u : 0u) | (b < 0 ? 4u : 0u);
 				rgbc = make_float4(max(r, 0.0f), max(gch, 0.0f), max(b, 0.0f), __uint_as_float(bits));
@@ -195,8 +197,13 @@ int launch_preprocess(int P, const float* means3D, const float* scales, const fl
 	cudaMemsetAsync(g.tile_count, 0, sizeof(uint32_t) * (size_t)num_tiles, stream);
 	if (P <= 0)
 		return GM_OK;
-	preprocess_kernel<<<(P + kThreads - 1) / kThreads, kThreads, 0, stream>>>(
-		P, means3D, scales, rotations, opacities, shs, cov3D_precomp, colors_precomp, vp, radii, g, prefiltered);
+	const dim3 grid((P + kThreads - 1) / kThreads);
+	if (colors_precomp == nullptr && sh_rows_vectorizable(shs, vp.M) && vp.M * 3 >= 3 * (vp.D + 1) * (vp.D + 1))
+		preprocess_kernel<true><<<grid, kThreads, 0, stream>>>(
+			P, means3D, scales, rotations, opacities, shs, cov3D_precomp, colors_precomp, vp, radii, g, prefiltered);
+	else
+		preprocess_kernel<false><<<grid, kThreads, 0, stream>>>(
+			P, means3D, scales, rotations, opacities, shs, cov3D_precomp, colors_precomp, vp, radii, g, prefiltered);
 	return GM_OK;
 }
 
