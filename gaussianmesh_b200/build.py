@@ -32,7 +32,7 @@ NVCC_FLAGS = [
     "-Xcompiler", "-fPIC",
     "-Xptxas", "-v",
     "-I", str(CSRC), "-I", str(PKG.parent / "include"),
-]
+] + os.environ.get("GM_NVCC_EXTRA", "").split()
 
 
 def _nvcc() -> str:

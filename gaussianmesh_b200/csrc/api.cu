@@ -45,10 +45,10 @@ int check_stage(const char* what, bool debug, cudaStream_t stream)
 // When enabled, every stage launch is bracketed by two events recorded on the launch stream; the
 // elapsed times are summed per stage in gm_profile_end.  Used by bench.py for the roofline of the
 // dominant kernel; off by default (no events, no overhead).
-enum Stage { kStPreprocess, kStTileScan, kStEmit, kStSortPack, kStBlendFwd, kStBlendBwd, kStGeomBwd, kStL1,
+enum Stage { kStDepthBuckets, kStPreprocess, kStTileScan, kStEmit, kStSortPack, kStBlendFwd, kStBlendBwd, kStGeomBwd, kStL1,
              kStMeshBindFwd, kStMeshBindBwd, kStDeform, kStShRotated, kStMarkVisible, kNumStages };
 static const char* const kStageNames[kNumStages] = {
-	"preprocess", "tile_scan", "emit", "sort_pack", "blend_forward", "blend_backward", "geometry_backward",
+	"depth_buckets", "preprocess", "tile_scan", "emit", "sort_pack", "blend_forward", "blend_backward", "geometry_backward",
 	"l1_loss", "mesh_bind_forward", "mesh_bind_backward", "deform", "sh_to_rgb_rotated", "mark_visible"};
 
 struct StageRecord { int stage; cudaEvent_t start, stop; };
@@ -101,6 +101,7 @@ static bool make_view(ViewParams& vp, int D, int M, const float* background, int
 	vp.tiles_y = (height + kTile - 1) / kTile;
 	vp.D = D;
 	vp.M = M;
+	vp.bucket_log2 = bucket_log2_for(vp.tiles_x * vp.tiles_y);
 	return width > 0 && height > 0;
 }
 
@@ -136,10 +137,12 @@ static int forward_stage0(char* geom_buffer, int P, const ViewParams& vp, const 
 	if (radii == nullptr)
 		radii = geom.internal_radii;
 
+	{ StageScope scope_(kStDepthBuckets, stream); launch_depth_buckets(P, means3D, vp, geom, stream); }
+	if (int rc = check_stage("depth_buckets", debug, stream)) return rc;
 	{ StageScope scope_(kStPreprocess, stream); launch_preprocess(P, means3D, scales, rotations, opacities, shs, cov3D_precomp, colors_precomp, vp, radii, geom,
 	                  prefiltered, stream); }
 	if (int rc = check_stage("preprocess", debug, stream)) return rc;
-	{ StageScope scope_(kStTileScan, stream); launch_tile_scan(num_tiles, geom, capacity, stream); }
+	{ StageScope scope_(kStTileScan, stream); launch_tile_scan(num_tiles, geom, capacity, vp, stream); }
 	if (int rc = check_stage("tile_scan", debug, stream)) return rc;
 	return GM_OK;
 }
@@ -158,7 +161,7 @@ static int forward_stage1(const GeometryState& geom, char* binning_buffer, char*
 
 	{ StageScope scope_(kStEmit, stream); launch_emit(P, radii, geom, binning, capacity, vp, stream); }
 	if (int rc = check_stage("emit", debug, stream)) return rc;
-	{ StageScope scope_(kStSortPack, stream); launch_sort_pack(num_tiles, geom, binning, capacity, stream); }
+	{ StageScope scope_(kStSortPack, stream); launch_sort_pack(num_tiles, geom, binning, capacity, vp, stream); }
 	if (int rc = check_stage("sort_pack", debug, stream)) return rc;
 	{ StageScope scope_(kStBlendFwd, stream); launch_blend_forward(geom, binning, img, capacity, vp, out_color, stream); }
 	if (int rc = check_stage("blend_forward", debug, stream)) return rc;

@@ -2,11 +2,16 @@
 //
 // The reference builds 64-bit (tile | depth) keys for every (Gaussian, tile) instance, radix-sorts
 // all R of them over 41-45 bits and then searches the sorted keys for tile boundaries
-// (dgr/cuda_rasterizer/rasterizer_impl.cu:70-138, 464-495).  Here the tile component never enters
-// a sort: preprocess counted instances per tile, `tile_scan` turns the counts into segment
-// offsets, `emit` drops each instance into its tile's segment, and `sort_pack` orders every
-// segment by (depth, gaussian id) inside shared memory and writes the packed, tile-contiguous
-// splat records that the blend kernels stage with bulk copies.
+// (dgr/cuda_rasterizer/rasterizer_impl.cu:70-138, 464-495).  Here neither the tile nor the coarse depth
+// order ever enters a sort:
+//   * preprocess counted instances per (tile, depth bucket) -- the bucket is a monotone function of depth
+//     (state.h), so bucket order is depth order;
+//   * `tile_scan` turns the counts into segment offsets (tile segments 4-aligned, buckets packed inside);
+//   * `emit` drops each instance into its (tile, bucket) range;
+//   * `sort_pack` sorts every bucket by (depth, gaussian id): buckets of up to 128 instances in REGISTERS by
+//     one warp (bitonic network over shuffles, no shared memory, no barriers), larger ones by the whole
+//     block in shared memory; then gathers the splat data and writes the packed, tile-contiguous records
+//     that the blend kernels stage with bulk copies.
 //
 // Ordering contract (what the blend result depends on): within a tile, ascending depth bits, ties
 // broken by ascending Gaussian id -- identical to a stable radix sort of keys emitted in id order
@@ -19,68 +24,110 @@ namespace gm {
 namespace {
 
 // ------------------------------------------------------------------------------------------------
-// tile_scan: exclusive scan of the aligned per-tile counts (one block).
+// tile_scan: one thread per tile.  total = sum of the tile's bucket counts; a chained scan over blocks
+// (ticketed, so a block only ever waits for blocks that have already started) of the 4-aligned totals
+// gives tile_start; inside a tile the bucket counts become bucket STARTS (bucket_cursor), which emit
+// advances to bucket ENDS.
 // ------------------------------------------------------------------------------------------------
-constexpr int kScanThreads = 1024;
+constexpr int kScanThreads = kScanTiles;
+constexpr unsigned long long kFlagAggregate = 1ull << 32, kFlagInclusive = 2ull << 32;
 
 __global__ void __launch_bounds__(kScanThreads)
-tile_scan_kernel(int num_tiles, GeometryState g, uint32_t capacity)
+tile_scan_kernel(int num_tiles, int bucket_log2, GeometryState g, uint32_t capacity)
 {
 	__shared__ uint32_t warp_sums[kScanThreads / 32];
+	__shared__ uint32_t s_block, s_base;
 	const int tid = threadIdx.x;
-	const int per_thread = (num_tiles + kScanThreads - 1) / kScanThreads;
-	const int begin = min(num_tiles, tid * per_thread);
-	const int end = min(num_tiles, begin + per_thread);
+	unsigned long long* const ticket = g.scan_state + kMaxScanBlocks;
+	if (tid == 0)
+		s_block = (uint32_t)atomicAdd(ticket, 1ull);
+	__syncthreads();
+	const uint32_t blk = s_block;
+	const int t = (int)blk * kScanTiles + tid;
+	const int B = 1 << bucket_log2;
 
-	uint32_t local = 0;
-	for (int t = begin; t < end; t++)
-		local += (g.tile_count[t] + (kSegAlign - 1)) & ~(uint32_t)(kSegAlign - 1);
+	uint32_t cnt[kMaxBuckets];
+	uint32_t total = 0;
+	if (t < num_tiles) {
+		const uint32_t* c = g.bucket_cursor + ((size_t)t << bucket_log2);
+#pragma unroll
+		for (int b = 0; b < kMaxBuckets; b++) {
+			cnt[b] = (b < B) ? c[b] : 0u;
+			total += cnt[b];
+		}
+	}
+	const uint32_t aligned = (total + (kSegAlign - 1)) & ~(uint32_t)(kSegAlign - 1);
 
-	// block-wide exclusive scan of `local`
-	uint32_t incl = local;
+	// block-wide scan of `aligned`
+	uint32_t incl = aligned;
 #pragma unroll
 	for (int o = 1; o < 32; o <<= 1) {
-		uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+		const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
 		if ((tid & 31) >= o) incl += v;
 	}
 	if ((tid & 31) == 31) warp_sums[tid >> 5] = incl;
 	__syncthreads();
-	if (tid < 32) {
-		uint32_t w = warp_sums[tid];
-		uint32_t wi = w;
+	uint32_t warp_off = 0, block_total = 0;
 #pragma unroll
-		for (int o = 1; o < 32; o <<= 1) {
-			uint32_t v = __shfl_up_sync(0xffffffffu, wi, o);
-			if (tid >= o) wi += v;
+	for (int w = 0; w < kScanThreads / 32; w++) {
+		if (w < (tid >> 5)) warp_off += warp_sums[w];
+		block_total += warp_sums[w];
+	}
+
+	// chained scan across blocks
+	if (tid == 0) {
+		volatile unsigned long long* state = g.scan_state;
+		uint32_t prefix = 0;
+		if (blk > 0) {
+			state[blk] = kFlagAggregate | block_total;
+			__threadfence();
+			int j = (int)blk - 1;
+			while (true) {
+				const unsigned long long v = state[j];
+				if (v & kFlagInclusive) { prefix += (uint32_t)v; break; }
+				if (v & kFlagAggregate) { prefix += (uint32_t)v; j--; }
+			}
 		}
-		warp_sums[tid] = wi - w;   // exclusive
+		state[blk] = kFlagInclusive | (unsigned long long)(prefix + block_total);
+		__threadfence();
+		s_base = prefix;
+		if (blk == gridDim.x - 1) {
+			const uint32_t run = prefix + block_total;
+			g.header->num_rendered = run;
+			g.header->capacity = capacity;
+			g.header->overflow = (run > capacity) ? 1u : 0u;
+			g.header->num_tiles = (uint32_t)num_tiles;
+			g.header->bucket_log2 = (uint32_t)bucket_log2;
+		}
 	}
 	__syncthreads();
-	uint32_t run = warp_sums[tid >> 5] + incl - local;
 
-	for (int t = begin; t < end; t++) {
-		g.tile_start[t] = run;
-		g.tile_fill[t] = 0;
-		run += (g.tile_count[t] + (kSegAlign - 1)) & ~(uint32_t)(kSegAlign - 1);
-	}
-	if (tid == kScanThreads - 1) {
-		g.header->num_rendered = run;
-		g.header->capacity = capacity;
-		g.header->overflow = (run > capacity) ? 1u : 0u;
-		g.header->num_tiles = (uint32_t)num_tiles;
+	if (t < num_tiles) {
+		const uint32_t start = s_base + warp_off + incl - aligned;
+		g.tile_start[t] = start;
+		g.tile_count[t] = total;
+		uint32_t* c = g.bucket_cursor + ((size_t)t << bucket_log2);
+		uint32_t at = start;
+#pragma unroll
+		for (int b = 0; b < kMaxBuckets; b++) {
+			if (b < B) {
+				c[b] = at;
+				at += cnt[b];
+			}
+		}
 	}
 }
 
 // ------------------------------------------------------------------------------------------------
-// emit: one thread per Gaussian, same rectangle walk and the same culling predicate as the count
-// in preprocess (so counts and emitted instances agree exactly).  Slot order inside a segment is
-// arbitrary; sort_pack makes it deterministic.
+// emit: one thread per Gaussian, same rectangle walk, the same culling predicate and the same bucket as
+// the count in preprocess (so counts and emitted instances agree exactly).  Slot order inside a bucket
+// is arbitrary; sort_pack makes it deterministic.
 // ------------------------------------------------------------------------------------------------
 constexpr int kEmitThreads = 256;
 
 __global__ void __launch_bounds__(kEmitThreads)
 emit_kernel(int P, const int* __restrict__ radii, GeometryState g, BinningState b, uint32_t capacity,
-            int W, int H, int tiles_x, int tiles_y)
+            int W, int H, int tiles_x, int tiles_y, int bucket_log2)
 {
 	const int idx = blockIdx.x * kEmitThreads + threadIdx.x;
 	if (idx >= P)
@@ -93,7 +140,9 @@ emit_kernel(int P, const int* __restrict__ radii, GeometryState g, BinningState 
 	if (thr < 0.0f)
 		return;
 	const float2 xy = g.means2D[idx];
-	const uint64_t key = ((uint64_t)__float_as_uint(g.depths[idx]) << 32) | (uint32_t)idx;
+	const float depth = g.depths[idx];
+	const uint64_t key = ((uint64_t)__float_as_uint(depth) << 32) | (uint32_t)idx;
+	const uint32_t bucket = g.depth_lut[depth_fine_bin(depth)];
 	int x0, y0, x1, y1;
 	tile_rect(xy, radius, tiles_x, tiles_y, x0, y0, x1, y1);
 	for (int ty = y0; ty < y1; ty++) {
@@ -104,9 +153,8 @@ emit_kernel(int P, const int* __restrict__ radii, GeometryState g, BinningState 
 			const float px1 = fminf(px0 + (kTile - 1), (float)(W - 1));
 			if (rect_cannot_contribute(xy.x, xy.y, co.x, co.y, co.z, thr, px0, py0, px1, py1))
 				continue;
-			const int tile = ty * tiles_x + tx;
-			const uint32_t slot = atomicAdd(&g.tile_fill[tile], 1u);
-			const uint32_t pos = g.tile_start[tile] + slot;
+			const uint32_t tile = (uint32_t)(ty * tiles_x + tx);
+			const uint32_t pos = atomicAdd(&g.bucket_cursor[((size_t)tile << bucket_log2) + bucket], 1u);
 			if (pos < capacity)
 				b.keys[pos] = key;
 		}
@@ -114,13 +162,86 @@ emit_kernel(int P, const int* __restrict__ radii, GeometryState g, BinningState 
 }
 
 // ------------------------------------------------------------------------------------------------
-// sort_pack: one block per tile.  Bitonic sorting network in the "flip" formulation (every
-// compare-exchange orders ascending), which needs no padding: a partner index >= n behaves as
-// +infinity and the exchange is simply skipped.  Segments up to kSortSmem keys are sorted in
-// shared memory; longer ones in place in global memory (rare, slow, still exact).
+// sort_pack: one block (8 warps) per tile.
 // ------------------------------------------------------------------------------------------------
 constexpr int kSortThreads = 256;
-constexpr int kSortSmem = 4096;   // keys; 32 KB
+constexpr int kSortWarps = kSortThreads / 32;
+constexpr int kSortSmem = 4096;       // keys; 32 KB -- block-wide path for oversized buckets
+constexpr int kWarpSortMax = 128;     // largest bucket one warp sorts in registers (4 keys per lane)
+
+__device__ __forceinline__ uint64_t shfl_xor_u64(uint64_t v, int lane_mask)
+{
+	const uint32_t lo = __shfl_xor_sync(0xffffffffu, (uint32_t)v, lane_mask);
+	const uint32_t hi = __shfl_xor_sync(0xffffffffu, (uint32_t)(v >> 32), lane_mask);
+	return ((uint64_t)hi << 32) | lo;
+}
+
+// Bitonic sort of 32*E keys held E per lane; element index e = r * 32 + lane (register r).
+// Ascending in e on return.  Padding keys must be UINT64_MAX.
+template <int E>
+__device__ __forceinline__ void warp_bitonic(uint64_t (&key)[E], int lane)
+{
+#pragma unroll
+	for (int k = 2; k <= 32 * E; k <<= 1) {
+#pragma unroll
+		for (int j = k >> 1; j > 0; j >>= 1) {
+			if (j >= 32) {
+				// partner lives in another register of the same lane; bit k of e depends only on r here
+#pragma unroll
+				for (int r = 0; r < E; r++) {
+					const int pr = r ^ (j >> 5);
+					if (pr > r) {
+						const bool up = (((r << 5) & k) == 0);
+						const uint64_t a = key[r], c = key[pr];
+						const bool swap = up ? (a > c) : (a < c);
+						key[r] = swap ? c : a;
+						key[pr] = swap ? a : c;
+					}
+				}
+			} else {
+#pragma unroll
+				for (int r = 0; r < E; r++) {
+					const int e = (r << 5) | lane;
+					const bool up = ((e & k) == 0);
+					const bool lower = ((lane & j) == 0);
+					const uint64_t mine = key[r];
+					const uint64_t other = shfl_xor_u64(mine, j);
+					const bool take_min = (lower == up);
+					key[r] = take_min ? (mine < other ? mine : other) : (mine > other ? mine : other);
+				}
+			}
+		}
+	}
+}
+
+__device__ __forceinline__ void pack_one(const GeometryState& g, const BinningState& b, uint32_t dst, uint32_t id)
+{
+	const float2 xy = g.means2D[id];
+	const float4 co = g.conic_opacity[id];
+	const float4 rgb = g.rgb_clamp[id];
+	b.rec_conic[dst] = co;
+	b.rec_xyrg[dst] = make_float4(xy.x, xy.y, rgb.x, rgb.y);
+	b.rec_bid[dst] = make_float2(rgb.z, __uint_as_float(id));
+}
+
+template <int E>
+__device__ __forceinline__ void warp_sort_pack(const GeometryState& g, const BinningState& b, uint32_t s0, uint32_t n,
+                                               int lane)
+{
+	uint64_t key[E];
+#pragma unroll
+	for (int r = 0; r < E; r++) {
+		const uint32_t e = (uint32_t)(r << 5) | lane;
+		key[r] = (e < n) ? b.keys[s0 + e] : ~0ull;
+	}
+	warp_bitonic<E>(key, lane);
+#pragma unroll
+	for (int r = 0; r < E; r++) {
+		const uint32_t e = (uint32_t)(r << 5) | lane;
+		if (e < n)
+			pack_one(g, b, s0 + e, (uint32_t)key[r]);
+	}
+}
 
 template <typename Ptr>
 __device__ __forceinline__ void compare_exchange(Ptr a, uint32_t i, uint32_t j, uint32_t n)
@@ -131,15 +252,16 @@ __device__ __forceinline__ void compare_exchange(Ptr a, uint32_t i, uint32_t j, 
 	}
 }
 
+// Block-wide bitonic network in the "flip" formulation (every compare-exchange orders ascending), which
+// needs no padding: a partner index >= n behaves as +infinity and the exchange is simply skipped.
 // k and s are powers of two, so every index is built from shifts and masks (lk = log2 k, ls = log2 s).
 template <typename Ptr>
-__device__ __forceinline__ void bitonic_sort(Ptr a, uint32_t n)
+__device__ __forceinline__ void block_bitonic(Ptr a, uint32_t n)
 {
 	uint32_t lm = 0;
 	while ((1u << lm) < n) lm++;
 	const uint32_t half = (1u << lm) >> 1;
 	for (uint32_t lk = 1; lk <= lm; lk++) {
-		// flip step: i in the lower half of each k-block pairs with its mirror image
 		const uint32_t hk_mask = (1u << (lk - 1)) - 1u;
 		for (uint32_t t = threadIdx.x; t < half; t += kSortThreads) {
 			const uint32_t off = t & hk_mask;
@@ -159,48 +281,68 @@ __device__ __forceinline__ void bitonic_sort(Ptr a, uint32_t n)
 }
 
 __global__ void __launch_bounds__(kSortThreads)
-sort_pack_kernel(GeometryState g, BinningState b, uint32_t capacity)
+sort_pack_kernel(GeometryState g, BinningState b, uint32_t capacity, int bucket_log2)
 {
 	__shared__ uint64_t s_keys[kSortSmem];
+	__shared__ uint32_t s_big[kMaxBuckets];     // buckets left to the block-wide path
+	__shared__ uint32_t s_num_big;
+
 	const int tile = blockIdx.x;
-	const uint32_t start = g.tile_start[tile];
-	if (start >= capacity)
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const uint32_t tile_start = g.tile_start[tile];
+	if (tile_start >= capacity || g.tile_count[tile] == 0)
 		return;
-	const uint32_t n = min(g.tile_count[tile], capacity - start);
-	if (n == 0)
-		return;
+	const int B = 1 << bucket_log2;
+	if (threadIdx.x == 0)
+		s_num_big = 0;
+	__syncthreads();
 
-	uint64_t* keys = b.keys + start;
-	const uint64_t* sorted;
-	if (n <= kSortSmem) {
-		for (uint32_t i = threadIdx.x; i < n; i += kSortThreads)
-			s_keys[i] = keys[i];
-		__syncthreads();
-		bitonic_sort(s_keys, n);
-		sorted = s_keys;
-	} else {
-		__syncthreads();
-		bitonic_sort(keys, n);
-		sorted = keys;
+	// bucket bounds: emit left bucket_cursor at the END of each bucket
+	const uint32_t* ends = g.bucket_cursor + ((size_t)tile << bucket_log2);
+	for (int bk = warp; bk < B; bk += kSortWarps) {
+		const uint32_t s0 = (bk == 0) ? tile_start : ends[bk - 1];
+		const uint32_t s1 = min(ends[bk], capacity);
+		if (s0 >= s1)
+			continue;
+		const uint32_t n = s1 - s0;
+		if (n <= 32) warp_sort_pack<1>(g, b, s0, n, lane);
+		else if (n <= 64) warp_sort_pack<2>(g, b, s0, n, lane);
+		else if (n <= kWarpSortMax) warp_sort_pack<4>(g, b, s0, n, lane);
+		else if (lane == 0) s_big[atomicAdd(&s_num_big, 1u)] = (uint32_t)bk;
 	}
+	__syncthreads();
 
-	// pack: gather the per-Gaussian splat data in blend order
-	for (uint32_t i = threadIdx.x; i < n; i += kSortThreads) {
-		const uint32_t id = (uint32_t)sorted[i];
-		const float2 xy = g.means2D[id];
-		const float4 co = g.conic_opacity[id];
-		const float4 rgb = g.rgb_clamp[id];
-		b.rec_conic[start + i] = co;
-		b.rec_xyrg[start + i] = make_float4(xy.x, xy.y, rgb.x, rgb.y);
-		b.rec_bid[start + i] = make_float2(rgb.z, __uint_as_float(id));
+	const uint32_t num_big = s_num_big;
+	for (uint32_t q = 0; q < num_big; q++) {
+		const int bk = (int)s_big[q];
+		const uint32_t s0 = (bk == 0) ? tile_start : ends[bk - 1];
+		const uint32_t n = min(ends[bk], capacity) - s0;
+		uint64_t* keys = b.keys + s0;
+		const uint64_t* sorted;
+		if (n <= kSortSmem) {
+			for (uint32_t i = threadIdx.x; i < n; i += kSortThreads)
+				s_keys[i] = keys[i];
+			__syncthreads();
+			block_bitonic(s_keys, n);
+			sorted = s_keys;
+		} else {
+			// longer than shared memory holds: in place in global memory (rare, slow, still exact)
+			block_bitonic(keys, n);
+			sorted = keys;
+		}
+		for (uint32_t i = threadIdx.x; i < n; i += kSortThreads)
+			pack_one(g, b, s0 + i, (uint32_t)sorted[i]);
+		__syncthreads();   // s_keys is reused by the next oversized bucket
 	}
 }
 
 } // namespace
 
-int launch_tile_scan(int num_tiles, const GeometryState& g, uint32_t capacity, cudaStream_t stream)
+int launch_tile_scan(int num_tiles, const GeometryState& g, uint32_t capacity, const ViewParams& vp, cudaStream_t stream)
 {
-	tile_scan_kernel<<<1, kScanThreads, 0, stream>>>(num_tiles, g, capacity);
+	if (num_tiles <= 0)
+		return GM_OK;
+	tile_scan_kernel<<<(num_tiles + kScanTiles - 1) / kScanTiles, kScanThreads, 0, stream>>>(num_tiles, vp.bucket_log2, g, capacity);
 	return GM_OK;
 }
 
@@ -210,14 +352,14 @@ int launch_emit(int P, const int* radii, const GeometryState& g, const BinningSt
 	if (P <= 0)
 		return GM_OK;
 	emit_kernel<<<(P + kEmitThreads - 1) / kEmitThreads, kEmitThreads, 0, stream>>>(
-		P, radii, g, b, capacity, vp.W, vp.H, vp.tiles_x, vp.tiles_y);
+		P, radii, g, b, capacity, vp.W, vp.H, vp.tiles_x, vp.tiles_y, vp.bucket_log2);
 	return GM_OK;
 }
 
 int launch_sort_pack(int num_tiles, const GeometryState& g, const BinningState& b, uint32_t capacity,
-                     cudaStream_t stream)
+                     const ViewParams& vp, cudaStream_t stream)
 {
-	sort_pack_kernel<<<num_tiles, kSortThreads, 0, stream>>>(g, b, capacity);
+	sort_pack_kernel<<<num_tiles, kSortThreads, 0, stream>>>(g, b, capacity, vp.bucket_log2);
 	return GM_OK;
 }
 

@@ -28,11 +28,21 @@ constexpr int kWarps = kThreads / 32;
 constexpr int kBatch = 256;
 constexpr int kComp = 9;   // colour r,g,b | q | q dx | q dy | q dx^2 | q dx dy | q dy^2
 
+// Per-warp queue of the splats of one 32-splat chunk that can reach the warp's pixel block, back to front,
+// and the parked sums of their nine moments.
+struct WarpQueue {
+	float4 conic[32];
+	float4 xyrg[32];
+	float2 bid[32];               // (blue, gaussian id as bits)
+	uint32_t pos[32];             // 0-based position in the tile's list
+	float park[32 * kComp];       // [queue slot * 9 + component]: stride 9 is bank-conflict free
+};
+
 struct __align__(128) BwdSmem {
 	float4 conic[2][kBatch];
 	float4 xyrg[2][kBatch];
 	float2 bid[2][kBatch];
-	float park[kWarps][32 * kComp];   // [warp][splat-in-chunk * 9 + component]: stride 9 is conflict free
+	WarpQueue queue[kWarps];
 	uint64_t full[2];
 	uint32_t warp_max[kWarps];
 };
@@ -162,7 +172,7 @@ blend_backward_kernel(GeometryState g, BinningState b, ImageState img, uint32_t 
 		bulk_g2s(s.bid[buf], b.rec_bid + off, cnt4 * 8u, &s.full[buf]);
 	};
 
-	float* const park = s.park[warp];
+	WarpQueue& q = s.queue[warp];
 	const int batch_hi = (int)((tile_last - 1) / kBatch);
 	if (tid == 0)
 		issue(batch_hi, 0);
@@ -180,41 +190,48 @@ blend_backward_kernel(GeometryState g, BinningState b, ImageState img, uint32_t 
 		// positions >= warp_last are behind every pixel of this warp (backward.cu:487-489)
 		const int cnt = min(min(kBatch, (int)n - batch_base), (int)warp_last - batch_base);
 		for (int base = (cnt > 0) ? ((cnt - 1) & ~31) : -1; base >= 0; base -= 32) {
+			// cull 32 splats in parallel against the warp's 8x4 pixel block; compact the survivors back to front
 			const int j = base + lane;
 			bool keep = false;
-			float4 my_co = make_float4(0.f, 0.f, 0.f, 0.f);
+			float4 co, xr;
 			if (j < cnt) {
-				my_co = s.conic[buf][j];
-				const float4 xr = s.xyrg[buf][j];
-				keep = !rect_cannot_contribute(xr.x, xr.y, my_co.x, my_co.y, my_co.z, cull_threshold(my_co.w),
+				co = s.conic[buf][j];
+				xr = s.xyrg[buf][j];
+				keep = !rect_cannot_contribute(xr.x, xr.y, co.x, co.y, co.z, cull_threshold(co.w),
 				                               wx0, wy0, wx1, wy1);
 			}
-			uint32_t mask = __ballot_sync(0xffffffffu, keep);
+			const uint32_t mask = __ballot_sync(0xffffffffu, keep);
+			if (mask == 0)
+				continue;
+			if (keep) {
+				const int slot = __popc(mask >> lane) - 1;          // highest list position first
+				q.conic[slot] = co;
+				q.xyrg[slot] = xr;
+				q.bid[slot] = s.bid[buf][j];
+				q.pos[slot] = (uint32_t)(batch_base + j);
+			}
+			__syncwarp();
+			const int n_keep = __popc(mask);
 			uint32_t touched = 0;
-			while (mask) {
-				const int k = 31 - __clz(mask);
-				mask &= ~(1u << k);
-				const int jj = base + k;
-				const float4 co = s.conic[buf][jj];
-				const float4 xr = s.xyrg[buf][jj];
-
+			for (int i = 0; i < n_keep; i++) {
+				const float4 c4 = q.conic[i];
+				const float4 x4 = q.xyrg[i];
 				// backward.cu:487-501
-				const float dx = xr.x - pixf_x, dy = xr.y - pixf_y;
-				const float power = -0.5f * (co.x * dx * dx + co.z * dy * dy) - co.y * dx * dy;
+				const float dx = x4.x - pixf_x, dy = x4.y - pixf_y;
+				const float power = -0.5f * (c4.x * dx * dx + c4.z * dy * dy) - c4.y * dx * dy;
 				const float G = expf(power);
-				const float alpha = min(0.99f, co.w * G);
-				const bool active = ((uint32_t)(batch_base + jj) < last_contributor) && !(power > 0.0f) &&
-				                    !(alpha < 1.0f / 255.0f);
+				const float alpha = min(0.99f, c4.w * G);
+				const bool active = (q.pos[i] < last_contributor) && !(power > 0.0f) && !(alpha < 1.0f / 255.0f);
 				if (!__any_sync(0xffffffffu, active))
 					continue;
-				touched |= 1u << k;
+				touched |= 1u << i;
 
 				float v[kComp];
 #pragma unroll
 				for (int c = 0; c < kComp; c++)
 					v[c] = 0.0f;
 				if (active) {
-					const float cb = s.bid[buf][jj].x;
+					const float cb = q.bid[i].x;
 					// backward.cu:503-534
 					const float rcp = __frcp_rn(1.f - alpha);
 					T = T * rcp;
@@ -223,18 +240,18 @@ blend_backward_kernel(GeometryState g, BinningState b, ImageState img, uint32_t 
 					accum_rec0 = last_alpha * last_color0 + keep_prev * accum_rec0;
 					accum_rec1 = last_alpha * last_color1 + keep_prev * accum_rec1;
 					accum_rec2 = last_alpha * last_color2 + keep_prev * accum_rec2;
-					last_color0 = xr.z; last_color1 = xr.w; last_color2 = cb;
+					last_color0 = x4.z; last_color1 = x4.w; last_color2 = cb;
 					last_alpha = alpha;
-					float dL_dalpha = (xr.z - accum_rec0) * dL_dpixel0 + (xr.w - accum_rec1) * dL_dpixel1 +
+					float dL_dalpha = (x4.z - accum_rec0) * dL_dpixel0 + (x4.w - accum_rec1) * dL_dpixel1 +
 					                  (cb - accum_rec2) * dL_dpixel2;
 					dL_dalpha = dL_dalpha * T + bg_term * rcp;
 					v[0] = dchannel_dcolor * dL_dpixel0;
 					v[1] = dchannel_dcolor * dL_dpixel1;
 					v[2] = dchannel_dcolor * dL_dpixel2;
 					// moments of q = G dL/dalpha (backward.cu:537-554 with the splat constants factored out)
-					const float q = G * dL_dalpha;
-					const float qdx = q * dx, qdy = q * dy;
-					v[3] = q;
+					const float qq = G * dL_dalpha;
+					const float qdx = qq * dx, qdy = qq * dy;
+					v[3] = qq;
 					v[4] = qdx;
 					v[5] = qdy;
 					v[6] = qdx * dx;
@@ -243,16 +260,17 @@ blend_backward_kernel(GeometryState g, BinningState b, ImageState img, uint32_t 
 				}
 				const float total = butterfly9(v, lane);
 				if ((lane & 3) == 0)
-					park[k * kComp + (lane >> 2)] = total;
+					q.park[i * kComp + (lane >> 2)] = total;
 				else if (lane == 2)
-					park[k * kComp + 8] = total;
+					q.park[i * kComp + 8] = total;
 			}
 			__syncwarp();
 			if ((touched >> lane) & 1u) {
-				// this lane owns splat j = base + lane of the chunk
-				const float* m = park + lane * kComp;
-				const uint32_t id = __float_as_uint(s.bid[buf][j].y);
-				const float a = my_co.x, bb = my_co.y, c = my_co.z, o = my_co.w;
+				// this lane sends queue slot `lane` to global memory
+				const float* m = q.park + lane * kComp;
+				const float4 c4 = q.conic[lane];
+				const uint32_t id = __float_as_uint(q.bid[lane].y);
+				const float a = c4.x, bb = c4.y, c = c4.z, o = c4.w;
 				const float Sq = m[3], Sx = m[4], Sy = m[5], Sxx = m[6], Sxy = m[7], Syy = m[8];
 				atomicAdd(&dL_dcolors[3 * (size_t)id + 0], m[0]);
 				atomicAdd(&dL_dcolors[3 * (size_t)id + 1], m[1]);
@@ -266,7 +284,7 @@ blend_backward_kernel(GeometryState g, BinningState b, ImageState img, uint32_t 
 				atomicAdd(&dL_dconic2D[4 * (size_t)id + 3], h * Syy);
 				atomicAdd(&dL_dopacity[id], Sq);
 			}
-			__syncwarp();   // the park row is rewritten by the next chunk
+			__syncwarp();   // queue and park rows are rewritten by the next chunk
 		}
 	}
 }

@@ -21,10 +21,18 @@ namespace {
 constexpr int kThreads = 256;
 constexpr int kBatch = 256;
 
+// Per-warp queue of the splats of one 32-splat chunk that can reach the warp's pixel block, in list order.
+struct WarpQueue {
+	float4 conic[32];
+	float4 xyrg[32];
+	float2 bpos[32];    // (blue, 1-based list position as bits)
+};
+
 struct __align__(128) FwdSmem {
 	float4 conic[2][kBatch];
 	float4 xyrg[2][kBatch];
 	float2 bid[2][kBatch];
+	WarpQueue queue[kThreads / 32];
 	uint64_t full[2];
 };
 
@@ -99,46 +107,58 @@ blend_forward_kernel(GeometryState g, BinningState b, ImageState img, uint32_t c
 			continue;
 
 		const int cnt = (int)min((uint32_t)kBatch, n - (uint32_t)batch * kBatch);
+		WarpQueue& q = s.queue[warp];
 		for (int base = 0; base < cnt; base += 32) {
+			// cull 32 splats in parallel against the warp's 8x4 pixel block and compact the survivors
 			const int j = base + lane;
 			bool keep = false;
+			float4 co, xr;
 			if (j < cnt) {
-				const float4 co = s.conic[buf][j];
-				const float4 xr = s.xyrg[buf][j];
+				co = s.conic[buf][j];
+				xr = s.xyrg[buf][j];
 				keep = !rect_cannot_contribute(xr.x, xr.y, co.x, co.y, co.z, cull_threshold(co.w),
 				                               wx0, wy0, wx1, wy1);
 			}
-			uint32_t mask = __ballot_sync(0xffffffffu, keep);
-			while (mask) {
-				const int k = __ffs(mask) - 1;
-				mask &= mask - 1;
-				const int jj = base + k;
-				if (!done) {
-					const float4 co = s.conic[buf][jj];
-					const float4 xr = s.xyrg[buf][jj];
+			const uint32_t mask = __ballot_sync(0xffffffffu, keep);
+			if (mask == 0)
+				continue;
+			if (keep) {
+				const int pos = __popc(mask & ((1u << lane) - 1u));
+				q.conic[pos] = co;
+				q.xyrg[pos] = xr;
+				q.bpos[pos] = make_float2(s.bid[buf][j].x, __uint_as_float((uint32_t)(batch * kBatch + j + 1)));
+			}
+			__syncwarp();
+			const int n_keep = __popc(mask);
+			if (!done) {
+#pragma unroll 2
+				for (int i = 0; i < n_keep; i++) {
+					const float4 c4 = q.conic[i];
+					const float4 x4 = q.xyrg[i];
 					// forward.cu:331-335
-					const float dx = xr.x - pixf_x, dy = xr.y - pixf_y;
-					const float power = -0.5f * (co.x * dx * dx + co.z * dy * dy) - co.y * dx * dy;
-					if (power <= 0.0f) {
-						// forward.cu:343-345
-						const float alpha = min(0.99f, co.w * expf(power));
-						if (!(alpha < 1.0f / 255.0f)) {
-							const float test_T = T * (1 - alpha);
-							if (test_T < 0.0001f) {
-								done = true;                   // forward.cu:347-351
-							} else {
-								const float cb = s.bid[buf][jj].x;
-								// forward.cu:354-355
-								C0 += xr.z * alpha * T;
-								C1 += xr.w * alpha * T;
-								C2 += cb * alpha * T;
-								T = test_T;
-								last_contributor = (uint32_t)(batch * kBatch + jj + 1);
-							}
-						}
+					const float dx = x4.x - pixf_x, dy = x4.y - pixf_y;
+					const float power = -0.5f * (c4.x * dx * dx + c4.z * dy * dy) - c4.y * dx * dy;
+					if (power > 0.0f)
+						continue;
+					// forward.cu:343-345
+					const float alpha = min(0.99f, c4.w * expf(power));
+					if (alpha < 1.0f / 255.0f)
+						continue;
+					const float test_T = T * (1 - alpha);
+					if (test_T < 0.0001f) {
+						done = true;                   // forward.cu:347-351
+						break;
 					}
+					const float2 bp = q.bpos[i];
+					// forward.cu:354-355
+					C0 += x4.z * alpha * T;
+					C1 += x4.w * alpha * T;
+					C2 += bp.x * alpha * T;
+					T = test_T;
+					last_contributor = __float_as_uint(bp.y);
 				}
 			}
+			__syncwarp();   // the queue is rewritten by the next chunk
 			if (__all_sync(0xffffffffu, done))
 				break;
 		}

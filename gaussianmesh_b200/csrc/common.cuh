@@ -314,6 +314,15 @@ __device__ __forceinline__ float cull_threshold(float opacity)
 	return (opacity < 1.0f / 255.0f) ? -1.0f : fmaxf(0.0f, logf(255.0f * opacity));
 }
 
+// ---- depth buckets (state.h) --------------------------------------------------------------------
+// Monotone in z for z > 0.2 (IEEE bit patterns of positive floats order like the values).
+__device__ __forceinline__ uint32_t depth_fine_bin(float z)
+{
+	const uint32_t bits = __float_as_uint(z);
+	const uint32_t d = (bits > kDepthBinBase) ? (bits - kDepthBinBase) >> kDepthBinShift : 0u;
+	return min(d, (uint32_t)(kDepthBins - 1));
+}
+
 // ---- small PTX wrappers: mbarrier + 1-D bulk copy (TMA, SASS UBLKCP) ----------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p)
 {

@@ -7,18 +7,20 @@ namespace gm {
 
 int launch_mark_visible(int P, const float* means3D, const float* viewmatrix, uint8_t* present, cudaStream_t stream);
 
+int launch_depth_buckets(int P, const float* means3D, const ViewParams& vp, const GeometryState& g, cudaStream_t stream);
+
 int launch_preprocess(int P, const float* means3D, const float* scales, const float* rotations,
                       const float* opacities, const float* shs, const float* cov3D_precomp,
                       const float* colors_precomp, const ViewParams& vp, int* radii,
                       const GeometryState& g, bool prefiltered, cudaStream_t stream);
 
-int launch_tile_scan(int num_tiles, const GeometryState& g, uint32_t capacity, cudaStream_t stream);
+int launch_tile_scan(int num_tiles, const GeometryState& g, uint32_t capacity, const ViewParams& vp, cudaStream_t stream);
 
 int launch_emit(int P, const int* radii, const GeometryState& g, const BinningState& b, uint32_t capacity,
                 const ViewParams& vp, cudaStream_t stream);
 
 int launch_sort_pack(int num_tiles, const GeometryState& g, const BinningState& b, uint32_t capacity,
-                     cudaStream_t stream);
+                     const ViewParams& vp, cudaStream_t stream);
 
 int launch_blend_forward(const GeometryState& g, const BinningState& b, const ImageState& img, uint32_t capacity,
                          const ViewParams& vp, float* out_color, cudaStream_t stream);

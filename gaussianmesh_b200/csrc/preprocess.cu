@@ -43,6 +43,74 @@ mark_visible_kernel(int P, const float* __restrict__ means3D, const float* __res
 	present[idx] = near_cull_passes(p, view, false, pv) ? 1 : 0;
 }
 
+// ---- depth buckets: histogram of visible depths, then the monotone fine-bin -> bucket table ------------
+constexpr int kHistThreads = 512;
+
+__global__ void __launch_bounds__(kHistThreads)
+depth_histogram_kernel(int P, const float* __restrict__ means3D, const float* __restrict__ view,
+                       uint32_t* __restrict__ hist)
+{
+	__shared__ uint32_t s_hist[kDepthBins];
+	for (int i = threadIdx.x; i < kDepthBins; i += kHistThreads)
+		s_hist[i] = 0;
+	const float v2 = view[2], v6 = view[6], v10 = view[10], v14 = view[14];
+	__syncthreads();
+	for (int idx = blockIdx.x * kHistThreads + threadIdx.x; idx < P; idx += gridDim.x * kHistThreads) {
+		const float z = v2 * means3D[3 * idx] + v6 * means3D[3 * idx + 1] + v10 * means3D[3 * idx + 2] + v14;
+		if (z > 0.2f)
+			atomicAdd(&s_hist[depth_fine_bin(z)], 1u);
+	}
+	__syncthreads();
+	for (int i = threadIdx.x; i < kDepthBins; i += kHistThreads) {
+		const uint32_t c = s_hist[i];
+		if (c != 0)
+			atomicAdd(&hist[i], c);
+	}
+}
+
+// One block.  lut[i] = floor(B * (number of depths in bins < i) / total): equal-count buckets, monotone in i.
+constexpr int kLutThreads = 1024;
+static_assert(kDepthBins % kLutThreads == 0, "bins per thread");
+
+__global__ void __launch_bounds__(kLutThreads)
+bucket_lut_kernel(const uint32_t* __restrict__ hist, uint8_t* __restrict__ lut, int bucket_log2)
+{
+	constexpr int kPer = kDepthBins / kLutThreads;
+	__shared__ uint32_t warp_sums[kLutThreads / 32];
+	const int tid = threadIdx.x;
+	uint32_t c[kPer], local = 0;
+#pragma unroll
+	for (int i = 0; i < kPer; i++) { c[i] = hist[tid * kPer + i]; local += c[i]; }
+	uint32_t incl = local;
+#pragma unroll
+	for (int o = 1; o < 32; o <<= 1) {
+		const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+		if ((tid & 31) >= o) incl += v;
+	}
+	if ((tid & 31) == 31) warp_sums[tid >> 5] = incl;
+	__syncthreads();
+	if (tid < 32) {
+		const uint32_t w = warp_sums[tid];
+		uint32_t wi = w;
+#pragma unroll
+		for (int o = 1; o < 32; o <<= 1) {
+			const uint32_t v = __shfl_up_sync(0xffffffffu, wi, o);
+			if (tid >= o) wi += v;
+		}
+		warp_sums[tid] = wi;   // inclusive
+	}
+	__syncthreads();
+	const uint32_t total = warp_sums[kLutThreads / 32 - 1];
+	uint32_t below = ((tid >> 5) ? warp_sums[(tid >> 5) - 1] : 0u) + incl - local;
+	const uint32_t B = 1u << bucket_log2;
+#pragma unroll
+	for (int i = 0; i < kPer; i++) {
+		const uint32_t b = total ? (uint32_t)(((uint64_t)below << bucket_log2) / total) : 0u;
+		lut[tid * kPer + i] = (uint8_t)min(b, B - 1u);
+		below += c[i];
+	}
+}
+
 template <bool kVecSH>
 __global__ void __launch_bounds__(kThreads)
 preprocess_kernel(int P,
@@ -61,6 +129,9 @@ preprocess_kernel(int P,
 	__shared__ float s_view[16];
 	__shared__ float s_proj[16];
 	__shared__ float s_cam[3];
+	__shared__ __align__(16) uint8_t s_lut[kDepthBins];
+	static_assert(kDepthBins == kThreads * 16, "one 16-byte load per thread");
+	reinterpret_cast<uint4*>(s_lut)[threadIdx.x] = reinterpret_cast<const uint4*>(g.depth_lut)[threadIdx.x];
 	if (threadIdx.x < 16) {
 		s_view[threadIdx.x] = vp.view[threadIdx.x];
 		s_proj[threadIdx.x] = vp.proj[threadIdx.x];
@@ -151,9 +222,10 @@ preprocess_kernel(int P,
 			my_radius_i = (int)my_radius;
 			visible = true;
 
-			// Per-tile instance count.  Tiles whose 16x16 pixel block cannot receive any alpha
-			// >= 1/255 from this Gaussian are skipped (rect_cannot_contribute is output-preserving).
+			// Per-(tile, depth bucket) instance count.  Tiles whose 16x16 pixel block cannot receive any
+			// alpha >= 1/255 from this Gaussian are skipped (rect_cannot_contribute is output-preserving).
 			const float thr = cull_threshold(opacity);
+			const uint32_t bucket = s_lut[depth_fine_bin(p_view.z)];
 			if (thr >= 0.0f) {
 				for (int ty = y0; ty < y1; ty++) {
 					const float py0 = (float)(ty * kTile);
@@ -163,7 +235,7 @@ preprocess_kernel(int P,
 						const float px1 = fminf(px0 + (kTile - 1), (float)(vp.W - 1));
 						if (!rect_cannot_contribute(point_image.x, point_image.y, conic.x, conic.y, conic.z, thr,
 						                            px0, py0, px1, py1))
-							atomicAdd(&g.tile_count[ty * vp.tiles_x + tx], 1u);
+							atomicAdd(&g.bucket_cursor[((size_t)(ty * vp.tiles_x + tx) << vp.bucket_log2) + bucket], 1u);
 					}
 				}
 			}
@@ -172,9 +244,9 @@ preprocess_kernel(int P,
 		radii[idx] = my_radius_i;
 	}
 
-	const int n_vis = __syncthreads_count(visible);
-	if (threadIdx.x == 0 && n_vis > 0)
-		atomicAdd(&g.header->num_visible, (uint32_t)n_vis);
+	const uint32_t vis_mask = __ballot_sync(0xffffffffu, visible);
+	if ((threadIdx.x & 31) == 0 && vis_mask != 0)
+		atomicAdd(&g.header->num_visible, (uint32_t)__popc(vis_mask));
 }
 
 } // namespace
@@ -187,6 +259,17 @@ int launch_mark_visible(int P, const float* means3D, const float* viewmatrix, ui
 	return GM_OK;
 }
 
+int launch_depth_buckets(int P, const float* means3D, const ViewParams& vp, const GeometryState& g, cudaStream_t stream)
+{
+	cudaMemsetAsync(g.depth_hist, 0, sizeof(uint32_t) * kDepthBins, stream);
+	if (P > 0) {
+		const int hist_blocks = min((P + kHistThreads - 1) / kHistThreads, 148 * 4);
+		depth_histogram_kernel<<<hist_blocks, kHistThreads, 0, stream>>>(P, means3D, vp.view, g.depth_hist);
+	}
+	bucket_lut_kernel<<<1, kLutThreads, 0, stream>>>(g.depth_hist, g.depth_lut, vp.bucket_log2);
+	return GM_OK;
+}
+
 int launch_preprocess(int P, const float* means3D, const float* scales, const float* rotations,
                       const float* opacities, const float* shs, const float* cov3D_precomp,
                       const float* colors_precomp, const ViewParams& vp, int* radii,
@@ -194,7 +277,8 @@ int launch_preprocess(int P, const float* means3D, const float* scales, const fl
 {
 	const int num_tiles = vp.tiles_x * vp.tiles_y;
 	cudaMemsetAsync(g.header, 0, sizeof(FrameHeader), stream);
-	cudaMemsetAsync(g.tile_count, 0, sizeof(uint32_t) * (size_t)num_tiles, stream);
+	cudaMemsetAsync(g.bucket_cursor, 0, sizeof(uint32_t) * ((size_t)num_tiles << vp.bucket_log2), stream);
+	cudaMemsetAsync(g.scan_state, 0, sizeof(unsigned long long) * ((size_t)kMaxScanBlocks + 1), stream);
 	if (P <= 0)
 		return GM_OK;
 	const dim3 grid((P + kThreads - 1) / kThreads);

@@ -24,6 +24,18 @@ constexpr int kSegAlign = 4;                   // tile segments start on a multi
                                                // => every record array offset is 32-byte aligned
 constexpr size_t kChunkAlign = 128;
 
+// Depth buckets.  Every tile's segment of the instance list is pre-partitioned into B = 2^bucket_log2
+// consecutive depth buckets by a MONOTONE map depth -> bucket (fine bin of the float's bit pattern, then a
+// lookup table built from the frame's depth histogram), so that sorting each small bucket by (depth, id)
+// sorts the whole tile.  B is the largest power of two <= kMaxBuckets with tiles * B <= kMaxBucketEntries.
+constexpr int kMaxBuckets = 16;
+constexpr size_t kMaxBucketEntries = (size_t)1 << 20;
+constexpr int kScanTiles = 256;                // tiles per block of the tile scan
+constexpr int kMaxScanBlocks = GM_MAX_TILES / kScanTiles;
+constexpr int kDepthBins = 4096;               // fine bins: (bits(z) - bits(0.2)) >> 16, 128 per octave
+constexpr uint32_t kDepthBinBase = 0x3E4CCCCDu; // bit pattern of 0.2f, the near-plane cull threshold
+constexpr int kDepthBinShift = 16;
+
 // Written by the tile-scan kernel, read by later stages and by gm_forward_status().
 struct FrameHeader {
 	uint32_t num_rendered;   // padded instance total of this view (sum of aligned tile counts)
@@ -31,7 +43,8 @@ struct FrameHeader {
 	uint32_t overflow;       // 1 if num_rendered exceeded the binning capacity handed to gm_forward
 	uint32_t capacity;       // binning capacity in instances used for this frame
 	uint32_t num_tiles;
-	uint32_t pad[27];
+	uint32_t bucket_log2;
+	uint32_t pad[26];
 };
 static_assert(sizeof(FrameHeader) == 128, "FrameHeader must be one 128-byte line");
 
@@ -45,7 +58,10 @@ struct GeometryState {
 	float4* rgb_clamp;        // [P]   (r, g, b, clamp bits as uint)               (forward.cu:63-70)
 	uint32_t* tile_count;     // [GM_MAX_TILES] instances per tile after exact tile culling
 	uint32_t* tile_start;     // [GM_MAX_TILES] first instance of the tile (multiple of kSegAlign)
-	uint32_t* tile_fill;      // [GM_MAX_TILES] emit cursor
+	uint32_t* bucket_cursor;  // [kMaxBucketEntries] per (tile, bucket): count -> start -> end (see binning.cu)
+	unsigned long long* scan_state;  // [kMaxScanBlocks + 1] chained-scan descriptors (flag << 32 | value) + ticket
+	uint32_t* depth_hist;     // [kDepthBins] visible-depth histogram of this frame
+	uint8_t* depth_lut;       // [kDepthBins] fine depth bin -> bucket (monotone)
 
 	static GeometryState fromChunk(char*& chunk, size_t P);
 };
@@ -94,7 +110,10 @@ inline GeometryState GeometryState::fromChunk(char*& chunk, size_t P)
 	obtain(chunk, g.rgb_clamp, P);
 	obtain(chunk, g.tile_count, (size_t)GM_MAX_TILES);
 	obtain(chunk, g.tile_start, (size_t)GM_MAX_TILES);
-	obtain(chunk, g.tile_fill, (size_t)GM_MAX_TILES);
+	obtain(chunk, g.bucket_cursor, kMaxBucketEntries);
+	obtain(chunk, g.scan_state, (size_t)kMaxScanBlocks + 1);
+	obtain(chunk, g.depth_hist, (size_t)kDepthBins);
+	obtain(chunk, g.depth_lut, (size_t)kDepthBins);
 	return g;
 }
 
@@ -131,6 +150,15 @@ struct ViewParams {
 	int W, H;
 	int tiles_x, tiles_y;
 	int D, M;
+	int bucket_log2;      // log2 of the number of depth buckets per tile
 };
+
+inline int bucket_log2_for(int num_tiles)
+{
+	int lg = 0;
+	while ((1 << (lg + 1)) <= kMaxBuckets && (size_t)num_tiles << (lg + 1) <= kMaxBucketEntries)
+		lg++;
+	return lg;
+}
 
 } // namespace gm
