@@ -135,16 +135,38 @@ emit_kernel(int P, const int* __restrict__ radii, GeometryState g, BinningState 
 	const int radius = radii[idx];
 	if (!(radius > 0))
 		return;
+	const float2 xy = g.means2D[idx];
+	int x0, y0, x1, y1;
+	tile_rect(xy, radius, tiles_x, tiles_y, x0, y0, x1, y1);
+	const int area = (x1 - x0) * (y1 - y0);
+	unsigned long long kept = g.tile_mask[idx];
+	if (area <= 64 && kept == 0ull)
+		return;
+	const float depth = g.depths[idx];
+	const uint64_t key = ((uint64_t)__float_as_uint(depth) << 32) | (uint32_t)idx;
+	const uint32_t bucket = g.depth_lut[depth_fine_bin(depth)];
+	uint32_t* const cursor = g.bucket_cursor + bucket;
+
+	if (area <= 64) {
+		// replay the mask preprocess recorded
+		for (int ty = y0; ty < y1; ty++) {
+			for (int tx = x0; tx < x1; tx++, kept >>= 1) {
+				if (kept & 1ull) {
+					const uint32_t tile = (uint32_t)(ty * tiles_x + tx);
+					const uint32_t pos = atomicAdd(&cursor[(size_t)tile << bucket_log2], 1u);
+					if (pos < capacity)
+						b.keys[pos] = key;
+				}
+			}
+		}
+		return;
+	}
+
+	// large rectangle: re-evaluate the culling exactly as preprocess did
 	const float4 co = g.conic_opacity[idx];
 	const float thr = cull_threshold(co.w);
 	if (thr < 0.0f)
 		return;
-	const float2 xy = g.means2D[idx];
-	const float depth = g.depths[idx];
-	const uint64_t key = ((uint64_t)__float_as_uint(depth) << 32) | (uint32_t)idx;
-	const uint32_t bucket = g.depth_lut[depth_fine_bin(depth)];
-	int x0, y0, x1, y1;
-	tile_rect(xy, radius, tiles_x, tiles_y, x0, y0, x1, y1);
 	for (int ty = y0; ty < y1; ty++) {
 		const float py0 = (float)(ty * kTile);
 		const float py1 = fminf(py0 + (kTile - 1), (float)(H - 1));
@@ -154,7 +176,7 @@ emit_kernel(int P, const int* __restrict__ radii, GeometryState g, BinningState 
 			if (rect_cannot_contribute(xy.x, xy.y, co.x, co.y, co.z, thr, px0, py0, px1, py1))
 				continue;
 			const uint32_t tile = (uint32_t)(ty * tiles_x + tx);
-			const uint32_t pos = atomicAdd(&g.bucket_cursor[((size_t)tile << bucket_log2) + bucket], 1u);
+			const uint32_t pos = atomicAdd(&cursor[(size_t)tile << bucket_log2], 1u);
 			if (pos < capacity)
 				b.keys[pos] = key;
 		}
@@ -219,9 +241,10 @@ __device__ __forceinline__ void pack_one(const GeometryState& g, const BinningSt
 	const float2 xy = g.means2D[id];
 	const float4 co = g.conic_opacity[id];
 	const float4 rgb = g.rgb_clamp[id];
-	b.rec_conic[dst] = co;
-	b.rec_xyrg[dst] = make_float4(xy.x, xy.y, rgb.x, rgb.y);
-	b.rec_bid[dst] = make_float2(rgb.z, __uint_as_float(id));
+	// streaming stores: the records are read once by the blend kernels, the per-Gaussian arrays stay in L2
+	__stcs(&b.rec_conic[dst], co);
+	__stcs(&b.rec_xyrg[dst], make_float4(xy.x, xy.y, rgb.x, rgb.y));
+	__stcs(&b.rec_bid[dst], make_float2(rgb.z, __uint_as_float(id)));
 }
 
 template <int E>
@@ -280,43 +303,46 @@ __device__ __forceinline__ void block_bitonic(Ptr a, uint32_t n)
 	}
 }
 
+// One WARP per (tile, bucket): buckets of up to kWarpSortMax instances are sorted in registers and packed with
+// no shared memory and no block barrier, so every warp is an independent latency chain.
 __global__ void __launch_bounds__(kSortThreads)
-sort_pack_kernel(GeometryState g, BinningState b, uint32_t capacity, int bucket_log2)
+bucket_sort_pack_kernel(GeometryState g, BinningState b, uint32_t capacity, int bucket_log2, uint32_t num_buckets_total)
+{
+	const int lane = threadIdx.x & 31;
+	const uint32_t gw = blockIdx.x * kSortWarps + (threadIdx.x >> 5);
+	if (gw >= num_buckets_total)
+		return;
+	const uint32_t tile = gw >> bucket_log2;
+	const uint32_t bk = gw & ((1u << bucket_log2) - 1u);
+	// bucket bounds: emit left bucket_cursor at the END of each bucket
+	const uint32_t s0 = (bk == 0) ? g.tile_start[tile] : g.bucket_cursor[gw - 1];
+	const uint32_t s1 = min(g.bucket_cursor[gw], capacity);
+	if (s0 >= s1)
+		return;
+	const uint32_t n = s1 - s0;
+	if (n <= 32) warp_sort_pack<1>(g, b, s0, n, lane);
+	else if (n <= 64) warp_sort_pack<2>(g, b, s0, n, lane);
+	else if (n <= kWarpSortMax) warp_sort_pack<4>(g, b, s0, n, lane);
+	// larger buckets are left to big_bucket_sort_pack_kernel
+}
+
+// One BLOCK per tile: the buckets the warp kernel skipped (more than kWarpSortMax instances).
+__global__ void __launch_bounds__(kSortThreads)
+big_bucket_sort_pack_kernel(GeometryState g, BinningState b, uint32_t capacity, int bucket_log2)
 {
 	__shared__ uint64_t s_keys[kSortSmem];
-	__shared__ uint32_t s_big[kMaxBuckets];     // buckets left to the block-wide path
-	__shared__ uint32_t s_num_big;
-
 	const int tile = blockIdx.x;
-	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	const uint32_t tile_start = g.tile_start[tile];
-	if (tile_start >= capacity || g.tile_count[tile] == 0)
+	if (tile_start >= capacity || g.tile_count[tile] <= (uint32_t)kWarpSortMax)
 		return;
 	const int B = 1 << bucket_log2;
-	if (threadIdx.x == 0)
-		s_num_big = 0;
-	__syncthreads();
-
-	// bucket bounds: emit left bucket_cursor at the END of each bucket
 	const uint32_t* ends = g.bucket_cursor + ((size_t)tile << bucket_log2);
-	for (int bk = warp; bk < B; bk += kSortWarps) {
+	for (int bk = 0; bk < B; bk++) {
 		const uint32_t s0 = (bk == 0) ? tile_start : ends[bk - 1];
 		const uint32_t s1 = min(ends[bk], capacity);
-		if (s0 >= s1)
-			continue;
+		if (s0 >= s1 || s1 - s0 <= (uint32_t)kWarpSortMax)
+			continue;                                  // uniform over the block
 		const uint32_t n = s1 - s0;
-		if (n <= 32) warp_sort_pack<1>(g, b, s0, n, lane);
-		else if (n <= 64) warp_sort_pack<2>(g, b, s0, n, lane);
-		else if (n <= kWarpSortMax) warp_sort_pack<4>(g, b, s0, n, lane);
-		else if (lane == 0) s_big[atomicAdd(&s_num_big, 1u)] = (uint32_t)bk;
-	}
-	__syncthreads();
-
-	const uint32_t num_big = s_num_big;
-	for (uint32_t q = 0; q < num_big; q++) {
-		const int bk = (int)s_big[q];
-		const uint32_t s0 = (bk == 0) ? tile_start : ends[bk - 1];
-		const uint32_t n = min(ends[bk], capacity) - s0;
 		uint64_t* keys = b.keys + s0;
 		const uint64_t* sorted;
 		if (n <= kSortSmem) {
@@ -327,6 +353,7 @@ sort_pack_kernel(GeometryState g, BinningState b, uint32_t capacity, int bucket_
 			sorted = s_keys;
 		} else {
 			// longer than shared memory holds: in place in global memory (rare, slow, still exact)
+			__syncthreads();
 			block_bitonic(keys, n);
 			sorted = keys;
 		}
@@ -359,7 +386,12 @@ int launch_emit(int P, const int* radii, const GeometryState& g, const BinningSt
 int launch_sort_pack(int num_tiles, const GeometryState& g, const BinningState& b, uint32_t capacity,
                      const ViewParams& vp, cudaStream_t stream)
 {
-	sort_pack_kernel<<<num_tiles, kSortThreads, 0, stream>>>(g, b, capacity, vp.bucket_log2);
+	if (num_tiles <= 0)
+		return GM_OK;
+	const uint32_t total = (uint32_t)num_tiles << vp.bucket_log2;
+	bucket_sort_pack_kernel<<<(total + kSortWarps - 1) / kSortWarps, kSortThreads, 0, stream>>>(
+		g, b, capacity, vp.bucket_log2, total);
+	big_bucket_sort_pack_kernel<<<num_tiles, kSortThreads, 0, stream>>>(g, b, capacity, vp.bucket_log2);
 	return GM_OK;
 }
 

@@ -226,19 +226,26 @@ preprocess_kernel(int P,
 			// alpha >= 1/255 from this Gaussian are skipped (rect_cannot_contribute is output-preserving).
 			const float thr = cull_threshold(opacity);
 			const uint32_t bucket = s_lut[depth_fine_bin(p_view.z)];
+			unsigned long long kept = 0ull;
 			if (thr >= 0.0f) {
+				int bit = 0;
 				for (int ty = y0; ty < y1; ty++) {
 					const float py0 = (float)(ty * kTile);
 					const float py1 = fminf(py0 + (kTile - 1), (float)(vp.H - 1));
-					for (int tx = x0; tx < x1; tx++) {
+					for (int tx = x0; tx < x1; tx++, bit++) {
 						const float px0 = (float)(tx * kTile);
 						const float px1 = fminf(px0 + (kTile - 1), (float)(vp.W - 1));
 						if (!rect_cannot_contribute(point_image.x, point_image.y, conic.x, conic.y, conic.z, thr,
-						                            px0, py0, px1, py1))
+						                            px0, py0, px1, py1)) {
 							atomicAdd(&g.bucket_cursor[((size_t)(ty * vp.tiles_x + tx) << vp.bucket_log2) + bucket], 1u);
+							if (bit < 64)
+								kept |= 1ull << bit;
+						}
 					}
 				}
 			}
+			// emit replays this mask instead of re-evaluating the culling (rects of more than 64 tiles re-evaluate)
+			g.tile_mask[idx] = kept;
 		} while (false);
 
 		radii[idx] = my_radius_i;

@@ -56,6 +56,7 @@ struct GeometryState {
 	float* cov3D;             // [6P]  world covariance, scale/rot path only       (forward.cu:146-151)
 	float4* conic_opacity;    // [P]   (a, b, c, opacity)                          (forward.cu:253)
 	float4* rgb_clamp;        // [P]   (r, g, b, clamp bits as uint)               (forward.cu:63-70)
+	unsigned long long* tile_mask;   // [P] bit (ty-y0)*(x1-x0)+(tx-x0): tile kept by the exact culling (rects of <= 64 tiles)
 	uint32_t* tile_count;     // [GM_MAX_TILES] instances per tile after exact tile culling
 	uint32_t* tile_start;     // [GM_MAX_TILES] first instance of the tile (multiple of kSegAlign)
 	uint32_t* bucket_cursor;  // [kMaxBucketEntries] per (tile, bucket): count -> start -> end (see binning.cu)
@@ -108,6 +109,7 @@ inline GeometryState GeometryState::fromChunk(char*& chunk, size_t P)
 	obtain(chunk, g.cov3D, 6 * P);
 	obtain(chunk, g.conic_opacity, P);
 	obtain(chunk, g.rgb_clamp, P);
+	obtain(chunk, g.tile_mask, P);
 	obtain(chunk, g.tile_count, (size_t)GM_MAX_TILES);
 	obtain(chunk, g.tile_start, (size_t)GM_MAX_TILES);
 	obtain(chunk, g.bucket_cursor, kMaxBucketEntries);
