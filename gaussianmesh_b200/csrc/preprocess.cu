@@ -228,16 +228,29 @@ preprocess_kernel(int P,
 			const uint32_t bucket = s_lut[depth_fine_bin(p_view.z)];
 			unsigned long long kept = 0ull;
 			if (thr >= 0.0f) {
-				int bit = 0;
-				for (int ty = y0; ty < y1; ty++) {
+				// The exact test below can only pass inside the ellipse q(d) <= 2 thr + slack, whose axis-aligned
+				// extent is sqrt((2 thr + slack) * cov_xx) by sqrt((2 thr + slack) * cov_yy).  Walking only the
+				// tiles that box overlaps (padded by a pixel and 1%) skips most corner tiles of the 3-sigma square
+				// without changing which tiles are kept.
+				const float lvl = 2.0f * thr + 0.05f;
+				const float ex = 1.01f * sqrtf(lvl * cov.x) + 1.0f, ey = 1.01f * sqrtf(lvl * cov.z) + 1.0f;
+				// (a degenerate conic is never culled by the exact test, so it keeps the whole square)
+				const bool tight = conic.x > 0.0f && conic.z > 0.0f && ex < 1.0e6f && ey < 1.0e6f;
+				const int tx_lo = tight ? max(x0, (int)floorf((point_image.x - ex) * (1.0f / kTile))) : x0;
+				const int tx_hi = tight ? min(x1, (int)floorf((point_image.x + ex) * (1.0f / kTile)) + 1) : x1;
+				const int ty_lo = tight ? max(y0, (int)floorf((point_image.y - ey) * (1.0f / kTile))) : y0;
+				const int ty_hi = tight ? min(y1, (int)floorf((point_image.y + ey) * (1.0f / kTile)) + 1) : y1;
+				const int w = x1 - x0;
+				for (int ty = ty_lo; ty < ty_hi; ty++) {
 					const float py0 = (float)(ty * kTile);
 					const float py1 = fminf(py0 + (kTile - 1), (float)(vp.H - 1));
-					for (int tx = x0; tx < x1; tx++, bit++) {
+					for (int tx = tx_lo; tx < tx_hi; tx++) {
 						const float px0 = (float)(tx * kTile);
 						const float px1 = fminf(px0 + (kTile - 1), (float)(vp.W - 1));
 						if (!rect_cannot_contribute(point_image.x, point_image.y, conic.x, conic.y, conic.z, thr,
 						                            px0, py0, px1, py1)) {
 							atomicAdd(&g.bucket_cursor[((size_t)(ty * vp.tiles_x + tx) << vp.bucket_log2) + bucket], 1u);
+							const int bit = (ty - y0) * w + (tx - x0);
 							if (bit < 64)
 								kept |= 1ull << bit;
 						}
