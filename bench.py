@@ -163,6 +163,11 @@ class OursArm:
         self.vb.render_into(cam, bg, self.fwd_out)
         return self.fwd_out
 
+    def setup(self, cams, bg):
+        # buffer sizing, not warm-up: the binning chunks are allocated once for the largest view of the shard
+        self.ts.reserve_for(cams, bg)
+        self.vb.reserve_for(cams, bg)
+
     def check(self):
         bad = self.ts.arena.verify() + self.vb.arena.verify()
         if bad:
@@ -205,6 +210,9 @@ class ReferenceArm:
     def forward(self, cam, bg):
         return self._frame(cam, bg).color
 
+    def setup(self, cams, bg):
+        pass
+
     def check(self):
         pass
 
@@ -231,6 +239,7 @@ def main():
     arm = OursArm(device, scene, WIDTH, HEIGHT) if args.impl == "ours" else ReferenceArm(device, scene, WIDTH, HEIGHT)
     K, Wm = args.steps, args.warmup
     nv = len(cams)
+    arm.setup(cams, bg)
 
     # ---------------------------------------------------------------- (1) device-resident training frames
     def train_resident(i):

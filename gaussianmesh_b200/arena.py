@@ -65,9 +65,27 @@ class RenderArena:
         instances = int(instances)
         if instances <= self.capacity:
             return
+        if self.capacity:
+            instances = max(instances, int(self.capacity * 1.5))     # geometric growth: few reallocations
         nbytes = int(lib.gm_required_binning(instances))
         self.binning = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
         self.capacity = int(lib.gm_binning_capacity(nbytes))
+
+    def reserve_for_views(self, P: int, D: int, M: int, background: torch.Tensor, W: int, H: int, view_args_list) -> int:
+        """Size the binning chunk for a known set of views before rendering them: one gm_forward_0 per view
+        (preprocess + count, one blocking 4-byte read each), then a single allocation.  Returns the largest count."""
+        self._ensure(P, W * H)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        tmp_radii = torch.empty(P, dtype=torch.int32, device=self.device)
+        worst = 0
+        for view_args in view_args_list:
+            n = check(lib.gm_forward_0(self.geom.data_ptr(), P, D, M, background.data_ptr(), W, H, *view_args, 0,
+                                       tmp_radii.data_ptr(), 0, stream), "gm_forward_0")
+            worst = max(worst, n)
+        self.high_water = max(self.high_water, worst)
+        self._want = max(self._want, int(worst * self.headroom) + 1024)
+        self.reserve(self._want)
+        return worst
 
     # ------------------------------------------------------------------ counters
     def _retire(self, slot: int) -> None:

@@ -203,7 +203,7 @@ emit_kernel(int P, const int* __restrict__ radii, GeometryState g, BinningState 
 constexpr int kSortThreads = 256;
 constexpr int kSortWarps = kSortThreads / 32;
 constexpr int kSortSmem = 4096;       // keys; 32 KB -- block-wide path for oversized buckets
-constexpr int kWarpSortMax = 128;     // largest bucket one warp sorts in registers (4 keys per lane)
+constexpr int kWarpSortMax = 256;     // largest bucket one warp sorts in registers (8 keys per lane)
 
 __device__ __forceinline__ uint64_t shfl_xor_u64(uint64_t v, int lane_mask)
 {
@@ -336,7 +336,8 @@ bucket_sort_pack_kernel(GeometryState g, BinningState b, uint32_t capacity, int 
 	const uint32_t n = s1 - s0;
 	if (n <= 32) warp_sort_pack<1>(g, b, s0, n, lane);
 	else if (n <= 64) warp_sort_pack<2>(g, b, s0, n, lane);
-	else if (n <= kWarpSortMax) warp_sort_pack<4>(g, b, s0, n, lane);
+	else if (n <= 128) warp_sort_pack<4>(g, b, s0, n, lane);
+	else if (n <= kWarpSortMax) warp_sort_pack<8>(g, b, s0, n, lane);
 	// larger buckets are left to big_bucket_sort_pack_kernel
 }
 

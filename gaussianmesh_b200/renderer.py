@@ -222,6 +222,11 @@ class ViewBatchRenderer:
                 cam.full_proj_transform.data_ptr(), cam.camera_center.data_ptr(),
                 math.tan(cam.FoVx * 0.5), math.tan(cam.FoVy * 0.5))
 
+    def reserve_for(self, cams: Sequence, bg: torch.Tensor) -> int:
+        """Size the arena for these views up front (setup, not rendering)."""
+        return self.arena.reserve_for_views(self.P, self.D, self.M, bg, cams[0].image_width, cams[0].image_height,
+                                            [self._view_args(c) for c in cams])
+
     def render_into(self, cam, bg: torch.Tensor, out: torch.Tensor) -> None:
         """Enqueue one view; `out` is a [3,H,W] float32 device tensor."""
         stream = torch.cuda.current_stream(self.device).cuda_stream
@@ -278,6 +283,10 @@ class TrainStep:
         return (p(self.means3D), p(self.shs), None, p(self.opacities), p(self.scales), 1.0, p(self.rotations), None,
                 p(cam.world_view_transform), p(cam.full_proj_transform), p(cam.camera_center),
                 math.tan(cam.FoVx * 0.5), math.tan(cam.FoVy * 0.5))
+
+    def reserve_for(self, cams: Sequence, bg: torch.Tensor) -> int:
+        """Size the arena for these views up front (setup, not rendering)."""
+        return self.arena.reserve_for_views(self.P, self.D, self.M, bg, self.W, self.H, [self._view_args(c) for c in cams])
 
     def step(self, cam, bg: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
         """Enqueue one training step; returns the (device) loss tensor.  No host synchronisation."""

@@ -154,6 +154,19 @@ def timed_sample(P: int, W: int, H: int, frames: int = 1) -> dict:
         backward(arrays, cams[f % len(cams)], bg, 3, fwd, dL)
     dt = time.perf_counter() - t0
     cores = int(os.environ.get("OMP_NUM_THREADS", os.cpu_count() or 1))
-    return {"value": frames / dt, "unit": "frames/s", "cores": cores, "kind": "port",
-            "sample": f"{frames} training frame(s) (forward + L1 + backward) of the same {P}-Gaussian {W}x{H} workload "
-                      f"through oracle/cpu_rasterizer.c (C + OpenMP restatement of the reference), {dt:.2f} s, loss {loss:.6f}"}
+    out = {"value": frames / dt, "unit": "frames/s", "cores": cores, "kind": "port",
+           "sample": f"{frames} training frame(s) (forward + L1 + backward) of the same {P}-Gaussian {W}x{H} workload "
+                     f"through oracle/cpu_rasterizer.c (C + OpenMP restatement of the reference), {dt:.2f} s, loss {loss:.6f}"}
+    # the reference's Python (Jittor) preprocess chain restated in numpy fp32 (oracle/python_path.py): mesh bind,
+    # activations, Python covariance and SH->RGB fallbacks, for the same number of Gaussians
+    from . import python_path as pp
+    V, F = synthetic.icosphere(4)
+    mesh = synthetic.mesh_bound_scene(P, V, F, seed=0)
+    t0 = time.perf_counter()
+    inp = pp.mesh_bound_inputs(mesh)
+    pp.build_covariance_from_scaling_rotation(inp["scales"], 1.0, inp["rotations"])
+    pp.sh_to_rgb(3, inp["shs"], inp["means3D"], cams[0].camera_center)
+    out["python_preprocess_ms"] = (time.perf_counter() - t0) * 1e3
+    out["python_preprocess_note"] = ("numpy fp32 restatement of get_xyz/get_scaling/get_rotation/get_opacity + "
+                                     "build_covariance_from_scaling_rotation + eval_sh for the same P (one frame)")
+    return out

@@ -18,6 +18,8 @@ def main(rep, kernel, top=25):
     for r in rows[h + 1:]:
         if len(r) <= ie:
             continue
+        if r[ie] == "Instructions Executed":      # a second launch of the same kernel follows: keep the first
+            break
         n, s = float(r[ie] or 0), float(r[smp] or 0)
         toks = r[src].split()
         op = toks[0] if toks and not toks[0].startswith("@") else (toks[1] if len(toks) > 1 else "?")
