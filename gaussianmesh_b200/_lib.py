@@ -16,6 +16,7 @@ GM_ERR_CUDA = -1
 GM_ERR_BAD_ARGUMENT = -2
 GM_ERR_TOO_MANY_TILES = -3
 GM_ERR_BINNING_OVERFLOW = -4
+GM_BACKWARD_OVERWRITE = 1
 
 _ERR_NAMES = {
     GM_ERR_CUDA: "GM_ERR_CUDA",
@@ -50,6 +51,8 @@ SIGNATURES = {
     "gm_geom_view": (None, [_p, _z, _p]),
     "gm_backward": (_i, [_i, _i, _i, _i, _p, _i, _i, _p, _p, _p, _p, _f, _p, _p, _p, _p, _p, _f, _f, _p,
                          _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _p]),
+    "gm_backward_ex": (_i, [_i, _i, _i, _i, _p, _i, _i, _p, _p, _p, _p, _f, _p, _p, _p, _p, _p, _f, _f, _p,
+                            _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _p]),
     "gm_mesh_bind_forward": (_i, [_i, _p, _p, _p, _p, _p, _p, _p, _f, _p, _p, _p, _p, _p, _p, _p, _p]),
     "gm_mesh_bind_backward": (_i, [_i, _p, _p, _p, _p, _p, _p, _p, _f, _p, _p, _p, _p, _p, _p, _p,
                                    _p, _p, _p, _p, _p, _p]),

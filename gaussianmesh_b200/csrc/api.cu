@@ -336,14 +336,14 @@ void gm_geom_view(char* geom_buffer, size_t P, void** out6)
 	out6[4] = g.rgb_clamp; out6[5] = g.tile_count;
 }
 
-int gm_backward(int P, int D, int M, int R, const float* background, int width, int height,
+int gm_backward_ex(int P, int D, int M, int R, const float* background, int width, int height,
                 const float* means3D, const float* shs, const float* colors_precomp, const float* scales,
                 float scale_modifier, const float* rotations, const float* cov3D_precomp,
                 const float* viewmatrix, const float* projmatrix, const float* campos, float tan_fovx,
                 float tan_fovy, const int* radii, char* geom_buffer, char* binning_buffer, char* image_buffer,
                 const float* dL_dpix, float* dL_dmean2D, float* dL_dconic, float* dL_dopacity,
                 float* dL_dcolor, float* dL_dmean3D, float* dL_dcov3D, float* dL_dsh, float* dL_dscale,
-                float* dL_drot, int debug, gm_stream_t stream_)
+                float* dL_drot, int debug, int flags, gm_stream_t stream_)
 {
 	cudaStream_t stream = (cudaStream_t)stream_;
 	ViewParams vp;
@@ -377,8 +377,23 @@ int gm_backward(int P, int D, int M, int R, const float* background, int width, 
 	const float* cov3D_ptr = sr_path ? geom.cov3D : cov3D_precomp;
 	{ StageScope scope_(kStGeomBwd, stream); launch_geometry_backward(P, means3D, radii, sh_path ? shs : nullptr, sr_path ? scales : nullptr,
 	                         sr_path ? rotations : nullptr, cov3D_ptr, vp, geom, dL_dmean2D, dL_dconic, dL_dcolor,
-	                         dL_dmean3D, dL_dcov3D, dL_dsh, dL_dscale, dL_drot, stream); }
+	                         dL_dmean3D, dL_dcov3D, dL_dsh, dL_dscale, dL_drot, (flags & GM_BACKWARD_OVERWRITE) != 0, stream); }
 	return check_stage("geometry_backward", debug != 0, stream);
+}
+
+int gm_backward(int P, int D, int M, int R, const float* background, int width, int height,
+                const float* means3D, const float* shs, const float* colors_precomp, const float* scales,
+                float scale_modifier, const float* rotations, const float* cov3D_precomp,
+                const float* viewmatrix, const float* projmatrix, const float* campos, float tan_fovx,
+                float tan_fovy, const int* radii, char* geom_buffer, char* binning_buffer, char* image_buffer,
+                const float* dL_dpix, float* dL_dmean2D, float* dL_dconic, float* dL_dopacity,
+                float* dL_dcolor, float* dL_dmean3D, float* dL_dcov3D, float* dL_dsh, float* dL_dscale,
+                float* dL_drot, int debug, gm_stream_t stream_)
+{
+	return gm_backward_ex(P, D, M, R, background, width, height, means3D, shs, colors_precomp, scales, scale_modifier,
+	                      rotations, cov3D_precomp, viewmatrix, projmatrix, campos, tan_fovx, tan_fovy, radii,
+	                      geom_buffer, binning_buffer, image_buffer, dL_dpix, dL_dmean2D, dL_dconic, dL_dopacity,
+	                      dL_dcolor, dL_dmean3D, dL_dcov3D, dL_dsh, dL_dscale, dL_drot, debug, 0, stream_);
 }
 
 int gm_mesh_bind_forward(int P, const float* bc_logits, const float* distance, const float* vertex1,

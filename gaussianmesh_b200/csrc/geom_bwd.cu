@@ -24,7 +24,9 @@ __device__ __forceinline__ float3 dnormvdv3(float3 v, float3 dv)   // auxiliary.
 	return r;
 }
 
-template <bool kVecSH>
+// kOverwrite: the five per-Gaussian output rows need not be pre-zeroed -- this kernel writes every element of
+// them (zeros for Gaussians that were not rendered and for SH coefficients above the active degree).
+template <bool kVecSH, bool kOverwrite>
 __global__ void __launch_bounds__(kThreads)
 geometry_backward_kernel(int P,
                          const float* __restrict__ means3D,
@@ -56,8 +58,31 @@ geometry_backward_kernel(int P,
 	__syncthreads();
 
 	const int idx = blockIdx.x * kThreads + threadIdx.x;
-	if (idx >= P || !(radii[idx] > 0))
+	if (idx >= P)
 		return;
+	if (!(radii[idx] > 0)) {
+		if (kOverwrite) {
+#pragma unroll
+			for (int i = 0; i < 3; i++) dL_dmean3D[3 * idx + i] = 0.0f;
+#pragma unroll
+			for (int i = 0; i < 6; i++) dL_dcov3D[6 * idx + i] = 0.0f;
+			if (shs != nullptr) {
+				float* dsh = dL_dsh + (size_t)idx * vp.M * 3;
+				if (kVecSH) {
+					for (int j4 = 0; j4 < (vp.M * 3) / 4; j4++)
+						reinterpret_cast<float4*>(dsh)[j4] = make_float4(0.f, 0.f, 0.f, 0.f);
+				} else {
+					for (int i = 0; i < vp.M * 3; i++) dsh[i] = 0.0f;
+				}
+			}
+			if (scales != nullptr) {
+#pragma unroll
+				for (int i = 0; i < 3; i++) dL_dscale[3 * idx + i] = 0.0f;
+				reinterpret_cast<float4*>(dL_drot)[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
+			}
+		}
+		return;
+	}
 
 	const float3 mean = make_float3(means3D[3 * idx], means3D[3 * idx + 1], means3D[3 * idx + 2]);
 
@@ -223,7 +248,23 @@ geometry_backward_kernel(int P,
 		}
 		// only coefficients up to `deg` are written (the caller's zeros stay above it, as in the reference)
 		float* dsh = dL_dsh + (size_t)idx * vp.M * 3;
-		if (kVecSH) {
+		if (kOverwrite) {
+			// `out` is zero above the active degree (B[k] == 0 there); rows longer than 16 coefficients get zeros
+			if (kVecSH) {
+				float4* dsh4 = reinterpret_cast<float4*>(dsh);
+#pragma unroll
+				for (int j4 = 0; j4 < 12; j4++)
+					if (4 * j4 < vp.M * 3)
+						dsh4[j4] = make_float4(out[4 * j4], out[4 * j4 + 1], out[4 * j4 + 2], out[4 * j4 + 3]);
+				for (int j4 = 12; j4 < (vp.M * 3) / 4; j4++)
+					dsh4[j4] = make_float4(0.f, 0.f, 0.f, 0.f);
+			} else {
+#pragma unroll
+				for (int i = 0; i < 48; i++)
+					if (i < vp.M * 3) dsh[i] = out[i];
+				for (int i = 48; i < vp.M * 3; i++) dsh[i] = 0.0f;
+			}
+		} else if (kVecSH) {
 			float4* dsh4 = reinterpret_cast<float4*>(dsh);
 #pragma unroll
 			for (int j4 = 0; j4 < 12; j4++) {
@@ -303,21 +344,21 @@ int launch_geometry_backward(int P, const float* means3D, const int* radii, cons
                              const float* rotations, const float* cov3Ds, const ViewParams& vp,
                              const GeometryState& g, const float* dL_dmean2D, const float* dL_dconic,
                              const float* dL_dcolor, float* dL_dmean3D, float* dL_dcov3D, float* dL_dsh,
-                             float* dL_dscale, float* dL_drot, cudaStream_t stream)
+                             float* dL_dscale, float* dL_drot, bool overwrite, cudaStream_t stream)
 {
 	if (P <= 0)
 		return GM_OK;
 	const dim3 grid((P + kThreads - 1) / kThreads);
 	const bool vec = sh_rows_vectorizable(shs, vp.M) && sh_rows_vectorizable(dL_dsh, vp.M) &&
 	                 vp.M * 3 >= 3 * (vp.D + 1) * (vp.D + 1);
-	if (vec)
-		geometry_backward_kernel<true><<<grid, kThreads, 0, stream>>>(
-			P, means3D, radii, shs, scales, rotations, cov3Ds, vp, g, dL_dmean2D, dL_dconic, dL_dcolor,
-			dL_dmean3D, dL_dcov3D, dL_dsh, dL_dscale, dL_drot);
-	else
-		geometry_backward_kernel<false><<<grid, kThreads, 0, stream>>>(
-			P, means3D, radii, shs, scales, rotations, cov3Ds, vp, g, dL_dmean2D, dL_dconic, dL_dcolor,
-			dL_dmean3D, dL_dcov3D, dL_dsh, dL_dscale, dL_drot);
+#define GM_LAUNCH_GEOM(V, O) geometry_backward_kernel<V, O><<<grid, kThreads, 0, stream>>>( \
+		P, means3D, radii, shs, scales, rotations, cov3Ds, vp, g, dL_dmean2D, dL_dconic, dL_dcolor, \
+		dL_dmean3D, dL_dcov3D, dL_dsh, dL_dscale, dL_drot)
+	if (vec && overwrite) GM_LAUNCH_GEOM(true, true);
+	else if (vec) GM_LAUNCH_GEOM(true, false);
+	else if (overwrite) GM_LAUNCH_GEOM(false, true);
+	else GM_LAUNCH_GEOM(false, false);
+#undef GM_LAUNCH_GEOM
 	return GM_OK;
 }
 

@@ -33,7 +33,7 @@ int launch_geometry_backward(int P, const float* means3D, const int* radii, cons
                              const float* rotations, const float* cov3Ds, const ViewParams& vp,
                              const GeometryState& g, const float* dL_dmean2D, const float* dL_dconic,
                              const float* dL_dcolor, float* dL_dmean3D, float* dL_dcov3D, float* dL_dsh,
-                             float* dL_dscale, float* dL_drot, cudaStream_t stream);
+                             float* dL_dscale, float* dL_drot, bool overwrite, cudaStream_t stream);
 
 int launch_mesh_bind_forward(int P, const float* bc_logits, const float* distance, const float* v1, const float* v2,
                              const float* v3, const float* normal, const float* r, float alpha_distance,

@@ -14,7 +14,7 @@ from typing import Optional, Tuple
 
 import torch
 
-from .._lib import lib, check, RasterizerError, GM_ERR_BAD_ARGUMENT
+from .._lib import lib, check, RasterizerError, GM_ERR_BAD_ARGUMENT, GM_BACKWARD_OVERWRITE
 
 # rasterize_points_deformed.py differs from rasterize_points.py only by forcing the number of SH
 # coefficients per Gaussian to 16 (reference :157 and :230); it passes `_force_m=16`.
@@ -186,22 +186,31 @@ def RasterizeGaussiansBackwardCUDA(
     # reference :301: M = sh.size(1) if sh.size(0) != 0 else 0 (the `_deformed` twin forces 16)
     M = _force_m if _force_m is not None else (int(sh.shape[1]) if sh.numel() != 0 else 0)
     Mg = int(sh.shape[1]) if sh.numel() != 0 else 0
-    # one zero-filled slab for all nine gradient tensors: 1 memset instead of 9 (reference :302-310)
-    sizes = [3 * P, 3 * P, 3 * P, P, 6 * P, Mg * 3 * P, 3 * P, 4 * P, 4 * P]
+    # One slab for all nine gradient tensors (reference :302-310 allocates nine zero tensors).  Only the four
+    # atomically accumulated ones are zero-filled; the per-Gaussian rows are written in full by
+    # gm_backward_ex(GM_BACKWARD_OVERWRITE).  Unused variants (e.g. dL_dsh on the colour path) are zero-filled too.
+    use_sh, use_sr = colors.numel() == 0, cov3D_precomp.numel() == 0
+    sizes = [3 * P, 4 * P, P, 3 * P,                                  # means2D, conic, opacity, colors (accumulated)
+             3 * P, 6 * P, Mg * 3 * P, 3 * P, 4 * P]                  # means3D, cov3D, sh, scales, rotations
     offs = [0]
-    for s in sizes:
-        offs.append(offs[-1] + ((s + 31) // 32) * 32)   # keep every tensor 128-byte aligned
-    slab = torch.zeros(offs[-1], dtype=torch.float32, device=dev)
+    for sz in sizes:
+        offs.append(offs[-1] + ((sz + 31) // 32) * 32)   # keep every tensor 128-byte aligned
+    slab = torch.empty(offs[-1], dtype=torch.float32, device=dev)
+    slab[:offs[4]].zero_()
     part = [slab[offs[i]:offs[i] + sizes[i]] for i in range(len(sizes))]
-    dL_dmeans3D = part[0].view(P, 3)
-    dL_dmeans2D = part[1].view(P, 3)
-    dL_dcolors = part[2].view(P, 3)
-    dL_dopacity = part[3].view(P, 1)
-    dL_dcov3D = part[4].view(P, 6)
-    dL_dsh = part[5].view(P, Mg, 3)
-    dL_dscales = part[6].view(P, 3)
-    dL_drotations = part[7].view(P, 4)
-    dL_dconic = part[8].view(P, 2, 2)
+    if not use_sh:
+        part[6].zero_()
+    if not use_sr:
+        part[7].zero_(); part[8].zero_()
+    dL_dmeans2D = part[0].view(P, 3)
+    dL_dconic = part[1].view(P, 2, 2)
+    dL_dopacity = part[2].view(P, 1)
+    dL_dcolors = part[3].view(P, 3)
+    dL_dmeans3D = part[4].view(P, 3)
+    dL_dcov3D = part[5].view(P, 6)
+    dL_dsh = part[6].view(P, Mg, 3)
+    dL_dscales = part[7].view(P, 3)
+    dL_drotations = part[8].view(P, 4)
     if P != 0:
         dL_dout_color = _f32(dL_dout_color, "dL_dout_color")
         H, W = int(dL_dout_color.shape[1]), int(dL_dout_color.shape[2])
@@ -214,13 +223,13 @@ def RasterizeGaussiansBackwardCUDA(
         projmatrix = _f32(projmatrix, "projmatrix")
         campos = _f32(campos, "campos")
         check(
-            lib.gm_backward(P, int(degree), M, int(R), _ptr(background), W, H, _ptr(means3D), _ptr(sh), _ptr(colors),
+            lib.gm_backward_ex(P, int(degree), M, int(R), _ptr(background), W, H, _ptr(means3D), _ptr(sh), _ptr(colors),
                             _ptr(scales), float(scale_modifier), _ptr(rotations), _ptr(cov3D_precomp),
                             _ptr(viewmatrix), _ptr(projmatrix), _ptr(campos), float(tan_fovx), float(tan_fovy),
                             _ptr(radii), _ptr(geomBuffer), _ptr(binningBuffer), _ptr(imageBuffer),
                             dL_dout_color.data_ptr(), dL_dmeans2D.data_ptr(), dL_dconic.data_ptr(),
                             dL_dopacity.data_ptr(), dL_dcolors.data_ptr(), dL_dmeans3D.data_ptr(),
                             dL_dcov3D.data_ptr(), _ptr(dL_dsh) if Mg else None, dL_dscales.data_ptr(),
-                            dL_drotations.data_ptr(), int(bool(debug)), _stream()),
-            "gm_backward")
+                            dL_drotations.data_ptr(), int(bool(debug)), GM_BACKWARD_OVERWRITE, _stream()),
+            "gm_backward_ex")
     return dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dmeans3D, dL_dcov3D, dL_dsh, dL_dscales, dL_drotations

@@ -22,7 +22,7 @@ import numpy as np
 import torch
 
 from . import mesh_gaussians as mg
-from ._lib import lib, check
+from ._lib import lib, check, GM_BACKWARD_OVERWRITE
 from .arena import RenderArena
 from .diff_gaussian_rasterizater import (GaussianRasterizationSettings, GaussianRasterizer, NewGaussianRasterizer)
 from .synthetic import Camera
@@ -269,13 +269,16 @@ class TrainStep:
         self.dL_dimg = torch.empty_like(self.image)
         self.loss = torch.zeros(1, dtype=torch.float32, device=self.device)
         self.radii = torch.empty(P, dtype=torch.int32, device=self.device)
-        sizes = {"means3D": 3 * P, "means2D": 3 * P, "colors": 3 * P, "opacity": P, "cov3D": 6 * P, "sh": 3 * M * P,
-                 "scales": 3 * P, "rotations": 4 * P, "conic": 4 * P}
+        # accumulated (atomically added) gradients first: only this part of the slab is zeroed per step; the
+        # per-Gaussian rows behind it are fully written by gm_backward_ex(GM_BACKWARD_OVERWRITE)
+        sizes = {"means2D": 3 * P, "conic": 4 * P, "opacity": P, "colors": 3 * P,
+                 "means3D": 3 * P, "cov3D": 6 * P, "sh": 3 * M * P, "scales": 3 * P, "rotations": 4 * P}
         offs, total = {}, 0
         for k, s in sizes.items():
             offs[k] = total
             total += ((s + 31) // 32) * 32
         self._slab = torch.empty(total, dtype=torch.float32, device=self.device)
+        self._accum = self._slab[:offs["means3D"]]
         self.grads = {k: self._slab[offs[k]:offs[k] + sizes[k]] for k in sizes}
 
     def _view_args(self, cam) -> tuple:
@@ -296,13 +299,14 @@ class TrainStep:
             self.P, self.D, self.M, bg, self.W, self.H, va, False, False, stream, out_color=self.image, radii=self.radii)
         check(lib.gm_l1_loss(self.image.numel(), self.image.data_ptr(), target.data_ptr(), self.loss.data_ptr(),
                              self.dL_dimg.data_ptr(), stream), "gm_l1_loss")
-        self._slab.zero_()
+        self._accum.zero_()
         g = self.grads
-        check(lib.gm_backward(self.P, self.D, self.M, cap, bg.data_ptr(), self.W, self.H, va[0], va[1], None, va[4], 1.0,
+        check(lib.gm_backward_ex(self.P, self.D, self.M, cap, bg.data_ptr(), self.W, self.H, va[0], va[1], None, va[4], 1.0,
                               va[6], None, va[8], va[9], va[10], va[11], va[12], self.radii.data_ptr(),
                               geom.data_ptr(), binning.data_ptr(), image_state.data_ptr(), self.dL_dimg.data_ptr(),
                               g["means2D"].data_ptr(), g["conic"].data_ptr(), g["opacity"].data_ptr(),
                               g["colors"].data_ptr(), g["means3D"].data_ptr(), g["cov3D"].data_ptr(),
-                              g["sh"].data_ptr(), g["scales"].data_ptr(), g["rotations"].data_ptr(), 0, stream),
-              "gm_backward")
+                                 g["sh"].data_ptr(), g["scales"].data_ptr(), g["rotations"].data_ptr(), 0,
+                                 GM_BACKWARD_OVERWRITE, stream),
+              "gm_backward_ex")
         return self.loss

@@ -141,6 +141,20 @@ int gm_backward(int P, int D, int M, int R, const float* background, int width, 
                 float* dL_dcolor, float* dL_dmean3D, float* dL_dcov3D, float* dL_dsh,
                 float* dL_dscale, float* dL_drot, int debug, gm_stream_t stream);
 
+/*  gm_backward with flags.  GM_BACKWARD_OVERWRITE: dL_dmean3D, dL_dcov3D, dL_dsh, dL_dscale and dL_drot need
+ *  NOT be pre-zeroed -- the call writes every element of them (zeros for Gaussians that were not rendered and
+ *  for SH coefficients above the active degree), which saves the caller a 256 B/Gaussian memset.  The four
+ *  accumulated buffers (dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolor) must still be zero. */
+#define GM_BACKWARD_OVERWRITE 1
+int gm_backward_ex(int P, int D, int M, int R, const float* background, int width, int height,
+                   const float* means3D, const float* shs, const float* colors_precomp, const float* scales,
+                   float scale_modifier, const float* rotations, const float* cov3D_precomp,
+                   const float* viewmatrix, const float* projmatrix, const float* campos, float tan_fovx,
+                   float tan_fovy, const int* radii, char* geom_buffer, char* binning_buffer, char* image_buffer,
+                   const float* dL_dpix, float* dL_dmean2D, float* dL_dconic, float* dL_dopacity,
+                   float* dL_dcolor, float* dL_dmean3D, float* dL_dcov3D, float* dL_dsh,
+                   float* dL_dscale, float* dL_drot, int debug, int flags, gm_stream_t stream);
+
 /* ---- mesh-bound Gaussian parametrisation (training side); replaces the Jittor op chains of
  *      MeshBasedGaussianModel.get_xyz / get_scaling / get_rotation / get_opacity
  *      (scene/mesh_based_gaussian_model.py:34-43,122-152):
