@@ -125,6 +125,30 @@ def build_workload(device, P, rank, world):
     return scene, cams_host, cams, targets_host, targets, cams_packed_host
 
 
+EDIT_P, EDIT_VIEWS = 500_000, 200
+
+
+def build_edit_workload(device, rank, world):
+    """Config 5: 500K mesh-bound Gaussians on the 5,120-face proxy mesh, rest pose -> twist-and-bend deformation,
+    200-frame orbit sharded over ranks."""
+    from gaussianmesh_b200 import synthetic
+    from gaussianmesh_b200.renderer import DeformedObject, shard_views, upload_cameras
+    from gaussianmesh_b200.mesh_gaussians import mesh_bind
+    V, F = synthetic.icosphere(4)
+    a = synthetic.mesh_bound_scene(EDIT_P, V, F, seed=0)
+    t = {k: torch.from_numpy(np.ascontiguousarray(v)).to(device) for k, v in a.items()}
+    with torch.no_grad():
+        pos, scales, rots, opac = mesh_bind(t["bc_logits"], torch.zeros_like(t["distance"]), t["log_scales"], t["rot_raw"],
+                                            t["opacity_logit"], t["vertex1"], t["vertex2"], t["vertex3"], t["normal"], t["r"])
+    weights = synthetic.barycentric_weights(pos.cpu().numpy(), V, a["triangles"]).astype(np.float32)
+    cov6 = torch.from_numpy(synthetic.packed_covariance(scales.cpu().numpy(), rots.cpu().numpy())).to(device)
+    obj = DeformedObject(pos, cov6, opac, t["shs"], a["triangles"], weights, V, device)
+    Vd, R, S = synthetic.twist_bend_deformation(V)
+    cams_host = synthetic.orbit_cameras(EDIT_VIEWS, WIDTH, HEIGHT)
+    cams_host = [cams_host[i] for i in shard_views(EDIT_VIEWS, world, rank)]
+    return obj, (Vd, R, S), upload_cameras(cams_host, device)
+
+
 def timed(fn, steps, warmup, barrier):
     """W untimed + K timed calls of fn(i); CUDA-event time in ms (this rank)."""
     for i in range(warmup):
@@ -304,6 +328,39 @@ def main():
     ms_fwd, _ = timed(fwd, K, Wm, barrier)
     arm.check()
     ms_fwd = max_over_ranks(ms_fwd)
+
+    # ---------------------------------------------------------------- (4) edit path (config 5): deform once, orbit render
+    obj, (Vd, Rv, Sv), edit_cams = build_edit_workload(device, rank, world)
+    white = torch.ones(3, dtype=torch.float32, device=device)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    ev0.record()
+    obj.deform(Vd, Rv, Sv)
+    ev1.record()
+    torch.cuda.synchronize()
+    deform_ms = ev0.elapsed_time(ev1)
+    ne = len(edit_cams)
+    if args.impl == "ours":
+        from gaussianmesh_b200.arena import RenderArena
+        edit_arena = RenderArena(device, strict=False)
+
+        def edit_frame(i):
+            obj.render_gaussian(edit_cams[i % ne], white, arena=edit_arena)
+        edit_frame(0)
+        edit_arena.reserve(int(edit_arena.high_water * 1.5))
+    else:
+        import refcuda
+
+        def edit_frame(i):
+            cam = edit_cams[i % ne]
+            colors = refcuda.edit_colors_torch(obj.deform_pos, cam.camera_center, obj.deform_rot, obj.shs, 3)
+            refcuda.RefFrame(white, obj.deform_pos, obj.opacity, cam.world_view_transform, cam.full_proj_transform,
+                             cam.camera_center, math.tan(cam.FoVx * 0.5), math.tan(cam.FoVy * 0.5), HEIGHT, WIDTH, 3,
+                             colors=colors, cov3D=obj.deform_cov6, M=16, sync=False)
+    ms_edit, _ = timed(edit_frame, K, Wm, barrier)
+    if args.impl == "ours" and edit_arena.verify():
+        raise RuntimeError("edit arena overflow inside the timed region")
+    ms_edit = max_over_ranks(ms_edit)
     clocks = sampler.stop() if sampler is not None else None
 
     if rank != 0:
@@ -325,6 +382,9 @@ def main():
         "e2e": {"value": N * K / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                 "ms_per_step": ms_e2e / K, "loss": loss_value},
         "forward": {"value": N * K / (ms_fwd * 1e-3), "unit": UNIT, "ms_per_frame": ms_fwd / K},
+        "edit": {"value": N * K / (ms_edit * 1e-3), "unit": UNIT, "ms_per_frame": ms_edit / K, "deform_ms": deform_ms,
+                 "workload": f"{EDIT_P} mesh-bound Gaussians (5,120-face proxy mesh), deformed once, {EDIT_VIEWS}-frame orbit "
+                             f"at {WIDTH}x{HEIGHT}: rotated-direction SH colours + forward with precomputed colour/covariance"},
         "clocks": clocks,
     }
     if args.impl == "reference":

@@ -82,6 +82,42 @@ def mesh_bind(bc_logits, distance, log_scale, rot_raw, opacity_logit, vertex1, v
                            r, alpha_distance)
 
 
+class _Activate(torch.autograd.Function):
+    """exp / normalise / sigmoid of a plain GaussianModel (scene/gaussian_model.py:27-41,96-116) in one kernel."""
+
+    @staticmethod
+    def forward(ctx, log_scale, rot_raw, opacity_logit):
+        log_scale, rot_raw, opacity_logit = map(_c, (log_scale, rot_raw, opacity_logit))
+        P = log_scale.shape[0]
+        dev = log_scale.device
+        scale = torch.empty(P, 3, dtype=torch.float32, device=dev)
+        rot = torch.empty(P, 4, dtype=torch.float32, device=dev)
+        opacity = torch.empty(P, 1, dtype=torch.float32, device=dev)
+        check(lib.gm_mesh_bind_forward(P, None, None, None, None, None, None, None, 0.0, _p(log_scale), _p(rot_raw),
+                                       _p(opacity_logit), None, _p(scale), _p(rot), _p(opacity), _stream()),
+              "gm_mesh_bind_forward")
+        ctx.save_for_backward(log_scale, rot_raw, opacity_logit)
+        return scale, rot, opacity
+
+    @staticmethod
+    def backward(ctx, g_scale, g_rot, g_opacity):
+        log_scale, rot_raw, opacity_logit = ctx.saved_tensors
+        P = log_scale.shape[0]
+        dev = log_scale.device
+        g_scale, g_rot, g_opacity = map(_c, (g_scale, g_rot, g_opacity))
+        alloc = lambda g, n: (torch.zeros if g is None else torch.empty)(P, n, dtype=torch.float32, device=dev)
+        d_ls, d_rr, d_ol = alloc(g_scale, 3), alloc(g_rot, 4), alloc(g_opacity, 1)
+        check(lib.gm_mesh_bind_backward(P, None, None, None, None, None, None, None, 0.0, _p(log_scale), _p(rot_raw),
+                                        _p(opacity_logit), None, _p(g_scale), _p(g_rot), _p(g_opacity), None, None,
+                                        _p(d_ls), _p(d_rr), _p(d_ol), _stream()), "gm_mesh_bind_backward")
+        return d_ls, d_rr, d_ol
+
+
+def activate(log_scale, rot_raw, opacity_logit):
+    """(get_scaling, get_rotation, get_opacity) of a plain GaussianModel, fused and differentiable."""
+    return _Activate.apply(log_scale, rot_raw, opacity_logit)
+
+
 def deform_gaussians(vertex_rest, vertex_deformed, vertex_R, vertex_S, gaussian_triangles, weights, pos, cov,
                      want_rot: bool = True):
     """SingleObjectDeform.deform_gaussian.  `cov` is [P,6] packed or [P,3,3] full.

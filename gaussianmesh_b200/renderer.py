@@ -120,6 +120,41 @@ class MeshGaussianModel:
     def get_number(self): return self._bc.shape[0]
 
 
+class GaussianModel:
+    """Accessors of the plain (background) GaussianModel, scene/gaussian_model.py:96-116, with the three
+    activations in one fused kernel."""
+
+    def __init__(self, arrays: Dict[str, np.ndarray], device, sh_degree: int = 3, requires_grad: bool = True):
+        t = lambda k: torch.from_numpy(np.ascontiguousarray(arrays[k])).to(device)
+        self._xyz = t("means3D").requires_grad_(requires_grad)
+        self._scaling = t("log_scales").requires_grad_(requires_grad)
+        self._rotation = t("rot_raw" if "rot_raw" in arrays else "rotations").requires_grad_(requires_grad)
+        self._opacity = t("opacity_logit").requires_grad_(requires_grad)
+        self._features = t("shs").requires_grad_(requires_grad)
+        self.active_sh_degree = sh_degree
+        self.max_sh_degree = 3
+        self.screenspace_points = torch.zeros(self._xyz.shape[0], 3, device=device, requires_grad=requires_grad)
+
+    def parameters(self) -> List[torch.Tensor]:
+        return [self._xyz, self._scaling, self._rotation, self._opacity, self._features]
+
+    def activate(self):
+        """(xyz, scaling, rotation, opacity)"""
+        s, r, o = mg.activate(self._scaling, self._rotation, self._opacity)
+        return self._xyz, s, r, o
+
+    @property
+    def get_xyz(self): return self._xyz
+    @property
+    def get_scaling(self): return self.activate()[1]
+    @property
+    def get_rotation(self): return self.activate()[2]
+    @property
+    def get_opacity(self): return self.activate()[3]
+    @property
+    def get_features(self): return self._features
+
+
 @dataclass
 class PipelineParams:
     """arguments/__init__.py:64-69; only the CUDA branches are implemented on this path."""
@@ -145,6 +180,39 @@ def render(viewpoint_camera, pc: MeshGaussianModel, pipe: PipelineParams, bg_col
                                        rotations=rotations, cov3D_precomp=None)
     return {"render": rendered_image, "viewspace_points": screenspace_points, "visibility_filter": radii > 0,
             "radii": radii, "vertex1": pc.vertex1, "vertex2": pc.vertex2, "vertex3": pc.vertex3, "scale": scales}
+
+
+def bg_render(viewpoint_camera, pc: GaussianModel, pipe: PipelineParams, bg_color: torch.Tensor,
+              scaling_modifier: float = 1.0, override_color: Optional[torch.Tensor] = None,
+              mesh_gaussians: Optional[MeshGaussianModel] = None, arena: Optional[RenderArena] = None
+              ) -> Dict[str, torch.Tensor]:
+    """reference gaussian_renderer/__init__.py:146-260: the background model is trainable, the mesh-bound
+    Gaussians (if given) are appended with their gradients stopped (:223-234)."""
+    if pipe.convert_SHs_python or pipe.compute_cov3D_python:
+        raise NotImplementedError("the Python SH / covariance fallbacks are the reference's slow path; "
+                                  "this renderer always uses the CUDA branches")
+    screenspace_points = pc.screenspace_points
+    means3D, scales, rotations, opacity = pc.activate()
+    shs, colors_precomp = (pc.get_features, None) if override_color is None else (None, override_color)
+    if mesh_gaussians is not None:
+        if shs is None:
+            raise Exception("override_color cannot be combined with mesh_gaussians (the reference concatenates SHs)")
+        screenspace_points = torch.cat([screenspace_points, mesh_gaussians.screenspace_points], dim=0)
+        with torch.no_grad():
+            m_xyz, m_scale, m_rot, m_opacity = mesh_gaussians.activate()
+            m_shs = mesh_gaussians.get_features.detach()
+        means3D = torch.cat([means3D, m_xyz], dim=0)
+        scales = torch.cat([scales, m_scale], dim=0)
+        rotations = torch.cat([rotations, m_rot], dim=0)
+        shs = torch.cat([shs, m_shs], dim=0)
+        opacity = torch.cat([opacity, m_opacity], dim=0)
+    raster_settings = make_settings(viewpoint_camera, bg_color, pc.active_sh_degree, scaling_modifier, pipe.debug)
+    rasterizer = GaussianRasterizer(raster_settings=raster_settings, arena=arena)
+    rendered_image, radii = rasterizer(means3D=means3D, means2D=screenspace_points, shs=shs,
+                                       colors_precomp=colors_precomp, opacities=opacity, scales=scales,
+                                       rotations=rotations, cov3D_precomp=None)
+    return {"render": rendered_image, "viewspace_points": screenspace_points, "visibility_filter": radii > 0,
+            "radii": radii}
 
 
 # ---------------------------------------------------------------------------------------------

@@ -133,3 +133,31 @@ class RefFrame:
         if M == 0:
             g["sh"] = g["sh"][:, :0]
         return g
+
+
+def edit_colors_torch(pos: torch.Tensor, campos: torch.Tensor, rot: torch.Tensor, shs: torch.Tensor, deg: int = 3) -> torch.Tensor:
+    """The reference's per-frame edit colours (edittool/__init__.py:442-448 + edittool/sh_utils.py:34-89) as the
+    same chain of elementwise / bmm tensor ops the Jittor code runs (torch standing in for Jittor)."""
+    C0 = 0.28209479177387814; C1 = 0.4886025119029199
+    C2 = [1.0925484305920792, -1.0925484305920792, 0.31539156525252005, -1.0925484305920792, 0.5462742152960396]
+    C3 = [-0.5900435899266435, 2.890611442640554, -0.4570457994644658, 0.3731763325901154, -0.4570457994644658,
+          1.445305721320277, -0.5900435899266435]
+    sh = shs.transpose(1, 2)
+    d = pos - campos.repeat(pos.shape[0], 1)
+    d = d / d.norm(dim=1, keepdim=True)
+    d = torch.matmul(rot.transpose(1, 2), d.unsqueeze(2)).squeeze(2)
+    result = C0 * sh[..., 0]
+    if deg > 0:
+        x, y, z = d[..., 0:1], d[..., 1:2], d[..., 2:3]
+        result = result - C1 * y * sh[..., 1] + C1 * z * sh[..., 2] - C1 * x * sh[..., 3]
+        if deg > 1:
+            xx, yy, zz = x * x, y * y, z * z
+            xy, yz, xz = x * y, y * z, x * z
+            result = (result + C2[0] * xy * sh[..., 4] + C2[1] * yz * sh[..., 5] + C2[2] * (2.0 * zz - xx - yy) * sh[..., 6]
+                      + C2[3] * xz * sh[..., 7] + C2[4] * (xx - yy) * sh[..., 8])
+            if deg > 2:
+                result = (result + C3[0] * y * (3 * xx - yy) * sh[..., 9] + C3[1] * xy * z * sh[..., 10]
+                          + C3[2] * y * (4 * zz - xx - yy) * sh[..., 11] + C3[3] * z * (2 * zz - 3 * xx - 3 * yy) * sh[..., 12]
+                          + C3[4] * x * (4 * zz - xx - yy) * sh[..., 13] + C3[5] * z * (xx - yy) * sh[..., 14]
+                          + C3[6] * x * (xx - 3 * yy) * sh[..., 15])
+    return torch.clamp(result + 0.5, min=0.0)

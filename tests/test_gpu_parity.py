@@ -529,3 +529,41 @@ def test_edit_render_matches_reference_rasterizer(cuda_device):
                cam, bgt, 3, "colors+cov", M=16)
     assert int((ref.radii > 0).sum()) > P // 4
     assert float((img - ref.color).abs().max()) <= FWD_TOL
+
+
+def test_bg_render_with_frozen_mesh_gaussians(cuda_device):
+    """bg_render (gaussian_renderer/__init__.py:146-260): trainable background model + mesh-bound Gaussians with
+    stopped gradients, against the reference rasterizer on the concatenated activations."""
+    _need_ref()
+    from gaussianmesh_b200 import synthetic
+    from gaussianmesh_b200.renderer import GaussianModel, MeshGaussianModel, PipelineParams, bg_render
+    dev = cuda_device
+    W, H = 320, 200
+    bg_arrays = synthetic.gaussian_scene(6_000, seed=21, extent=3.0, log_scale_mean=math.log(0.03))
+    V, F = synthetic.icosphere(3)
+    mesh_arrays = synthetic.mesh_bound_scene(5_000, V, F, seed=22)
+    pc = GaussianModel(bg_arrays, dev)
+    mesh = MeshGaussianModel(mesh_arrays, dev)
+    cam = scenes.camera(dev, W, H, index=4)
+    bgt = torch.tensor([0.05, 0.1, 0.15], device=dev)
+    out = bg_render(cam, pc, PipelineParams(), bgt, mesh_gaussians=mesh)
+    dL = (torch.rand(3, H, W, generator=torch.Generator().manual_seed(5)) - 0.5).to(dev)
+    out["render"].backward(dL)
+    assert mesh._bc.grad is None and mesh._features.grad is None          # stop_grad on the mesh set
+    with torch.no_grad():
+        xyz_b, s_b, r_b, o_b = pc.activate()
+        xyz_m, s_m, r_m, o_m = mesh.activate()
+    sc = {"means3D": torch.cat([xyz_b, xyz_m]).contiguous(), "scales": torch.cat([s_b, s_m]).contiguous(),
+          "rotations": torch.cat([r_b, r_m]).contiguous(), "opacities": torch.cat([o_b, o_m]).contiguous(),
+          "shs": torch.cat([pc._features.detach(), mesh._features.detach()]).contiguous()}
+    ref = _ref(sc, cam, bgt, 3, "sh")
+    assert torch.equal(out["radii"], ref.radii)
+    assert float((out["render"].detach() - ref.color).abs().max()) <= FWD_TOL
+    rg = ref.backward(dL)
+    n = 6_000
+    assert scenes.rel_err(pc._xyz.grad, rg["means3D"][:n]) <= BWD_TOL
+    assert scenes.rel_err(pc._features.grad, rg["sh"][:n]) <= BWD_TOL
+    # through the activations: d/dlog_scale = dscale * scale, d/dlogit = dopacity * o (1 - o)
+    assert scenes.rel_err(pc._scaling.grad, rg["scales"][:n] * s_b) <= BWD_TOL
+    assert scenes.rel_err(pc._opacity.grad, rg["opacity"][:n] * o_b * (1 - o_b)) <= BWD_TOL
+    assert scenes.rel_err(pc.screenspace_points.grad, rg["means2D"][:n]) <= BWD_TOL
