@@ -258,6 +258,62 @@ class DeformedObject:
         return image
 
 
+class SceneRenderer:
+    """SceneVisualTool (edittool/__init__.py:133-231): a static background Gaussian set plus any number of
+    deformable mesh-bound objects rendered together.
+
+    The reference re-concatenates every attribute of every set on every frame, factorises the covariances
+    back into (scale, quaternion) with a batched `eigh` plus a host-side determinant sign fix, and renders
+    through the scale/rotation path with the un-rotated SHs (:181-219).  Sigma = V diag(lambda) V^T is the
+    covariance it started from, so this class renders the same Gaussians through the precomputed-covariance path
+    directly (SHs evaluated in CUDA, M forced to 16 as in rasterize_points_deformed.py): no eigh, no host
+    round trip, and the concatenation is rebuilt only when an object is added or deformed."""
+
+    def __init__(self, device, bg_means3D=None, bg_cov=None, bg_opacity=None, bg_shs=None):
+        self.device = torch.device(device)
+        self.objects: List[DeformedObject] = []
+        f = lambda a: None if a is None else torch.as_tensor(a, dtype=torch.float32).contiguous().to(self.device)
+        self.bg = None if bg_means3D is None else (f(bg_means3D), _pack_cov(f(bg_cov)), f(bg_opacity), f(bg_shs))
+        self._cat = None
+        self.arena = RenderArena(self.device, strict=False)
+
+    def add_gaussian(self, obj: "DeformedObject") -> None:
+        self.objects.append(obj)
+        self._cat = None
+
+    def deform_one_gaussian(self, index: int, vertex_deformed, vertex_R, vertex_S) -> None:
+        self.objects[index].deform(vertex_deformed, vertex_R, vertex_S)
+        self._cat = None
+
+    def _gather(self):
+        if self._cat is None:
+            parts = ([self.bg] if self.bg is not None else []) + \
+                    [(o.deform_pos, o.deform_cov6, o.opacity, o.shs) for o in self.objects]
+            self._cat = tuple(torch.cat([p[i] for p in parts], dim=0).contiguous() for i in range(4))
+        return self._cat
+
+    def render_gaussian(self, cam, bg: Optional[torch.Tensor] = None) -> torch.Tensor:
+        means3D, cov6, opacity, shs = self._gather()
+        if bg is None:
+            bg = torch.ones(3, dtype=torch.float32, device=self.device)      # edittool/__init__.py:166
+        rasterizer = NewGaussianRasterizer(make_settings(cam, bg, 3), arena=self.arena)
+        with torch.no_grad():
+            image, _ = rasterizer(means3D=means3D, means2D=torch.zeros_like(means3D), shs=shs, colors_precomp=None,
+                                  opacities=opacity, scales=None, rotations=None, cov3D_precomp=cov6)
+        bad = self.arena.overflowed
+        if bad:                      # first frames of a new view set: grow and render again
+            self.arena.verify()
+            return self.render_gaussian(cam, bg)
+        return image
+
+
+def _pack_cov(c: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
+    """strip_symmetric (edittool/general_utils.py:26-37) for [P,3,3]; [P,6] passes through."""
+    if c is None or c.dim() == 2:
+        return c
+    return torch.stack([c[:, 0, 0], c[:, 0, 1], c[:, 0, 2], c[:, 1, 1], c[:, 1, 2], c[:, 2, 2]], dim=1).contiguous()
+
+
 # ---------------------------------------------------------------------------------------------
 # sync-free batch rendering of independent views
 # ---------------------------------------------------------------------------------------------

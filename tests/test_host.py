@@ -182,3 +182,49 @@ def test_two_rank_view_shard_over_gloo(tmp_path):
     for i, cam in enumerate(cams):
         img = cpu_oracle.forward(arrays, cam, np.zeros(3, np.float32), 3)["color"]
         assert hashlib.sha1(img.tobytes()).hexdigest() == res["hash"][str(i)]
+
+
+def test_mesh_gaussian_ply_roundtrip_and_schema(tmp_path):
+    """The PLY schema of MeshBasedGaussianModel.save_ply / load_ply (scene/mesh_based_gaussian_model.py:290-409)."""
+    from gaussianmesh_b200 import io, synthetic
+    V, F = synthetic.icosphere(1)
+    a = synthetic.mesh_bound_scene(300, V, F, seed=3)
+    rec = {"xyz": np.random.default_rng(0).normal(size=(300, 3)).astype(np.float32), "normal": a["normal"],
+           "bc_logits": a["bc_logits"], "vertex1": a["vertex1"], "vertex2": a["vertex2"], "vertex3": a["vertex3"],
+           "distance": a["distance"], "vertex_index": a["triangles"], "r": a["r"], "face_id": a["face_id"][:, None],
+           "shs": a["shs"], "opacity_logit": a["opacity_logit"], "log_scales": a["log_scales"], "rot_raw": a["rot_raw"]}
+    path = str(tmp_path / "point_cloud.ply")
+    io.save_mesh_gaussian_ply(path, rec)
+    header = open(path, "rb").read(4096).split(b"end_header")[0].decode()
+    props = [l.split()[-1] for l in header.splitlines() if l.startswith("property")]
+    assert props == io.mesh_gaussian_attributes(45) and len(props) == 24 + 3 + 45 + 1 + 3 + 4
+    assert all(l.split()[1] == "float" for l in header.splitlines() if l.startswith("property"))
+    assert props[:9] == ['x', 'y', 'z', 'nx', 'ny', 'nz', 'ca', 'cb', 'cc'] and props[18:24] == ['dis', 'v_index1', 'v_index2', 'v_index3', 'radius', 'face_id']
+    back = io.load_mesh_gaussian_ply(path)
+    for k in ("xyz", "bc_logits", "vertex1", "vertex2", "vertex3", "normal", "distance", "opacity_logit", "r", "shs",
+              "log_scales", "rot_raw"):
+        assert np.array_equal(back[k], rec[k].astype(np.float32)), k
+    assert np.array_equal(back["vertex_index"], a["triangles"]) and np.array_equal(back["face_id"][:, 0], a["face_id"])
+    # f_dc / f_rest are channel-major on disk: f_rest_0..14 are the red channel of coefficients 1..15
+    v = io.read_ply_vertices(path)
+    assert np.array_equal(v["f_rest_0"], a["shs"][:, 1, 0]) and np.array_equal(v["f_rest_15"], a["shs"][:, 1, 1])
+    assert np.array_equal(v["f_dc_2"], a["shs"][:, 0, 2])
+
+
+def test_cameras_json_roundtrip(tmp_path):
+    """camera_to_JSON (utils/camera_utils.py:64-84) <-> ObjectVisualTool.get_camera (edittool/__init__.py:547-584)."""
+    import json
+    from gaussianmesh_b200 import io, synthetic
+    cams = synthetic.orbit_cameras(5, 640, 360)
+    entries = io.cameras_to_json(cams)
+    assert set(entries[0]) == {"id", "img_name", "width", "height", "position", "rotation", "fy", "fx"}
+    assert np.allclose(entries[0]["position"], cams[0].camera_center, atol=1e-5)
+    path = tmp_path / "cameras.json"
+    path.write_text(json.dumps(entries))
+    back = io.load_cameras_json(str(path))
+    for a, b in zip(cams, back):
+        assert (a.image_width, a.image_height) == (b.image_width, b.image_height)
+        assert abs(a.FoVx - b.FoVx) < 1e-6 and abs(a.FoVy - b.FoVy) < 1e-6
+        assert np.allclose(a.world_view_transform, b.world_view_transform, atol=1e-5)
+        assert np.allclose(a.full_proj_transform, b.full_proj_transform, atol=1e-4)
+        assert np.allclose(a.camera_center, b.camera_center, atol=1e-5)
