@@ -233,7 +233,7 @@ blend_backward_kernel(GeometryState g, BinningState b, ImageState img, uint32_t 
 				if (active) {
 					const float cb = q.bid[i].x;
 					// backward.cu:503-534
-					const float rcp = __frcp_rn(1.f - alpha);
+					const float rcp = __fdividef(1.f, 1.f - alpha);   // MUFU.RCP: 1 ulp, far inside the 1e-3 gradient tolerance
 					T = T * rcp;
 					const float dchannel_dcolor = alpha * T;
 					const float keep_prev = 1.f - last_alpha;

@@ -320,10 +320,14 @@ def _pack_cov(c: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
 class ViewBatchRenderer:
     """Forward-render many views of one static Gaussian set on one GPU with no host synchronisation
     inside the loop.  Overflowed frames (arena high-water mark too low) are re-rendered after the
-    batch, so results never depend on the arena size."""
+    batch, so results never depend on the arena size.
+
+    `lanes` > 1 renders that many frames concurrently, each on its own CUDA stream with its own arena: the
+    latency-bound stages of one frame (preprocess, emit, sort) overlap the issue-bound blend of another."""
 
     def __init__(self, device, means3D, opacities, shs=None, colors_precomp=None, scales=None, rotations=None,
-                 cov3D_precomp=None, sh_degree: int = 3, scale_modifier: float = 1.0, force_m: Optional[int] = None):
+                 cov3D_precomp=None, sh_degree: int = 3, scale_modifier: float = 1.0, force_m: Optional[int] = None,
+                 lanes: int = 1):
         self.device = torch.device(device)
         c = lambda t: None if t is None else t.detach().to(self.device, torch.float32).contiguous()
         self.means3D, self.opacities, self.shs = c(means3D), c(opacities), c(shs)
@@ -336,8 +340,13 @@ class ViewBatchRenderer:
         self.D = sh_degree
         self.M = force_m if force_m is not None else (self.shs.shape[1] if self.shs is not None else 0)
         self.scale_modifier = scale_modifier
-        self.arena = RenderArena(self.device, strict=False)
-        self.radii = torch.empty(self.P, dtype=torch.int32, device=self.device)
+        self.lanes = max(1, int(lanes))
+        self.arenas = [RenderArena(self.device, strict=False) for _ in range(self.lanes)]
+        self.arena = self.arenas[0]
+        self._radii = [torch.empty(self.P, dtype=torch.int32, device=self.device) for _ in range(self.lanes)]
+        self.radii = self._radii[0]
+        self._streams = [torch.cuda.Stream(self.device) for _ in range(self.lanes)] if self.lanes > 1 else [None]
+        self._count = 0
 
     def _view_args(self, cam) -> tuple:
         p = lambda t: None if t is None else t.data_ptr()
@@ -347,30 +356,73 @@ class ViewBatchRenderer:
                 math.tan(cam.FoVx * 0.5), math.tan(cam.FoVy * 0.5))
 
     def reserve_for(self, cams: Sequence, bg: torch.Tensor) -> int:
-        """Size the arena for these views up front (setup, not rendering)."""
-        return self.arena.reserve_for_views(self.P, self.D, self.M, bg, cams[0].image_width, cams[0].image_height,
-                                            [self._view_args(c) for c in cams])
+        """Size the arenas for these views up front (setup, not rendering)."""
+        worst = self.arenas[0].reserve_for_views(self.P, self.D, self.M, bg, cams[0].image_width, cams[0].image_height,
+                                                 [self._view_args(c) for c in cams])
+        for a in self.arenas[1:]:
+            a._ensure(self.P, cams[0].image_width * cams[0].image_height)
+            a.high_water = worst
+            a._want = self.arenas[0]._want
+            a.reserve(a._want)
+        return worst
 
-    def render_into(self, cam, bg: torch.Tensor, out: torch.Tensor) -> None:
-        """Enqueue one view; `out` is a [3,H,W] float32 device tensor."""
-        stream = torch.cuda.current_stream(self.device).cuda_stream
-        self.arena.forward(self.P, self.D, self.M, bg, cam.image_width, cam.image_height, self._view_args(cam),
-                           False, False, stream, out_color=out, radii=self.radii)
+    # fork / join of the side streams around a batch (no-ops with one lane)
+    def begin_batch(self) -> None:
+        if self.lanes > 1:
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(self.device))
+            for s in self._streams:
+                s.wait_event(ev)
+
+    def end_batch(self) -> None:
+        if self.lanes > 1:
+            cur = torch.cuda.current_stream(self.device)
+            for s in self._streams:
+                ev = torch.cuda.Event()
+                ev.record(s)
+                cur.wait_event(ev)
+
+    def render_into(self, cam, bg: torch.Tensor, out: torch.Tensor) -> int:
+        """Enqueue one view; `out` is a [3,H,W] float32 device tensor.  Returns the lane used."""
+        lane = self._count % self.lanes
+        self._count += 1
+        va = self._view_args(cam)
+        if self.lanes == 1:
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+            self.arenas[0].forward(self.P, self.D, self.M, bg, cam.image_width, cam.image_height, va, False, False,
+                                   stream, out_color=out, radii=self._radii[0])
+        else:
+            with torch.cuda.stream(self._streams[lane]):
+                self.arenas[lane].forward(self.P, self.D, self.M, bg, cam.image_width, cam.image_height, va, False, False,
+                                          self._streams[lane].cuda_stream, out_color=out, radii=self._radii[lane])
+        return lane
+
+    def verify(self) -> List[Tuple[int, int]]:
+        """(lane, frame-in-lane) of every frame that overflowed its arena; arenas are grown."""
+        return [(l, f) for l, a in enumerate(self.arenas) for f in a.verify()]
 
     def render_views(self, cams: Sequence, bg: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         """Render all `cams` (DeviceCamera) into out [n,3,H,W]; returns it.  One sync at the end."""
         n = len(cams)
         if out is None:
             out = torch.empty(n, 3, cams[0].image_height, cams[0].image_width, dtype=torch.float32, device=self.device)
-        first = self.arena.frames
+        first = [a.frames for a in self.arenas]
+        where = {}
+        self.begin_batch()
         for i, cam in enumerate(cams):
+            lane = self._count % self.lanes
+            where[(lane, self.arenas[lane].frames)] = i
             self.render_into(cam, bg, out[i])
-        for frame in self.arena.verify():          # grown arena; re-render the frames that did not fit
-            i = frame - first
-            if 0 <= i < n:
+        self.end_batch()
+        redo = [where[k] for k in self.verify() if k in where]
+        if redo:
+            self.begin_batch()
+            for i in redo:              # grown arenas; re-render the frames that did not fit
                 self.render_into(cams[i], bg, out[i])
-        if self.arena.verify():
-            raise RuntimeError("arena overflow persisted after growth")   # cannot happen: grown to the high-water mark
+            self.end_batch()
+            if self.verify():
+                raise RuntimeError("arena overflow persisted after growth")   # cannot happen: grown to the high-water mark
+        del first
         return out
 
 

@@ -389,6 +389,12 @@ def test_view_batch_renderer_and_overflow_recovery(cuda_device):
     vb = ViewBatchRenderer(dev, sc["means3D"], sc["opacities"], shs=sc["shs"], scales=sc["scales"], rotations=sc["rotations"])
     batch = vb.render_views(cams, bgt)
     assert torch.equal(batch, singles)
+    # two frames in flight on two streams / arenas give the same images
+    vb3 = ViewBatchRenderer(dev, sc["means3D"], sc["opacities"], shs=sc["shs"], scales=sc["scales"], rotations=sc["rotations"],
+                            lanes=2)
+    assert torch.equal(vb3.render_views(cams, bgt), singles)
+    vb3.arenas[1]._want = 64; vb3.arenas[1].capacity = 0; vb3.arenas[1].high_water = 0; vb3.arenas[1].headroom = 1.0
+    assert torch.equal(vb3.render_views(cams, bgt), singles)      # one lane overflows and recovers
     # an arena that is far too small must be detected, grown and the frames re-rendered
     vb2 = ViewBatchRenderer(dev, sc["means3D"], sc["opacities"], shs=sc["shs"], scales=sc["scales"], rotations=sc["rotations"])
     vb2.arena._want = 64
