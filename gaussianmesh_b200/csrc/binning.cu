@@ -135,20 +135,21 @@ emit_kernel(int P, const int* __restrict__ radii, GeometryState g, BinningState 
 	const int radius = radii[idx];
 	if (!(radius > 0))
 		return;
+	// kept-tile mask recorded by preprocess (zero for culled splats and for rectangles of more than 64 tiles,
+	// which large_tiles_kernel places)
+	unsigned long long kept = g.tile_mask[idx];
+	if (kept == 0ull)
+		return;
 	const float2 xy = g.means2D[idx];
 	int x0, y0, x1, y1;
 	tile_rect(xy, radius, tiles_x, tiles_y, x0, y0, x1, y1);
-	const int area = (x1 - x0) * (y1 - y0);
-	unsigned long long kept = g.tile_mask[idx];
-	if (area <= 64 && kept == 0ull)
-		return;
 	const float depth = g.depths[idx];
 	const uint64_t key = ((uint64_t)__float_as_uint(depth) << 32) | (uint32_t)idx;
 	const uint32_t bucket = g.depth_lut[depth_fine_bin(depth)];
 	uint32_t* const cursor = g.bucket_cursor + bucket;
 
-	if (area <= 64) {
-		// replay the mask preprocess recorded, four instances at a time: the four slot atomics are in flight
+	{
+		// replay the mask, four instances at a time: the four slot atomics are in flight
 		// together, so a Gaussian costs ceil(n/4) memory round trips instead of n
 		const uint32_t w = (uint32_t)(x1 - x0);
 		const uint32_t inv_w = (65536u + w - 1u) / w;       // (bit * inv_w) >> 16 == bit / w for bit < 64, w <= 64
@@ -173,26 +174,47 @@ emit_kernel(int P, const int* __restrict__ radii, GeometryState g, BinningState 
 				if (tiles[u] != 0xffffffffu && pos[u] < capacity)
 					b.keys[pos[u]] = key;
 		}
-		return;
 	}
+}
 
-	// large rectangle: re-evaluate the culling exactly as preprocess did
-	const float4 co = g.conic_opacity[idx];
-	const float thr = cull_threshold(co.w);
-	if (thr < 0.0f)
-		return;
-	for (int ty = y0; ty < y1; ty++) {
-		const float py0 = (float)(ty * kTile);
-		const float py1 = fminf(py0 + (kTile - 1), (float)(H - 1));
-		for (int tx = x0; tx < x1; tx++) {
-			const float px0 = (float)(tx * kTile);
+// ------------------------------------------------------------------------------------------------
+// large_tiles: Gaussians whose tile rectangle exceeds 64 tiles (close-up splats).  One warp per Gaussian,
+// lanes stride over the rectangle.  The SAME kernel binary runs the count pass (phase 0, before tile_scan)
+// and the placement pass (phase 1, with emit), so the culling predicate gives identical answers in both.
+// ------------------------------------------------------------------------------------------------
+constexpr int kLargeThreads = 256;
+
+__global__ void __launch_bounds__(kLargeThreads)
+large_tiles_kernel(int phase, const int* __restrict__ radii, GeometryState g, uint64_t* __restrict__ keys,
+                   uint32_t capacity, int W, int H, int tiles_x, int tiles_y, int bucket_log2)
+{
+	const int lane = threadIdx.x & 31;
+	const uint32_t warps = gridDim.x * (kLargeThreads / 32);
+	const uint32_t n = g.header->num_large;
+	for (uint32_t e = blockIdx.x * (kLargeThreads / 32) + (threadIdx.x >> 5); e < n; e += warps) {
+		const uint32_t idx = g.large_list[e];
+		const float4 co = g.conic_opacity[idx];
+		const float thr = cull_threshold(co.w);
+		if (thr < 0.0f)
+			continue;
+		const float2 xy = g.means2D[idx];
+		const float depth = g.depths[idx];
+		const uint64_t key = ((uint64_t)__float_as_uint(depth) << 32) | idx;
+		uint32_t* const cursor = g.bucket_cursor + g.depth_lut[depth_fine_bin(depth)];
+		int x0, y0, x1, y1;
+		tile_rect(xy, radii[idx], tiles_x, tiles_y, x0, y0, x1, y1);
+		const int w = x1 - x0, area = w * (y1 - y0);
+		for (int t = lane; t < area; t += 32) {
+			const int ty = y0 + t / w, tx = x0 + t % w;
+			const float px0 = (float)(tx * kTile), py0 = (float)(ty * kTile);
 			const float px1 = fminf(px0 + (kTile - 1), (float)(W - 1));
+			const float py1 = fminf(py0 + (kTile - 1), (float)(H - 1));
 			if (rect_cannot_contribute(xy.x, xy.y, co.x, co.y, co.z, thr, px0, py0, px1, py1))
 				continue;
 			const uint32_t tile = (uint32_t)(ty * tiles_x + tx);
 			const uint32_t pos = atomicAdd(&cursor[(size_t)tile << bucket_log2], 1u);
-			if (pos < capacity)
-				b.keys[pos] = key;
+			if (phase == 1 && pos < capacity)
+				keys[pos] = key;
 		}
 	}
 }
@@ -388,6 +410,14 @@ int launch_tile_scan(int num_tiles, const GeometryState& g, uint32_t capacity, c
 	return GM_OK;
 }
 
+int launch_large_tiles(int phase, const int* radii, const GeometryState& g, const BinningState* b, uint32_t capacity,
+                       const ViewParams& vp, cudaStream_t stream)
+{
+	large_tiles_kernel<<<148, kLargeThreads, 0, stream>>>(phase, radii, g, b ? b->keys : nullptr, capacity, vp.W, vp.H,
+	                                                     vp.tiles_x, vp.tiles_y, vp.bucket_log2);
+	return GM_OK;
+}
+
 int launch_emit(int P, const int* radii, const GeometryState& g, const BinningState& b, uint32_t capacity,
                 const ViewParams& vp, cudaStream_t stream)
 {
@@ -395,6 +425,7 @@ int launch_emit(int P, const int* radii, const GeometryState& g, const BinningSt
 		return GM_OK;
 	emit_kernel<<<(P + kEmitThreads - 1) / kEmitThreads, kEmitThreads, 0, stream>>>(
 		P, radii, g, b, capacity, vp.W, vp.H, vp.tiles_x, vp.tiles_y, vp.bucket_log2);
+	launch_large_tiles(1, radii, g, &b, capacity, vp, stream);
 	return GM_OK;
 }
 

@@ -16,6 +16,10 @@ int launch_preprocess(int P, const float* means3D, const float* scales, const fl
 
 int launch_tile_scan(int num_tiles, const GeometryState& g, uint32_t capacity, const ViewParams& vp, cudaStream_t stream);
 
+// phase 0: count the instances of the large-rectangle Gaussians per (tile, bucket); phase 1: place them.
+int launch_large_tiles(int phase, const int* radii, const GeometryState& g, const BinningState* b, uint32_t capacity,
+                       const ViewParams& vp, cudaStream_t stream);
+
 int launch_emit(int P, const int* radii, const GeometryState& g, const BinningState& b, uint32_t capacity,
                 const ViewParams& vp, cudaStream_t stream);
 

@@ -241,18 +241,23 @@ preprocess_kernel(int P,
 				const int ty_lo = tight ? max(y0, (int)floorf((point_image.y - ey) * (1.0f / kTile))) : y0;
 				const int ty_hi = tight ? min(y1, (int)floorf((point_image.y + ey) * (1.0f / kTile)) + 1) : y1;
 				const int w = x1 - x0;
-				for (int ty = ty_lo; ty < ty_hi; ty++) {
-					const float py0 = (float)(ty * kTile);
-					const float py1 = fminf(py0 + (kTile - 1), (float)(vp.H - 1));
-					for (int tx = tx_lo; tx < tx_hi; tx++) {
-						const float px0 = (float)(tx * kTile);
-						const float px1 = fminf(px0 + (kTile - 1), (float)(vp.W - 1));
-						if (!rect_cannot_contribute(point_image.x, point_image.y, conic.x, conic.y, conic.z, thr,
-						                            px0, py0, px1, py1)) {
-							atomicAdd(&g.bucket_cursor[((size_t)(ty * vp.tiles_x + tx) << vp.bucket_log2) + bucket], 1u);
-							const int bit = (ty - y0) * w + (tx - x0);
-							if (bit < 64)
-								kept |= 1ull << bit;
+				if (w * (y1 - y0) > 64) {
+					// too many tiles for a 64-bit mask (and for one thread): large_tiles_kernel walks this rectangle
+					// with a whole warp, once to count and once to place, in ONE kernel binary so both passes agree
+					g.large_list[atomicAdd(&g.header->num_large, 1u)] = (uint32_t)idx;
+				} else {
+					for (int ty = ty_lo; ty < ty_hi; ty++) {
+						const float py0 = (float)(ty * kTile);
+						const float py1 = fminf(py0 + (kTile - 1), (float)(vp.H - 1));
+						uint32_t* const row = g.bucket_cursor + (((size_t)ty * vp.tiles_x) << vp.bucket_log2) + bucket;
+						for (int tx = tx_lo; tx < tx_hi; tx++) {
+							const float px0 = (float)(tx * kTile);
+							const float px1 = fminf(px0 + (kTile - 1), (float)(vp.W - 1));
+							if (!rect_cannot_contribute(point_image.x, point_image.y, conic.x, conic.y, conic.z, thr,
+							                            px0, py0, px1, py1)) {
+								atomicAdd(&row[(size_t)tx << vp.bucket_log2], 1u);
+								kept |= 1ull << ((ty - y0) * w + (tx - x0));
+							}
 						}
 					}
 				}
@@ -308,6 +313,7 @@ int launch_preprocess(int P, const float* means3D, const float* scales, const fl
 	else
 		preprocess_kernel<false><<<grid, kThreads, 0, stream>>>(
 			P, means3D, scales, rotations, opacities, shs, cov3D_precomp, colors_precomp, vp, radii, g, prefiltered);
+	launch_large_tiles(0, radii, g, nullptr, 0, vp, stream);      // count pass for rectangles of more than 64 tiles
 	return GM_OK;
 }
 

@@ -44,7 +44,8 @@ struct FrameHeader {
 	uint32_t capacity;       // binning capacity in instances used for this frame
 	uint32_t num_tiles;
 	uint32_t bucket_log2;
-	uint32_t pad[26];
+	uint32_t num_large;      // Gaussians whose tile rectangle exceeds 64 tiles (walked by large_tiles_kernel)
+	uint32_t pad[25];
 };
 static_assert(sizeof(FrameHeader) == 128, "FrameHeader must be one 128-byte line");
 
@@ -57,6 +58,7 @@ struct GeometryState {
 	float4* conic_opacity;    // [P]   (a, b, c, opacity)                          (forward.cu:253)
 	float4* rgb_clamp;        // [P]   (r, g, b, clamp bits as uint)               (forward.cu:63-70)
 	unsigned long long* tile_mask;   // [P] bit (ty-y0)*(x1-x0)+(tx-x0): tile kept by the exact culling (rects of <= 64 tiles)
+	uint32_t* large_list;     // [P] ids of the Gaussians with rectangles of more than 64 tiles
 	uint32_t* tile_count;     // [GM_MAX_TILES] instances per tile after exact tile culling
 	uint32_t* tile_start;     // [GM_MAX_TILES] first instance of the tile (multiple of kSegAlign)
 	uint32_t* bucket_cursor;  // [kMaxBucketEntries] per (tile, bucket): count -> start -> end (see binning.cu)
@@ -110,6 +112,7 @@ inline GeometryState GeometryState::fromChunk(char*& chunk, size_t P)
 	obtain(chunk, g.conic_opacity, P);
 	obtain(chunk, g.rgb_clamp, P);
 	obtain(chunk, g.tile_mask, P);
+	obtain(chunk, g.large_list, P);
 	obtain(chunk, g.tile_count, (size_t)GM_MAX_TILES);
 	obtain(chunk, g.tile_start, (size_t)GM_MAX_TILES);
 	obtain(chunk, g.bucket_cursor, kMaxBucketEntries);

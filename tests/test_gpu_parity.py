@@ -82,6 +82,8 @@ CASES = [
     ("colors_scalerot", 4_000, 128, 128, 3, "colors", (0.2, 0.2, 0.2), {}),
     ("big_splats", 3_000, 160, 160, 3, "sh", (0.0, 0.0, 0.0), {"log_scale_mean": math.log(0.15)}),
     ("dense_small_image", 20_000, 64, 48, 3, "sh", (0.1, 0.1, 0.1), {"log_scale_mean": math.log(0.05), "extent": 1.0}),
+    # splats whose tile rectangle exceeds 64 tiles: emit re-evaluates the culling instead of replaying the mask
+    ("huge_splats", 600, 400, 400, 3, "sh", (0.0, 0.0, 0.0), {"log_scale_mean": math.log(0.8), "extent": 1.5}),
 ]
 
 
@@ -164,6 +166,7 @@ def test_final_transmittance_matches(cuda_device):
 
 GRAD_CASES = [
     ("sh3_scalerot", 10_000, 256, 256, 3, "sh", (0.0, 0.0, 0.0)),
+    ("huge_splats", 400, 320, 320, 3, "sh", (0.0, 0.0, 0.0)),
     ("colors_cov_bg", 6_000, 200, 136, 3, "colors+cov", (0.4, 0.7, 1.0)),
     ("sh1_scalerot_bg", 6_000, 128, 128, 1, "sh", (1.0, 1.0, 1.0)),
 ]
@@ -173,7 +176,7 @@ GRAD_CASES = [
 def test_backward_matches_reference(cuda_device, name, P, W, H, degree, variant, bg):
     _need_ref()
     dev = cuda_device
-    sc = _scene(dev, P, seed=11, grad=True)
+    sc = _scene(dev, P, seed=11, grad=True, **({"log_scale_mean": math.log(0.8), "extent": 1.5} if name == "huge_splats" else {}))
     cam = scenes.camera(dev, W, H, index=3)
     bgt = torch.tensor(bg, dtype=torch.float32, device=dev)
     color, radii = _ours(sc, cam, bgt, degree, variant)
