@@ -449,7 +449,8 @@ def main():
                        "peak_source": peak_src, "unit": "GB/s", "frac": stages[top].get("frac_of_hbm_peak"),
                        "traffic": traffic, "algorithmic_bytes": alg.get(top)}
     out["stages"] = stages
-    out["gpu_launches"] = int(sum(v[1] for v in prof.values()))
+    kernels_per_stage = {"depth_buckets": 2, "preprocess": 2, "emit": 2, "sort_pack": 2}    # the rest launch one kernel
+    out["gpu_launches"] = int(sum(v[1] * kernels_per_stage.get(k, 1) for k, v in prof.items()))
     out["host_enqueue_ms_per_step"] = enqueue_ms / K
     out["ms_per_step_with_stage_events"] = ms_prof / K
     out["instances_per_frame"] = need
