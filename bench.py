@@ -54,6 +54,7 @@ def parse_args():
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--gaussians", type=int, default=P_GAUSS, help="debug only: a smaller scene is NOT the benchmark")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-presize", action="store_true", help="profiling runs: skip the arena sizing pass over the views")
     ap.add_argument("--cpu-sample-frames", type=int, default=1)
     return ap.parse_args()
 
@@ -275,7 +276,8 @@ def main():
     arm = OursArm(device, scene, WIDTH, HEIGHT) if args.impl == "ours" else ReferenceArm(device, scene, WIDTH, HEIGHT)
     K, Wm = args.steps, args.warmup
     nv = len(cams)
-    arm.setup(cams, bg)
+    if not args.no_presize:
+        arm.setup(cams, bg)
 
     # ---------------------------------------------------------------- (1) device-resident training frames
     def train_resident(i):

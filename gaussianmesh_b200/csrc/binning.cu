@@ -360,26 +360,21 @@ bucket_sort_pack_kernel(GeometryState g, BinningState b, uint32_t capacity, int 
 	else if (n <= 64) warp_sort_pack<2>(g, b, s0, n, lane);
 	else if (n <= 128) warp_sort_pack<4>(g, b, s0, n, lane);
 	else if (n <= kWarpSortMax) warp_sort_pack<8>(g, b, s0, n, lane);
-	// larger buckets are left to big_bucket_sort_pack_kernel
+	else if (lane == 0) g.big_list[atomicAdd(&g.header->num_big, 1u)] = gw;   // left to big_bucket_sort_pack_kernel
 }
 
-// One BLOCK per tile: the buckets the warp kernel skipped (more than kWarpSortMax instances).
+// The buckets the warp kernel skipped (more than kWarpSortMax instances), one BLOCK per bucket, taken from the
+// list the warp kernel filled.  A fixed small grid: with no oversized bucket the kernel is a few microseconds.
 __global__ void __launch_bounds__(kSortThreads)
 big_bucket_sort_pack_kernel(GeometryState g, BinningState b, uint32_t capacity, int bucket_log2)
 {
 	__shared__ uint64_t s_keys[kSortSmem];
-	const int tile = blockIdx.x;
-	const uint32_t tile_start = g.tile_start[tile];
-	if (tile_start >= capacity || g.tile_count[tile] <= (uint32_t)kWarpSortMax)
-		return;
-	const int B = 1 << bucket_log2;
-	const uint32_t* ends = g.bucket_cursor + ((size_t)tile << bucket_log2);
-	for (int bk = 0; bk < B; bk++) {
-		const uint32_t s0 = (bk == 0) ? tile_start : ends[bk - 1];
-		const uint32_t s1 = min(ends[bk], capacity);
-		if (s0 >= s1 || s1 - s0 <= (uint32_t)kWarpSortMax)
-			continue;                                  // uniform over the block
-		const uint32_t n = s1 - s0;
+	const uint32_t num_big = g.header->num_big;
+	for (uint32_t e = blockIdx.x; e < num_big; e += gridDim.x) {
+		const uint32_t gw = g.big_list[e];
+		const uint32_t bk = gw & ((1u << bucket_log2) - 1u);
+		const uint32_t s0 = (bk == 0) ? g.tile_start[gw >> bucket_log2] : g.bucket_cursor[gw - 1];
+		const uint32_t n = min(g.bucket_cursor[gw], capacity) - s0;
 		uint64_t* keys = b.keys + s0;
 		const uint64_t* sorted;
 		if (n <= kSortSmem) {
@@ -390,13 +385,12 @@ big_bucket_sort_pack_kernel(GeometryState g, BinningState b, uint32_t capacity, 
 			sorted = s_keys;
 		} else {
 			// longer than shared memory holds: in place in global memory (rare, slow, still exact)
-			__syncthreads();
 			block_bitonic(keys, n);
 			sorted = keys;
 		}
 		for (uint32_t i = threadIdx.x; i < n; i += kSortThreads)
 			pack_one(g, b, s0 + i, (uint32_t)sorted[i]);
-		__syncthreads();   // s_keys is reused by the next oversized bucket
+		__syncthreads();   // s_keys is reused by the next bucket
 	}
 }
 
@@ -437,7 +431,7 @@ int launch_sort_pack(int num_tiles, const GeometryState& g, const BinningState& 
 	const uint32_t total = (uint32_t)num_tiles << vp.bucket_log2;
 	bucket_sort_pack_kernel<<<(total + kSortWarps - 1) / kSortWarps, kSortThreads, 0, stream>>>(
 		g, b, capacity, vp.bucket_log2, total);
-	big_bucket_sort_pack_kernel<<<num_tiles, kSortThreads, 0, stream>>>(g, b, capacity, vp.bucket_log2);
+	big_bucket_sort_pack_kernel<<<148 * 4, kSortThreads, 0, stream>>>(g, b, capacity, vp.bucket_log2);
 	return GM_OK;
 }
 

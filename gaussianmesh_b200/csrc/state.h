@@ -45,7 +45,8 @@ struct FrameHeader {
 	uint32_t num_tiles;
 	uint32_t bucket_log2;
 	uint32_t num_large;      // Gaussians whose tile rectangle exceeds 64 tiles (walked by large_tiles_kernel)
-	uint32_t pad[25];
+	uint32_t num_big;        // (tile, bucket) ranges too long for the register sort (big_bucket_sort_pack_kernel)
+	uint32_t pad[24];
 };
 static_assert(sizeof(FrameHeader) == 128, "FrameHeader must be one 128-byte line");
 
@@ -62,6 +63,7 @@ struct GeometryState {
 	uint32_t* tile_count;     // [GM_MAX_TILES] instances per tile after exact tile culling
 	uint32_t* tile_start;     // [GM_MAX_TILES] first instance of the tile (multiple of kSegAlign)
 	uint32_t* bucket_cursor;  // [kMaxBucketEntries] per (tile, bucket): count -> start -> end (see binning.cu)
+	uint32_t* big_list;       // [kMaxBucketEntries] flat (tile, bucket) ids of the oversized buckets
 	unsigned long long* scan_state;  // [kMaxScanBlocks + 1] chained-scan descriptors (flag << 32 | value) + ticket
 	uint32_t* depth_hist;     // [kDepthBins] visible-depth histogram of this frame
 	uint8_t* depth_lut;       // [kDepthBins] fine depth bin -> bucket (monotone)
@@ -116,6 +118,7 @@ inline GeometryState GeometryState::fromChunk(char*& chunk, size_t P)
 	obtain(chunk, g.tile_count, (size_t)GM_MAX_TILES);
 	obtain(chunk, g.tile_start, (size_t)GM_MAX_TILES);
 	obtain(chunk, g.bucket_cursor, kMaxBucketEntries);
+	obtain(chunk, g.big_list, kMaxBucketEntries);
 	obtain(chunk, g.scan_state, (size_t)kMaxScanBlocks + 1);
 	obtain(chunk, g.depth_hist, (size_t)kDepthBins);
 	obtain(chunk, g.depth_lut, (size_t)kDepthBins);

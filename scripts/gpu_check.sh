@@ -12,8 +12,8 @@ echo "bench ours exit $?"; tail -c 3000 gpurun_out/bench_ours_${tag}.json; tail 
 timeout 600 python bench.py --impl reference --steps 20 --warmup 3 > gpurun_out/bench_ref_${tag}.json 2> gpurun_out/bench_ref_${tag}.err
 echo "bench ref exit $?"; tail -c 2000 gpurun_out/bench_ref_${tag}.json; tail -5 gpurun_out/bench_ref_${tag}.err
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_${tag}.csv \
-    python bench.py --steps 3 --warmup 2 --no-cpu-baseline > gpurun_out/ncu_bench_${tag}.log 2>&1
+    python bench.py --steps 3 --warmup 2 --no-cpu-baseline --no-presize > gpurun_out/ncu_bench_${tag}.log 2>&1
 echo "ncu exit $?"
-timeout 900 ncu --set full --clock-control none --import-source on -k "regex:^(blend|emit|geometry|preprocess|bucket_sort|big_bucket|tile_scan|depth_hist|bucket_lut|l1_kernel)" -s 24 -c 12 -f \
-    -o gpurun_out/prof_${tag} python bench.py --steps 3 --warmup 2 --no-cpu-baseline > gpurun_out/ncu_full_${tag}.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k "regex:^(blend|emit|geometry|preprocess|bucket_sort|big_bucket|large_tiles|tile_scan|depth_hist|bucket_lut|l1_kernel)" -s 32 -c 13 -f \
+    -o gpurun_out/prof_${tag} python bench.py --steps 3 --warmup 2 --no-cpu-baseline --no-presize > gpurun_out/ncu_full_${tag}.log 2>&1
 echo "ncu full exit $?"
