@@ -145,10 +145,19 @@ def build_edit_workload(device, rank, world):
     weights = synthetic.barycentric_weights(pos.cpu().numpy(), V, a["triangles"]).astype(np.float32)
     cov6 = torch.from_numpy(synthetic.packed_covariance(scales.cpu().numpy(), rots.cpu().numpy())).to(device)
     obj = DeformedObject(pos, cov6, opac, t["shs"], a["triangles"], weights, V, device)
-    Vd, R, S = synthetic.twist_bend_deformation(V)
+    Vd, _, _ = synthetic.twist_bend_deformation(V)
+    # per-vertex rotation / shear of the deformation: ACAP GetRS on the GPU (the reference calls pyACAP on the CPU)
+    from gaussianmesh_b200.acap import pyACAP
+    tool = pyACAP((V, F), device=device)
+    tool.GetRS(V, Vd, 1, 0)                                    # warm-up
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    R1, S1 = tool.GetRS(V, Vd, 1, 0)
+    torch.cuda.synchronize()
+    acap_ms = (time.perf_counter() - t0) * 1e3
     cams_host = synthetic.orbit_cameras(EDIT_VIEWS, WIDTH, HEIGHT)
     cams_host = [cams_host[i] for i in shard_views(EDIT_VIEWS, world, rank)]
-    return obj, (Vd, R, S), upload_cameras(cams_host, device)
+    return obj, (Vd, R1.reshape(-1, 3, 3), S1.reshape(-1, 3, 3)), upload_cameras(cams_host, device), acap_ms
 
 
 def timed(fn, steps, warmup, barrier, pre=None, post=None):
@@ -345,7 +354,7 @@ def main():
     ms_fwd = max_over_ranks(ms_fwd)
 
     # ---------------------------------------------------------------- (4) edit path (config 5): deform once, orbit render
-    obj, (Vd, Rv, Sv), edit_cams = build_edit_workload(device, rank, world)
+    obj, (Vd, Rv, Sv), edit_cams, acap_ms = build_edit_workload(device, rank, world)
     white = torch.ones(3, dtype=torch.float32, device=device)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
@@ -399,6 +408,7 @@ def main():
         "forward": {"value": N * K / (ms_fwd * 1e-3), "unit": UNIT, "ms_per_frame": ms_fwd / K,
                     "frames_in_flight": FORWARD_LANES if args.impl == "ours" else 1},
         "edit": {"value": N * K / (ms_edit * 1e-3), "unit": UNIT, "ms_per_frame": ms_edit / K, "deform_ms": deform_ms,
+                 "acap_get_rs_ms": acap_ms,
                  "workload": f"{EDIT_P} mesh-bound Gaussians (5,120-face proxy mesh), deformed once, {EDIT_VIEWS}-frame orbit "
                              f"at {WIDTH}x{HEIGHT}: rotated-direction SH colours + forward with precomputed colour/covariance"},
         "clocks": clocks,

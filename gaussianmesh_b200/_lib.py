@@ -59,6 +59,9 @@ SIGNATURES = {
     "gm_deform_gaussians": (_i, [_i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _i, _p, _p, _p, _p]),
     "gm_sh_to_rgb_rotated": (_i, [_i, _i, _i, _p, _p, _p, _p, _p, _p]),
     "gm_l1_loss": (_i, [_z, _p, _p, _p, _p, _p]),
+    "gm_acap_build_rings": (_i, [_i, _i, _p, _p, _p, _p, _p]),
+    "gm_acap_rest": (_i, [_i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "gm_acap_get_rs": (_i, [_i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
 }
 
 

@@ -46,10 +46,12 @@ int check_stage(const char* what, bool debug, cudaStream_t stream)
 // elapsed times are summed per stage in gm_profile_end.  Used by bench.py for the roofline of the
 // dominant kernel; off by default (no events, no overhead).
 enum Stage { kStDepthBuckets, kStPreprocess, kStTileScan, kStEmit, kStSortPack, kStBlendFwd, kStBlendBwd, kStGeomBwd, kStL1,
-             kStMeshBindFwd, kStMeshBindBwd, kStDeform, kStShRotated, kStMarkVisible, kNumStages };
+             kStMeshBindFwd, kStMeshBindBwd, kStDeform, kStShRotated, kStMarkVisible, kStAcapRest, kStAcapGetRS,
+             kNumStages };
 static const char* const kStageNames[kNumStages] = {
 	"depth_buckets", "preprocess", "tile_scan", "emit", "sort_pack", "blend_forward", "blend_backward", "geometry_backward",
-	"l1_loss", "mesh_bind_forward", "mesh_bind_backward", "deform", "sh_to_rgb_rotated", "mark_visible"};
+	"l1_loss", "mesh_bind_forward", "mesh_bind_backward", "deform", "sh_to_rgb_rotated", "mark_visible", "acap_rest",
+	"acap_get_rs"};
 
 struct StageRecord { int stage; cudaEvent_t start, stop; };
 static std::mutex g_profile_mutex;
@@ -459,6 +461,48 @@ int gm_sh_to_rgb_rotated(int P, int D, int M, const float* pos, const float* cam
 		return GM_ERR_BAD_ARGUMENT;
 	{ StageScope scope_(kStShRotated, (cudaStream_t)stream); launch_sh_rotated(P, D, M, pos, campos, rot, shs, rgb, (cudaStream_t)stream); }
 	return check_stage("sh_to_rgb_rotated", false, (cudaStream_t)stream);
+}
+
+int gm_acap_build_rings(int num_vertices, int num_faces, const int32_t* faces_host, int32_t* ring_offsets_host,
+                        int32_t* ring_neighbours_host, int32_t* face_offsets_host, int32_t* face_list_host)
+{
+	if (num_vertices < 0 || num_faces < 0 || (num_faces > 0 && !faces_host) || !ring_offsets_host || !face_offsets_host ||
+	    (num_faces > 0 && (!ring_neighbours_host || !face_list_host)))
+		return GM_ERR_BAD_ARGUMENT;
+	return acap_build_rings_host(num_vertices, num_faces, faces_host, ring_offsets_host, ring_neighbours_host,
+	                             face_offsets_host, face_list_host);
+}
+
+int gm_acap_rest(int num_vertices, const double* vertex_rest, const int32_t* faces, const int32_t* ring_offsets,
+                 const int32_t* ring_neighbours, const int32_t* face_offsets, const int32_t* face_list,
+                 double* sqrt_w, double* rest_normals, double* ata_inv, gm_stream_t stream)
+{
+	if (num_vertices < 0)
+		return GM_ERR_BAD_ARGUMENT;
+	if (num_vertices > 0 && (!vertex_rest || !faces || !ring_offsets || !ring_neighbours || !face_offsets || !face_list ||
+	                         !sqrt_w || !rest_normals || !ata_inv))
+		return GM_ERR_BAD_ARGUMENT;
+	{ StageScope scope_(kStAcapRest, (cudaStream_t)stream);
+	  launch_acap_rest(num_vertices, vertex_rest, faces, ring_offsets, ring_neighbours, face_offsets, face_list, sqrt_w,
+	                   rest_normals, ata_inv, (cudaStream_t)stream); }
+	return check_stage("acap_rest", false, (cudaStream_t)stream);
+}
+
+int gm_acap_get_rs(int num_vertices, const double* vertex_rest, const double* vertex_deformed, const int32_t* faces,
+                   const int32_t* ring_offsets, const int32_t* ring_neighbours, const int32_t* face_offsets,
+                   const int32_t* face_list, const double* sqrt_w, const double* rest_normals, const double* ata_inv,
+                   double* normals_scratch, float* R_out, float* S_out, gm_stream_t stream)
+{
+	if (num_vertices < 0)
+		return GM_ERR_BAD_ARGUMENT;
+	if (num_vertices > 0 && (!vertex_rest || !vertex_deformed || !faces || !ring_offsets || !ring_neighbours ||
+	                         !face_offsets || !face_list || !sqrt_w || !rest_normals || !ata_inv || !normals_scratch ||
+	                         !R_out || !S_out))
+		return GM_ERR_BAD_ARGUMENT;
+	{ StageScope scope_(kStAcapGetRS, (cudaStream_t)stream);
+	  launch_acap_get_rs(num_vertices, vertex_rest, vertex_deformed, faces, ring_offsets, ring_neighbours, face_offsets,
+	                     face_list, sqrt_w, rest_normals, ata_inv, normals_scratch, R_out, S_out, (cudaStream_t)stream); }
+	return check_stage("acap_get_rs", false, (cudaStream_t)stream);
 }
 
 int gm_l1_loss(size_t numel, const float* img, const float* target, float* loss, float* dL_dimg, gm_stream_t stream)

@@ -58,6 +58,15 @@ int launch_deform(int P, const float* V, const float* Vd, const float* VR, const
 int launch_sh_rotated(int P, int D, int M, const float* pos, const float* campos, const float* rot, const float* shs,
                       float* rgb, cudaStream_t stream);
 
+int launch_acap_rest(int Vn, const double* V, const int* F, const int* ring_off, const int* ring, const int* face_off,
+                     const int* face_list, double* sqrt_w, double* normals, double* ata_inv, cudaStream_t stream);
+
+int launch_acap_get_rs(int Vn, const double* V0, const double* V1, const int* F, const int* ring_off, const int* ring,
+                       const int* face_off, const int* face_list, const double* sqrt_w, const double* n0,
+                       const double* ata_inv, double* n1_scratch, float* R_out, float* S_out, cudaStream_t stream);
+
+int acap_build_rings_host(int Vn, int Fn, const int* F, int* ring_off, int* ring, int* face_off, int* face_list);
+
 int launch_l1(size_t numel, const float* img, const float* target, float* loss, float* dL_dimg, cudaStream_t stream);
 
 } // namespace gm

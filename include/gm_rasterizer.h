@@ -204,6 +204,30 @@ int gm_sh_to_rgb_rotated(int P, int D, int M, const float* pos /*[P,3]*/, const 
                          const float* rot /*[P,3,3] or NULL*/, const float* shs,
                          float* rgb /*[P,3]*/, gm_stream_t stream);
 
+/* ---- ACAP rotation / shear per vertex; replaces pyACAP.pyACAP(mesh).GetRS(ref_V, def_V, _R = 1, ncpu)
+ *      (edittool/__init__.py:102,109; ACAP/pyACAPv1.zip: mainpy.cpp:60-64, src/FeatureVector.cpp:81-173,428-590,
+ *      src/Align.cpp:31-100).  float64 arithmetic like the reference.
+ *
+ *  gm_acap_build_rings (HOST arrays): cyclically ordered one-ring neighbours of every vertex and the vertex ->
+ *  incident-face lists of a triangle mesh.  ring_neighbours_host needs 3*num_faces + num_vertices entries,
+ *  face_list_host 3*num_faces; the two offset arrays num_vertices + 1.
+ *  gm_acap_rest (device, once per rest mesh): per ring entry the factor applied to the edge vector (fourth root of
+ *  the cotangent weight), the unit vertex normals and per vertex (sum p p^T)^-1 (9 doubles, row-major).
+ *  gm_acap_get_rs (device, per deformed mesh): R_out[Vn,3,3] (= the TRANSPOSE of the polar rotation, as pyACAP
+ *  returns it) and S_out[Vn,3,3], float32 row-major, ready for gm_deform_gaussians. */
+int gm_acap_build_rings(int num_vertices, int num_faces, const int32_t* faces_host /*[Fn,3]*/,
+                        int32_t* ring_offsets_host, int32_t* ring_neighbours_host,
+                        int32_t* face_offsets_host, int32_t* face_list_host);
+int gm_acap_rest(int num_vertices, const double* vertex_rest /*[Vn,3]*/, const int32_t* faces /*[Fn,3]*/,
+                 const int32_t* ring_offsets, const int32_t* ring_neighbours, const int32_t* face_offsets,
+                 const int32_t* face_list, double* sqrt_w /*[ring entries]*/, double* rest_normals /*[Vn,3]*/,
+                 double* ata_inv /*[Vn,9]*/, gm_stream_t stream);
+int gm_acap_get_rs(int num_vertices, const double* vertex_rest, const double* vertex_deformed /*[Vn,3]*/,
+                   const int32_t* faces, const int32_t* ring_offsets, const int32_t* ring_neighbours,
+                   const int32_t* face_offsets, const int32_t* face_list, const double* sqrt_w,
+                   const double* rest_normals, const double* ata_inv, double* normals_scratch /*[Vn,3]*/,
+                   float* R_out /*[Vn,3,3]*/, float* S_out /*[Vn,3,3]*/, gm_stream_t stream);
+
 /* ---- L1 loss of config 4 (utils/loss_utils.py:17-18): writes mean|img-target| to *loss and
  *      dL/dimg = sign(img-target)/numel to dL_dimg (may be NULL).  numel = 3*W*H. ------------- */
 int gm_l1_loss(size_t numel, const float* img, const float* target, float* loss /*[1]*/,

@@ -660,3 +660,40 @@ def test_ply_and_cameras_json_feed_the_renderer(cuda_device, tmp_path):
     assert torch.equal(img_mem, img_disk_model)                              # float32 PLY is lossless
     assert float((img_mem - img_disk_cam).abs().max()) <= 2e-3               # camera went through JSON text + inverses
     assert float(img_mem.max()) > 0.05
+
+
+def test_acap_get_rs_matches_golden_and_oracle(cuda_device):
+    """pyACAP.GetRS on the GPU: the reference's own golden vectors (ACAP zip, 1.obj -> 2.obj) and the numpy oracle."""
+    import os
+    from gaussianmesh_b200.acap import pyACAP
+    from gaussianmesh_b200 import synthetic
+    from oracle import acap_np
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "acap_1_to_2.npz"))
+    tool = pyACAP((g["V_rest"], g["F"]), device=cuda_device)
+    R1, S1 = tool.GetRS(g["V_rest"], g["V_deformed"], 1, 8)
+    R, S = R1.reshape(-1, 3, 3).cpu().numpy(), S1.reshape(-1, 3, 3).cpu().numpy()
+    assert np.abs(R - g["R_gold"]).max() <= 3e-5 and np.abs(S - g["S_gold"]).max() <= 3e-5
+    rest = acap_np.rest_state(g["V_rest"], g["F"])
+    Ro, So = acap_np.get_rs(rest, g["V_deformed"])
+    assert np.abs(R - Ro).max() <= 1e-6 and np.abs(S - So).max() <= 1e-6          # float32 outputs of a float64 kernel
+    # a larger mesh with the analytic twist-and-bend deformation, and a mesh with boundary
+    V, F = synthetic.icosphere(4)
+    Vd, _, _ = synthetic.twist_bend_deformation(V)
+    for faces in (F, F[: F.shape[0] // 3]):
+        tool = pyACAP((V, faces), device=cuda_device)
+        R1, S1 = tool.GetRS(V, Vd, 1, 8)
+        Ro, So = acap_np.get_rs(acap_np.rest_state(V, faces), Vd)
+        assert np.abs(R1.reshape(-1, 3, 3).cpu().numpy() - Ro).max() <= 2e-6
+        assert np.abs(S1.reshape(-1, 3, 3).cpu().numpy() - So).max() <= 2e-6
+    # feeds the deform kernel exactly like the reference's edit path
+    from gaussianmesh_b200.renderer import DeformedObject
+    arrays = synthetic.mesh_bound_scene(2000, V, F, seed=1)
+    t = scenes.to_dev(arrays, cuda_device)
+    bc = torch.softmax(t["bc_logits"], dim=1)
+    pos = bc[:, 0:1] * t["vertex1"] + bc[:, 1:2] * t["vertex2"] + bc[:, 2:3] * t["vertex3"]
+    w = synthetic.barycentric_weights(pos.cpu().numpy(), V, arrays["triangles"]).astype(np.float32)
+    obj = DeformedObject(pos, scenes.packed_cov(t["scales"], t["rotations"]), t["opacities"], t["shs"], arrays["triangles"], w, V, cuda_device)
+    tool = pyACAP((V, F), device=cuda_device)
+    R1, S1 = tool.GetRS(V, Vd, 1, 8)
+    obj.deform(Vd, R1.reshape(-1, 3, 3), S1.reshape(-1, 3, 3))
+    assert torch.isfinite(obj.deform_cov6).all() and float((obj.deform_pos - obj.pos).abs().max()) > 0.05

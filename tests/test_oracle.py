@@ -265,3 +265,59 @@ def test_python_mesh_bind_and_deform_identities():
     assert np.abs(p3 - proj @ Q.T).max() <= 1e-5
     assert np.abs(c3 - Q @ cov @ Q.T).max() <= 1e-6 * max(1.0, np.abs(cov).max())
     assert np.abs(r3 - Q).max() <= 1e-6
+
+
+# ------------------------------------------------------------------------------------------------ ACAP (8f-3)
+def test_acap_oracle_matches_the_reference_golden_vectors():
+    """oracle/acap_np.py against the vectors that ship inside the reference's ACAP zip (test/LOGRNEW.txt, test/S.txt for
+    test/1.obj -> test/2.obj); the files carry 6 significant digits."""
+    from oracle import acap_np
+    g = np.load(os.path.join(ROOT, "tests", "golden", "acap_1_to_2.npz"))
+    rest = acap_np.rest_state(g["V_rest"], g["F"])
+    R, S = acap_np.get_rs(rest, g["V_deformed"])
+    assert np.abs(R - g["R_gold"]).max() <= 3e-5 and np.abs(R - g["R_gold"]).mean() <= 2e-6
+    assert np.abs(S - g["S_gold"]).max() <= 3e-5 and np.abs(S - g["S_gold"]).mean() <= 2e-6
+    # polar factors: R^T (= r) is a proper rotation, S symmetric, r S reproduces the fitted affine map's action
+    r = np.swapaxes(R, 1, 2)
+    assert np.abs(r @ R - np.eye(3)).max() <= 1e-12 and np.all(np.linalg.det(r) > 0)
+    assert np.abs(S - np.swapaxes(S, 1, 2)).max() <= 1e-12
+
+
+def test_acap_identity_and_rigid_motion():
+    from oracle import acap_np
+    V, F = synthetic.icosphere(2)
+    V = V.astype(np.float64)
+    rest = acap_np.rest_state(V, F)
+    R, S = acap_np.get_rs(rest, V)
+    assert np.abs(R - np.eye(3)).max() <= 1e-12 and np.abs(S - np.eye(3)).max() <= 1e-12
+    th = 0.9
+    Q = np.array([[math.cos(th), -math.sin(th), 0], [math.sin(th), math.cos(th), 0], [0, 0, 1.0]])
+    R, S = acap_np.get_rs(rest, 1.7 * V @ Q.T + np.array([0.3, -1.0, 2.0]))
+    assert np.abs(np.swapaxes(R, 1, 2) - Q).max() <= 1e-10          # GetRS hands back r^T
+    assert np.abs(S - 1.7 * np.eye(3)).max() <= 1e-10
+
+
+def test_acap_ring_builder_matches_oracle():
+    """The C++ one-ring builder of the library (host code, no GPU needed) against the Python restatement, on a closed
+    mesh and on a mesh with boundary."""
+    import ctypes as C
+    from gaussianmesh_b200._lib import lib
+    from oracle import acap_np
+    V, F = synthetic.icosphere(2)
+    open_F = F[: F.shape[0] // 2]                                       # half a sphere: boundary fans
+    for faces in (F, open_F):
+        faces = np.ascontiguousarray(faces, np.int32)
+        Vn = V.shape[0]
+        ro, rn = np.zeros(Vn + 1, np.int32), np.zeros(3 * len(faces) + Vn, np.int32)
+        fo, fl = np.zeros(Vn + 1, np.int32), np.zeros(3 * len(faces), np.int32)
+        p = lambda a: a.ctypes.data_as(C.c_void_p)
+        assert lib.gm_acap_build_rings(Vn, len(faces), p(faces), p(ro), p(rn), p(fo), p(fl)) == 0
+        off, nbr = acap_np.one_rings(Vn, faces)
+        assert np.array_equal(ro, off)
+        for v in range(Vn):
+            a, b = rn[ro[v]:ro[v + 1]].tolist(), nbr[off[v]:off[v + 1]].tolist()
+            assert sorted(a) == sorted(b)
+            if a:       # same cyclic sequence (closed fans may start anywhere; chains start at the same end)
+                k = b.index(a[0])
+                assert a == b[k:] + b[:k]
+            assert sorted(fl[fo[v]:fo[v + 1]].tolist()) == sorted(np.nonzero((faces == v).any(axis=1))[0].tolist())
