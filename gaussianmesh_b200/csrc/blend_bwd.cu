@@ -16,7 +16,9 @@
 //     received a contribution, instead of one per (pixel, splat).
 // Summation order differs from the reference's (which is itself non-deterministic), hence the 1e-3
 // relative tolerance of the gradient parity tests.
+#include <cstdlib>
 #include "common.cuh"
+#include "packed.cuh"
 #include "kernels.h"
 
 namespace gm {
@@ -289,6 +291,324 @@ blend_backward_kernel(GeometryState g, BinningState b, ImageState img, uint32_t 
 	}
 }
 
+// ---- two splats per iteration, packed fp32x2 arithmetic -------------------------------------------
+// Same decomposition as above, but the queue holds the surviving splats in PAIRS (A = further back, B = the next
+// one towards the camera) and everything that does not sit on the T / accum_rec recurrences is evaluated for
+// both splats with one FADD2 / FMUL2 / FFMA2 per pair of scalar operations (packed.cuh): d, power, G, alpha
+// (bit-identical to the forward's, so both passes take the same alpha / T decisions), the dL/dalpha dot product
+// and the nine moments.  An inactive splat is carried with alpha = 0 and G = 0: T / (1 - 0) == T, the pending
+// (last_alpha, last_color) term is folded into accum_rec one splat early (accum_rec <- la lc + (1 - la) accum_rec
+// followed by la <- 0 is the same recurrence), and all nine moments are zero.  The 2 x 9 moments are summed over
+// the 32 pixels by one transposing butterfly: the first exchange (lane ^ 16) also separates the two splats,
+// lanes 0-15 finish splat A and lanes 16-31 splat B.
+struct WarpQueueP {
+	// [field][slot][4]: slot k holds splats 2k (A) and 2k+1 (B) of the compacted chunk, back to front
+	//   0: xA xB yA yB   1: aA aB -bA -bB   2: cA cB oA oB   3: rA rB gA gB   4: bA bB posA posB (0-based, as bits)
+	float v[5][16][4];
+	uint32_t id[32];
+	float park[32 * kComp];
+};
+
+struct __align__(128) BwdSmemP {
+	float4 conic[2][kBatch];
+	float4 xyrg[2][kBatch];
+	float2 bid[2][kBatch];
+	WarpQueueP queue[kWarps];
+	uint64_t full[2];
+	uint32_t warp_max[kWarps];
+};
+
+// Sum nine packed pairs over the warp.  On return lane l holds, for splat (l >> 4) of the pair, the total of
+// component (l & 1) ? 8 : ((l >> 1) & 7).
+__device__ __forceinline__ float butterfly18(const f2 (&v)[kComp], int lane)
+{
+	// xor 16: separates the splats -- lanes 0-15 keep the lo halves, lanes 16-31 the hi halves
+	// (PRMT with a per-lane selector: one instruction per select, where `?:` on the two halves turns into
+	// pairs of predicated moves)
+	const uint32_t sel_keep = (lane & 16) ? 0x7654u : 0x3210u, sel_send = sel_keep ^ 0x4444u;
+	float w[kComp];
+#pragma unroll
+	for (int i = 0; i < kComp; i++) {
+		const uint32_t a = __float_as_uint(lo(v[i])), b = __float_as_uint(hi(v[i]));
+		const float keep = __uint_as_float(__byte_perm(a, b, sel_keep));
+		const float send = __uint_as_float(__byte_perm(a, b, sel_send));
+		w[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+	}
+	// xor 8: 8 -> 4
+	const bool h3 = lane & 8;
+	float u[4];
+#pragma unroll
+	for (int i = 0; i < 4; i++) {
+		const float keep = h3 ? w[i + 4] : w[i];
+		const float send = h3 ? w[i] : w[i + 4];
+		u[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+	}
+	float e = w[8] + __shfl_xor_sync(0xffffffffu, w[8], 8);
+	// xor 4: 4 -> 2
+	const bool h2 = lane & 4;
+	float y[2];
+#pragma unroll
+	for (int i = 0; i < 2; i++) {
+		const float keep = h2 ? u[i + 2] : u[i];
+		const float send = h2 ? u[i] : u[i + 2];
+		y[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+	}
+	e += __shfl_xor_sync(0xffffffffu, e, 4);
+	// xor 2: 2 -> 1
+	const bool h1 = lane & 2;
+	float z;
+	{
+		const float keep = h1 ? y[1] : y[0];
+		const float send = h1 ? y[0] : y[1];
+		z = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+	}
+	e += __shfl_xor_sync(0xffffffffu, e, 2);
+	// xor 1: even lanes finish z, odd lanes finish component 8
+	const bool h0 = lane & 1;
+	const float keep = h0 ? e : z;
+	const float send = h0 ? z : e;
+	return keep + __shfl_xor_sync(0xffffffffu, send, 1);
+}
+
+__global__ void __launch_bounds__(kThreads)
+blend_backward_pairs_kernel(GeometryState g, BinningState b, ImageState img, uint32_t capacity,
+                            int W, int H, int tiles_x, const float* __restrict__ bg_color,
+                            const float* __restrict__ dL_dpixels,
+                            float* __restrict__ dL_dmean2D,   // [P,3]
+                            float* __restrict__ dL_dconic2D,  // [P,4]
+                            float* __restrict__ dL_dopacity,  // [P]
+                            float* __restrict__ dL_dcolors)   // [P,3]
+{
+	__shared__ BwdSmemP s;
+
+	const int tile = blockIdx.x;
+	const int tile_x = tile % tiles_x, tile_y = tile / tiles_x;
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+	const int bx0 = tile_x * kTile + (warp & 1) * 8;
+	const int by0 = tile_y * kTile + (warp >> 1) * 4;
+	const int px = bx0 + (lane & 7), py = by0 + (lane >> 3);
+	const bool inside = px < W && py < H;
+	const uint32_t pix_id = (uint32_t)W * py + px;
+	const f2 npx = pk1(-(float)px), npy = pk1(-(float)py);
+	const float wx0 = (float)bx0, wy0 = (float)by0;
+	const float wx1 = (float)min(bx0 + 7, W - 1), wy1 = (float)min(by0 + 3, H - 1);
+
+	const uint32_t start = g.tile_start[tile];
+	uint32_t n = 0;
+	if (start < capacity)
+		n = min(g.tile_count[tile], capacity - start);
+
+	// backward.cu:430-448
+	const float T_final = inside ? img.accum_alpha[pix_id] : 0.0f;
+	float T = T_final;
+	const uint32_t last_contributor = inside ? min(img.n_contrib[pix_id], n) : 0u;
+
+	// how far back does this warp / this tile have to go?
+	uint32_t warp_last = last_contributor;
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1)
+		warp_last = max(warp_last, __shfl_xor_sync(0xffffffffu, warp_last, o));
+	if (lane == 0)
+		s.warp_max[warp] = warp_last;
+	if (tid == 0) {
+		mbar_init(&s.full[0], 1);
+		mbar_init(&s.full[1], 1);
+		fence_mbar_init();
+	}
+	__syncthreads();
+	uint32_t tile_last = 0;
+#pragma unroll
+	for (int w = 0; w < kWarps; w++)
+		tile_last = max(tile_last, s.warp_max[w]);
+	if (tile_last == 0)
+		return;
+
+	float dL_dpixel0 = 0.0f, dL_dpixel1 = 0.0f, dL_dpixel2 = 0.0f;
+	if (inside) {
+		const size_t HW = (size_t)H * W;
+		dL_dpixel0 = dL_dpixels[0 * HW + pix_id];
+		dL_dpixel1 = dL_dpixels[1 * HW + pix_id];
+		dL_dpixel2 = dL_dpixels[2 * HW + pix_id];
+	}
+	// accum_rec and the pending (last_alpha * last_color, 1 - last_alpha) term of backward.cu:509-515
+	float acc0 = 0.0f, acc1 = 0.0f, acc2 = 0.0f;
+	float pend0 = 0.0f, pend1 = 0.0f, pend2 = 0.0f, keep_prev = 1.0f;
+
+	// backward.cu:455-461: d(pixel offset)/d(NDC mean); applied once per (warp, splat) below
+	const float ddelx_dx = 0.5 * W;
+	const float ddely_dy = 0.5 * H;
+	// backward.cu:531-534: dL/dalpha += (-T_final / (1 - alpha)) * (bg . dL/dpixel)
+	const f2 bg_term = pk1(-T_final * (bg_color[0] * dL_dpixel0 + bg_color[1] * dL_dpixel1 + bg_color[2] * dL_dpixel2));
+	const f2 dLp0 = pk1(dL_dpixel0), dLp1 = pk1(dL_dpixel1), dLp2 = pk1(dL_dpixel2);
+	const f2 neg_half = pk1(-0.5f), neg_one = pk1(-1.0f), one = pk1(1.0f);
+
+	auto issue = [&](int batch, int buf) {
+		const uint32_t off = start + (uint32_t)batch * kBatch;
+		const uint32_t cnt = min((uint32_t)kBatch, n - (uint32_t)batch * kBatch);
+		const uint32_t cnt4 = (cnt + 3u) & ~3u;
+		mbar_arrive_expect_tx(&s.full[buf], cnt4 * 40u);
+		bulk_g2s(s.conic[buf], b.rec_conic + off, cnt4 * 16u, &s.full[buf]);
+		bulk_g2s(s.xyrg[buf], b.rec_xyrg + off, cnt4 * 16u, &s.full[buf]);
+		bulk_g2s(s.bid[buf], b.rec_bid + off, cnt4 * 8u, &s.full[buf]);
+	};
+
+	WarpQueueP& q = s.queue[warp];
+	const int batch_hi = (int)((tile_last - 1) / kBatch);
+	if (tid == 0)
+		issue(batch_hi, 0);
+
+	for (int it = 0, batch = batch_hi; batch >= 0; it++, batch--) {
+		const int buf = it & 1;
+		// every warp has finished batch+1 (buffer buf^1) before it is overwritten
+		if (it > 0)
+			__syncthreads();
+		if (tid == 0 && batch > 0)
+			issue(batch - 1, buf ^ 1);
+		mbar_wait(&s.full[buf], (uint32_t)(it >> 1) & 1u);
+
+		const int batch_base = batch * kBatch;
+		// positions >= warp_last are behind every pixel of this warp (backward.cu:487-489)
+		const int cnt = min(min(kBatch, (int)n - batch_base), (int)warp_last - batch_base);
+		for (int base = (cnt > 0) ? ((cnt - 1) & ~31) : -1; base >= 0; base -= 32) {
+			// cull 32 splats in parallel against the warp's 8x4 pixel block; compact the survivors back to front
+			const int j = base + lane;
+			bool keep = false;
+			float4 co, xr;
+			if (j < cnt) {
+				co = s.conic[buf][j];
+				xr = s.xyrg[buf][j];
+				keep = !rect_cannot_contribute(xr.x, xr.y, co.x, co.y, co.z, cull_threshold(co.w),
+				                               wx0, wy0, wx1, wy1);
+			}
+			const uint32_t mask = __ballot_sync(0xffffffffu, keep);
+			if (mask == 0)
+				continue;
+			const int n_keep = __popc(mask);
+			{
+				// one non-surviving lane pads an odd queue with a splat that no pixel accepts (position 2^32 - 1)
+				const bool pad = !keep && (n_keep & 1) && lane == (__ffs(~mask) - 1);
+				if (keep || pad) {
+					const int at = keep ? __popc(mask >> lane) - 1 : n_keep;   // highest list position first
+					const int slot = at >> 1, h = at & 1;
+					const float2 bi = keep ? s.bid[buf][j] : make_float2(0.0f, 0.0f);
+					q.v[0][slot][h] = keep ? xr.x : 0.0f;
+					q.v[0][slot][2 + h] = keep ? xr.y : 0.0f;
+					q.v[1][slot][h] = keep ? co.x : 0.0f;
+					q.v[1][slot][2 + h] = keep ? -co.y : 0.0f;
+					q.v[2][slot][h] = keep ? co.z : 0.0f;
+					q.v[2][slot][2 + h] = keep ? co.w : 0.0f;
+					q.v[3][slot][h] = keep ? xr.z : 0.0f;
+					q.v[3][slot][2 + h] = keep ? xr.w : 0.0f;
+					q.v[4][slot][h] = bi.x;
+					q.v[4][slot][2 + h] = __uint_as_float(keep ? (uint32_t)(batch_base + j) : 0xffffffffu);
+					q.id[at] = __float_as_uint(bi.y);
+				}
+			}
+			__syncwarp();
+			const int n_pairs = (n_keep + 1) >> 1;
+			uint32_t touched = 0;
+			for (int k = 0; k < n_pairs; k++) {
+				const ulonglong2 XY = *reinterpret_cast<const ulonglong2*>(q.v[0][k]);
+				const ulonglong2 AB = *reinterpret_cast<const ulonglong2*>(q.v[1][k]);
+				const ulonglong2 CO = *reinterpret_cast<const ulonglong2*>(q.v[2][k]);
+				const float4 BP = *reinterpret_cast<const float4*>(q.v[4][k]);
+				// backward.cu:487-501, the forward's instruction sequence
+				const f2 dx = add2(XY.x, npx), dy = add2(XY.y, npy);
+				f2 t = mul2(dy, CO.x);
+				const f2 u = mul2(dx, AB.x);
+				t = mul2(dy, t);
+				const f2 sq = fma2(dx, u, t);
+				const f2 vv = mul2(dx, AB.y);
+				const f2 ww = mul2(dy, vv);
+				const f2 power = fma2(sq, neg_half, ww);
+				const f2 G = exp2x(power);
+				const f2 al = mul2(CO.y, G);
+				const float aA = fminf(lo(al), 0.99f), aB = fminf(hi(al), 0.99f);
+				const bool skipA = (__float_as_uint(BP.z) >= last_contributor) | (lo(power) > 0.0f) | (aA < 1.0f / 255.0f);
+				const bool skipB = (__float_as_uint(BP.w) >= last_contributor) | (hi(power) > 0.0f) | (aB < 1.0f / 255.0f);
+				if (__all_sync(0xffffffffu, skipA & skipB))
+					continue;
+				touched |= 3u << (2 * k);
+
+				const f2 e2 = pk(skipA ? 0.0f : aA, skipB ? 0.0f : aB);
+				const f2 Ge = pk(skipA ? 0.0f : lo(G), skipB ? 0.0f : hi(G));
+				// backward.cu:503-507: T <- T / (1 - alpha).  MUFU.RCP: 1 ulp, far inside the 1e-3 gradient tolerance
+				const f2 om = fma2(e2, neg_one, one);
+				const float rcpA = __fdividef(1.f, lo(om)), rcpB = __fdividef(1.f, hi(om));
+				const float TA = T * rcpA, TB = TA * rcpB;
+				T = TB;
+				const f2 T2 = pk(TA, TB), rcp2 = pk(rcpA, rcpB);
+				const f2 dchannel_dcolor = mul2(e2, T2);
+				// backward.cu:509-521: accum_rec, walked A then B
+				const ulonglong2 RG = *reinterpret_cast<const ulonglong2*>(q.v[3][k]);
+				const f2 col0 = RG.x, col1 = RG.y, col2 = pk(BP.x, BP.y);
+				const f2 ac0 = mul2(e2, col0), ac1 = mul2(e2, col1), ac2 = mul2(e2, col2);
+				const float accA0 = fmaf(keep_prev, acc0, pend0), accA1 = fmaf(keep_prev, acc1, pend1),
+				            accA2 = fmaf(keep_prev, acc2, pend2);
+				acc0 = fmaf(lo(om), accA0, lo(ac0));
+				acc1 = fmaf(lo(om), accA1, lo(ac1));
+				acc2 = fmaf(lo(om), accA2, lo(ac2));
+				pend0 = hi(ac0); pend1 = hi(ac1); pend2 = hi(ac2);
+				keep_prev = hi(om);
+				const f2 d0 = fma2(pk(accA0, acc0), neg_one, col0);
+				const f2 d1 = fma2(pk(accA1, acc1), neg_one, col1);
+				const f2 d2 = fma2(pk(accA2, acc2), neg_one, col2);
+				f2 dL_dalpha = fma2(d2, dLp2, fma2(d1, dLp1, mul2(d0, dLp0)));
+				// backward.cu:526-534
+				dL_dalpha = fma2(dL_dalpha, T2, mul2(bg_term, rcp2));
+
+				f2 v[kComp];
+				v[0] = mul2(dchannel_dcolor, dLp0);
+				v[1] = mul2(dchannel_dcolor, dLp1);
+				v[2] = mul2(dchannel_dcolor, dLp2);
+				// moments of q = G dL/dalpha (backward.cu:537-554 with the splat constants factored out)
+				const f2 qq = mul2(Ge, dL_dalpha);
+				const f2 qdx = mul2(qq, dx), qdy = mul2(qq, dy);
+				v[3] = qq;
+				v[4] = qdx;
+				v[5] = qdy;
+				v[6] = mul2(qdx, dx);
+				v[7] = mul2(qdx, dy);
+				v[8] = mul2(qdy, dy);
+				const float total = butterfly18(v, lane);
+				const int entry = 2 * k + (lane >> 4);
+				if ((lane & 1) == 0)
+					q.park[entry * kComp + ((lane >> 1) & 7)] = total;
+				else if ((lane & 15) == 1)
+					q.park[entry * kComp + 8] = total;
+			}
+			__syncwarp();
+			if ((touched >> lane) & 1u) {
+				// this lane sends queue entry `lane` to global memory (unless no pixel accepted it)
+				const float* m = q.park + lane * kComp;
+				const float Sq = m[3], Sx = m[4], Sy = m[5], Sxx = m[6], Sxy = m[7], Syy = m[8];
+				const float m0 = m[0], m1 = m[1], m2 = m[2];
+				const uint32_t any = (__float_as_uint(m0) | __float_as_uint(m1) | __float_as_uint(m2) | __float_as_uint(Sq) |
+				                      __float_as_uint(Sx) | __float_as_uint(Sy) | __float_as_uint(Sxx) | __float_as_uint(Sxy) |
+				                      __float_as_uint(Syy)) << 1;
+				if (any != 0) {
+					const int slot = lane >> 1, h = lane & 1;
+					const float a = q.v[1][slot][h], bb = -q.v[1][slot][2 + h], c = q.v[2][slot][h], o = q.v[2][slot][2 + h];
+					const uint32_t id = q.id[lane];
+					atomicAdd(&dL_dcolors[3 * (size_t)id + 0], m0);
+					atomicAdd(&dL_dcolors[3 * (size_t)id + 1], m1);
+					atomicAdd(&dL_dcolors[3 * (size_t)id + 2], m2);
+					// dL/dG = o dL/dalpha;  dG/ddelx = -G (a dx + b dy);  dG/ddely = -G (c dy + b dx)
+					atomicAdd(&dL_dmean2D[3 * (size_t)id + 0], -o * ddelx_dx * (a * Sx + bb * Sy));
+					atomicAdd(&dL_dmean2D[3 * (size_t)id + 1], -o * ddely_dy * (c * Sy + bb * Sx));
+					const float hh = -0.5f * o;
+					atomicAdd(&dL_dconic2D[4 * (size_t)id + 0], hh * Sxx);
+					atomicAdd(&dL_dconic2D[4 * (size_t)id + 1], hh * Sxy);
+					atomicAdd(&dL_dconic2D[4 * (size_t)id + 3], hh * Syy);
+					atomicAdd(&dL_dopacity[id], Sq);
+				}
+			}
+			__syncwarp();   // queue and park rows are rewritten by the next chunk
+		}
+	}
+}
+
 } // namespace
 
 int launch_blend_backward(const GeometryState& g, const BinningState& b, const ImageState& img, uint32_t capacity,
@@ -298,8 +618,14 @@ int launch_blend_backward(const GeometryState& g, const BinningState& b, const I
 	const int num_tiles = vp.tiles_x * vp.tiles_y;
 	if (num_tiles <= 0)
 		return GM_OK;
-	blend_backward_kernel<<<num_tiles, kThreads, 0, stream>>>(
-		g, b, img, capacity, vp.W, vp.H, vp.tiles_x, vp.bg, dL_dpix, dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolor);
+	// GM_BLEND_SCALAR=1 selects the one-splat-per-iteration kernel (kept for A/B measurements)
+	static const bool scalar = std::getenv("GM_BLEND_SCALAR") != nullptr && std::getenv("GM_BLEND_SCALAR")[0] == '1';
+	if (scalar)
+		blend_backward_kernel<<<num_tiles, kThreads, 0, stream>>>(
+			g, b, img, capacity, vp.W, vp.H, vp.tiles_x, vp.bg, dL_dpix, dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolor);
+	else
+		blend_backward_pairs_kernel<<<num_tiles, kThreads, 0, stream>>>(
+			g, b, img, capacity, vp.W, vp.H, vp.tiles_x, vp.bg, dL_dpix, dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolor);
 	return GM_OK;
 }
 

@@ -11,7 +11,9 @@
 //     that block (rect_cannot_contribute, exact), so only splats that can reach the block are
 //     evaluated per pixel.  Skipped splats are exactly those for which every pixel of the block
 //     would hit one of the reference's `continue`s, so no output bit changes.
+#include <cstdlib>
 #include "common.cuh"
+#include "packed.cuh"
 #include "kernels.h"
 
 namespace gm {
@@ -176,6 +178,206 @@ blend_forward_kernel(GeometryState g, BinningState b, ImageState img, uint32_t c
 	}
 }
 
+// ---- two splats per iteration, packed fp32x2 arithmetic -------------------------------------------
+// Same decomposition as above (one CTA per tile, a warp per 8x4 pixel block, exact warp-level culling into a
+// per-warp queue), but the queue holds the surviving splats in PAIRS and the per-pixel arithmetic that does
+// not depend on the running transmittance -- d = xy - pixf, power, exp, opacity * G, feature * alpha
+// (forward.cu:331-343,355) -- is evaluated for both splats of a pair with one FADD2 / FMUL2 / FFMA2 per pair of
+// scalar operations (packed.cuh; sm_100a).  Every packed operation rounds exactly like the scalar one the
+// reference compiles to, so the alpha / T decisions stay bit-identical.  Only the T recurrence
+// (forward.cu:346-356) is walked splat by splat, and the reference's `continue` / `break` become predicates
+// that zero the splat's alpha: feature * 0 * T added to C leaves C untouched and T * (1 - 0) == T, so no output
+// bit moves.  `done` is carried as the pixel's alpha threshold (1/255 while live, +inf afterwards).
+struct WarpQueueP {
+	// [field][slot][4]: slot k holds splats 2k (A) and 2k+1 (B) of the compacted chunk
+	//   0: xA xB yA yB   1: aA aB -bA -bB   2: cA cB oA oB   3: rA rB gA gB   4: bA bB posA posB (1-based, as bits)
+	float v[5][16][4];
+};
+
+struct __align__(128) FwdSmemP {
+	float4 conic[2][kBatch];
+	float4 xyrg[2][kBatch];
+	float2 bid[2][kBatch];
+	WarpQueueP queue[kThreads / 32];
+	uint64_t full[2];
+};
+
+__global__ void __launch_bounds__(kThreads)
+blend_forward_pairs_kernel(GeometryState g, BinningState b, ImageState img, uint32_t capacity,
+                           int W, int H, int tiles_x, const float* __restrict__ bg_color,
+                           float* __restrict__ out_color)
+{
+	__shared__ FwdSmemP s;
+
+	const int tile = blockIdx.x;
+	const int tile_x = tile % tiles_x, tile_y = tile / tiles_x;
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+	// 8x4 pixel block per warp
+	const int bx0 = tile_x * kTile + (warp & 1) * 8;
+	const int by0 = tile_y * kTile + (warp >> 1) * 4;
+	const int px = bx0 + (lane & 7), py = by0 + (lane >> 3);
+	const bool inside = px < W && py < H;
+	const f2 npx = pk1(-(float)px), npy = pk1(-(float)py);
+	const float wx0 = (float)bx0, wy0 = (float)by0;
+	const float wx1 = (float)min(bx0 + 7, W - 1), wy1 = (float)min(by0 + 3, H - 1);
+
+	const uint32_t start = g.tile_start[tile];
+	uint32_t n = 0;
+	if (start < capacity)
+		n = min(g.tile_count[tile], capacity - start);
+	const int num_batches = (int)((n + kBatch - 1) / kBatch);
+
+	if (tid == 0) {
+		mbar_init(&s.full[0], 1);
+		mbar_init(&s.full[1], 1);
+		fence_mbar_init();
+	}
+	__syncthreads();
+
+	auto issue = [&](int batch) {
+		const uint32_t off = start + (uint32_t)batch * kBatch;
+		const uint32_t cnt = min((uint32_t)kBatch, n - (uint32_t)batch * kBatch);
+		const uint32_t cnt4 = (cnt + 3u) & ~3u;
+		const int buf = batch & 1;
+		mbar_arrive_expect_tx(&s.full[buf], cnt4 * 40u);
+		bulk_g2s(s.conic[buf], b.rec_conic + off, cnt4 * 16u, &s.full[buf]);
+		bulk_g2s(s.xyrg[buf], b.rec_xyrg + off, cnt4 * 16u, &s.full[buf]);
+		bulk_g2s(s.bid[buf], b.rec_bid + off, cnt4 * 8u, &s.full[buf]);
+	};
+	if (tid == 0 && num_batches > 0)
+		issue(0);
+
+	// forward.cu:294-298
+	const float kInf = __int_as_float(0x7f800000);
+	float thr = inside ? 1.0f / 255.0f : kInf;
+	float T = 1.0f;
+	uint32_t last_contributor = 0;
+	float C0 = 0.0f, C1 = 0.0f, C2 = 0.0f;
+	const f2 neg_half = pk1(-0.5f);
+
+	for (int batch = 0; batch < num_batches; batch++) {
+		// forward.cu:303-306 (block-wide early exit); this barrier also frees the buffer that the
+		// next bulk copy overwrites, because every thread has finished batch-1 by now.
+		if (__syncthreads_and(thr == kInf)) {
+			// the bulk copy of this batch may still be in flight; it must land before the block
+			// (and with it the shared memory it targets) is retired
+			if (tid == 0)
+				mbar_wait(&s.full[batch & 1], (uint32_t)(batch >> 1) & 1u);
+			break;
+		}
+		if (tid == 0 && batch + 1 < num_batches)
+			issue(batch + 1);
+		const int buf = batch & 1;
+		mbar_wait(&s.full[buf], (uint32_t)(batch >> 1) & 1u);
+
+		if (__all_sync(0xffffffffu, thr == kInf))
+			continue;
+
+		const int cnt = (int)min((uint32_t)kBatch, n - (uint32_t)batch * kBatch);
+		WarpQueueP& q = s.queue[warp];
+		for (int base = 0; base < cnt; base += 32) {
+			// cull 32 splats in parallel against the warp's 8x4 pixel block and compact the survivors
+			const int j = base + lane;
+			bool keep = false;
+			float4 co, xr;
+			if (j < cnt) {
+				co = s.conic[buf][j];
+				xr = s.xyrg[buf][j];
+				keep = !rect_cannot_contribute(xr.x, xr.y, co.x, co.y, co.z, cull_threshold(co.w),
+				                               wx0, wy0, wx1, wy1);
+			}
+			const uint32_t mask = __ballot_sync(0xffffffffu, keep);
+			if (mask == 0)
+				continue;
+			const int n_keep = __popc(mask);
+			{
+				// the lane behind the last survivor pads an odd queue with a splat of opacity 0 (alpha == 0: skipped)
+				const int pos = keep ? __popc(mask & ((1u << lane) - 1u)) : n_keep;
+				const bool pad = !keep && (n_keep & 1) && lane == (__ffs(~mask) - 1);
+				if (keep || pad) {
+					const int slot = pos >> 1, h = pos & 1;
+					q.v[0][slot][h] = keep ? xr.x : 0.0f;
+					q.v[0][slot][2 + h] = keep ? xr.y : 0.0f;
+					q.v[1][slot][h] = keep ? co.x : 0.0f;
+					q.v[1][slot][2 + h] = keep ? -co.y : 0.0f;
+					q.v[2][slot][h] = keep ? co.z : 0.0f;
+					q.v[2][slot][2 + h] = keep ? co.w : 0.0f;
+					q.v[3][slot][h] = keep ? xr.z : 0.0f;
+					q.v[3][slot][2 + h] = keep ? xr.w : 0.0f;
+					q.v[4][slot][h] = keep ? s.bid[buf][j].x : 0.0f;
+					q.v[4][slot][2 + h] = __uint_as_float(keep ? (uint32_t)(batch * kBatch + j + 1) : 0u);
+				}
+			}
+			__syncwarp();
+			const int n_pairs = (n_keep + 1) >> 1;
+#pragma unroll 2
+			for (int k = 0; k < n_pairs; k++) {
+				const ulonglong2 XY = *reinterpret_cast<const ulonglong2*>(q.v[0][k]);
+				const ulonglong2 AB = *reinterpret_cast<const ulonglong2*>(q.v[1][k]);
+				const ulonglong2 CO = *reinterpret_cast<const ulonglong2*>(q.v[2][k]);
+				// forward.cu:331-335: d = xy - pixf; power = -0.5 (a dx dx + c dy dy) - b dx dy
+				const f2 dx = add2(XY.x, npx), dy = add2(XY.y, npy);
+				f2 t = mul2(dy, CO.x);
+				const f2 u = mul2(dx, AB.x);
+				t = mul2(dy, t);
+				const f2 sq = fma2(dx, u, t);
+				const f2 v = mul2(dx, AB.y);
+				const f2 w = mul2(dy, v);
+				const f2 power = fma2(sq, neg_half, w);
+				// forward.cu:343: alpha = min(0.99, opacity * exp(power))
+				const f2 al = mul2(CO.y, exp2x(power));
+				const float aA = fminf(lo(al), 0.99f), aB = fminf(hi(al), 0.99f);
+				const float4 BP = *reinterpret_cast<const float4*>(q.v[4][k]);
+
+				// splat A -- forward.cu:336,344: the two `continue`s zero alpha; :346-351: test_T = T (1 - alpha), a
+				// skipped splat gives T back (T >= 1e-4 while the pixel is live), a terminating one freezes the pixel
+				const bool sA = (lo(power) > 0.0f) | (aA < thr);
+				const float eA = sA ? 0.0f : aA;
+				const float ttA = __fmul_rn(T, __fadd_rn(1.0f, -eA));
+				const bool tA = ttA < 0.0001f;
+				thr = tA ? kInf : thr;
+				const float wA = tA ? 0.0f : eA;
+				const float TA = T;
+				T = tA ? T : ttA;
+				last_contributor = (sA | tA) ? last_contributor : __float_as_uint(BP.z);
+				// splat B
+				const bool sB = (hi(power) > 0.0f) | (aB < thr);
+				const float eB = sB ? 0.0f : aB;
+				const float ttB = __fmul_rn(T, __fadd_rn(1.0f, -eB));
+				const bool tB = ttB < 0.0001f;
+				thr = tB ? kInf : thr;
+				const float wB = tB ? 0.0f : eB;
+				const float TB = T;
+				T = tB ? T : ttB;
+				last_contributor = (sB | tB) ? last_contributor : __float_as_uint(BP.w);
+
+				// forward.cu:354-355: C += (feature * alpha) * T
+				const ulonglong2 RG = *reinterpret_cast<const ulonglong2*>(q.v[3][k]);
+				const f2 w2 = pk(wA, wB);
+				const f2 cr = mul2(w2, RG.x), cg = mul2(w2, RG.y), cb = mul2(w2, pk(BP.x, BP.y));
+				C0 = __fmaf_rn(TB, hi(cr), __fmaf_rn(TA, lo(cr), C0));
+				C1 = __fmaf_rn(TB, hi(cg), __fmaf_rn(TA, lo(cg), C1));
+				C2 = __fmaf_rn(TB, hi(cb), __fmaf_rn(TA, lo(cb), C2));
+			}
+			__syncwarp();   // the queue is rewritten by the next chunk
+			if (__all_sync(0xffffffffu, thr == kInf))
+				break;
+		}
+	}
+
+	// forward.cu:366-373
+	if (inside) {
+		const uint32_t pix_id = (uint32_t)W * py + px;
+		img.accum_alpha[pix_id] = T;
+		img.n_contrib[pix_id] = last_contributor;
+		const size_t HW = (size_t)H * W;
+		out_color[0 * HW + pix_id] = C0 + T * bg_color[0];
+		out_color[1 * HW + pix_id] = C1 + T * bg_color[1];
+		out_color[2 * HW + pix_id] = C2 + T * bg_color[2];
+	}
+}
+
 } // namespace
 
 int launch_blend_forward(const GeometryState& g, const BinningState& b, const ImageState& img, uint32_t capacity,
@@ -184,7 +386,12 @@ int launch_blend_forward(const GeometryState& g, const BinningState& b, const Im
 	const int num_tiles = vp.tiles_x * vp.tiles_y;
 	if (num_tiles <= 0)
 		return GM_OK;
-	blend_forward_kernel<<<num_tiles, kThreads, 0, stream>>>(g, b, img, capacity, vp.W, vp.H, vp.tiles_x, vp.bg, out_color);
+	// GM_BLEND_SCALAR=1 selects the one-pixel-per-thread kernel (kept for A/B measurements)
+	static const bool scalar = std::getenv("GM_BLEND_SCALAR") != nullptr && std::getenv("GM_BLEND_SCALAR")[0] == '1';
+	if (scalar)
+		blend_forward_kernel<<<num_tiles, kThreads, 0, stream>>>(g, b, img, capacity, vp.W, vp.H, vp.tiles_x, vp.bg, out_color);
+	else
+		blend_forward_pairs_kernel<<<num_tiles, kThreads, 0, stream>>>(g, b, img, capacity, vp.W, vp.H, vp.tiles_x, vp.bg, out_color);
 	return GM_OK;
 }
 
