@@ -370,7 +370,7 @@ __device__ __forceinline__ float butterfly18(const f2 (&v)[kComp], int lane)
 	return keep + __shfl_xor_sync(0xffffffffu, send, 1);
 }
 
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 4)
 blend_backward_pairs_kernel(GeometryState g, BinningState b, ImageState img, uint32_t capacity,
                             int W, int H, int tiles_x, const float* __restrict__ bg_color,
                             const float* __restrict__ dL_dpixels,
@@ -454,6 +454,9 @@ blend_backward_pairs_kernel(GeometryState g, BinningState b, ImageState img, uin
 	};
 
 	WarpQueueP& q = s.queue[warp];
+	// where this lane parks its butterfly18 result of pair 0 (entry lane >> 4, component as described there)
+	float* const park_lane = q.park + (lane >> 4) * kComp + ((lane & 1) ? 8 : ((lane >> 1) & 7));
+	const bool park_writer = (lane & 1) == 0 || (lane & 15) == 1;
 	const int batch_hi = (int)((tile_last - 1) / kBatch);
 	if (tid == 0)
 		issue(batch_hi, 0);
@@ -507,8 +510,9 @@ blend_backward_pairs_kernel(GeometryState g, BinningState b, ImageState img, uin
 			}
 			__syncwarp();
 			const int n_pairs = (n_keep + 1) >> 1;
-			uint32_t touched = 0;
-			for (int k = 0; k < n_pairs; k++) {
+			uint32_t touched = 0, pair_bits = 3u;
+			float* park_at = park_lane;
+			for (int k = 0; k < n_pairs; k++, pair_bits <<= 2, park_at += 2 * kComp) {
 				const ulonglong2 XY = *reinterpret_cast<const ulonglong2*>(q.v[0][k]);
 				const ulonglong2 AB = *reinterpret_cast<const ulonglong2*>(q.v[1][k]);
 				const ulonglong2 CO = *reinterpret_cast<const ulonglong2*>(q.v[2][k]);
@@ -529,13 +533,13 @@ blend_backward_pairs_kernel(GeometryState g, BinningState b, ImageState img, uin
 				const bool skipB = (__float_as_uint(BP.w) >= last_contributor) | (hi(power) > 0.0f) | (aB < 1.0f / 255.0f);
 				if (__all_sync(0xffffffffu, skipA & skipB))
 					continue;
-				touched |= 3u << (2 * k);
+				touched |= pair_bits;
 
 				const f2 e2 = pk(skipA ? 0.0f : aA, skipB ? 0.0f : aB);
 				const f2 Ge = pk(skipA ? 0.0f : lo(G), skipB ? 0.0f : hi(G));
 				// backward.cu:503-507: T <- T / (1 - alpha).  MUFU.RCP: 1 ulp, far inside the 1e-3 gradient tolerance
 				const f2 om = fma2(e2, neg_one, one);
-				const float rcpA = __fdividef(1.f, lo(om)), rcpB = __fdividef(1.f, hi(om));
+				const float rcpA = rcp_approx_ftz(lo(om)), rcpB = rcp_approx_ftz(hi(om));
 				const float TA = T * rcpA, TB = TA * rcpB;
 				T = TB;
 				const f2 T2 = pk(TA, TB), rcp2 = pk(rcpA, rcpB);
@@ -572,11 +576,8 @@ blend_backward_pairs_kernel(GeometryState g, BinningState b, ImageState img, uin
 				v[7] = mul2(qdx, dy);
 				v[8] = mul2(qdy, dy);
 				const float total = butterfly18(v, lane);
-				const int entry = 2 * k + (lane >> 4);
-				if ((lane & 1) == 0)
-					q.park[entry * kComp + ((lane >> 1) & 7)] = total;
-				else if ((lane & 15) == 1)
-					q.park[entry * kComp + 8] = total;
+				if (park_writer)
+					*park_at = total;
 			}
 			__syncwarp();
 			if ((touched >> lane) & 1u) {

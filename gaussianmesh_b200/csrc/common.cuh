@@ -289,15 +289,17 @@ __device__ __forceinline__ bool rect_cannot_contribute(float mx, float my, float
 	if (!(a > 0.0f) || !(c > 0.0f))
 		return false;   // degenerate conic: leave it to the per-pixel test
 
+	// The edge minimiser only has to be near the true one: q is stationary there, so the few-ulp error of the
+	// approximate division moves q by a second-order amount, far below the margins kept at the end.
 	float qmin = 3.0e38f;
 	if (!in_x) {
 		const float dx = (dx0 > 0.0f) ? dx0 : dx1;                  // facing vertical edge
-		const float dy = fminf(dy1, fmaxf(dy0, -b * dx / c));
+		const float dy = fminf(dy1, fmaxf(dy0, __fdividef(-b * dx, c)));
 		qmin = fminf(qmin, a * dx * dx + 2.0f * b * dx * dy + c * dy * dy);
 	}
 	if (!in_y) {
 		const float dy = (dy0 > 0.0f) ? dy0 : dy1;                  // facing horizontal edge
-		const float dx = fminf(dx1, fmaxf(dx0, -b * dy / a));
+		const float dx = fminf(dx1, fmaxf(dx0, __fdividef(-b * dy, a)));
 		qmin = fminf(qmin, a * dx * dx + 2.0f * b * dx * dy + c * dy * dy);
 	}
 	const float ex = fmaxf(fabsf(dx0), fabsf(dx1));
@@ -311,7 +313,8 @@ __device__ __forceinline__ float cull_threshold(float opacity)
 {
 	// log(255*o) rounded up a little; negative (=> never contributes) only if o*1 < 1/255 exactly as
 	// the blend kernels would evaluate it (alpha = o * exp(power) <= o for power <= 0).
-	return (opacity < 1.0f / 255.0f) ? -1.0f : fmaxf(0.0f, logf(255.0f * opacity));
+	// __logf (MUFU.LG2) is within ~1e-6 here (255*o in [1, 255]); 1e-4 on top keeps the threshold an upper bound.
+	return (opacity < 1.0f / 255.0f) ? -1.0f : fmaxf(0.0f, __logf(255.0f * opacity)) + 1.0e-4f;
 }
 
 // ---- depth buckets (state.h) --------------------------------------------------------------------
