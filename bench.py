@@ -12,6 +12,9 @@ Rank 0 prints ONE JSON line.  Keys (see DESIGN.md "Measurement"):
   e2e                   the same step driven with HOST inputs: per step the camera (140 B) and the target image
                         (24.9 MB) are copied from pinned host memory and the loss is read back
   forward               forward-only rendering of the rank's view shard (config 3), frames/s
+  edit                  config 5: deform once, then rotated-direction SH colours + forward per orbit frame
+  train_iteration       the whole iteration of train_mesh_gaussian.py:73-147 on mesh-bound Gaussians (bind, render,
+                        L1 + D-SSIM + mesh-restrict loss, backward, densification statistics, Adam), iterations/s
   roofline              the dominant kernel: algorithmic bytes / CUDA-event time / measured HBM peak
   cpu_baseline          the CPU oracle (oracle/, C + OpenMP restatement of the reference) on the host cores,
                         bounded sample, rank 0 at N=1 only
@@ -158,6 +161,98 @@ def build_edit_workload(device, rank, world):
     cams_host = synthetic.orbit_cameras(EDIT_VIEWS, WIDTH, HEIGHT)
     cams_host = [cams_host[i] for i in shard_views(EDIT_VIEWS, world, rank)]
     return obj, (Vd, R1.reshape(-1, 3, 3), S1.reshape(-1, 3, 3)), upload_cameras(cams_host, device), acap_ms
+
+
+def build_iteration_workload(P):
+    """Section 5: BASELINE config 2 at the headline size -- P mesh-bound Gaussians on the 5,120-face proxy mesh."""
+    from gaussianmesh_b200 import synthetic
+    V, F = synthetic.icosphere(4)
+    return synthetic.mesh_bound_scene(P, V, F, seed=0)
+
+
+class OursIteration:
+    """train_mesh_gaussian.py:73-147 through gaussianmesh_b200.training.TrainingIteration."""
+
+    def __init__(self, device, arrays, W, H):
+        from gaussianmesh_b200.renderer import MeshGaussianModel
+        from gaussianmesh_b200.training import OptimizationParams, TrainingIteration
+        self.model = MeshGaussianModel(arrays, device, requires_grad=False)
+        self.it = TrainingIteration(self.model, OptimizationParams(), W, H)
+
+    def setup(self, cams, bg):
+        self.it.reserve_for(cams, bg)
+
+    def step(self, cam, bg, gt):
+        return self.it.step(cam, bg, gt)
+
+    def check(self):
+        if self.it.arena.verify():
+            raise RuntimeError("arena overflow inside the timed training-iteration region")
+
+
+class ReferenceIteration:
+    """The same iteration the way the reference writes it, torch standing in for Jittor (which cannot be installed):
+    elementwise bind / activations with an autograd tape (scene/mesh_based_gaussian_model.py:122-174, incl. the
+    per-frame concat of f_dc / f_rest), the UNMODIFIED reference CUDA rasterizer (oracle/_ref), conv2d SSIM + L1 +
+    mesh_restrict_loss (utils/loss_utils.py, restated in oracle/train_np.py), indexed densification statistics
+    (train_mesh_gaussian.py:117-121) and Adam over the seven parameter groups."""
+
+    def __init__(self, device, arrays, W, H):
+        import refcuda
+        from gaussianmesh_b200.training import OptimizationParams
+        self.rc, self.W, self.H = refcuda, W, H
+        t = {k: torch.from_numpy(np.ascontiguousarray(v)).to(device) for k, v in arrays.items()}
+        self.t = t
+        leaf = lambda x: x.clone().requires_grad_(True)
+        self.bc, self.distance = leaf(t["bc_logits"]), leaf(t["distance"])
+        self.f_dc, self.f_rest = leaf(t["shs"][:, :1].contiguous()), leaf(t["shs"][:, 1:].contiguous())
+        self.opacity, self.scaling, self.rotation = leaf(t["opacity_logit"]), leaf(t["log_scales"]), leaf(t["rot_raw"])
+        o = self.o = OptimizationParams()
+        self.optimizer = torch.optim.Adam([
+            {"params": [self.bc], "lr": o.position_lr_init}, {"params": [self.distance], "lr": o.position_lr_init},
+            {"params": [self.f_dc], "lr": o.feature_lr}, {"params": [self.f_rest], "lr": o.feature_lr / 20.0},
+            {"params": [self.opacity], "lr": o.opacity_lr}, {"params": [self.scaling], "lr": o.scaling_lr},
+            {"params": [self.rotation], "lr": o.rotation_lr}], lr=0.0, eps=1e-15, foreach=False, fused=False)
+        P = self.bc.shape[0]
+        self.max_radii2D = torch.zeros(P, device=device)
+        self.grad_accum = torch.zeros(P, 1, device=device)
+        self.denom = torch.zeros(P, 1, device=device)
+
+    def setup(self, cams, bg):
+        pass
+
+    def step(self, cam, bg, gt):
+        from oracle import train_np
+        t, o = self.t, self.o
+        bc = torch.softmax(self.bc, dim=1)
+        xyz = bc[:, 0:1] * t["vertex1"] + bc[:, 1:2] * t["vertex2"] + bc[:, 2:3] * t["vertex3"] \
+            + 4.0 * t["r"] * (torch.sigmoid(self.distance) - 0.5) * t["normal"]
+        scales = torch.exp(self.scaling)
+        rot = torch.nn.functional.normalize(self.rotation, dim=1)
+        opac = torch.sigmoid(self.opacity)
+        shs = torch.cat((self.f_dc, self.f_rest), dim=1)
+        fr = self.rc.RefFrame(bg, xyz.detach(), opac.detach(), cam.world_view_transform, cam.full_proj_transform,
+                              cam.camera_center, math.tan(cam.FoVx * 0.5), math.tan(cam.FoVy * 0.5), self.H, self.W, 3,
+                              shs=shs.detach(), scales=scales.detach(), rotations=rot.detach(), sync=False)
+        img = fr.color.requires_grad_(True)
+        photo, _, _ = train_np.photometric_loss(img, gt, o.lambda_dssim)
+        photo.backward()
+        rg = fr.backward(img.grad, sync=False)
+        ab, ac = t["vertex2"] - t["vertex1"], t["vertex3"] - t["vertex1"]
+        radius = torch.sqrt(torch.norm(torch.cross(ab, ac, dim=1), dim=1))
+        mr = torch.clamp(scales.max(dim=1).values - o.alpha_mrloss * radius, min=0).sum()
+        torch.autograd.backward([xyz, scales, rot, opac, shs, mr],
+                                [rg["means3D"], rg["scales"], rg["rotations"], rg["opacity"], rg["sh"], None])
+        vis = fr.radii > 0
+        self.max_radii2D[vis] = torch.maximum(self.max_radii2D[vis], fr.radii[vis].float())
+        self.grad_accum[vis] += torch.norm(rg["means2D"][vis, :2], dim=-1, keepdim=True)
+        self.denom[vis] += 1
+        self.optimizer.step()
+        self.optimizer.zero_grad()
+        return photo.detach() + mr.detach()
+
+    def check(self):
+        pass
 
 
 def timed(fn, steps, warmup, barrier, pre=None, post=None):
@@ -385,6 +480,28 @@ def main():
     if args.impl == "ours" and edit_arena.verify():
         raise RuntimeError("edit arena overflow inside the timed region")
     ms_edit = max_over_ranks(ms_edit)
+    del obj, edit_cams
+    if args.impl == "ours":
+        del edit_arena
+
+    # ---------------------------------------------------------------- (5) full training iteration
+    it_arrays = build_iteration_workload(P)
+    it_arm = (OursIteration if args.impl == "ours" else ReferenceIteration)(device, it_arrays, WIDTH, HEIGHT)
+    if not args.no_presize:
+        it_arm.setup(cams, bg)
+
+    def train_iteration(i):
+        it_arm.step(cams[i % nv], bg, targets[i % TARGET_POOL])
+
+    it_prof = None
+    ms_it, _ = timed(train_iteration, K, Wm, barrier)
+    if args.impl == "ours":
+        from gaussianmesh_b200 import _lib
+        _lib.profile_begin()
+        ms_it_prof, _ = timed(train_iteration, K, 0, barrier)
+        it_prof = _lib.profile_end()
+    it_arm.check()
+    ms_it = max_over_ranks(ms_it)
     clocks = sampler.stop() if sampler is not None else None
 
     if rank != 0:
@@ -411,6 +528,11 @@ def main():
                  "acap_get_rs_ms": acap_ms,
                  "workload": f"{EDIT_P} mesh-bound Gaussians (5,120-face proxy mesh), deformed once, {EDIT_VIEWS}-frame orbit "
                              f"at {WIDTH}x{HEIGHT}: rotated-direction SH colours + forward with precomputed colour/covariance"},
+        "train_iteration": {"value": N * K / (ms_it * 1e-3), "unit": "iterations/s", "ms_per_iteration": ms_it / K,
+                            "workload": f"{P} mesh-bound Gaussians (5,120-face proxy mesh) at {WIDTH}x{HEIGHT}: learning-rate "
+                                        "schedule, bind + activations, render, (1-l) L1 + l (1-SSIM) + mesh-restrict loss, "
+                                        "full backward, densification statistics, Adam over all parameters "
+                                        "(train_mesh_gaussian.py:73-147 without densify_and_prune)"},
         "clocks": clocks,
     }
     if args.impl == "reference":
@@ -461,6 +583,17 @@ def main():
                        "peak_source": peak_src, "unit": "GB/s", "frac": stages[top].get("frac_of_hbm_peak"),
                        "traffic": traffic, "algorithmic_bytes": alg.get(top)}
     out["stages"] = stages
+    numel_params = float(sum(v.size for k, v in it_arrays.items()
+                             if k in ("bc_logits", "distance", "shs", "opacity_logit", "log_scales", "rot_raw")))
+    it_alg = {"photometric_loss": 36.0 * npx, "adam": 28.0 * numel_params, "mesh_bind_forward": (64.0 + 32.0 + 44.0) * P,
+              "mesh_bind_backward": (64.0 + 32.0 + 44.0 + 44.0) * P, "mesh_restrict_loss": 60.0 * P, "densify_stats": 28.0 * P}
+    it_stages = {k: {"ms_per_launch": v[0] / v[1], "launches": v[1], "share": v[0] / ms_it_prof} for k, v in it_prof.items()}
+    for k, st in it_stages.items():
+        if k in it_alg:
+            st["algorithmic_bytes"] = it_alg[k]
+            st["achieved_gbs"] = it_alg[k] / (st["ms_per_launch"] * 1e-3) / 1e9
+            st["frac_of_hbm_peak"] = st["achieved_gbs"] / peak
+    out["train_iteration"]["stages"] = it_stages
     kernels_per_stage = {"depth_buckets": 2, "preprocess": 2, "emit": 2, "sort_pack": 2}    # the rest launch one kernel
     out["gpu_launches"] = int(sum(v[1] * kernels_per_stage.get(k, 1) for k, v in prof.items()))
     out["host_enqueue_ms_per_step"] = enqueue_ms / K

@@ -30,6 +30,13 @@ _i = C.c_int
 _f = C.c_float
 _z = C.c_size_t
 
+class AdamTensor(C.Structure):
+    """gm_adam_tensor of include/gm_rasterizer.h"""
+    _fields_ = [("param", C.c_void_p), ("grad", C.c_void_p), ("exp_avg", C.c_void_p), ("exp_avg_sq", C.c_void_p),
+                ("numel", C.c_size_t), ("lr", C.c_float), ("lr_head", C.c_float), ("period", C.c_uint32),
+                ("split", C.c_uint32)]
+
+
 # name -> (restype, argtypes); the order of arguments is that of include/gm_rasterizer.h
 _VIEW_ARGS = [_p, _p, _p, _p, _p, _f, _p, _p, _p, _p, _p, _f, _f]  # means3D .. tan_fovy
 SIGNATURES = {
@@ -59,6 +66,11 @@ SIGNATURES = {
     "gm_deform_gaussians": (_i, [_i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _i, _p, _p, _p, _p]),
     "gm_sh_to_rgb_rotated": (_i, [_i, _i, _i, _p, _p, _p, _p, _p, _p]),
     "gm_l1_loss": (_i, [_z, _p, _p, _p, _p, _p]),
+    "gm_photometric_scratch_bytes": (_z, [_i, _i, _i]),
+    "gm_photometric_loss": (_i, [_i, _i, _i, _p, _p, _f, _p, _p, _p, _p]),
+    "gm_mesh_restrict_loss": (_i, [_i, _p, _p, _p, _p, _f, _p, _p, _i, _p]),
+    "gm_adam_step": (_i, [_i, C.POINTER(AdamTensor), _i, _f, _f, _f, _p]),
+    "gm_densify_stats": (_i, [_i, _p, _p, _p, _p, _p, _p]),
     "gm_acap_build_rings": (_i, [_i, _i, _p, _p, _p, _p, _p]),
     "gm_acap_rest": (_i, [_i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
     "gm_acap_get_rs": (_i, [_i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),

@@ -23,7 +23,8 @@ OUT_DIR = PKG / "diff_gaussian_rasterizater"
 LIB = OUT_DIR / "libCudaRasterizer.so"
 BUILD = PKG / "build"
 
-SOURCES = ["api.cu", "preprocess.cu", "binning.cu", "blend_fwd.cu", "blend_bwd.cu", "geom_bwd.cu", "mesh.cu", "acap.cu"]
+SOURCES = ["api.cu", "preprocess.cu", "binning.cu", "blend_fwd.cu", "blend_bwd.cu", "geom_bwd.cu", "mesh.cu", "acap.cu", "loss.cu",
+           "optimizer.cu"]
 
 NVCC_FLAGS = [
     "-std=c++17", "-O3",

@@ -47,11 +47,12 @@ int check_stage(const char* what, bool debug, cudaStream_t stream)
 // dominant kernel; off by default (no events, no overhead).
 enum Stage { kStDepthBuckets, kStPreprocess, kStTileScan, kStEmit, kStSortPack, kStBlendFwd, kStBlendBwd, kStGeomBwd, kStL1,
              kStMeshBindFwd, kStMeshBindBwd, kStDeform, kStShRotated, kStMarkVisible, kStAcapRest, kStAcapGetRS,
+             kStPhotometric, kStMeshRestrict, kStAdam, kStDensifyStats,
              kNumStages };
 static const char* const kStageNames[kNumStages] = {
 	"depth_buckets", "preprocess", "tile_scan", "emit", "sort_pack", "blend_forward", "blend_backward", "geometry_backward",
 	"l1_loss", "mesh_bind_forward", "mesh_bind_backward", "deform", "sh_to_rgb_rotated", "mark_visible", "acap_rest",
-	"acap_get_rs"};
+	"acap_get_rs", "photometric_loss", "mesh_restrict_loss", "adam", "densify_stats"};
 
 struct StageRecord { int stage; cudaEvent_t start, stop; };
 static std::mutex g_profile_mutex;
@@ -511,6 +512,57 @@ int gm_l1_loss(size_t numel, const float* img, const float* target, float* loss,
 		return GM_ERR_BAD_ARGUMENT;
 	{ StageScope scope_(kStL1, (cudaStream_t)stream); launch_l1(numel, img, target, loss, dL_dimg, (cudaStream_t)stream); }
 	return check_stage("l1_loss", false, (cudaStream_t)stream);
+}
+
+size_t gm_photometric_scratch_bytes(int C, int H, int W) { return photometric_scratch_bytes(C, H, W); }
+
+int gm_photometric_loss(int C, int H, int W, const float* img, const float* gt, float lambda_dssim, char* scratch,
+                        float* out, float* dL_dimg, gm_stream_t stream)
+{
+	if (C < 0 || H < 0 || W < 0 || out == nullptr || scratch == nullptr)
+		return GM_ERR_BAD_ARGUMENT;
+	if ((size_t)C * H * W > 0 && (!img || !gt))
+		return GM_ERR_BAD_ARGUMENT;
+	{ StageScope scope_(kStPhotometric, (cudaStream_t)stream);
+	  launch_photometric(C, H, W, img, gt, lambda_dssim, scratch, out, dL_dimg, (cudaStream_t)stream); }
+	return check_stage("photometric_loss", false, (cudaStream_t)stream);
+}
+
+int gm_mesh_restrict_loss(int P, const float* scale, const float* vertex1, const float* vertex2, const float* vertex3,
+                          float weight, float* loss, float* dL_dscale, int accumulate, gm_stream_t stream)
+{
+	if (P < 0 || loss == nullptr || (P > 0 && (!scale || !vertex1 || !vertex2 || !vertex3)))
+		return GM_ERR_BAD_ARGUMENT;
+	{ StageScope scope_(kStMeshRestrict, (cudaStream_t)stream);
+	  launch_mesh_restrict(P, scale, vertex1, vertex2, vertex3, weight, loss, dL_dscale, accumulate, (cudaStream_t)stream); }
+	return check_stage("mesh_restrict_loss", false, (cudaStream_t)stream);
+}
+
+int gm_adam_step(int num_tensors, const gm_adam_tensor* tensors_host, int step, float beta1, float beta2, float eps,
+                 gm_stream_t stream)
+{
+	if (num_tensors < 0 || step < 1 || (num_tensors > 0 && tensors_host == nullptr))
+		return GM_ERR_BAD_ARGUMENT;
+	for (int i = 0; i < num_tensors; i++) {
+		const gm_adam_tensor& t = tensors_host[i];
+		if (t.numel > 0 && (!t.param || !t.grad || !t.exp_avg || !t.exp_avg_sq))
+			return GM_ERR_BAD_ARGUMENT;
+		if (t.period > 0 && t.split > t.period)
+			return GM_ERR_BAD_ARGUMENT;
+	}
+	{ StageScope scope_(kStAdam, (cudaStream_t)stream);
+	  launch_adam(num_tensors, tensors_host, step, beta1, beta2, eps, (cudaStream_t)stream); }
+	return check_stage("adam", false, (cudaStream_t)stream);
+}
+
+int gm_densify_stats(int P, const int32_t* radii, const float* dL_dmean2D, float* max_radii2D, float* grad_accum,
+                     float* denom, gm_stream_t stream)
+{
+	if (P < 0 || (P > 0 && (!radii || !dL_dmean2D || !max_radii2D || !grad_accum || !denom)))
+		return GM_ERR_BAD_ARGUMENT;
+	{ StageScope scope_(kStDensifyStats, (cudaStream_t)stream);
+	  launch_densify_stats(P, radii, dL_dmean2D, max_radii2D, grad_accum, denom, (cudaStream_t)stream); }
+	return check_stage("densify_stats", false, (cudaStream_t)stream);
 }
 
 } // extern "C"

@@ -283,15 +283,17 @@ __device__ __forceinline__ void pack_one(const GeometryState& g, const BinningSt
 	__stcs(&b.rec_bid[dst], make_float2(rgb.z, __uint_as_float(id)));
 }
 
+// Sort the n <= 32*E keys at `src` (global or shared memory) in registers and write their packed records to list
+// positions s0 .. s0+n-1.
 template <int E>
-__device__ __forceinline__ void warp_sort_pack(const GeometryState& g, const BinningState& b, uint32_t s0, uint32_t n,
-                                               int lane)
+__device__ __forceinline__ void warp_sort_pack(const GeometryState& g, const BinningState& b, const uint64_t* src,
+                                               uint32_t s0, uint32_t n, int lane)
 {
 	uint64_t key[E];
 #pragma unroll
 	for (int r = 0; r < E; r++) {
 		const uint32_t e = (uint32_t)(r << 5) | lane;
-		key[r] = (e < n) ? b.keys[s0 + e] : ~0ull;
+		key[r] = (e < n) ? src[e] : ~0ull;
 	}
 	warp_bitonic<E>(key, lane);
 #pragma unroll
@@ -356,19 +358,34 @@ bucket_sort_pack_kernel(GeometryState g, BinningState b, uint32_t capacity, int 
 	if (s0 >= s1)
 		return;
 	const uint32_t n = s1 - s0;
-	if (n <= 32) warp_sort_pack<1>(g, b, s0, n, lane);
-	else if (n <= 64) warp_sort_pack<2>(g, b, s0, n, lane);
-	else if (n <= 128) warp_sort_pack<4>(g, b, s0, n, lane);
-	else if (n <= kWarpSortMax) warp_sort_pack<8>(g, b, s0, n, lane);
+	if (n <= 32) warp_sort_pack<1>(g, b, b.keys + s0, s0, n, lane);
+	else if (n <= 64) warp_sort_pack<2>(g, b, b.keys + s0, s0, n, lane);
+	else if (n <= 128) warp_sort_pack<4>(g, b, b.keys + s0, s0, n, lane);
+	else if (n <= kWarpSortMax) warp_sort_pack<8>(g, b, b.keys + s0, s0, n, lane);
 	else if (lane == 0) g.big_list[atomicAdd(&g.header->num_big, 1u)] = gw;   // left to big_bucket_sort_pack_kernel
 }
 
 // The buckets the warp kernel skipped (more than kWarpSortMax instances), one BLOCK per bucket, taken from the
-// list the warp kernel filled.  A fixed small grid: with no oversized bucket the kernel is a few microseconds.
+// list the warp kernel filled.  Gaussians bound to a surface put most of a tile's instances into one or two of the
+// global depth buckets, so this path has to be as cheap per key as the warp path: the block splits the bucket into
+// up to 128 SUB-BUCKETS by linear interpolation of the depth bits between the bucket's own minimum and maximum
+// (monotone in depth, equal depths share a sub-bucket -- so concatenating sorted sub-buckets is the sorted bucket),
+// scatters the keys through shared memory, and its eight warps sort the sub-buckets in registers exactly like
+// bucket_sort_pack_kernel.  A sub-bucket that still exceeds kWarpSortMax (many equal depths) sends the whole
+// bucket through the block-wide bitonic network; a bucket larger than shared memory is sorted in place in global
+// memory (rare, slow, still exact).
+constexpr int kSubMax = 128;          // sub-buckets per big bucket
+constexpr int kSubTarget = 48;        // aimed-at keys per sub-bucket
+constexpr size_t kBigSmemBytes = 2 * (size_t)kSortSmem * sizeof(uint64_t);
+
 __global__ void __launch_bounds__(kSortThreads)
 big_bucket_sort_pack_kernel(GeometryState g, BinningState b, uint32_t capacity, int bucket_log2)
 {
-	__shared__ uint64_t s_keys[kSortSmem];
+	extern __shared__ __align__(16) unsigned char big_smem[];
+	uint64_t* const s_keys = reinterpret_cast<uint64_t*>(big_smem);      // [kSortSmem] as loaded
+	uint64_t* const s_part = s_keys + kSortSmem;                          // [kSortSmem] partitioned by sub-bucket
+	__shared__ uint32_t s_cnt[kSubMax], s_off[kSubMax + 1], s_lo[kSortWarps], s_hi[kSortWarps], s_fallback;
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	const uint32_t num_big = g.header->num_big;
 	for (uint32_t e = blockIdx.x; e < num_big; e += gridDim.x) {
 		const uint32_t gw = g.big_list[e];
@@ -376,21 +393,92 @@ big_bucket_sort_pack_kernel(GeometryState g, BinningState b, uint32_t capacity, 
 		const uint32_t s0 = (bk == 0) ? g.tile_start[gw >> bucket_log2] : g.bucket_cursor[gw - 1];
 		const uint32_t n = min(g.bucket_cursor[gw], capacity) - s0;
 		uint64_t* keys = b.keys + s0;
-		const uint64_t* sorted;
-		if (n <= kSortSmem) {
-			for (uint32_t i = threadIdx.x; i < n; i += kSortThreads)
-				s_keys[i] = keys[i];
-			__syncthreads();
-			block_bitonic(s_keys, n);
-			sorted = s_keys;
-		} else {
-			// longer than shared memory holds: in place in global memory (rare, slow, still exact)
+		if (n > kSortSmem) {
 			block_bitonic(keys, n);
-			sorted = keys;
+			for (uint32_t i = threadIdx.x; i < n; i += kSortThreads)
+				pack_one(g, b, s0 + i, (uint32_t)keys[i]);
+			continue;
 		}
+		// load, depth range of the bucket
+		uint32_t lo = 0xffffffffu, hi = 0u;
+		for (uint32_t i = threadIdx.x; i < n; i += kSortThreads) {
+			const uint64_t k = keys[i];
+			s_keys[i] = k;
+			lo = min(lo, (uint32_t)(k >> 32));
+			hi = max(hi, (uint32_t)(k >> 32));
+		}
+#pragma unroll
+		for (int o = 16; o > 0; o >>= 1) {
+			lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+			hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+		}
+		if (lane == 0) { s_lo[warp] = lo; s_hi[warp] = hi; }
+		if (threadIdx.x < kSubMax) s_cnt[threadIdx.x] = 0u;
+		if (threadIdx.x == 0) s_fallback = 0u;
+		__syncthreads();
+#pragma unroll
+		for (int w = 0; w < kSortWarps; w++) {
+			lo = min(lo, s_lo[w]);
+			hi = max(hi, s_hi[w]);
+		}
+		uint32_t S = 1;
+		while (S < (uint32_t)kSubMax && S * kSubTarget < n) S <<= 1;
+		// float arithmetic is monotone (conversion, multiplication by a positive constant, truncation)
+		const float scale = (float)S / ((float)(hi - lo) + 1.0f);
+		auto sub_of = [&](uint64_t k) {
+			return min(S - 1u, (uint32_t)((float)((uint32_t)(k >> 32) - lo) * scale));
+		};
 		for (uint32_t i = threadIdx.x; i < n; i += kSortThreads)
-			pack_one(g, b, s0 + i, (uint32_t)sorted[i]);
-		__syncthreads();   // s_keys is reused by the next bucket
+			atomicAdd(&s_cnt[sub_of(s_keys[i])], 1u);
+		__syncthreads();
+		if (warp == 0) {
+			// exclusive scan of up to 128 counts, four per lane
+			uint32_t c[4], sum = 0;
+#pragma unroll
+			for (int u = 0; u < 4; u++) {
+				c[u] = (uint32_t)(4 * lane + u) < S ? s_cnt[4 * lane + u] : 0u;
+				sum += c[u];
+			}
+			uint32_t incl = sum;
+#pragma unroll
+			for (int o = 1; o < 32; o <<= 1) {
+				const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+				if (lane >= o) incl += v;
+			}
+			uint32_t at = incl - sum;
+#pragma unroll
+			for (int u = 0; u < 4; u++) {
+				if ((uint32_t)(4 * lane + u) < S) {
+					s_off[4 * lane + u] = at;
+					s_cnt[4 * lane + u] = at;              // becomes the scatter cursor
+				}
+				at += c[u];
+			}
+			if (lane == 31) s_off[S] = at;
+		}
+		__syncthreads();
+		for (uint32_t i = threadIdx.x; i < n; i += kSortThreads) {
+			const uint64_t k = s_keys[i];
+			s_part[atomicAdd(&s_cnt[sub_of(k)], 1u)] = k;
+		}
+		__syncthreads();
+		for (uint32_t sb = warp; sb < S; sb += kSortWarps) {
+			const uint32_t o0 = s_off[sb], m = s_off[sb + 1] - o0;
+			if (m == 0) continue;
+			if (m <= 32) warp_sort_pack<1>(g, b, s_part + o0, s0 + o0, m, lane);
+			else if (m <= 64) warp_sort_pack<2>(g, b, s_part + o0, s0 + o0, m, lane);
+			else if (m <= 128) warp_sort_pack<4>(g, b, s_part + o0, s0 + o0, m, lane);
+			else if (m <= kWarpSortMax) warp_sort_pack<8>(g, b, s_part + o0, s0 + o0, m, lane);
+			else if (lane == 0) s_fallback = 1u;
+		}
+		__syncthreads();
+		if (s_fallback) {
+			// s_part is a permutation of the bucket; the total order is unique, so re-packing is idempotent
+			block_bitonic(s_part, n);
+			for (uint32_t i = threadIdx.x; i < n; i += kSortThreads)
+				pack_one(g, b, s0 + i, (uint32_t)s_part[i]);
+		}
+		__syncthreads();   // the shared arrays are reused by the next bucket
 	}
 }
 
@@ -431,7 +519,9 @@ int launch_sort_pack(int num_tiles, const GeometryState& g, const BinningState& 
 	const uint32_t total = (uint32_t)num_tiles << vp.bucket_log2;
 	bucket_sort_pack_kernel<<<(total + kSortWarps - 1) / kSortWarps, kSortThreads, 0, stream>>>(
 		g, b, capacity, vp.bucket_log2, total);
-	big_bucket_sort_pack_kernel<<<148 * 4, kSortThreads, 0, stream>>>(g, b, capacity, vp.bucket_log2);
+	// 64 KB of dynamic shared memory: three blocks per SM
+	cudaFuncSetAttribute(big_bucket_sort_pack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBigSmemBytes);
+	big_bucket_sort_pack_kernel<<<148 * 3, kSortThreads, kBigSmemBytes, stream>>>(g, b, capacity, vp.bucket_log2);
 	return GM_OK;
 }
 

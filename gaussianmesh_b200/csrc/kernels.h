@@ -69,4 +69,14 @@ int acap_build_rings_host(int Vn, int Fn, const int* F, int* ring_off, int* ring
 
 int launch_l1(size_t numel, const float* img, const float* target, float* loss, float* dL_dimg, cudaStream_t stream);
 
+size_t photometric_scratch_bytes(int C, int H, int W);
+int launch_photometric(int C, int H, int W, const float* img, const float* gt, float lambda, char* scratch, float* out,
+                       float* dL_dimg, cudaStream_t stream);
+int launch_mesh_restrict(int P, const float* scale, const float* v1, const float* v2, const float* v3, float weight,
+                         float* loss, float* dL_dscale, int accumulate, cudaStream_t stream);
+int launch_adam(int n, const gm_adam_tensor* tensors, int step, float beta1, float beta2, float eps,
+                cudaStream_t stream);
+int launch_densify_stats(int P, const int* radii, const float* dL_dmean2D, float* max_radii2D, float* grad_accum,
+                         float* denom, cudaStream_t stream);
+
 } // namespace gm

@@ -1,11 +1,14 @@
-// Training-loss kernels around the rasterizer op: SSIM with its gradient and the mesh-restrict
-// regulariser of train_mesh_gaussian.py:92-94.
+// Training-loss kernels around the rasterizer op: the photometric loss of
+// train_mesh_gaussian.py:91-94, (1 - lambda) L1 + lambda (1 - SSIM), with its gradient, and the mesh-restrict
+// regulariser.
 //
-//   ssim                 utils/loss_utils.py:36-82: 11x11 Gaussian window (sigma 1.5), zero padding, per channel,
+//   l1 / ssim            utils/loss_utils.py:17-18,36-82: 11x11 Gaussian window (sigma 1.5), zero padding, per channel,
 //                        C1 = 0.01^2, C2 = 0.03^2, mean over all elements.  The reference runs five grouped conv2d
 //                        launches plus ~15 elementwise kernels (and their autograd mirrors); here one kernel produces
-//                        the SSIM sum and the three partial-derivative maps, a second convolves those maps into
-//                        dL/dimg1.  Separable passes through shared memory, one 16x16 output tile per block.
+//                        the L1 sum, the SSIM sum and the three partial-derivative maps of the SSIM map, a second
+//                        convolves those maps into dL/dimg and adds the L1 sign term.  Separable passes through shared
+//                        memory, one 16x16 output tile per block; the last block to finish folds the two sums into
+//                        (loss, L1, SSIM), so the whole loss is two launches and no host round trip.
 //   mesh_restrict_loss   utils/loss_utils.py:84-107: sum(max(0, max_k scale_k - weight * sqrt(|(v2-v1) x (v3-v1)|)))
 #include "common.cuh"
 #include "kernels.h"
@@ -14,44 +17,81 @@ namespace gm {
 
 namespace {
 
-constexpr int kT = 16;            // output tile edge
+constexpr int kT = 32;            // output tile edge
 constexpr int kR = 5;             // window radius (11 taps)
-constexpr int kIn = kT + 2 * kR;  // 26
+constexpr int kIn = kT + 2 * kR;  // 42
+constexpr int kSeg = 4;           // outputs per thread along the filter direction (register blocking)
+constexpr int kPT = 256;          // threads per block
 constexpr float kC1 = 0.01f * 0.01f, kC2 = 0.03f * 0.03f;
 
 // gaussian(11, 1.5) of utils/loss_utils.py:23-25, normalised
 __constant__ float c_win[11] = {0.00102838f, 0.00759876f, 0.03600077f, 0.10936069f, 0.21300554f, 0.26601172f,
                                 0.21300554f, 0.10936069f, 0.03600077f, 0.00759876f, 0.00102838f};
 
+// head of the caller's scratch chunk; the three derivative maps follow at kMapsOffset
+struct PhotoSums {
+	float l1, ssim;
+	unsigned int done;
+	unsigned int pad;
+};
+constexpr size_t kMapsOffset = 128;
+
 __device__ __forceinline__ float block_sum(float v, float* warp_part)
 {
 #pragma unroll
 	for (int o = 16; o > 0; o >>= 1)
 		v += __shfl_xor_sync(0xffffffffu, v, o);
-	const int tid = threadIdx.y * kT + threadIdx.x;
+	const int tid = threadIdx.x;
+	__syncthreads();                                           // warp_part may still be read from a previous call
 	if ((tid & 31) == 0) warp_part[tid >> 5] = v;
 	__syncthreads();
 	float s = 0.0f;
 	if (tid == 0)
-		for (int w = 0; w < kT * kT / 32; w++) s += warp_part[w];
+		for (int w = 0; w < kPT / 32; w++) s += warp_part[w];
 	return s;
 }
 
-__global__ void __launch_bounds__(kT * kT)
-ssim_forward_kernel(int H, int W, const float* __restrict__ img1, const float* __restrict__ img2,
-                    float* __restrict__ ssim_sum, float* __restrict__ dmaps /* [3][C][H][W] or null */, size_t plane_all)
+// Both kernels filter a 32x32 output tile (42x42 with the halo) separably through shared memory.  Every thread
+// produces kSeg = 4 adjacent outputs along the filter direction from 14 staged inputs, so a tap costs one FMA and
+// 0.3 shared-memory loads instead of one FMA and one load.
+//   horizontal pass: work item = (row of the 42, group of 4 columns): 42 x 8 items over 256 threads
+//   vertical pass:   work item = (group of 4 rows, column): warp w owns rows 4w..4w+3, lane = column
+template <int Q>
+__device__ __forceinline__ void vertical4(const float (*s_h)[kIn][kT + 1], int row0, int col, float (&out)[Q][kSeg])
+{
+#pragma unroll
+	for (int q = 0; q < Q; q++) {
+		float v[kSeg + 10];
+#pragma unroll
+		for (int k = 0; k < kSeg + 10; k++)
+			v[k] = s_h[q][row0 + k][col];
+#pragma unroll
+		for (int j = 0; j < kSeg; j++) {
+			float acc = 0.0f;
+#pragma unroll
+			for (int k = 0; k < 11; k++)
+				acc += c_win[k] * v[j + k];
+			out[q][j] = acc;
+		}
+	}
+}
+
+__global__ void __launch_bounds__(kPT)
+photometric_forward_kernel(int H, int W, const float* __restrict__ img1, const float* __restrict__ img2,
+                           PhotoSums* __restrict__ sums, float* __restrict__ dmaps /* [3][C][H][W] or null */,
+                           size_t plane_all, float lambda, float inv_numel, float* __restrict__ out /* [3] */)
 {
 	__shared__ float s_x[kIn][kIn + 1], s_y[kIn][kIn + 1];
 	__shared__ float s_h[5][kIn][kT + 1];
-	__shared__ float warp_part[kT * kT / 32];
+	__shared__ float warp_part[kPT / 32];
 	const int ch = blockIdx.z;
 	const int x0 = blockIdx.x * kT, y0 = blockIdx.y * kT;
 	const size_t plane = (size_t)H * W;
 	const float* a = img1 + ch * plane;
 	const float* b = img2 + ch * plane;
-	const int tid = threadIdx.y * kT + threadIdx.x;
+	const int tid = threadIdx.x;
 
-	for (int i = tid; i < kIn * kIn; i += kT * kT) {
+	for (int i = tid; i < kIn * kIn; i += kPT) {
 		const int ly = i / kIn, lx = i % kIn;
 		const int gy = y0 + ly - kR, gx = x0 + lx - kR;
 		const bool in = gy >= 0 && gy < H && gx >= 0 && gx < W;
@@ -59,61 +99,97 @@ ssim_forward_kernel(int H, int W, const float* __restrict__ img1, const float* _
 		s_y[ly][lx] = in ? b[(size_t)gy * W + gx] : 0.0f;
 	}
 	__syncthreads();
-	// horizontal pass: 26 rows x 16 columns, five quantities
-	for (int i = tid; i < kIn * kT; i += kT * kT) {
-		const int ly = i / kT, lx = i % kT;
-		float m1 = 0, m2 = 0, xx = 0, yy = 0, xy = 0;
+	// horizontal pass, five quantities: x, y, x^2, y^2, xy
+	for (int i = tid; i < kIn * (kT / kSeg); i += kPT) {
+		const int ly = i / (kT / kSeg), c0 = (i % (kT / kSeg)) * kSeg;
+		float u[kSeg + 10], v[kSeg + 10];
 #pragma unroll
-		for (int k = 0; k < 11; k++) {
-			const float w = c_win[k], u = s_x[ly][lx + k], v = s_y[ly][lx + k];
-			m1 += w * u; m2 += w * v; xx += w * u * u; yy += w * v * v; xy += w * u * v;
+		for (int k = 0; k < kSeg + 10; k++) {
+			u[k] = s_x[ly][c0 + k];
+			v[k] = s_y[ly][c0 + k];
 		}
-		s_h[0][ly][lx] = m1; s_h[1][ly][lx] = m2; s_h[2][ly][lx] = xx; s_h[3][ly][lx] = yy; s_h[4][ly][lx] = xy;
+		float acc[5][kSeg];
+#pragma unroll
+		for (int j = 0; j < kSeg; j++)
+#pragma unroll
+			for (int q = 0; q < 5; q++) acc[q][j] = 0.0f;
+#pragma unroll
+		for (int k = 0; k < kSeg + 10; k++) {
+			const float xx = u[k] * u[k], yy = v[k] * v[k], xy = u[k] * v[k];
+#pragma unroll
+			for (int j = 0; j < kSeg; j++) {
+				const int tap = k - j;
+				if (tap >= 0 && tap < 11) {
+					const float w = c_win[tap];
+					acc[0][j] += w * u[k]; acc[1][j] += w * v[k];
+					acc[2][j] += w * xx; acc[3][j] += w * yy; acc[4][j] += w * xy;
+				}
+			}
+		}
+#pragma unroll
+		for (int q = 0; q < 5; q++)
+#pragma unroll
+			for (int j = 0; j < kSeg; j++) s_h[q][ly][c0 + j] = acc[q][j];
 	}
 	__syncthreads();
-	const int lx = threadIdx.x, ly = threadIdx.y;
-	const int gx = x0 + lx, gy = y0 + ly;
-	float val = 0.0f;
-	if (gx < W && gy < H) {
-		float mu1 = 0, mu2 = 0, exx = 0, eyy = 0, exy = 0;
+	const int lx = tid & 31, ly0 = (tid >> 5) * kSeg;
+	const int gx = x0 + lx;
+	float mom[5][kSeg];
+	vertical4<5>(s_h, ly0, lx, mom);
+	float val_sum = 0.0f, l1_sum = 0.0f;
 #pragma unroll
-		for (int k = 0; k < 11; k++) {
-			const float w = c_win[k];
-			mu1 += w * s_h[0][ly + k][lx]; mu2 += w * s_h[1][ly + k][lx];
-			exx += w * s_h[2][ly + k][lx]; eyy += w * s_h[3][ly + k][lx]; exy += w * s_h[4][ly + k][lx];
-		}
-		const float mu1_sq = mu1 * mu1, mu2_sq = mu2 * mu2, mu12 = mu1 * mu2;
-		const float s1 = exx - mu1_sq, s2 = eyy - mu2_sq, s12 = exy - mu12;
-		const float A1 = 2.0f * mu12 + kC1, A2 = 2.0f * s12 + kC2;
-		const float B1 = mu1_sq + mu2_sq + kC1, B2 = s1 + s2 + kC2;
-		const float inv = 1.0f / (B1 * B2);
-		val = A1 * A2 * inv;                                   // utils/loss_utils.py:77
-		if (dmaps != nullptr) {
-			const size_t at = ch * plane + (size_t)gy * W + gx;
-			// partial derivatives of the map w.r.t. the three window averages img1 enters: E[x], E[x^2], E[xy]
-			dmaps[at] = (2.0f * mu2 * A2 - 2.0f * mu2 * A1) * inv - val * (2.0f * mu1 / B1 - 2.0f * mu1 / B2);
-			dmaps[plane_all + at] = -val / B2;
-			dmaps[2 * plane_all + at] = 2.0f * A1 * inv;
+	for (int j = 0; j < kSeg; j++) {
+		const int gy = y0 + ly0 + j;
+		if (gx < W && gy < H) {
+			const float mu1 = mom[0][j], mu2 = mom[1][j];
+			const float mu1_sq = mu1 * mu1, mu2_sq = mu2 * mu2, mu12 = mu1 * mu2;
+			const float s1 = mom[2][j] - mu1_sq, s2 = mom[3][j] - mu2_sq, s12 = mom[4][j] - mu12;
+			const float A1 = 2.0f * mu12 + kC1, A2 = 2.0f * s12 + kC2;
+			const float B1 = mu1_sq + mu2_sq + kC1, B2 = s1 + s2 + kC2;
+			const float inv = 1.0f / (B1 * B2);
+			const float val = A1 * A2 * inv;                       // utils/loss_utils.py:77
+			val_sum += val;
+			l1_sum += fabsf(s_x[ly0 + j + kR][lx + kR] - s_y[ly0 + j + kR][lx + kR]);   // utils/loss_utils.py:18
+			if (dmaps != nullptr) {
+				const size_t at = ch * plane + (size_t)gy * W + gx;
+				// partial derivatives of the map w.r.t. the three window averages img1 enters: E[x], E[x^2], E[xy]
+				dmaps[at] = (2.0f * mu2 * A2 - 2.0f * mu2 * A1) * inv - val * (2.0f * mu1 / B1 - 2.0f * mu1 / B2);
+				dmaps[plane_all + at] = -val / B2;
+				dmaps[2 * plane_all + at] = 2.0f * A1 * inv;
+			}
 		}
 	}
-	const float s = block_sum(val, warp_part);
-	if (tid == 0)
-		atomicAdd(ssim_sum, s);
+	const float s_ssim = block_sum(val_sum, warp_part);
+	const float s_l1 = block_sum(l1_sum, warp_part);
+	if (tid == 0) {
+		atomicAdd(&sums->ssim, s_ssim);
+		atomicAdd(&sums->l1, s_l1);
+		__threadfence();
+		const unsigned int total = gridDim.x * gridDim.y * gridDim.z;
+		if (atomicAdd(&sums->done, 1u) == total - 1) {
+			// last block: every other block's sums are visible (fence before its ticket)
+			const float L1 = atomicAdd(&sums->l1, 0.0f) * inv_numel;
+			const float S = atomicAdd(&sums->ssim, 0.0f) * inv_numel;
+			out[0] = (1.0f - lambda) * L1 + lambda * (1.0f - S);   // train_mesh_gaussian.py:94 without mrloss
+			out[1] = L1;
+			out[2] = S;
+		}
+	}
 }
 
-// dL/dimg1 += scale * (conv(D_mu) + 2 x conv(D_xx) + y conv(D_xy))
-__global__ void __launch_bounds__(kT * kT)
-ssim_backward_kernel(int H, int W, const float* __restrict__ img1, const float* __restrict__ img2,
-                     const float* __restrict__ dmaps, size_t plane_all, const float* __restrict__ scale_dev, float scale_host,
-                     float* __restrict__ dL_dimg1, int accumulate)
+// dL/dimg = (1 - lambda) sign(x - y) / numel  -  lambda / numel * (conv(D_mu) + 2 x conv(D_xx) + y conv(D_xy))
+__global__ void __launch_bounds__(kPT)
+photometric_backward_kernel(int H, int W, const float* __restrict__ img1, const float* __restrict__ img2,
+                            const float* __restrict__ dmaps, size_t plane_all, float l1_scale, float ssim_scale,
+                            float* __restrict__ dL_dimg1)
 {
 	__shared__ float s_d[3][kIn][kIn + 1];
 	__shared__ float s_h[3][kIn][kT + 1];
 	const int ch = blockIdx.z;
 	const int x0 = blockIdx.x * kT, y0 = blockIdx.y * kT;
 	const size_t plane = (size_t)H * W;
-	const int tid = threadIdx.y * kT + threadIdx.x;
-	for (int i = tid; i < kIn * kIn; i += kT * kT) {
+	const int tid = threadIdx.x;
+	for (int i = tid; i < kIn * kIn; i += kPT) {
 		const int ly = i / kIn, lx = i % kIn;
 		const int gy = y0 + ly - kR, gx = x0 + lx - kR;
 		const bool in = gy >= 0 && gy < H && gx >= 0 && gx < W;
@@ -123,29 +199,39 @@ ssim_backward_kernel(int H, int W, const float* __restrict__ img1, const float* 
 			s_d[m][ly][lx] = in ? dmaps[m * plane_all + at] : 0.0f;
 	}
 	__syncthreads();
-	for (int i = tid; i < kIn * kT; i += kT * kT) {
-		const int ly = i / kT, lx = i % kT;
-		float acc[3] = {0, 0, 0};
+	for (int i = tid; i < kIn * (kT / kSeg); i += kPT) {
+		const int ly = i / (kT / kSeg), c0 = (i % (kT / kSeg)) * kSeg;
 #pragma unroll
-		for (int k = 0; k < 11; k++)
+		for (int m = 0; m < 3; m++) {
+			float v[kSeg + 10];
 #pragma unroll
-			for (int m = 0; m < 3; m++) acc[m] += c_win[k] * s_d[m][ly][lx + k];
+			for (int k = 0; k < kSeg + 10; k++)
+				v[k] = s_d[m][ly][c0 + k];
 #pragma unroll
-		for (int m = 0; m < 3; m++) s_h[m][ly][lx] = acc[m];
+			for (int j = 0; j < kSeg; j++) {
+				float acc = 0.0f;
+#pragma unroll
+				for (int k = 0; k < 11; k++)
+					acc += c_win[k] * v[j + k];
+				s_h[m][ly][c0 + j] = acc;
+			}
+		}
 	}
 	__syncthreads();
-	const int lx = threadIdx.x, ly = threadIdx.y;
-	const int gx = x0 + lx, gy = y0 + ly;
-	if (gx < W && gy < H) {
-		float acc[3] = {0, 0, 0};
+	const int lx = tid & 31, ly0 = (tid >> 5) * kSeg;
+	const int gx = x0 + lx;
+	float acc[3][kSeg];
+	vertical4<3>(s_h, ly0, lx, acc);
 #pragma unroll
-		for (int k = 0; k < 11; k++)
-#pragma unroll
-			for (int m = 0; m < 3; m++) acc[m] += c_win[k] * s_h[m][ly + k][lx];
-		const size_t at = ch * plane + (size_t)gy * W + gx;
-		const float scale = scale_host * (scale_dev ? scale_dev[0] : 1.0f);
-		const float g = scale * (acc[0] + 2.0f * img1[at] * acc[1] + img2[at] * acc[2]);
-		dL_dimg1[at] = accumulate ? dL_dimg1[at] + g : g;
+	for (int j = 0; j < kSeg; j++) {
+		const int gy = y0 + ly0 + j;
+		if (gx < W && gy < H) {
+			const size_t at = ch * plane + (size_t)gy * W + gx;
+			const float x = img1[at], y = img2[at];
+			const float d = x - y;
+			const float sgn = d > 0.0f ? 1.0f : (d < 0.0f ? -1.0f : 0.0f);
+			dL_dimg1[at] = l1_scale * sgn + ssim_scale * (acc[0][j] + 2.0f * x * acc[1][j] + y * acc[2][j]);
+		}
 	}
 }
 
@@ -153,7 +239,8 @@ constexpr int kThreads = 256;
 
 __global__ void __launch_bounds__(kThreads)
 mesh_restrict_kernel(int P, const float* __restrict__ scale, const float* __restrict__ v1, const float* __restrict__ v2,
-                     const float* __restrict__ v3, float weight, float* __restrict__ loss, float* __restrict__ dL_dscale)
+                     const float* __restrict__ v3, float weight, float* __restrict__ loss, float* __restrict__ dL_dscale,
+                     int accumulate)
 {
 	__shared__ float warp_part[kThreads / 32];
 	float part = 0.0f;
@@ -170,9 +257,14 @@ mesh_restrict_kernel(int P, const float* __restrict__ scale, const float* __rest
 		if (dL_dscale != nullptr) {
 			// gradient of max goes to the first maximal component
 			const int k = (s0 >= s1 && s0 >= s2) ? 0 : (s1 >= s2 ? 1 : 2);
-			dL_dscale[3 * i] = (on && k == 0) ? 1.0f : 0.0f;
-			dL_dscale[3 * i + 1] = (on && k == 1) ? 1.0f : 0.0f;
-			dL_dscale[3 * i + 2] = (on && k == 2) ? 1.0f : 0.0f;
+#pragma unroll
+			for (int c = 0; c < 3; c++) {
+				const float g = (on && k == c) ? 1.0f : 0.0f;
+				if (!accumulate)
+					dL_dscale[3 * i + c] = g;
+				else if (g != 0.0f)
+					dL_dscale[3 * i + c] += g;
+			}
 		}
 	}
 #pragma unroll
@@ -189,33 +281,40 @@ mesh_restrict_kernel(int P, const float* __restrict__ scale, const float* __rest
 
 } // namespace
 
-int launch_ssim_forward(int C, int H, int W, const float* img1, const float* img2, float* ssim_sum, float* dmaps,
-                        cudaStream_t stream)
+size_t photometric_scratch_bytes(int C, int H, int W)
 {
-	cudaMemsetAsync(ssim_sum, 0, sizeof(float), stream);
-	if (C <= 0 || H <= 0 || W <= 0) return GM_OK;
-	const dim3 grid((W + kT - 1) / kT, (H + kT - 1) / kT, C), block(kT, kT);
-	ssim_forward_kernel<<<grid, block, 0, stream>>>(H, W, img1, img2, ssim_sum, dmaps, (size_t)C * H * W);
-	return GM_OK;
+	if (C <= 0 || H <= 0 || W <= 0) return kMapsOffset;
+	return kMapsOffset + 3 * (size_t)C * H * W * sizeof(float);
 }
 
-int launch_ssim_backward(int C, int H, int W, const float* img1, const float* img2, const float* dmaps,
-                         const float* scale_dev, float scale_host, float* dL_dimg1, int accumulate, cudaStream_t stream)
+int launch_photometric(int C, int H, int W, const float* img, const float* gt, float lambda, char* scratch, float* out,
+                       float* dL_dimg, cudaStream_t stream)
 {
-	if (C <= 0 || H <= 0 || W <= 0) return GM_OK;
-	const dim3 grid((W + kT - 1) / kT, (H + kT - 1) / kT, C), block(kT, kT);
-	ssim_backward_kernel<<<grid, block, 0, stream>>>(H, W, img1, img2, dmaps, (size_t)C * H * W, scale_dev, scale_host,
-	                                                 dL_dimg1, accumulate);
+	PhotoSums* sums = reinterpret_cast<PhotoSums*>(scratch);
+	float* dmaps = reinterpret_cast<float*>(scratch + kMapsOffset);
+	cudaMemsetAsync(sums, 0, sizeof(PhotoSums), stream);
+	if (C <= 0 || H <= 0 || W <= 0) {
+		cudaMemsetAsync(out, 0, 3 * sizeof(float), stream);
+		return GM_OK;
+	}
+	const size_t numel = (size_t)C * H * W;
+	const float inv_numel = 1.0f / (float)numel;
+	const dim3 grid((W + kT - 1) / kT, (H + kT - 1) / kT, C), block(kPT);
+	photometric_forward_kernel<<<grid, block, 0, stream>>>(H, W, img, gt, sums, dL_dimg ? dmaps : nullptr, numel, lambda,
+	                                                       inv_numel, out);
+	if (dL_dimg != nullptr)
+		photometric_backward_kernel<<<grid, block, 0, stream>>>(H, W, img, gt, dmaps, numel, (1.0f - lambda) * inv_numel,
+		                                                        -lambda * inv_numel, dL_dimg);
 	return GM_OK;
 }
 
 int launch_mesh_restrict(int P, const float* scale, const float* v1, const float* v2, const float* v3, float weight,
-                         float* loss, float* dL_dscale, cudaStream_t stream)
+                         float* loss, float* dL_dscale, int accumulate, cudaStream_t stream)
 {
 	cudaMemsetAsync(loss, 0, sizeof(float), stream);
 	if (P <= 0) return GM_OK;
 	const int blocks = min(148 * 8, (P + kThreads - 1) / kThreads);
-	mesh_restrict_kernel<<<blocks, kThreads, 0, stream>>>(P, scale, v1, v2, v3, weight, loss, dL_dscale);
+	mesh_restrict_kernel<<<blocks, kThreads, 0, stream>>>(P, scale, v1, v2, v3, weight, loss, dL_dscale, accumulate);
 	return GM_OK;
 }
 

@@ -1,0 +1,339 @@
+"""The rest of one training iteration around the rasterizer op.
+
+  l1_loss / ssim / photometric_loss   utils/loss_utils.py:17-18,36-82 and the combination of
+                                      train_mesh_gaussian.py:91,94, fused with their gradient (two launches)
+  mesh_restrict_loss                  utils/loss_utils.py:84-107
+  get_expon_lr_func                   utils/general_utils.py:29-62 (host arithmetic)
+  Adam                                the jt.nn.Adam(l, lr=0.0, eps=1e-15) of
+                                      scene/mesh_based_gaussian_model.py:248-258: every group in ONE launch
+  TrainingIteration                   train_mesh_gaussian.py:73-147 for a fixed set of Gaussians: learning-rate
+                                      schedule, bind + render, loss, backward, densification statistics, Adam --
+                                      through the C ABI on reused buffers, no autograd tape, no host round trip
+
+torch is plumbing (device memory, streams, autograd hooks); all arithmetic is in libCudaRasterizer.so.  No CPU path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from ._lib import lib, check, AdamTensor, RasterizerError, GM_ERR_BAD_ARGUMENT, GM_BACKWARD_OVERWRITE
+from .arena import RenderArena
+from .mesh_gaussians import _c, _p, _stream, l1_loss  # noqa: F401  (l1_loss re-exported)
+
+
+# ---------------------------------------------------------------------------------------------
+# losses
+# ---------------------------------------------------------------------------------------------
+def _photometric(img: torch.Tensor, gt: torch.Tensor, lambda_dssim: float, want_grad: bool):
+    img, gt = _c(img), _c(gt)
+    if img.dim() == 4 and img.shape[0] == 1:
+        img, gt = img[0], gt[0]
+    if img.dim() != 3 or img.shape != gt.shape:
+        raise RasterizerError("photometric_loss", GM_ERR_BAD_ARGUMENT, "expected two [C,H,W] images of the same shape")
+    Cc, H, W = img.shape
+    scratch = torch.empty(lib.gm_photometric_scratch_bytes(Cc, H, W), dtype=torch.uint8, device=img.device)
+    out = torch.empty(3, dtype=torch.float32, device=img.device)
+    grad = torch.empty_like(img) if want_grad else None
+    check(lib.gm_photometric_loss(Cc, H, W, _p(img), _p(gt), float(lambda_dssim), _p(scratch), _p(out), _p(grad),
+                                  _stream()), "gm_photometric_loss")
+    return out, grad
+
+
+class _Photometric(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, img, gt, lambda_dssim):
+        out, grad = _photometric(img, gt, lambda_dssim, True)
+        ctx.save_for_backward(grad)
+        ctx.shape = img.shape
+        ctx.mark_non_differentiable(out)
+        return out[0].clone(), out
+
+    @staticmethod
+    def backward(ctx, g, _g_parts):
+        (grad,) = ctx.saved_tensors
+        return (grad * g).view(ctx.shape), None, None
+
+
+def photometric_loss(image: torch.Tensor, gt_image: torch.Tensor, lambda_dssim: float = 0.2, return_parts: bool = False):
+    """(1 - lambda_dssim) * l1_loss(image, gt) + lambda_dssim * (1 - ssim(image, gt))
+    (train_mesh_gaussian.py:91,94 without the mrloss term), differentiable w.r.t. `image`.
+    With return_parts also returns the device tensor (loss, L1, SSIM)."""
+    loss, parts = _Photometric.apply(image, gt_image, float(lambda_dssim))
+    return (loss, parts) if return_parts else loss
+
+
+class _SSIM(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, img1, img2):
+        out, grad = _photometric(img1, img2, 1.0, True)     # loss = 1 - ssim
+        ctx.save_for_backward(grad)
+        ctx.shape = img1.shape
+        return out[2].clone()
+
+    @staticmethod
+    def backward(ctx, g):
+        (grad,) = ctx.saved_tensors
+        return (grad * (-g)).view(ctx.shape), None
+
+
+def ssim(img1: torch.Tensor, img2: torch.Tensor, window_size: int = 11, size_average: bool = True) -> torch.Tensor:
+    """utils/loss_utils.py:36-82; differentiable w.r.t. img1 (the rendered image).  Only the configuration the
+    training loop uses (11-tap window, mean over everything) exists on the device."""
+    if window_size != 11 or not size_average:
+        raise NotImplementedError("ssim: only window_size=11, size_average=True (train_mesh_gaussian.py:94) is implemented")
+    return _SSIM.apply(img1, img2)
+
+
+class _MeshRestrict(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, scale, point1, point2, point3, weight):
+        scale, point1, point2, point3 = map(_c, (scale, point1, point2, point3))
+        P = scale.shape[0]
+        loss = torch.empty(1, dtype=torch.float32, device=scale.device)
+        grad = torch.empty_like(scale)
+        check(lib.gm_mesh_restrict_loss(P, _p(scale), _p(point1), _p(point2), _p(point3), float(weight), _p(loss),
+                                        _p(grad), 0, _stream()), "gm_mesh_restrict_loss")
+        ctx.save_for_backward(grad)
+        return loss.view(())
+
+    @staticmethod
+    def backward(ctx, g):
+        (grad,) = ctx.saved_tensors
+        return grad * g, None, None, None, None
+
+
+def mesh_restrict_loss(scale, point1, point2, point3, weight: float = 10) -> torch.Tensor:
+    """utils/loss_utils.py:102-107: sum(clamp(max(scale, dim=1) - weight * circumradius, min=0)); differentiable w.r.t.
+    `scale` (the vertices are constants of the model)."""
+    return _MeshRestrict.apply(scale, point1, point2, point3, weight)
+
+
+# ---------------------------------------------------------------------------------------------
+# schedule + optimizer
+# ---------------------------------------------------------------------------------------------
+def get_expon_lr_func(lr_init, lr_final, lr_delay_steps=0, lr_delay_mult=1.0, max_steps=1000000):
+    """utils/general_utils.py:29-62: log-linear interpolation from lr_init to lr_final with an optional
+    sine-eased delay."""
+    def helper(step):
+        if step < 0 or (lr_init == 0.0 and lr_final == 0.0):
+            return 0.0
+        if lr_delay_steps > 0:
+            delay_rate = lr_delay_mult + (1 - lr_delay_mult) * np.sin(0.5 * np.pi * np.clip(step / lr_delay_steps, 0, 1))
+        else:
+            delay_rate = 1.0
+        t = np.clip(step / max_steps, 0, 1)
+        log_lerp = np.exp(np.log(lr_init) * (1 - t) + np.log(lr_final) * t)
+        return delay_rate * log_lerp
+    return helper
+
+
+@dataclass
+class OptimizationParams:
+    """arguments/__init__.py:71-91 (defaults)."""
+    iterations: int = 30_000
+    position_lr_init: float = 0.00016
+    position_lr_final: float = 0.0000016
+    position_lr_delay_mult: float = 0.01
+    position_lr_max_steps: int = 30_000
+    feature_lr: float = 0.0025
+    opacity_lr: float = 0.05
+    scaling_lr: float = 0.005
+    rotation_lr: float = 0.001
+    percent_dense: float = 0.01
+    lambda_dssim: float = 0.2
+    densification_interval: int = 200
+    opacity_reset_interval: int = 3000
+    densify_from_iter: int = 500
+    densify_until_iter: int = 15_000
+    densify_grad_threshold: float = 0.0002
+    random_background: bool = True
+    alpha_mrloss: float = 6
+
+
+class Adam:
+    """jt.nn.Adam(param_groups, lr, eps, betas) as the reference uses it
+    (scene/mesh_based_gaussian_model.py:248-258): per-group learning rates, dense update of every element.
+    `param_groups` is a list of {'params': [tensor, ...], 'lr': float, 'name': str}; a group may add
+    'lr_head', 'period', 'split' to give elements with (index mod period) < split their own rate.
+    step() updates every tensor of every group with ONE kernel launch."""
+
+    def __init__(self, param_groups: Sequence[dict], lr: float = 0.0, eps: float = 1e-8, betas=(0.9, 0.999)):
+        self.lr, self.eps, self.betas = lr, eps, betas
+        self.param_groups: List[dict] = []
+        self.n_step = 0
+        self.state: Dict[int, Dict[str, torch.Tensor]] = {}
+        for g in param_groups:
+            self.add_param_group(g)
+
+    def add_param_group(self, group: dict) -> None:
+        g = dict(group)
+        g["params"] = list(g["params"])
+        for p in g["params"]:
+            if not p.is_cuda or p.dtype != torch.float32 or not p.is_contiguous():
+                raise RasterizerError("Adam", GM_ERR_BAD_ARGUMENT, "parameters must be contiguous float32 CUDA tensors")
+            self.state[id(p)] = {"exp_avg": torch.zeros_like(p), "exp_avg_sq": torch.zeros_like(p)}
+        self.param_groups.append(g)
+
+    def zero_grad(self) -> None:
+        for g in self.param_groups:
+            for p in g["params"]:
+                p.grad = None
+
+    def step(self, grads: Optional[Dict[int, torch.Tensor]] = None) -> None:
+        """`grads` maps id(param) -> gradient tensor; default is param.grad.  Parameters without a gradient are
+        skipped (a stop_grad parameter in the reference)."""
+        self.n_step += 1
+        rows, keep = [], []
+        for g in self.param_groups:
+            lr = float(g.get("lr", self.lr))
+            for p in g["params"]:
+                gr = p.grad if grads is None else grads.get(id(p))
+                if gr is None:
+                    continue
+                gr = _c(gr)
+                if gr.numel() != p.numel():
+                    raise RasterizerError("Adam", GM_ERR_BAD_ARGUMENT, "gradient / parameter size mismatch")
+                keep.append(gr)
+                st = self.state[id(p)]
+                rows.append(AdamTensor(p.data_ptr(), gr.data_ptr(), st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr(),
+                                       p.numel(), lr, float(g.get("lr_head", lr)), int(g.get("period", 0)),
+                                       int(g.get("split", 0))))
+        if not rows:
+            return
+        table = (AdamTensor * len(rows))(*rows)
+        check(lib.gm_adam_step(len(rows), table, self.n_step, float(self.betas[0]), float(self.betas[1]), float(self.eps),
+                               _stream()), "gm_adam_step")
+
+
+# ---------------------------------------------------------------------------------------------
+# one training iteration on reused buffers
+# ---------------------------------------------------------------------------------------------
+class TrainingIteration:
+    """train_mesh_gaussian.py:73-147 for a fixed set of mesh-bound Gaussians (no densify_and_prune, which changes
+    the tensor shapes): update_learning_rate -> bind + activations -> render -> (1-l) L1 + l (1-SSIM) + mrloss ->
+    backward through the rasterizer and the binding -> densification statistics -> Adam.  Twelve kernel stages per
+    iteration, nothing allocated, nothing read back.  `model` is a renderer.MeshGaussianModel; its parameter
+    tensors are updated in place."""
+
+    def __init__(self, model, opt: OptimizationParams, W: int, H: int, spatial_lr_scale: float = 1.0):
+        self.model, self.opt, self.W, self.H = model, opt, W, H
+        dev = model._bc.device
+        self.device = dev
+        P, M = model._bc.shape[0], model._features.shape[1]
+        self.P, self.M = P, M
+        f = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)
+        self.xyz, self.scale, self.rot, self.opacity = f(P, 3), f(P, 3), f(P, 4), f(P, 1)
+        self.image, self.dL_dimg = f(3, H, W), f(3, H, W)
+        self.radii = torch.empty(P, dtype=torch.int32, device=dev)
+        self.losses = torch.zeros(4, dtype=torch.float32, device=dev)     # loss w/o mrloss, L1, SSIM, mrloss
+        self.scratch = torch.empty(lib.gm_photometric_scratch_bytes(3, H, W), dtype=torch.uint8, device=dev)
+        self.arena = RenderArena(dev, strict=False)
+        # gradient slab: the atomically accumulated part first (zeroed per step), overwritten rows behind it
+        sizes = {"means2D": 3 * P, "conic": 4 * P, "opacity": P, "colors": 3 * P,
+                 "means3D": 3 * P, "cov3D": 6 * P, "sh": 3 * M * P, "scales": 3 * P, "rotations": 4 * P,
+                 "bc": 3 * P, "distance": P, "log_scale": 3 * P, "rot_raw": 4 * P, "opacity_logit": P}
+        offs, total = {}, 0
+        for k, s in sizes.items():
+            offs[k] = total
+            total += ((s + 31) // 32) * 32
+        self._slab = torch.empty(total, dtype=torch.float32, device=dev)
+        self._accum = self._slab[:offs["means3D"]]
+        self.grads = {k: self._slab[offs[k]:offs[k] + sizes[k]] for k in sizes}
+        # densification statistics (scene/mesh_based_gaussian_model.py:241,245-246)
+        self.max_radii2D = torch.zeros(P, dtype=torch.float32, device=dev)
+        self.bc_gradient_accum = torch.zeros(P, 1, dtype=torch.float32, device=dev)
+        self.denom = torch.zeros(P, 1, dtype=torch.float32, device=dev)
+        # optimizer (scene/mesh_based_gaussian_model.py:248-262); f_dc / f_rest share one [P,16,3] tensor
+        pos_lr = opt.position_lr_init * spatial_lr_scale
+        self.optimizer = Adam([
+            {"params": [model._bc], "lr": pos_lr, "name": "bc"},
+            {"params": [model._distance], "lr": pos_lr, "name": "distance"},
+            {"params": [model._features], "lr": opt.feature_lr / 20.0, "lr_head": opt.feature_lr, "period": 3 * M,
+             "split": 3, "name": "features"},
+            {"params": [model._opacity], "lr": opt.opacity_lr, "name": "opacity"},
+            {"params": [model._scaling], "lr": opt.scaling_lr, "name": "scaling"},
+            {"params": [model._rotation], "lr": opt.rotation_lr, "name": "rotation"},
+        ], lr=0.0, eps=1e-15)
+        self.bc_scheduler_args = get_expon_lr_func(lr_init=pos_lr, lr_final=opt.position_lr_final * spatial_lr_scale,
+                                                   lr_delay_mult=opt.position_lr_delay_mult,
+                                                   max_steps=opt.position_lr_max_steps)
+        g = self.grads
+        self._grad_of = {id(model._bc): g["bc"], id(model._distance): g["distance"], id(model._features): g["sh"],
+                         id(model._opacity): g["opacity_logit"], id(model._scaling): g["log_scale"],
+                         id(model._rotation): g["rot_raw"]}
+        self.iteration = 0
+
+    # scene/mesh_based_gaussian_model.py:280-288
+    def update_learning_rate(self, iteration: int) -> float:
+        lr = float(self.bc_scheduler_args(iteration))
+        for g in self.optimizer.param_groups:
+            if g["name"] in ("bc", "distance"):
+                g["lr"] = lr
+        return lr
+
+    def _bind(self, stream) -> None:
+        m = self.model
+        check(lib.gm_mesh_bind_forward(self.P, _p(m._bc), _p(m._distance), _p(m.vertex1), _p(m.vertex2), _p(m.vertex3),
+                                       _p(m.normal), _p(m.r), float(m.alpha_distance), _p(m._scaling), _p(m._rotation),
+                                       _p(m._opacity), _p(self.xyz), _p(self.scale), _p(self.rot), _p(self.opacity),
+                                       stream), "gm_mesh_bind_forward")
+
+    def _view_args(self, cam) -> tuple:
+        p = lambda t: t.data_ptr()
+        return (p(self.xyz), p(self.model._features), None, p(self.opacity), p(self.scale), 1.0, p(self.rot), None,
+                p(cam.world_view_transform), p(cam.full_proj_transform), p(cam.camera_center),
+                math.tan(cam.FoVx * 0.5), math.tan(cam.FoVy * 0.5))
+
+    def reserve_for(self, cams: Sequence, bg: torch.Tensor) -> int:
+        """Size the arena for these views with the current parameters (setup, not training)."""
+        self._bind(torch.cuda.current_stream(self.device).cuda_stream)
+        return self.arena.reserve_for_views(self.P, self.model.active_sh_degree, self.M, bg, self.W, self.H,
+                                            [self._view_args(c) for c in cams])
+
+    def step(self, cam, bg: torch.Tensor, gt_image: torch.Tensor, iteration: Optional[int] = None,
+             optimizer_step: bool = True) -> torch.Tensor:
+        """Enqueue one iteration; returns the device tensor (photometric loss, L1, SSIM, mrloss) -- the reference's
+        `loss` is [0] + [3].  No host synchronisation."""
+        m, opt = self.model, self.opt
+        self.iteration = self.iteration + 1 if iteration is None else iteration
+        it = self.iteration
+        self.update_learning_rate(it)
+        if it % 1000 == 0 and m.active_sh_degree < m.max_sh_degree:          # train_mesh_gaussian.py:80-81
+            m.active_sh_degree += 1
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        D = m.active_sh_degree
+        self._bind(stream)
+        va = self._view_args(cam)
+        cap, _, _, geom, binning, image_state = self.arena.forward(
+            self.P, D, self.M, bg, self.W, self.H, va, False, False, stream, out_color=self.image, radii=self.radii)
+        check(lib.gm_photometric_loss(3, self.H, self.W, _p(self.image), _p(gt_image), float(opt.lambda_dssim),
+                                      _p(self.scratch), _p(self.losses), _p(self.dL_dimg), stream), "gm_photometric_loss")
+        self._accum.zero_()
+        g = self.grads
+        check(lib.gm_backward_ex(self.P, D, self.M, cap, bg.data_ptr(), self.W, self.H, va[0], va[1], None, va[4], 1.0,
+                                 va[6], None, va[8], va[9], va[10], va[11], va[12], self.radii.data_ptr(),
+                                 geom.data_ptr(), binning.data_ptr(), image_state.data_ptr(), self.dL_dimg.data_ptr(),
+                                 _p(g["means2D"]), _p(g["conic"]), _p(g["opacity"]), _p(g["colors"]), _p(g["means3D"]),
+                                 _p(g["cov3D"]), _p(g["sh"]), _p(g["scales"]), _p(g["rotations"]), 0,
+                                 GM_BACKWARD_OVERWRITE, stream), "gm_backward_ex")
+        # train_mesh_gaussian.py:93: mrloss on the activated scale; its gradient joins the rasterizer's dL/dscale
+        check(lib.gm_mesh_restrict_loss(self.P, _p(self.scale), _p(m.vertex1), _p(m.vertex2), _p(m.vertex3),
+                                        float(opt.alpha_mrloss), self.losses.data_ptr() + 12, _p(g["scales"]), 1, stream),
+              "gm_mesh_restrict_loss")
+        check(lib.gm_mesh_bind_backward(self.P, _p(m._bc), _p(m._distance), _p(m.vertex1), _p(m.vertex2), _p(m.vertex3),
+                                        _p(m.normal), _p(m.r), float(m.alpha_distance), _p(m._scaling), _p(m._rotation),
+                                        _p(m._opacity), _p(g["means3D"]), _p(g["scales"]), _p(g["rotations"]),
+                                        _p(g["opacity"]), _p(g["bc"]), _p(g["distance"]), _p(g["log_scale"]),
+                                        _p(g["rot_raw"]), _p(g["opacity_logit"]), stream), "gm_mesh_bind_backward")
+        if it < opt.densify_until_iter:                                       # train_mesh_gaussian.py:114-121
+            check(lib.gm_densify_stats(self.P, _p(self.radii), _p(g["means2D"]), _p(self.max_radii2D),
+                                       _p(self.bc_gradient_accum), _p(self.denom), stream), "gm_densify_stats")
+        if optimizer_step and it < opt.iterations:                            # train_mesh_gaussian.py:136-147
+            self.optimizer.step(self._grad_of)
+        return self.losses

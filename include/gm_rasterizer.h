@@ -233,6 +233,50 @@ int gm_acap_get_rs(int num_vertices, const double* vertex_rest, const double* ve
 int gm_l1_loss(size_t numel, const float* img, const float* target, float* loss /*[1]*/,
                float* dL_dimg, gm_stream_t stream);
 
+/* ---- the rest of one training iteration around the op (train_mesh_gaussian.py:85-147) -------
+ *
+ *  gm_photometric_loss: out[0] = (1 - lambda) L1 + lambda (1 - SSIM), out[1] = L1 = mean|img - gt|,
+ *  out[2] = SSIM(img, gt) (utils/loss_utils.py:17-18,36-82: 11x11 Gaussian window, sigma 1.5, zero padding, per
+ *  channel, mean over all C*H*W elements; train_mesh_gaussian.py:91,94).  If dL_dimg != NULL it receives
+ *  d out[0] / d img ([C,H,W]).  `scratch` is a caller-owned chunk of gm_photometric_scratch_bytes(C,H,W) bytes.
+ *  Two kernel launches, no host synchronisation. */
+size_t gm_photometric_scratch_bytes(int C, int H, int W);
+int gm_photometric_loss(int C, int H, int W, const float* img, const float* gt, float lambda_dssim, char* scratch,
+                        float* out /*[3]*/, float* dL_dimg, gm_stream_t stream);
+
+/*  gm_mesh_restrict_loss (utils/loss_utils.py:84-107, train_mesh_gaussian.py:93):
+ *  *loss = sum_i max(0, max_k scale[i,k] - weight * sqrt(|(v2-v1) x (v3-v1)|)).  If dL_dscale != NULL it receives the
+ *  gradient w.r.t. scale ([P,3]; 1 at the first maximal component of an active Gaussian) -- written when
+ *  accumulate == 0, added when accumulate != 0 (on top of the rasterizer's dL/dscale). */
+int gm_mesh_restrict_loss(int P, const float* scale /*[P,3]*/, const float* vertex1, const float* vertex2,
+                          const float* vertex3 /*[P,3] each*/, float weight, float* loss /*[1]*/, float* dL_dscale,
+                          int accumulate, gm_stream_t stream);
+
+/*  gm_adam_step: one Adam update of every listed tensor in one pass (the reference's
+ *  jt.nn.Adam(l, lr=0.0, eps=1e-15), scene/mesh_based_gaussian_model.py:248-258, stepped at
+ *  train_mesh_gaussian.py:136-147):  m <- b1 m + (1-b1) g;  v <- b2 v + (1-b2) g g;
+ *  p <- p - m * lr * sqrt(1 - b2^step) / (1 - b1^step) / (sqrt(v) + eps).   `tensors_host` is a HOST array; `step`
+ *  is 1-based.  If period > 0, element i uses lr_head when (i mod period) < split and lr otherwise (one
+ *  [P,16,3] feature tensor carrying the f_dc and f_rest learning rates). */
+typedef struct gm_adam_tensor {
+	float* param;
+	const float* grad;
+	float* exp_avg;
+	float* exp_avg_sq;
+	size_t numel;
+	float lr;
+	float lr_head;
+	uint32_t period;
+	uint32_t split;
+} gm_adam_tensor;
+int gm_adam_step(int num_tensors, const gm_adam_tensor* tensors_host, int step, float beta1, float beta2, float eps,
+                 gm_stream_t stream);
+
+/*  gm_densify_stats (train_mesh_gaussian.py:117-121, scene/mesh_based_gaussian_model.py:587-589): for every Gaussian
+ *  with radii > 0:  max_radii2D = max(max_radii2D, radii);  grad_accum += |dL_dmean2D.xy|;  denom += 1. */
+int gm_densify_stats(int P, const int32_t* radii, const float* dL_dmean2D /*[P,3]*/, float* max_radii2D /*[P]*/,
+                     float* grad_accum /*[P]*/, float* denom /*[P]*/, gm_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

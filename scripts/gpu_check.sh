@@ -17,3 +17,6 @@ echo "ncu exit $?"
 timeout 900 ncu --set full --clock-control none --import-source on -k "regex:^(blend|emit|geometry|preprocess|bucket_sort|big_bucket|large_tiles|tile_scan|depth_hist|bucket_lut|l1_kernel)" -s 32 -c 13 -f \
     -o gpurun_out/prof_${tag} python bench.py --steps 3 --warmup 2 --no-cpu-baseline --no-presize > gpurun_out/ncu_full_${tag}.log 2>&1
 echo "ncu full exit $?"
+timeout 900 ncu --set full --clock-control none --import-source on -k "regex:^(photometric|adam_kernel|densify_stats|mesh_restrict|mesh_bind)" -s 14 -c 7 -f \
+    -o gpurun_out/prof_iter_${tag} python bench.py --steps 3 --warmup 2 --no-cpu-baseline --no-presize > gpurun_out/ncu_iter_${tag}.log 2>&1
+echo "ncu iteration kernels exit $?"

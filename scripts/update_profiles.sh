@@ -40,15 +40,15 @@ cat /tmp/ncu_${tag}.md
 echo "## Opcode mix of the two blend kernels (scripts/sass_profile.py)"
 echo
 echo '```'
-python scripts/sass_profile.py gpurun_out/prof_${tag}.ncu-rep blend_backward_kernel 14
-python scripts/sass_profile.py gpurun_out/prof_${tag}.ncu-rep blend_forward_kernel 14
+python scripts/sass_profile.py gpurun_out/prof_${tag}.ncu-rep blend_backward_pairs_kernel 14
+python scripts/sass_profile.py gpurun_out/prof_${tag}.ncu-rep blend_forward_pairs_kernel 14
 echo '```'
 echo
 echo "## Hottest source lines (scripts/line_profile.py)"
 echo
 echo '```'
-python scripts/line_profile.py gpurun_out/prof_${tag}.ncu-rep blend_backward_kernel 12
-python scripts/line_profile.py gpurun_out/prof_${tag}.ncu-rep blend_forward_kernel 10
+python scripts/line_profile.py gpurun_out/prof_${tag}.ncu-rep blend_backward_pairs_kernel 12
+python scripts/line_profile.py gpurun_out/prof_${tag}.ncu-rep blend_forward_pairs_kernel 10
 echo '```'
 } > profiles/r1_ncu_summary.md
 rm -f profiles/r1_bench_ours_prelim.json

@@ -321,3 +321,94 @@ def test_acap_ring_builder_matches_oracle():
                 k = b.index(a[0])
                 assert a == b[k:] + b[:k]
             assert sorted(fl[fo[v]:fo[v + 1]].tolist()) == sorted(np.nonzero((faces == v).any(axis=1))[0].tolist())
+
+
+# ------------------------------------------------------------------------------------------------ training pieces
+def test_ssim_oracle_against_scipy_float64():
+    """oracle/train_np.ssim (conv2d restatement of utils/loss_utils.py:36-82) against an independent float64
+    separable-filter formulation (scipy.ndimage.correlate1d with zero padding)."""
+    import torch
+    from scipy.ndimage import correlate1d
+    from oracle import train_np
+    rng = np.random.default_rng(3)
+    a = rng.uniform(0, 1, (3, 37, 53)).astype(np.float32)
+    b = np.clip(a + rng.normal(0, 0.1, a.shape), 0, 1).astype(np.float32)
+    w = np.exp(-(np.arange(11) - 5) ** 2 / (2 * 1.5 ** 2))
+    w /= w.sum()
+    filt = lambda x: correlate1d(correlate1d(x.astype(np.float64), w, axis=1, mode="constant"), w, axis=2, mode="constant")
+    mu1, mu2 = filt(a), filt(b)
+    s1, s2, s12 = filt(a * a.astype(np.float64)) - mu1 ** 2, filt(b * b.astype(np.float64)) - mu2 ** 2, filt(a.astype(np.float64) * b) - mu1 * mu2
+    ref = (((2 * mu1 * mu2 + 1e-4) * (2 * s12 + 9e-4)) / ((mu1 ** 2 + mu2 ** 2 + 1e-4) * (s1 + s2 + 9e-4))).mean()
+    got = float(train_np.ssim(torch.from_numpy(a), torch.from_numpy(b)))
+    assert abs(got - ref) <= 2e-6
+    assert abs(float(train_np.ssim(torch.from_numpy(a), torch.from_numpy(a))) - 1.0) <= 1e-6
+    # window: normalised, symmetric, the 11 taps the device kernel hard-codes
+    win = train_np.gaussian(11, 1.5).numpy()
+    assert abs(win.sum() - 1) <= 1e-6 and np.allclose(win, win[::-1])
+    assert np.allclose(win, [0.00102838, 0.00759876, 0.03600077, 0.10936069, 0.21300554, 0.26601172,
+                             0.21300554, 0.10936069, 0.03600077, 0.00759876, 0.00102838], atol=1e-8)
+
+
+def test_photometric_gradient_against_finite_differences():
+    from oracle import train_np
+    rng = np.random.default_rng(4)
+    a = rng.uniform(0.1, 0.9, (3, 20, 23))
+    b = rng.uniform(0.1, 0.9, (3, 20, 23))
+    loss, l1, s, g = train_np.photometric_loss_and_grad(a, b, 0.2, dtype=__import__("torch").float64)
+    assert abs(loss - (0.8 * l1 + 0.2 * (1 - s))) <= 1e-12
+    for idx in [(0, 0, 0), (1, 10, 11), (2, 19, 22), (0, 5, 17)]:
+        e = 1e-6
+        ap, am = a.copy(), a.copy()
+        ap[idx] += e
+        am[idx] -= e
+        fd = (train_np.photometric_loss_and_grad(ap, b, 0.2, dtype=__import__("torch").float64)[0]
+              - train_np.photometric_loss_and_grad(am, b, 0.2, dtype=__import__("torch").float64)[0]) / (2 * e)
+        assert abs(fd - g[idx]) <= 1e-7 + 1e-5 * abs(fd)
+
+
+def test_adam_oracle_against_torch_adam():
+    """jittor's Adam folds the bias correction into the step size and adds eps to the uncorrected sqrt(v);
+    with eps = 1e-15 that is torch.optim.Adam to rounding."""
+    import torch
+    from oracle import train_np
+    rng = np.random.default_rng(5)
+    p0 = rng.normal(0, 1, 1000).astype(np.float32)
+    tp = torch.nn.Parameter(torch.from_numpy(p0.copy()).double())
+    opt = torch.optim.Adam([tp], lr=0.01, eps=1e-15)
+    p, m, v = p0.copy(), np.zeros_like(p0), np.zeros_like(p0)
+    for n in range(1, 6):
+        g = rng.normal(0, 1, 1000).astype(np.float32)
+        tp.grad = torch.from_numpy(g).double()
+        opt.step()
+        p, m, v = train_np.adam_step(p, g, m, v, 0.01, n)
+    assert np.abs(p - tp.detach().numpy()).max() <= 2e-6
+    # per-element learning rates (the f_dc / f_rest split of one feature tensor)
+    lr = np.where(np.arange(96) % 48 < 3, 0.0025, 0.0025 / 20)
+    q, _, _ = train_np.adam_step(np.zeros(96, np.float32), np.ones(96, np.float32), np.zeros(96, np.float32),
+                                 np.zeros(96, np.float32), lr, 1)
+    assert np.allclose(q, -lr, rtol=1e-5)
+
+
+def test_mesh_restrict_lr_schedule_and_densify_stats_oracles():
+    from oracle import train_np
+    from gaussianmesh_b200.training import get_expon_lr_func
+    # equilateral triangle of edge 2: |AB x AC| = 2 sqrt(3), "circumradius" = sqrt of that
+    p1 = np.array([[0, 0, 0]], np.float32)
+    p2 = np.array([[2, 0, 0]], np.float32)
+    p3 = np.array([[1, math.sqrt(3), 0]], np.float32)
+    r = math.sqrt(2 * math.sqrt(3))
+    loss, g = train_np.mesh_restrict_loss(np.array([[0.1, 30.0, 0.2]], np.float32), p1, p2, p3, weight=10)
+    assert abs(loss - (30.0 - 10 * r)) <= 1e-4 and g.tolist() == [[0.0, 1.0, 0.0]]
+    loss, g = train_np.mesh_restrict_loss(np.array([[0.1, 3.0, 0.2]], np.float32), p1, p2, p3, weight=10)
+    assert loss == 0.0 and not g.any()
+    # schedule: host mirror == oracle, end points as documented (utils/general_utils.py:36-41)
+    a = train_np.get_expon_lr_func(1.6e-4, 1.6e-6, lr_delay_mult=0.01, max_steps=30000)
+    b = get_expon_lr_func(1.6e-4, 1.6e-6, lr_delay_mult=0.01, max_steps=30000)
+    for step in (0, 1, 100, 15000, 30000, 40000):
+        assert a(step) == b(step)
+    assert abs(a(0) - 1.6e-4) <= 1e-12 and abs(a(30000) - 1.6e-6) <= 1e-12 and a(-1) == 0.0
+    radii = np.array([0, 3, 7, 0], np.int32)
+    gr = np.array([[3, 4, 9], [3, 4, 9], [0, 1, 9], [5, 5, 9]], np.float32)
+    mr, acc, den = train_np.densify_stats(radii, gr, np.array([1, 5, 1, 9], np.float32), np.zeros((4, 1), np.float32),
+                                          np.zeros((4, 1), np.float32))
+    assert mr.tolist() == [1, 5, 7, 9] and acc[:, 0].tolist() == [0, 5, 1, 0] and den[:, 0].tolist() == [0, 1, 1, 0]
