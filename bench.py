@@ -189,6 +189,9 @@ class OursIteration:
         if self.it.arena.verify():
             raise RuntimeError("arena overflow inside the timed training-iteration region")
 
+    def counters(self):
+        return self.it.arena.last_info
+
 
 class ReferenceIteration:
     """The same iteration the way the reference writes it, torch standing in for Jittor (which cannot be installed):
@@ -594,6 +597,9 @@ def main():
             st["achieved_gbs"] = it_alg[k] / (st["ms_per_launch"] * 1e-3) / 1e9
             st["frac_of_hbm_peak"] = st["achieved_gbs"] / peak
     out["train_iteration"]["stages"] = it_stages
+    it_info = it_arm.counters()
+    out["train_iteration"]["instances_per_frame"] = it_info[0]
+    out["train_iteration"]["visible_gaussians"] = it_info[1]
     kernels_per_stage = {"depth_buckets": 2, "preprocess": 2, "emit": 2, "sort_pack": 2}    # the rest launch one kernel
     out["gpu_launches"] = int(sum(v[1] * kernels_per_stage.get(k, 1) for k, v in prof.items()))
     out["host_enqueue_ms_per_step"] = enqueue_ms / K

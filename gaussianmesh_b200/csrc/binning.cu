@@ -376,14 +376,13 @@ bucket_sort_pack_kernel(GeometryState g, BinningState b, uint32_t capacity, int 
 // memory (rare, slow, still exact).
 constexpr int kSubMax = 128;          // sub-buckets per big bucket
 constexpr int kSubTarget = 48;        // aimed-at keys per sub-bucket
-constexpr size_t kBigSmemBytes = 2 * (size_t)kSortSmem * sizeof(uint64_t);
+constexpr size_t kBigSmemBytes = (size_t)kSortSmem * sizeof(uint64_t);
 
 __global__ void __launch_bounds__(kSortThreads)
 big_bucket_sort_pack_kernel(GeometryState g, BinningState b, uint32_t capacity, int bucket_log2)
 {
 	extern __shared__ __align__(16) unsigned char big_smem[];
-	uint64_t* const s_keys = reinterpret_cast<uint64_t*>(big_smem);      // [kSortSmem] as loaded
-	uint64_t* const s_part = s_keys + kSortSmem;                          // [kSortSmem] partitioned by sub-bucket
+	uint64_t* const s_part = reinterpret_cast<uint64_t*>(big_smem);      // [kSortSmem] keys partitioned by sub-bucket
 	__shared__ uint32_t s_cnt[kSubMax], s_off[kSubMax + 1], s_lo[kSortWarps], s_hi[kSortWarps], s_fallback;
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	const uint32_t num_big = g.header->num_big;
@@ -399,13 +398,12 @@ big_bucket_sort_pack_kernel(GeometryState g, BinningState b, uint32_t capacity, 
 				pack_one(g, b, s0 + i, (uint32_t)keys[i]);
 			continue;
 		}
-		// load, depth range of the bucket
+		// depth range of the bucket (the keys were just written by emit: the three passes over them hit L2)
 		uint32_t lo = 0xffffffffu, hi = 0u;
 		for (uint32_t i = threadIdx.x; i < n; i += kSortThreads) {
-			const uint64_t k = keys[i];
-			s_keys[i] = k;
-			lo = min(lo, (uint32_t)(k >> 32));
-			hi = max(hi, (uint32_t)(k >> 32));
+			const uint32_t d = (uint32_t)(keys[i] >> 32);
+			lo = min(lo, d);
+			hi = max(hi, d);
 		}
 #pragma unroll
 		for (int o = 16; o > 0; o >>= 1) {
@@ -429,7 +427,7 @@ big_bucket_sort_pack_kernel(GeometryState g, BinningState b, uint32_t capacity, 
 			return min(S - 1u, (uint32_t)((float)((uint32_t)(k >> 32) - lo) * scale));
 		};
 		for (uint32_t i = threadIdx.x; i < n; i += kSortThreads)
-			atomicAdd(&s_cnt[sub_of(s_keys[i])], 1u);
+			atomicAdd(&s_cnt[sub_of(keys[i])], 1u);
 		__syncthreads();
 		if (warp == 0) {
 			// exclusive scan of up to 128 counts, four per lane
@@ -458,7 +456,7 @@ big_bucket_sort_pack_kernel(GeometryState g, BinningState b, uint32_t capacity, 
 		}
 		__syncthreads();
 		for (uint32_t i = threadIdx.x; i < n; i += kSortThreads) {
-			const uint64_t k = s_keys[i];
+			const uint64_t k = keys[i];
 			s_part[atomicAdd(&s_cnt[sub_of(k)], 1u)] = k;
 		}
 		__syncthreads();
@@ -519,9 +517,8 @@ int launch_sort_pack(int num_tiles, const GeometryState& g, const BinningState& 
 	const uint32_t total = (uint32_t)num_tiles << vp.bucket_log2;
 	bucket_sort_pack_kernel<<<(total + kSortWarps - 1) / kSortWarps, kSortThreads, 0, stream>>>(
 		g, b, capacity, vp.bucket_log2, total);
-	// 64 KB of dynamic shared memory: three blocks per SM
-	cudaFuncSetAttribute(big_bucket_sort_pack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBigSmemBytes);
-	big_bucket_sort_pack_kernel<<<148 * 3, kSortThreads, kBigSmemBytes, stream>>>(g, b, capacity, vp.bucket_log2);
+	// 32 KB of dynamic shared memory, 48 registers: six blocks per SM
+	big_bucket_sort_pack_kernel<<<148 * 6, kSortThreads, kBigSmemBytes, stream>>>(g, b, capacity, vp.bucket_log2);
 	return GM_OK;
 }
 

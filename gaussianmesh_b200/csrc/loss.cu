@@ -56,6 +56,44 @@ __device__ __forceinline__ float block_sum(float v, float* warp_part)
 // 0.3 shared-memory loads instead of one FMA and one load.
 //   horizontal pass: work item = (row of the 42, group of 4 columns): 42 x 8 items over 256 threads
 //   vertical pass:   work item = (group of 4 rows, column): warp w owns rows 4w..4w+3, lane = column
+// Stage the 42x42 input tile of M planes (zero outside the image = conv2d's padding): warp w takes rows w, w+8, ...,
+// three rows at a time with every global load issued before the first shared-memory store.
+template <int M>
+__device__ __forceinline__ void load_tile(float (*dst)[kIn][kIn + 1], const float* const (&src)[M], int H, int W,
+                                          int x0, int y0, int tid)
+{
+	const int lane = tid & 31, warp = tid >> 5;
+	const int gx_a = x0 - kR + lane, gx_b = gx_a + 32;
+	const bool in_a = gx_a >= 0 && gx_a < W, in_b = lane + 32 < kIn && gx_b >= 0 && gx_b < W;
+#pragma unroll
+	for (int r0 = 0; r0 < kIn; r0 += 3 * (kPT / 32)) {
+		float va[3][M], vb[3][M];
+#pragma unroll
+		for (int u = 0; u < 3; u++) {
+			const int ly = r0 + u * (kPT / 32) + warp;
+			const int gy = y0 - kR + ly;
+			const bool row = ly < kIn && gy >= 0 && gy < H;
+			const size_t base = (size_t)gy * W;
+#pragma unroll
+			for (int m = 0; m < M; m++) {
+				va[u][m] = (row && in_a) ? __ldg(src[m] + base + gx_a) : 0.0f;
+				vb[u][m] = (row && in_b) ? __ldg(src[m] + base + gx_b) : 0.0f;
+			}
+		}
+#pragma unroll
+		for (int u = 0; u < 3; u++) {
+			const int ly = r0 + u * (kPT / 32) + warp;
+			if (ly < kIn) {
+#pragma unroll
+				for (int m = 0; m < M; m++) {
+					dst[m][ly][lane] = va[u][m];
+					if (lane + 32 < kIn) dst[m][ly][lane + 32] = vb[u][m];
+				}
+			}
+		}
+	}
+}
+
 template <int Q>
 __device__ __forceinline__ void vertical4(const float (*s_h)[kIn][kT + 1], int row0, int col, float (&out)[Q][kSeg])
 {
@@ -81,22 +119,18 @@ photometric_forward_kernel(int H, int W, const float* __restrict__ img1, const f
                            PhotoSums* __restrict__ sums, float* __restrict__ dmaps /* [3][C][H][W] or null */,
                            size_t plane_all, float lambda, float inv_numel, float* __restrict__ out /* [3] */)
 {
-	__shared__ float s_x[kIn][kIn + 1], s_y[kIn][kIn + 1];
+	__shared__ float s_in[2][kIn][kIn + 1];
 	__shared__ float s_h[5][kIn][kT + 1];
 	__shared__ float warp_part[kPT / 32];
+	float (*const s_x)[kIn + 1] = s_in[0];
+	float (*const s_y)[kIn + 1] = s_in[1];
 	const int ch = blockIdx.z;
 	const int x0 = blockIdx.x * kT, y0 = blockIdx.y * kT;
 	const size_t plane = (size_t)H * W;
-	const float* a = img1 + ch * plane;
-	const float* b = img2 + ch * plane;
 	const int tid = threadIdx.x;
-
-	for (int i = tid; i < kIn * kIn; i += kPT) {
-		const int ly = i / kIn, lx = i % kIn;
-		const int gy = y0 + ly - kR, gx = x0 + lx - kR;
-		const bool in = gy >= 0 && gy < H && gx >= 0 && gx < W;
-		s_x[ly][lx] = in ? a[(size_t)gy * W + gx] : 0.0f;       // zero padding (conv2d padding = 5)
-		s_y[ly][lx] = in ? b[(size_t)gy * W + gx] : 0.0f;
+	{
+		const float* const src[2] = {img1 + ch * plane, img2 + ch * plane};
+		load_tile<2>(s_in, src, H, W, x0, y0, tid);
 	}
 	__syncthreads();
 	// horizontal pass, five quantities: x, y, x^2, y^2, xy
@@ -146,15 +180,17 @@ photometric_forward_kernel(int H, int W, const float* __restrict__ img1, const f
 			const float s1 = mom[2][j] - mu1_sq, s2 = mom[3][j] - mu2_sq, s12 = mom[4][j] - mu12;
 			const float A1 = 2.0f * mu12 + kC1, A2 = 2.0f * s12 + kC2;
 			const float B1 = mu1_sq + mu2_sq + kC1, B2 = s1 + s2 + kC2;
-			const float inv = 1.0f / (B1 * B2);
+			// MUFU.RCP reciprocals (1 ulp): far inside the 1e-5 / 1e-3 tolerances of the loss and its gradient
+			const float rB1 = __fdividef(1.0f, B1), rB2 = __fdividef(1.0f, B2);
+			const float inv = rB1 * rB2;
 			const float val = A1 * A2 * inv;                       // utils/loss_utils.py:77
 			val_sum += val;
 			l1_sum += fabsf(s_x[ly0 + j + kR][lx + kR] - s_y[ly0 + j + kR][lx + kR]);   // utils/loss_utils.py:18
 			if (dmaps != nullptr) {
 				const size_t at = ch * plane + (size_t)gy * W + gx;
 				// partial derivatives of the map w.r.t. the three window averages img1 enters: E[x], E[x^2], E[xy]
-				dmaps[at] = (2.0f * mu2 * A2 - 2.0f * mu2 * A1) * inv - val * (2.0f * mu1 / B1 - 2.0f * mu1 / B2);
-				dmaps[plane_all + at] = -val / B2;
+				dmaps[at] = 2.0f * mu2 * (A2 - A1) * inv - val * 2.0f * mu1 * (rB1 - rB2);
+				dmaps[plane_all + at] = -val * rB2;
 				dmaps[2 * plane_all + at] = 2.0f * A1 * inv;
 			}
 		}
@@ -189,14 +225,9 @@ photometric_backward_kernel(int H, int W, const float* __restrict__ img1, const 
 	const int x0 = blockIdx.x * kT, y0 = blockIdx.y * kT;
 	const size_t plane = (size_t)H * W;
 	const int tid = threadIdx.x;
-	for (int i = tid; i < kIn * kIn; i += kPT) {
-		const int ly = i / kIn, lx = i % kIn;
-		const int gy = y0 + ly - kR, gx = x0 + lx - kR;
-		const bool in = gy >= 0 && gy < H && gx >= 0 && gx < W;
-		const size_t at = ch * plane + (size_t)gy * W + gx;
-#pragma unroll
-		for (int m = 0; m < 3; m++)
-			s_d[m][ly][lx] = in ? dmaps[m * plane_all + at] : 0.0f;
+	{
+		const float* const src[3] = {dmaps + ch * plane, dmaps + plane_all + ch * plane, dmaps + 2 * plane_all + ch * plane};
+		load_tile<3>(s_d, src, H, W, x0, y0, tid);
 	}
 	__syncthreads();
 	for (int i = tid; i < kIn * (kT / kSeg); i += kPT) {

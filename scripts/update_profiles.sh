@@ -27,6 +27,17 @@ for k,v in sorted(d['stages'].items(), key=lambda kv:-kv[1]['ms_per_launch']):
 print()
 print(f"step {d['ms_per_step']:.4f} ms ({d['value']:.1f} frames/s), with stage events {d['ms_per_step_with_stage_events']:.4f} ms, e2e {d['e2e']['ms_per_step']:.4f} ms ({d['e2e']['value']:.1f} frames/s), forward {d['forward']['ms_per_frame']:.4f} ms, edit {d['edit']['ms_per_frame']:.4f} ms; clocks {d['clocks']}")
 r=json.load(open('gpurun_out/bench_ref_${tag}.json'))
+it=d.get('train_iteration')
+if it:
+    print()
+    print(f"full training iteration (section 5): {it['ms_per_iteration']:.4f} ms ({it['value']:.1f} iterations/s); reference-style composition {r['train_iteration']['ms_per_iteration']:.4f} ms ({r['train_iteration']['value']:.1f} iterations/s)")
+    print()
+    print("| iteration stage | ms / launch | share | algorithmic MB | frac of measured HBM peak |")
+    print("|---|---:|---:|---:|---:|")
+    for k,v in sorted(it['stages'].items(), key=lambda kv:-kv[1]['ms_per_launch']):
+        ab=v.get('algorithmic_bytes')
+        print(f"| {k} | {v['ms_per_launch']:.4f} | {100*v['share']:.1f}% | {ab/1e6:.0f} | {v['frac_of_hbm_peak']:.3f} |" if ab else f"| {k} | {v['ms_per_launch']:.4f} | {100*v['share']:.1f}% | | |")
+    print()
 print(f"reference arm: step {r['ms_per_step']:.4f} ms ({r['value']:.1f} frames/s), e2e {r['e2e']['value']:.1f} frames/s, forward {r['forward']['ms_per_frame']:.4f} ms, edit {r['edit']['ms_per_frame']:.4f} ms")
 PY
 } > profiles/r1_launches.md
@@ -37,6 +48,11 @@ echo "Command: \`ncu --set full --clock-control none --import-source on -k regex
 echo "Extracted with \`scripts/ncu_summary.py\`; DRAM bytes per launch are also in \`profiles/dram_traffic.json\` (read by bench.py for \`roofline.traffic\`).  Percentages are ncu's (of its own peaks)."
 echo
 cat /tmp/ncu_${tag}.md
+if [ -f gpurun_out/prof_iter_${tag}.ncu-rep ]; then
+echo "## Kernels of the full training iteration (bench section 5; \`-k regex:^(photometric|adam_kernel|densify_stats|mesh_restrict|mesh_bind) -s 14 -c 7\`)"
+echo
+python scripts/ncu_summary.py gpurun_out/prof_iter_${tag}.ncu-rep
+fi
 echo "## Opcode mix of the two blend kernels (scripts/sass_profile.py)"
 echo
 echo '```'
