@@ -504,7 +504,33 @@ def main():
         ms_it_prof, _ = timed(train_iteration, K, 0, barrier)
         it_prof = _lib.profile_end()
     it_arm.check()
+    it_info = it_arm.counters() if args.impl == "ours" else None
     ms_it = max_over_ranks(ms_it)
+
+    # ---------------------------------------------------------------- (6) view-parallel training (N > 1 only)
+    view_parallel = None
+    if args.impl == "ours" and world > 1:
+        from gaussianmesh_b200.renderer import MeshGaussianModel
+        from gaussianmesh_b200.training import OptimizationParams
+        from gaussianmesh_b200.view_parallel import ViewParallelTrainer
+        del it_arm
+        view_parallel = {"global_batch_views": world,
+                         "workload": "the section-5 iteration with one view per rank per step: gradients averaged over the "
+                                     "ranks, one optimizer step per global batch"}
+        for mode in ("nccl", "p2p"):
+            try:
+                vp_model = MeshGaussianModel(it_arrays, device, requires_grad=False)
+                vp = ViewParallelTrainer(vp_model, OptimizationParams(), WIDTH, HEIGHT, mode=mode)
+                if not args.no_presize:
+                    vp.reserve_for(cams, bg)
+                ms_vp, _ = timed(lambda i: vp.step(cams[i % nv], bg, targets[i % TARGET_POOL]), K, Wm, barrier)
+                if vp.it.arena.verify():
+                    raise RuntimeError("arena overflow inside the timed view-parallel region")
+                ms_vp = max_over_ranks(ms_vp)
+                view_parallel[mode] = {"ms_per_step": ms_vp / K, "views_per_s": world * K / (ms_vp * 1e-3)}
+                del vp, vp_model
+            except Exception as ex:       # keep the headline numbers if symmetric memory is unavailable on a box
+                view_parallel[mode] = {"error": repr(ex)[:300]}
     clocks = sampler.stop() if sampler is not None else None
 
     if rank != 0:
@@ -538,6 +564,11 @@ def main():
                                         "(train_mesh_gaussian.py:73-147 without densify_and_prune)"},
         "clocks": clocks,
     }
+    if view_parallel is not None:
+        view_parallel["exchange"] = {"nccl": "ncclAllReduce of the flat gradient vector + replicated one-launch Adam",
+                                     "p2p": "gm_adam_step_sharded_p2p: reduce-scatter + Adam + all-gather in one kernel over "
+                                            "NVLink peer memory (symmetric memory), optimizer state sharded"}
+        out["view_parallel"] = view_parallel
     if args.impl == "reference":
         out["impl"] = "reference"
         out["gpu_launches"] = 0
@@ -597,7 +628,6 @@ def main():
             st["achieved_gbs"] = it_alg[k] / (st["ms_per_launch"] * 1e-3) / 1e9
             st["frac_of_hbm_peak"] = st["achieved_gbs"] / peak
     out["train_iteration"]["stages"] = it_stages
-    it_info = it_arm.counters()
     out["train_iteration"]["instances_per_frame"] = it_info[0]
     out["train_iteration"]["visible_gaussians"] = it_info[1]
     kernels_per_stage = {"depth_buckets": 2, "preprocess": 2, "emit": 2, "sort_pack": 2}    # the rest launch one kernel

@@ -37,6 +37,12 @@ class AdamTensor(C.Structure):
                 ("split", C.c_uint32)]
 
 
+class AdamSegment(C.Structure):
+    """gm_adam_segment of include/gm_rasterizer.h"""
+    _fields_ = [("offset", C.c_size_t), ("numel", C.c_size_t), ("lr", C.c_float), ("lr_head", C.c_float),
+                ("period", C.c_uint32), ("split", C.c_uint32)]
+
+
 # name -> (restype, argtypes); the order of arguments is that of include/gm_rasterizer.h
 _VIEW_ARGS = [_p, _p, _p, _p, _p, _f, _p, _p, _p, _p, _p, _f, _f]  # means3D .. tan_fovy
 SIGNATURES = {
@@ -70,6 +76,9 @@ SIGNATURES = {
     "gm_photometric_loss": (_i, [_i, _i, _i, _p, _p, _f, _p, _p, _p, _p]),
     "gm_mesh_restrict_loss": (_i, [_i, _p, _p, _p, _p, _f, _p, _p, _i, _p]),
     "gm_adam_step": (_i, [_i, C.POINTER(AdamTensor), _i, _f, _f, _f, _p]),
+    "gm_adam_shard_range": (None, [_z, _i, _i, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
+    "gm_adam_step_sharded_p2p": (_i, [_i, _i, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), _i, C.POINTER(AdamSegment), _z,
+                                      _p, _p, _i, _f, _f, _f, _p]),
     "gm_densify_stats": (_i, [_i, _p, _p, _p, _p, _p, _p]),
     "gm_acap_build_rings": (_i, [_i, _i, _p, _p, _p, _p, _p]),
     "gm_acap_rest": (_i, [_i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),

@@ -555,6 +555,44 @@ int gm_adam_step(int num_tensors, const gm_adam_tensor* tensors_host, int step, 
 	return check_stage("adam", false, (cudaStream_t)stream);
 }
 
+void gm_adam_shard_range(size_t total, int world, int rank, size_t* lo, size_t* hi)
+{
+	// contiguous shards of whole 32-float blocks (a block never straddles two tensors)
+	const size_t blocks = (total + 31) / 32;
+	const size_t base = world > 0 ? blocks / (size_t)world : 0, extra = world > 0 ? blocks % (size_t)world : 0;
+	const size_t r = (size_t)rank;
+	const size_t b0 = r * base + (r < extra ? r : extra);
+	const size_t b1 = b0 + base + (r < extra ? 1 : 0);
+	*lo = b0 * 32 < total ? b0 * 32 : total;
+	*hi = b1 * 32 < total ? b1 * 32 : total;
+}
+
+int gm_adam_step_sharded_p2p(int world, int rank, const float* const* grads_host, float* const* params_host,
+                             int num_segments, const gm_adam_segment* segments_host, size_t total, float* exp_avg,
+                             float* exp_avg_sq, int step, float beta1, float beta2, float eps, gm_stream_t stream)
+{
+	if (world < 1 || world > GM_MAX_PEERS || rank < 0 || rank >= world || num_segments < 0 || num_segments > 8 || step < 1)
+		return GM_ERR_BAD_ARGUMENT;
+	if (!grads_host || !params_host || (num_segments > 0 && !segments_host) || (total & 3) != 0)
+		return GM_ERR_BAD_ARGUMENT;
+	for (int q = 0; q < world; q++)
+		if (!grads_host[q] || !params_host[q])
+			return GM_ERR_BAD_ARGUMENT;
+	for (int s = 0; s < num_segments; s++) {
+		const gm_adam_segment& sg = segments_host[s];
+		if ((sg.offset & 31) != 0 || sg.offset + sg.numel > total || (sg.period > 0 && sg.split > sg.period))
+			return GM_ERR_BAD_ARGUMENT;
+	}
+	size_t lo, hi;
+	gm_adam_shard_range(total, world, rank, &lo, &hi);
+	if (hi > lo && (!exp_avg || !exp_avg_sq))
+		return GM_ERR_BAD_ARGUMENT;
+	{ StageScope scope_(kStAdam, (cudaStream_t)stream);
+	  launch_adam_sharded_p2p(world, rank, grads_host, params_host, num_segments, segments_host, total, exp_avg,
+	                          exp_avg_sq, step, beta1, beta2, eps, (cudaStream_t)stream); }
+	return check_stage("adam_sharded_p2p", false, (cudaStream_t)stream);
+}
+
 int gm_densify_stats(int P, const int32_t* radii, const float* dL_dmean2D, float* max_radii2D, float* grad_accum,
                      float* denom, gm_stream_t stream)
 {

@@ -76,6 +76,9 @@ int launch_mesh_restrict(int P, const float* scale, const float* v1, const float
                          float* loss, float* dL_dscale, int accumulate, cudaStream_t stream);
 int launch_adam(int n, const gm_adam_tensor* tensors, int step, float beta1, float beta2, float eps,
                 cudaStream_t stream);
+int launch_adam_sharded_p2p(int world, int rank, const float* const* grads, float* const* params, int num_segments,
+                            const gm_adam_segment* segments, size_t total, float* exp_avg, float* exp_avg_sq, int step,
+                            float beta1, float beta2, float eps, cudaStream_t stream);
 int launch_densify_stats(int P, const int* radii, const float* dL_dmean2D, float* max_radii2D, float* grad_accum,
                          float* denom, cudaStream_t stream);
 

@@ -12,6 +12,14 @@
 //                   written per element, 128-bit accesses.  A tensor may carry two learning rates with a period
 //                   (features kept as one [P,16,3] tensor: the first 3 floats of every 48 are f_dc, the rest f_rest
 //                   with lr / 20), so the per-frame concat of get_features (:167-170) never has to exist.
+//   adam (view-parallel)  SURVEY.md 8f-4 "view-parallel DP": every rank renders its own view and holds the whole
+//                   model; the gradient exchange, the update and the parameter broadcast are ONE kernel over NVLink
+//                   peer memory.  Rank r owns the r-th contiguous shard of the flat parameter vector: it LOADS that
+//                   shard of every rank's gradient buffer (P2P reads, summed and scaled by 1/world), applies Adam
+//                   with its shard of the moments (the only copy -- optimizer state is sharded) and STORES the new
+//                   parameters into every rank's parameter buffer (P2P writes).  Per rank and step (world-1)/world
+//                   of the gradient bytes cross NVLink in each direction, against 2x that plus a full-size Adam pass
+//                   for all-reduce followed by a replicated update.
 //   densify_stats   train_mesh_gaussian.py:117-121 + scene/mesh_based_gaussian_model.py:587-589:
 //                   max_radii2D = max(max_radii2D, radii), bc_gradient_accum += |dL/dmean2D.xy|, denom += 1 for the
 //                   visible Gaussians -- five indexed Jittor kernels, one here.
@@ -86,6 +94,64 @@ adam_kernel(const __grid_constant__ AdamTable tab, float b0, float b1, float bia
 	}
 }
 
+struct ShardedAdamArgs {
+	const float* grads[GM_MAX_PEERS];
+	float* params[GM_MAX_PEERS];
+	gm_adam_segment seg[kAdamMaxTensors];
+	int world, num_segments;
+	size_t lo, hi;                 // this rank's shard of the flat vector, multiples of 4
+	float* exp_avg;                // [hi - lo]
+	float* exp_avg_sq;
+};
+
+__global__ void __launch_bounds__(kThreads)
+adam_sharded_p2p_kernel(const __grid_constant__ ShardedAdamArgs a, float b0, float b1, float bias, float eps,
+                        float inv_world)
+{
+	const size_t i = a.lo + ((size_t)blockIdx.x * kThreads + threadIdx.x) * 4;
+	if (i >= a.hi)
+		return;
+	// which tensor does this float4 belong to?  Segments start at multiples of 32 floats, so it never straddles two.
+	int k = -1;
+#pragma unroll
+	for (int s = 0; s < kAdamMaxTensors; s++)
+		if (s < a.num_segments && i >= a.seg[s].offset && i < a.seg[s].offset + a.seg[s].numel)
+			k = s;
+	if (k < 0)
+		return;                                                    // alignment padding between tensors
+	const gm_adam_segment& sg = a.seg[k];
+	const size_t rel = i - sg.offset;
+	float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+	for (int r = 0; r < GM_MAX_PEERS; r++) {
+		if (r < a.world) {
+			const float4 t = *reinterpret_cast<const float4*>(a.grads[r] + i);    // peer memory for r != this rank
+			g.x += t.x; g.y += t.y; g.z += t.z; g.w += t.w;
+		}
+	}
+	float gv[4] = {g.x * inv_world, g.y * inv_world, g.z * inv_world, g.w * inv_world};
+	float4 p4 = *reinterpret_cast<const float4*>(a.params[0] + i);                 // params[0] is this rank's own buffer
+	float pv[4] = {p4.x, p4.y, p4.z, p4.w};
+	float4 m4 = *reinterpret_cast<const float4*>(a.exp_avg + (i - a.lo));
+	float4 v4 = *reinterpret_cast<const float4*>(a.exp_avg_sq + (i - a.lo));
+	float mv[4] = {m4.x, m4.y, m4.z, m4.w}, vv[4] = {v4.x, v4.y, v4.z, v4.w};
+	unsigned int r = sg.period > 0 ? (unsigned int)(rel % sg.period) : 0u;
+#pragma unroll
+	for (int c = 0; c < 4; c++) {
+		const float lr = (sg.period > 0 && r < sg.split) ? sg.lr_head : sg.lr;
+		r = (r + 1 == sg.period) ? 0u : r + 1;
+		if (rel + c < sg.numel)
+			adam_one(pv[c], gv[c], mv[c], vv[c], b0, b1, lr * bias, eps);
+	}
+	*reinterpret_cast<float4*>(a.exp_avg + (i - a.lo)) = make_float4(mv[0], mv[1], mv[2], mv[3]);
+	*reinterpret_cast<float4*>(a.exp_avg_sq + (i - a.lo)) = make_float4(vv[0], vv[1], vv[2], vv[3]);
+	const float4 out = make_float4(pv[0], pv[1], pv[2], pv[3]);
+#pragma unroll
+	for (int q = 0; q < GM_MAX_PEERS; q++)
+		if (q < a.world)
+			*reinterpret_cast<float4*>(a.params[q] + i) = out;
+}
+
 __global__ void __launch_bounds__(kThreads)
 densify_stats_kernel(int P, const int* __restrict__ radii, const float* __restrict__ dL_dmean2D,
                      float* __restrict__ max_radii2D, float* __restrict__ grad_accum, float* __restrict__ denom)
@@ -124,6 +190,35 @@ int launch_adam(int n, const gm_adam_tensor* tensors, int step, float beta1, flo
 		if (blocks > 0)
 			adam_kernel<<<blocks, kThreads, 0, stream>>>(tab, beta1, beta2, (float)bias, eps);
 	}
+	return GM_OK;
+}
+
+int launch_adam_sharded_p2p(int world, int rank, const float* const* grads, float* const* params, int num_segments,
+                            const gm_adam_segment* segments, size_t total, float* exp_avg, float* exp_avg_sq, int step,
+                            float beta1, float beta2, float eps, cudaStream_t stream)
+{
+	ShardedAdamArgs a;
+	a.world = world;
+	a.num_segments = num_segments;
+	// own buffer first, then the peers in ring order: every rank starts its P2P traffic on a different link
+	for (int q = 0; q < world; q++) {
+		a.grads[q] = grads[(rank + q) % world];
+		a.params[q] = params[(rank + q) % world];
+	}
+	for (int s = 0; s < num_segments; s++)
+		a.seg[s] = segments[s];
+	size_t lo, hi;
+	gm_adam_shard_range(total, world, rank, &lo, &hi);
+	a.lo = lo;
+	a.hi = hi;
+	a.exp_avg = exp_avg;
+	a.exp_avg_sq = exp_avg_sq;
+	if (hi <= lo)
+		return GM_OK;
+	const double bias = sqrt(1.0 - pow((double)beta2, (double)step)) / (1.0 - pow((double)beta1, (double)step));
+	const size_t vecs = (hi - lo + 3) / 4;
+	adam_sharded_p2p_kernel<<<(unsigned int)((vecs + kThreads - 1) / kThreads), kThreads, 0, stream>>>(
+		a, beta1, beta2, (float)bias, eps, 1.0f / (float)world);
 	return GM_OK;
 }
 

@@ -221,13 +221,42 @@ class TrainingIteration:
     iteration, nothing allocated, nothing read back.  `model` is a renderer.MeshGaussianModel; its parameter
     tensors are updated in place."""
 
-    def __init__(self, model, opt: OptimizationParams, W: int, H: int, spatial_lr_scale: float = 1.0):
+    # parameter tensors in the order of the flat parameter / gradient vectors: (model attribute, gradient name, row width)
+    PARAMS = (("_features", "sh", None), ("_bc", "bc", 3), ("_distance", "distance", 1), ("_scaling", "log_scale", 3),
+              ("_rotation", "rot_raw", 4), ("_opacity", "opacity_logit", 1))
+
+    def __init__(self, model, opt: OptimizationParams, W: int, H: int, spatial_lr_scale: float = 1.0,
+                 alloc=None, flat_params: bool = False):
+        """`alloc(numel)` returns a float32 device vector (default torch.empty); the view-parallel trainer passes a
+        symmetric-memory allocator.  The gradients of the six parameter tensors always live in ONE flat vector
+        (`param_grads`, tensors at 32-float aligned offsets: `layout`); with flat_params the parameters themselves
+        are moved into a vector of the same layout (`flat_parameters`) and the model's tensors become views of it."""
         self.model, self.opt, self.W, self.H = model, opt, W, H
         dev = model._bc.device
         self.device = dev
         P, M = model._bc.shape[0], model._features.shape[1]
         self.P, self.M = P, M
         f = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)
+        if alloc is None:
+            alloc = lambda n: torch.empty(n, dtype=torch.float32, device=dev)
+        self.layout, total = {}, 0
+        for attr, gname, width in self.PARAMS:
+            n = getattr(model, attr).numel()
+            self.layout[gname] = (total, n)
+            total += ((n + 31) // 32) * 32
+        self.flat_numel = total
+        self.param_grads = alloc(total)
+        self.param_grads.zero_()
+        self.flat_parameters = None
+        if flat_params:
+            self.flat_parameters = alloc(total)
+            self.flat_parameters.zero_()
+            for attr, gname, _ in self.PARAMS:
+                off, n = self.layout[gname]
+                old = getattr(model, attr)
+                view = self.flat_parameters[off:off + n].view(old.shape)
+                view.copy_(old.detach())
+                setattr(model, attr, view)
         self.xyz, self.scale, self.rot, self.opacity = f(P, 3), f(P, 3), f(P, 4), f(P, 1)
         self.image, self.dL_dimg = f(3, H, W), f(3, H, W)
         self.radii = torch.empty(P, dtype=torch.int32, device=dev)
@@ -236,8 +265,7 @@ class TrainingIteration:
         self.arena = RenderArena(dev, strict=False)
         # gradient slab: the atomically accumulated part first (zeroed per step), overwritten rows behind it
         sizes = {"means2D": 3 * P, "conic": 4 * P, "opacity": P, "colors": 3 * P,
-                 "means3D": 3 * P, "cov3D": 6 * P, "sh": 3 * M * P, "scales": 3 * P, "rotations": 4 * P,
-                 "bc": 3 * P, "distance": P, "log_scale": 3 * P, "rot_raw": 4 * P, "opacity_logit": P}
+                 "means3D": 3 * P, "cov3D": 6 * P, "scales": 3 * P, "rotations": 4 * P}
         offs, total = {}, 0
         for k, s in sizes.items():
             offs[k] = total
@@ -245,6 +273,8 @@ class TrainingIteration:
         self._slab = torch.empty(total, dtype=torch.float32, device=dev)
         self._accum = self._slab[:offs["means3D"]]
         self.grads = {k: self._slab[offs[k]:offs[k] + sizes[k]] for k in sizes}
+        for gname, (off, n) in self.layout.items():
+            self.grads[gname] = self.param_grads[off:off + n]
         # densification statistics (scene/mesh_based_gaussian_model.py:241,245-246)
         self.max_radii2D = torch.zeros(P, dtype=torch.float32, device=dev)
         self.bc_gradient_accum = torch.zeros(P, 1, dtype=torch.float32, device=dev)
@@ -296,10 +326,22 @@ class TrainingIteration:
         return self.arena.reserve_for_views(self.P, self.model.active_sh_degree, self.M, bg, self.W, self.H,
                                             [self._view_args(c) for c in cams])
 
+    def adam_segments(self):
+        """The flat layout as (offset, numel, lr, lr_head, period, split) rows with the CURRENT learning rates."""
+        by_attr = {id(p): g for g in self.optimizer.param_groups for p in g["params"]}
+        rows = []
+        for attr, gname, _ in self.PARAMS:
+            g = by_attr[id(getattr(self.model, attr))]
+            off, n = self.layout[gname]
+            lr = float(g["lr"])
+            rows.append((off, n, lr, float(g.get("lr_head", lr)), int(g.get("period", 0)), int(g.get("split", 0))))
+        return rows
+
     def step(self, cam, bg: torch.Tensor, gt_image: torch.Tensor, iteration: Optional[int] = None,
              optimizer_step: bool = True) -> torch.Tensor:
         """Enqueue one iteration; returns the device tensor (photometric loss, L1, SSIM, mrloss) -- the reference's
-        `loss` is [0] + [3].  No host synchronisation."""
+        `loss` is [0] + [3].  No host synchronisation.  With optimizer_step=False the iteration stops after the
+        backward pass and the statistics (gradients in `param_grads`): the view-parallel trainer exchanges them."""
         m, opt = self.model, self.opt
         self.iteration = self.iteration + 1 if iteration is None else iteration
         it = self.iteration

@@ -1,0 +1,141 @@
+"""View-parallel training (SURVEY.md 8e "if training were sharded", 8f-4): one process per GPU, every rank holds the
+whole model and renders ITS view of a global batch of `world` views; the first -- and only -- exchange step of this
+repository is the gradient average before the optimizer.  The reference has no counterpart (it is single-GPU); the
+semantics are those of plain data parallelism over views: the loss is the mean over the batch's views, densification
+statistics are accumulated per view as train_mesh_gaussian.py:117-121 does for consecutive iterations.
+
+Two exchange modes:
+
+  "p2p"   gm_adam_step_sharded_p2p: gradient reduce-scatter + Adam + parameter all-gather fused in ONE kernel over
+          NVLink peer memory.  Parameters and gradients live in symmetric memory (torch.distributed._symmetric_memory:
+          cuMem allocations mapped into every rank); rank r reads shard r of every rank's gradient vector, updates it
+          with its shard of the Adam moments (optimizer state is sharded, ZeRO-1 style) and writes the new parameters
+          into every rank's parameter vector.  Two device-side barriers bracket the kernel; no host synchronisation.
+  "nccl"  the baseline the fused kernel is measured against: ncclAllReduce of the flat gradient vector followed by the
+          replicated one-launch Adam (gm_adam_step) on every rank.
+
+`GradientExchange` is the device-agnostic part (torch.distributed only), covered on CPU by a world-size-2 gloo test.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import torch
+
+from ._lib import lib, check, AdamSegment, RasterizerError, GM_ERR_BAD_ARGUMENT
+from .training import OptimizationParams, TrainingIteration
+
+
+class GradientExchange:
+    """Averages flat gradient vectors and merges per-view densification statistics over the ranks of a process group."""
+
+    def __init__(self, group=None):
+        import torch.distributed as dist
+        self.dist = dist
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+
+    def average_(self, flat: torch.Tensor) -> torch.Tensor:
+        if self.world > 1:
+            self.dist.all_reduce(flat, op=self.dist.ReduceOp.SUM, group=self.group)
+            flat.mul_(1.0 / self.world)
+        return flat
+
+    def merge_stats_(self, max_radii2D: torch.Tensor, grad_accum: torch.Tensor, denom: torch.Tensor,
+                     inc_max: torch.Tensor, inc_sum: torch.Tensor) -> None:
+        """inc_max [P]: this rank's radii where visible, else 0; inc_sum [2,P]: (|dL/dmean2D.xy|, 1) where visible.
+        After the call the persistent statistics hold what `world` consecutive single-view iterations would have
+        left (scene/mesh_based_gaussian_model.py:587-589, train_mesh_gaussian.py:117-121)."""
+        if self.world > 1:
+            self.dist.all_reduce(inc_max, op=self.dist.ReduceOp.MAX, group=self.group)
+            self.dist.all_reduce(inc_sum, op=self.dist.ReduceOp.SUM, group=self.group)
+        torch.maximum(max_radii2D, inc_max, out=max_radii2D)
+        grad_accum.view(-1).add_(inc_sum[0])
+        denom.view(-1).add_(inc_sum[1])
+
+
+class ViewParallelTrainer:
+    """One view per rank per step.  `model` must hold identical parameters on every rank."""
+
+    def __init__(self, model, opt: OptimizationParams, W: int, H: int, mode: str = "p2p", group=None,
+                 spatial_lr_scale: float = 1.0):
+        import torch.distributed as dist
+        if mode not in ("p2p", "nccl"):
+            raise ValueError("mode must be 'p2p' or 'nccl'")
+        self.mode = mode
+        self.exchange = GradientExchange(group)
+        self.world, self.rank = self.exchange.world, self.exchange.rank
+        dev = model._bc.device
+        self._handles = []
+        alloc = None
+        if mode == "p2p" and self.world > 1:
+            import torch.distributed._symmetric_memory as symm_mem
+            self._symm = symm_mem
+            self._group = group if group is not None else dist.group.WORLD
+
+            def alloc(n):
+                t = symm_mem.empty(n, dtype=torch.float32, device=dev)
+                self._handles.append((t, symm_mem.rendezvous(t, self._group)))
+                return t
+        self.it = TrainingIteration(model, opt, W, H, spatial_lr_scale, alloc=alloc, flat_params=(mode == "p2p"))
+        it = self.it
+        P = it.P
+        self._inc_max = torch.zeros(P, dtype=torch.float32, device=dev)
+        self._inc_sum = torch.zeros(2, P, dtype=torch.float32, device=dev)
+        self.n_step = 0
+        if mode == "p2p":
+            lo, hi = C.c_size_t(), C.c_size_t()
+            lib.gm_adam_shard_range(it.flat_numel, self.world, self.rank, C.byref(lo), C.byref(hi))
+            self.shard = (lo.value, hi.value)
+            n = max(hi.value - lo.value, 4)
+            self.exp_avg = torch.zeros(n, dtype=torch.float32, device=dev)          # this rank's shard only
+            self.exp_avg_sq = torch.zeros(n, dtype=torch.float32, device=dev)
+            if self.world > 1:
+                (g_t, g_h), (p_t, p_h) = self._handles[0], self._handles[1]        # alloc order: param_grads, flat_parameters
+                assert g_t.data_ptr() == it.param_grads.data_ptr() and p_t.data_ptr() == it.flat_parameters.data_ptr()
+                self._grad_ptrs = (C.c_void_p * self.world)(*[int(x) for x in g_h.buffer_ptrs])
+                self._param_ptrs = (C.c_void_p * self.world)(*[int(x) for x in p_h.buffer_ptrs])
+                self._barrier = p_h
+            else:
+                self._grad_ptrs = (C.c_void_p * 1)(it.param_grads.data_ptr())
+                self._param_ptrs = (C.c_void_p * 1)(it.flat_parameters.data_ptr())
+                self._barrier = None
+
+    def reserve_for(self, cams: Sequence, bg: torch.Tensor) -> int:
+        return self.it.reserve_for(cams, bg)
+
+    def _device_barrier(self, channel: int) -> None:
+        if self._barrier is not None:
+            self._barrier.barrier(channel=channel)
+
+    def step(self, cam, bg: torch.Tensor, gt_image: torch.Tensor, iteration: Optional[int] = None) -> torch.Tensor:
+        """Enqueue one global step (this rank's view); returns this rank's (photometric loss, L1, SSIM, mrloss)."""
+        it = self.it
+        # per-view statistics into zeroed increments, merged over ranks below
+        keep = (it.max_radii2D, it.bc_gradient_accum, it.denom)
+        self._inc_max.zero_()
+        self._inc_sum.zero_()
+        it.max_radii2D, it.bc_gradient_accum, it.denom = self._inc_max, self._inc_sum[0], self._inc_sum[1]
+        try:
+            losses = it.step(cam, bg, gt_image, iteration, optimizer_step=False)
+        finally:
+            it.max_radii2D, it.bc_gradient_accum, it.denom = keep
+        self.n_step += 1
+        stream = torch.cuda.current_stream(it.device).cuda_stream
+        if it.iteration < it.opt.iterations:
+            if self.mode == "nccl":
+                self.exchange.average_(it.param_grads)
+                it.optimizer.step(it._grad_of)
+            else:
+                rows = it.adam_segments()
+                segs = (AdamSegment * len(rows))(*[AdamSegment(*r) for r in rows])
+                self._device_barrier(0)          # every rank's gradients are complete
+                check(lib.gm_adam_step_sharded_p2p(self.world, self.rank, self._grad_ptrs, self._param_ptrs, len(rows), segs,
+                                                   it.flat_numel, self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(),
+                                                   self.n_step, 0.9, 0.999, 1e-15, stream), "gm_adam_step_sharded_p2p")
+                self._device_barrier(1)          # every rank's parameter stores have landed
+        if it.iteration < it.opt.densify_until_iter:
+            self.exchange.merge_stats_(it.max_radii2D, it.bc_gradient_accum, it.denom, self._inc_max, self._inc_sum)
+        return losses

@@ -272,6 +272,31 @@ typedef struct gm_adam_tensor {
 int gm_adam_step(int num_tensors, const gm_adam_tensor* tensors_host, int step, float beta1, float beta2, float eps,
                  gm_stream_t stream);
 
+/*  View-parallel training (no counterpart in the reference, which is single-GPU): every rank holds
+ *  the whole model in ONE flat float vector of `total` floats (tensors at 32-float aligned offsets, described by
+ *  `segments_host`), renders its own view, and leaves its gradient in a flat buffer of the same layout.
+ *  gm_adam_step_sharded_p2p is the gradient exchange + update + parameter broadcast in one kernel over peer memory:
+ *  rank r loads shard r (gm_adam_shard_range) of every rank's gradient buffer, averages, applies the Adam update of
+ *  gm_adam_step with ITS shard of the moments (exp_avg / exp_avg_sq hold hi - lo floats) and stores the new parameters
+ *  into every rank's parameter buffer.  grads_host / params_host are HOST arrays of `world` DEVICE pointers
+ *  (index = rank; entries of other ranks are peer mappings of their buffers, e.g. CUDA IPC / symmetric memory).
+ *  The caller orders the kernel between two cross-rank barriers (all gradients written before; all parameter
+ *  stores landed after).  world <= GM_MAX_PEERS, num_segments <= 8. */
+#define GM_MAX_PEERS 8
+typedef struct gm_adam_segment {
+	size_t offset;          /* first float of the tensor in the flat vector (multiple of 32) */
+	size_t numel;
+	float lr;
+	float lr_head;
+	uint32_t period;
+	uint32_t split;
+} gm_adam_segment;
+void gm_adam_shard_range(size_t total, int world, int rank, size_t* lo, size_t* hi);
+int gm_adam_step_sharded_p2p(int world, int rank, const float* const* grads_host, float* const* params_host,
+                             int num_segments, const gm_adam_segment* segments_host, size_t total,
+                             float* exp_avg, float* exp_avg_sq, int step, float beta1, float beta2, float eps,
+                             gm_stream_t stream);
+
 /*  gm_densify_stats (train_mesh_gaussian.py:117-121, scene/mesh_based_gaussian_model.py:587-589): for every Gaussian
  *  with radii > 0:  max_radii2D = max(max_radii2D, radii);  grad_accum += |dL_dmean2D.xy|;  denom += 1. */
 int gm_densify_stats(int P, const int32_t* radii, const float* dL_dmean2D /*[P,3]*/, float* max_radii2D /*[P]*/,

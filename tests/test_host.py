@@ -228,3 +228,55 @@ def test_cameras_json_roundtrip(tmp_path):
         assert np.allclose(a.world_view_transform, b.world_view_transform, atol=1e-5)
         assert np.allclose(a.full_proj_transform, b.full_proj_transform, atol=1e-4)
         assert np.allclose(a.camera_center, b.camera_center, atol=1e-5)
+
+
+_EXCHANGE_WORKER = r"""
+import os, sys, json
+sys.path.insert(0, {root!r})
+import torch
+import torch.distributed as dist
+dist.init_process_group("gloo")
+from gaussianmesh_b200.view_parallel import GradientExchange
+ex = GradientExchange()
+r = ex.rank
+flat = torch.arange(10, dtype=torch.float32) * (r + 1)                 # rank 0: i, rank 1: 2 i  -> mean 1.5 i
+ex.average_(flat)
+max_r = torch.tensor([1.0, 5.0, 0.0, 9.0]); acc = torch.zeros(4, 1); den = torch.ones(4, 1)
+inc_max = torch.tensor([0.0, 7.0, 3.0, 0.0]) if r == 0 else torch.tensor([2.0, 0.0, 4.0, 0.0])
+inc_sum = torch.tensor([[0.0, 0.5, 0.25, 0.0], [0.0, 1.0, 1.0, 0.0]]) if r == 0 else torch.tensor([[1.0, 0.0, 0.75, 0.0], [1.0, 0.0, 1.0, 0.0]])
+ex.merge_stats_(max_r, acc, den, inc_max, inc_sum)
+out = [None] * ex.world
+dist.all_gather_object(out, {{"flat": flat.tolist(), "max": max_r.tolist(), "acc": acc.view(-1).tolist(), "den": den.view(-1).tolist()}})
+if r == 0:
+    print(json.dumps(out))
+dist.destroy_process_group()
+"""
+
+
+def test_gradient_exchange_two_ranks_over_gloo(tmp_path):
+    """The device-agnostic half of view-parallel training (gradient average, per-view densification statistics merged
+    as consecutive single-view iterations would leave them) at world_size 2 on CPU."""
+    script = tmp_path / "exchange_worker.py"
+    script.write_text(_EXCHANGE_WORKER.format(root=ROOT))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29733", str(script)]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=dict(os.environ, OMP_NUM_THREADS="1"))
+    assert out.returncode == 0, out.stderr[-2000:]
+    import json
+    res = json.loads([l for l in out.stdout.splitlines() if l.startswith("[")][-1])
+    assert len(res) == 2 and res[0] == res[1]
+    assert res[0]["flat"] == [1.5 * i for i in range(10)]
+    assert res[0]["max"] == [2.0, 7.0, 4.0, 9.0] and res[0]["acc"] == [1.0, 0.5, 1.0, 0.0] and res[0]["den"] == [2.0, 2.0, 3.0, 1.0]
+
+
+def test_adam_shard_ranges_partition_the_flat_vector(built_lib):
+    import ctypes as C
+    from gaussianmesh_b200._lib import lib
+    for total, world in [(1000, 3), (64, 2), (32, 4), (60_000_096, 8), (0, 2), (96, 1)]:
+        at = 0
+        for r in range(world):
+            lo, hi = C.c_size_t(), C.c_size_t()
+            lib.gm_adam_shard_range(total, world, r, C.byref(lo), C.byref(hi))
+            assert lo.value == at and hi.value >= lo.value and (lo.value % 32 == 0 or lo.value == total)
+            at = hi.value
+        assert at == total
