@@ -92,6 +92,10 @@ class MeshGaussianModel:
         self._features = t("shs").requires_grad_(requires_grad)
         self.vertex1, self.vertex2, self.vertex3 = t("vertex1"), t("vertex2"), t("vertex3")
         self.normal, self.r = t("normal"), t("r")
+        # mesh bookkeeping carried through densification (scene/mesh_based_gaussian_model.py:59-66); optional
+        self.vertex_index = t("triangles").long() if "triangles" in arrays else None
+        self.fid = t("face_id").long().view(-1, 1) if "face_id" in arrays else None
+        self.v = t("mesh_vertices") if "mesh_vertices" in arrays else None
         self.alpha_distance = alpha_distance
         self.active_sh_degree = sh_degree
         self.max_sh_degree = 3

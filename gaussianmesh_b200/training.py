@@ -232,8 +232,17 @@ class TrainingIteration:
         (`param_grads`, tensors at 32-float aligned offsets: `layout`); with flat_params the parameters themselves
         are moved into a vector of the same layout (`flat_parameters`) and the model's tensors become views of it."""
         self.model, self.opt, self.W, self.H = model, opt, W, H
-        dev = model._bc.device
-        self.device = dev
+        self.device = model._bc.device
+        self.spatial_lr_scale = spatial_lr_scale
+        self._alloc, self._flat = alloc, flat_params
+        self.iteration = 0
+        self._allocate()
+
+    def _allocate(self) -> None:
+        """Buffers, gradient layout and a fresh optimizer for the model's CURRENT number of Gaussians (construction,
+        and again after densify_and_prune changed it)."""
+        model, opt, W, H, dev = self.model, self.opt, self.W, self.H, self.device
+        alloc, flat_params, spatial_lr_scale = self._alloc, self._flat, self.spatial_lr_scale
         P, M = model._bc.shape[0], model._features.shape[1]
         self.P, self.M = P, M
         f = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)
@@ -297,7 +306,111 @@ class TrainingIteration:
         self._grad_of = {id(model._bc): g["bc"], id(model._distance): g["distance"], id(model._features): g["sh"],
                          id(model._opacity): g["opacity_logit"], id(model._scaling): g["log_scale"],
                          id(model._rotation): g["rot_raw"]}
-        self.iteration = 0
+
+    # ------------------------------------------------------------------------------------------
+    # densification (scene/mesh_based_gaussian_model.py:482-585): infrequent model surgery -- every
+    # densification_interval iterations -- done with tensor indexing; it is data movement, not arithmetic
+    # ------------------------------------------------------------------------------------------
+    def densify_and_prune(self, max_grad: float, min_opacity: float = 0.005, extent: float = 0.0,
+                          max_screen_size=None, N: int = 4) -> int:
+        """reference :581-585: grads = bc_gradient_accum / denom (NaN -> 0), then densify_and_split.  (The reference
+        ignores min_opacity / extent / max_screen_size as well.)  Returns the number of Gaussians that were split."""
+        grads = self.bc_gradient_accum / self.denom
+        grads[grads.isnan()] = 0.0
+        return self.densify_and_split(grads, max_grad, extent, N)
+
+    def densify_and_split(self, grads: torch.Tensor, grad_threshold: float, scene_extent: float = 0.0, N: int = 4) -> int:
+        """reference :504-563 + utils/general_utils.py:133-212: every Gaussian whose mean screen-space gradient reaches
+        the threshold is replaced by N children on the 4-way split of its face (N = 5 keeps a copy on the parent face):
+        barycentric logits 1/3, distance 0, scale / 3.2, everything else inherited; the three edge midpoints become new
+        mesh vertices; the survivors keep their Adam moments, children start at zero; statistics restart."""
+        if N not in (4, 5):
+            raise ValueError("N must be 4 or 5 (split_mesh_and_gaussian / split_mesh_and_gaussian_pro)")
+        if self._flat:
+            raise NotImplementedError("densification of a symmetric-memory (view-parallel) model is not implemented")
+        m = self.model
+        sel = grads.reshape(-1) >= grad_threshold
+        S = int(sel.sum().item())                       # the reference reads this back too (:514)
+        if S == 0:
+            return 0
+        keep = ~sel
+        rep = lambda t: t[sel].repeat_interleave(N, dim=0)
+        dev = self.device
+        a, b, c = m.vertex1[sel], m.vertex2[sel], m.vertex3[sel]
+        ab, ac, bc_ = (a + b) / 2, (a + c) / 2, (b + c) / 2
+        # utils/general_utils.py:137-151 (+191-193 for N = 5): child k's triangle
+        v1 = [a, ab, ac, ab] + ([a] if N == 5 else [])
+        v2 = [ab, b, bc_, bc_] + ([b] if N == 5 else [])
+        v3 = [ac, bc_, c, ac] + ([c] if N == 5 else [])
+        stack = lambda parts: torch.stack(parts, dim=1).reshape(S * N, 3)
+        new = {
+            "_bc": torch.full((S * N, 3), 1.0 / 3.0, dtype=torch.float32, device=dev),
+            "_distance": torch.zeros(S * N, 1, dtype=torch.float32, device=dev),
+            "_features": rep(m._features), "_opacity": rep(m._opacity), "_rotation": rep(m._rotation),
+            "_scaling": torch.log(rep(torch.exp(m._scaling)) / (4 * 0.8)),
+        }
+        const = {"vertex1": stack(v1), "vertex2": stack(v2), "vertex3": stack(v3), "normal": rep(m.normal), "r": rep(m.r)}
+        if getattr(m, "fid", None) is not None:
+            const["fid"] = rep(m.fid)
+        if getattr(m, "vertex_index", None) is not None:
+            v_origin_num = int(m.v.shape[0]) if getattr(m, "v", None) is not None else int(m.vertex_index.max().item()) + 1
+            idx = m.vertex_index[sel].unsqueeze(1).repeat(1, N, 1)                       # [S,N,3]
+            tmp = torch.arange(S * 3, device=dev, dtype=idx.dtype).view(S, 3) + v_origin_num
+            idx[:, 0, 1], idx[:, 0, 2] = tmp[:, 0], tmp[:, 1]                           # utils/general_utils.py:160-168
+            idx[:, 1, 0], idx[:, 1, 2] = tmp[:, 0], tmp[:, 2]
+            idx[:, 2, 0], idx[:, 2, 1] = tmp[:, 1], tmp[:, 2]
+            idx[:, 3, 0], idx[:, 3, 1], idx[:, 3, 2] = tmp[:, 0], tmp[:, 2], tmp[:, 1]
+            const["vertex_index"] = idx.reshape(S * N, 3)
+            if getattr(m, "v", None) is not None:
+                m.v = torch.cat([m.v, torch.stack([ab, ac, bc_], dim=1).reshape(S * 3, 3)], dim=0)   # :153-155
+        # survivors first, children behind them (concat then prune_points, :547-563)
+        old_state = {attr: self.optimizer.state[id(getattr(m, attr))] for attr, _, _ in self.PARAMS}
+        moments = {}
+        for attr, _, _ in self.PARAMS:
+            old = getattr(m, attr)
+            st = old_state[attr]
+            moments[attr] = (torch.cat([st["exp_avg"][keep], torch.zeros_like(new[attr])], dim=0),
+                             torch.cat([st["exp_avg_sq"][keep], torch.zeros_like(new[attr])], dim=0))
+            setattr(m, attr, torch.cat([old.detach()[keep], new[attr]], dim=0).contiguous())
+        for name, val in const.items():
+            setattr(m, name, torch.cat([getattr(m, name)[keep], val], dim=0).contiguous())
+        m.screenspace_points = torch.zeros(m._bc.shape[0], 3, device=dev)
+        n_step, lr_groups = self.optimizer.n_step, {g["name"]: g["lr"] for g in self.optimizer.param_groups}
+        persistent = {k: getattr(self, k) for k in ("arena", "losses", "image", "dL_dimg", "scratch")}
+        self._allocate()                                 # buffers for the new size, statistics restart at zero (:499-501)
+        for k, v in persistent.items():
+            setattr(self, k, v)
+        self.optimizer.n_step = n_step
+        for g in self.optimizer.param_groups:
+            g["lr"] = lr_groups[g["name"]]
+        for attr, _, _ in self.PARAMS:
+            st = self.optimizer.state[id(getattr(m, attr))]
+            st["exp_avg"], st["exp_avg_sq"] = moments[attr][0].contiguous(), moments[attr][1].contiguous()
+        return S
+
+    def reset_opacity(self) -> None:
+        """reference :334-339: opacity <- inverse_sigmoid(min(sigmoid(opacity), 0.01)), its Adam moments zeroed
+        (replace_tensor_to_optimizer, :411-422).  In place: the tensor keeps its address (and its place in a flat vector)."""
+        m = self.model
+        x = torch.minimum(torch.sigmoid(m._opacity), torch.full_like(m._opacity, 0.01))
+        m._opacity.copy_(torch.log(x / (1 - x)))
+        st = self.optimizer.state[id(m._opacity)]
+        st["exp_avg"].zero_()
+        st["exp_avg_sq"].zero_()
+
+    def after_backward(self, white_background: bool = False) -> bool:
+        """The bookkeeping of train_mesh_gaussian.py:114-131 that follows the statistics: densify every
+        densification_interval iterations, reset the opacities every opacity_reset_interval.  Returns the reference's
+        `update_flag` (True: this iteration's optimizer step is skipped, :139)."""
+        it, opt = self.iteration, self.opt
+        update_flag = False
+        if it < opt.densify_until_iter:
+            if it > opt.densify_from_iter and it % opt.densification_interval == 0:
+                self.densify_and_prune(opt.densify_grad_threshold, 0.005, 0.0, 20 if it > opt.opacity_reset_interval else None, 5)
+                update_flag = True
+            if it % opt.opacity_reset_interval == 0 or (white_background and it == opt.densify_from_iter):
+                self.reset_opacity()
+        return update_flag
 
     # scene/mesh_based_gaussian_model.py:280-288
     def update_learning_rate(self, iteration: int) -> float:
@@ -338,10 +451,12 @@ class TrainingIteration:
         return rows
 
     def step(self, cam, bg: torch.Tensor, gt_image: torch.Tensor, iteration: Optional[int] = None,
-             optimizer_step: bool = True) -> torch.Tensor:
+             optimizer_step: bool = True, densify: bool = False) -> torch.Tensor:
         """Enqueue one iteration; returns the device tensor (photometric loss, L1, SSIM, mrloss) -- the reference's
         `loss` is [0] + [3].  No host synchronisation.  With optimizer_step=False the iteration stops after the
-        backward pass and the statistics (gradients in `param_grads`): the view-parallel trainer exchanges them."""
+        backward pass and the statistics (gradients in `param_grads`): the view-parallel trainer exchanges them.
+        With densify=True the densification / opacity-reset schedule of the reference runs after the statistics (one
+        host read-back on the iterations that densify, like the reference's)."""
         m, opt = self.model, self.opt
         self.iteration = self.iteration + 1 if iteration is None else iteration
         it = self.iteration
@@ -376,6 +491,8 @@ class TrainingIteration:
         if it < opt.densify_until_iter:                                       # train_mesh_gaussian.py:114-121
             check(lib.gm_densify_stats(self.P, _p(self.radii), _p(g["means2D"]), _p(self.max_radii2D),
                                        _p(self.bc_gradient_accum), _p(self.denom), stream), "gm_densify_stats")
+        if densify and self.after_backward():                                  # train_mesh_gaussian.py:123-131,139
+            return self.losses
         if optimizer_step and it < opt.iterations:                            # train_mesh_gaussian.py:136-147
             self.optimizer.step(self._grad_of)
         return self.losses

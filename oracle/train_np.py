@@ -143,3 +143,84 @@ def densify_stats(radii: np.ndarray, viewspace_grad: np.ndarray, max_radii2D: np
     grad_accum[vis] += np.linalg.norm(viewspace_grad[vis, :2], axis=-1, keepdims=True).reshape(grad_accum[vis].shape)
     denom[vis] += 1
     return max_radii2D, grad_accum, denom
+
+
+# ---- scene/mesh_based_gaussian_model.py:504-585, utils/general_utils.py:133-212 ----------------------
+def split_mesh_and_gaussian(new_vertex1, new_vertex2, new_vertex3, new_v, new_v_index, v_origin_num, N=4):
+    """utils/general_utils.py:133-170 (N = 4) and :172-212 (N = 5); arrays are [S,N,3] ([S,3,3] for new_v)."""
+    a = new_vertex1[:, 0, :].copy()
+    b = new_vertex2[:, 0, :].copy()
+    c = new_vertex3[:, 0, :].copy()
+    new_vertex1[:, 0, :] = a
+    new_vertex1[:, 1, :] = (a + b) / 2
+    new_vertex1[:, 2, :] = (a + c) / 2
+    new_vertex1[:, 3, :] = (a + b) / 2
+    new_vertex2[:, 0, :] = (a + b) / 2
+    new_vertex2[:, 1, :] = b
+    new_vertex2[:, 2, :] = (c + b) / 2
+    new_vertex2[:, 3, :] = (b + c) / 2
+    new_vertex3[:, 0, :] = (a + c) / 2
+    new_vertex3[:, 1, :] = (c + b) / 2
+    new_vertex3[:, 2, :] = c
+    new_vertex3[:, 3, :] = (a + c) / 2
+    if N == 5:
+        new_vertex1[:, 4, :] = a
+        new_vertex2[:, 4, :] = b
+        new_vertex3[:, 4, :] = c
+    new_v[:, 0, :] = (a + b) / 2
+    new_v[:, 1, :] = (a + c) / 2
+    new_v[:, 2, :] = (b + c) / 2
+    tmp = np.arange(new_v.shape[0] * 3).reshape(new_v.shape[0], 3)
+    new_v_index[:, 0, 1] = tmp[:, 0] + v_origin_num
+    new_v_index[:, 0, 2] = tmp[:, 1] + v_origin_num
+    new_v_index[:, 1, 0] = tmp[:, 0] + v_origin_num
+    new_v_index[:, 1, 2] = tmp[:, 2] + v_origin_num
+    new_v_index[:, 2, 0] = tmp[:, 1] + v_origin_num
+    new_v_index[:, 2, 1] = tmp[:, 2] + v_origin_num
+    new_v_index[:, 3, 0] = tmp[:, 0] + v_origin_num
+    new_v_index[:, 3, 1] = tmp[:, 2] + v_origin_num
+    new_v_index[:, 3, 2] = tmp[:, 1] + v_origin_num
+    return new_vertex1, new_vertex2, new_vertex3, new_v, new_v_index
+
+
+def densify_and_split(model: Dict[str, np.ndarray], moments: Dict[str, Tuple[np.ndarray, np.ndarray]], grads: np.ndarray,
+                      grad_threshold: float, N: int = 4):
+    """scene/mesh_based_gaussian_model.py:504-563 on a dict of numpy arrays (bc, distance, f_dc, f_rest, opacity,
+    scaling, rotation: the parameters; vertex1..3, normal, r, fid, vertex_index: per-Gaussian constants; v: the mesh
+    vertices).  `moments[name]` = (m, values) of the seven parameter groups.  Returns (model', moments', selected)."""
+    sel = grads.reshape(-1) >= grad_threshold
+    if sel.sum() == 0:
+        return model, moments, sel
+    S = int(sel.sum())
+    rep = lambda x: np.repeat(x[sel][:, None], N, axis=1)
+    gaussian_num = S * N
+    new_bc = np.ones((gaussian_num, 3), f32) / 3
+    new_distance = np.zeros((gaussian_num, 1), f32)
+    new_v_index = rep(model["vertex_index"])
+    new_v = np.zeros((S, 3, 3), f32)
+    nv1, nv2, nv3, new_v, new_v_index = split_mesh_and_gaussian(rep(model["vertex1"]), rep(model["vertex2"]),
+                                                                 rep(model["vertex3"]), new_v, new_v_index,
+                                                                 model["v"].shape[0], N)
+    new = {
+        "bc": new_bc, "distance": new_distance,
+        "f_dc": rep(model["f_dc"]).reshape(gaussian_num, -1, 3), "f_rest": rep(model["f_rest"]).reshape(gaussian_num, -1, 3),
+        "opacity": rep(model["opacity"]).reshape(gaussian_num, -1),
+        "scaling": np.log(np.exp(model["scaling"].astype(f32))[sel][:, None].repeat(N, axis=1).reshape(gaussian_num, 3) / f32(4 * 0.8)).astype(f32),
+        "rotation": rep(model["rotation"]).reshape(gaussian_num, 4),
+        "vertex1": nv1.reshape(gaussian_num, 3), "vertex2": nv2.reshape(gaussian_num, 3), "vertex3": nv3.reshape(gaussian_num, 3),
+        "vertex_index": new_v_index.reshape(gaussian_num, 3),
+        "r": rep(model["r"]).reshape(gaussian_num, -1), "fid": rep(model["fid"]).reshape(gaussian_num, -1),
+        "normal": rep(model["normal"]).reshape(gaussian_num, 3),
+    }
+    keep = ~sel                                   # concat, then prune_points(selected) (:547-563)
+    out = {k: np.concatenate([model[k][keep], new[k]], axis=0) for k in new}
+    out["v"] = np.concatenate([model["v"], new_v.reshape(-1, 3)], axis=0)
+    mom = {k: (np.concatenate([m[keep], np.zeros_like(new[k])], axis=0), np.concatenate([v[keep], np.zeros_like(new[k])], axis=0))
+           for k, (m, v) in moments.items()}
+    return out, mom, sel
+
+
+def reset_opacity(opacity_logit: np.ndarray) -> np.ndarray:
+    """scene/mesh_based_gaussian_model.py:334-339"""
+    x = np.minimum(1.0 / (1.0 + np.exp(-opacity_logit.astype(f32))), f32(0.01)).astype(f32)
+    return np.log(x / (1 - x)).astype(f32)

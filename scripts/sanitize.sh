@@ -24,6 +24,37 @@ for (P, W, H, kw) in [(3000, 200, 120, {}), (6000, 48, 48, dict(extent=0.3, log_
     ts.step(cam, bg, target); ts.step(cam, bg, target)
     torch.cuda.synchronize()
     print("case", P, W, H, "ok", float(color.mean()), int((radii > 0).sum()))
+
+# surface shell: the sub-bucket path of big_bucket_sort_pack_kernel (with exact duplicates: its block-wide fallback)
+P, W, H = 40000, 160, 120
+sc = scenes.free_scene(P, dev, seed=3)
+g = torch.Generator(device="cpu").manual_seed(5)
+d = torch.randn(P, 3, generator=g); d = d / d.norm(dim=1, keepdim=True)
+shell = (1.5 + 0.002 * torch.randn(P, 1, generator=g)) * d
+shell[P // 2: P // 2 + P // 4] = shell[0]
+cam = scenes.camera(dev, W, H, index=1)
+bg = torch.zeros(3, device=dev)
+color, radii = GaussianRasterizer(make_settings(cam, bg, 3))(shell.to(dev).contiguous(), torch.zeros(P, 3, device=dev), sc["opacities"] * 0.1,
+                                                             shs=sc["shs"], scales=sc["scales"], rotations=sc["rotations"])
+torch.cuda.synchronize()
+print("case shell ok", float(color.mean()), int((radii > 0).sum()))
+
+# the training iteration: photometric loss, mesh-restrict loss, bind, densification statistics, Adam; fused exchange at world 1
+from gaussianmesh_b200 import synthetic
+from gaussianmesh_b200.renderer import MeshGaussianModel
+from gaussianmesh_b200.training import OptimizationParams, TrainingIteration
+from gaussianmesh_b200.view_parallel import ViewParallelTrainer
+P, W, H = 3001, 150, 70
+V, F = synthetic.icosphere(2)
+arrays = synthetic.mesh_bound_scene(P, V, F, seed=0)
+cam = scenes.camera(dev, W, H, index=0)
+target = torch.rand(3, H, W, device=dev)
+it = TrainingIteration(MeshGaussianModel(arrays, dev, requires_grad=False), OptimizationParams(alpha_mrloss=0.05), W, H)
+it.step(cam, bg, target); losses = it.step(cam, bg, target)
+vp = ViewParallelTrainer(MeshGaussianModel(arrays, dev, requires_grad=False), OptimizationParams(alpha_mrloss=0.05), W, H, mode="p2p")
+vp.step(cam, bg, target); vp.step(cam, bg, target)
+torch.cuda.synchronize()
+print("case iteration ok", losses.tolist())
 PY
 for tool in memcheck racecheck synccheck; do
   timeout 900 compute-sanitizer --tool $tool --print-limit 20 python /tmp/san_case.py > gpurun_out/sanitize_$tool.log 2>&1

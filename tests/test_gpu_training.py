@@ -219,3 +219,69 @@ def test_training_iteration_matches_autograd_composition(cuda_device):
     assert np.array_equal(it.max_radii2D.cpu().numpy(), max_r)
     assert np.array_equal(it.denom.cpu().numpy(), den)
     assert np.abs(it.bc_gradient_accum.cpu().numpy() - acc).max() <= 1e-3 * acc.max()
+
+
+@pytest.mark.parametrize("N", [4, 5])
+def test_densify_and_split_matches_oracle(cuda_device, N):
+    """scene/mesh_based_gaussian_model.py:504-585: after two iterations (so the Adam moments and the statistics are
+    populated), split every Gaussian above a threshold and compare every tensor of the model, the new mesh vertices /
+    indices and the surviving optimizer state with the numpy restatement; then keep training on the new set."""
+    from gaussianmesh_b200 import synthetic
+    from gaussianmesh_b200.renderer import MeshGaussianModel
+    from gaussianmesh_b200.training import OptimizationParams, TrainingIteration
+    dev = cuda_device
+    P, W, H = 6_000, 200, 136
+    V, F = synthetic.icosphere(2)
+    arrays = synthetic.mesh_bound_scene(P, V, F, seed=6)
+    arrays["mesh_vertices"] = V.astype(np.float32)
+    model = MeshGaussianModel(arrays, dev, requires_grad=False)
+    it = TrainingIteration(model, OptimizationParams(), W, H)
+    cam = scenes.camera(dev, W, H, index=0)
+    bg = torch.zeros(3, device=dev)
+    gt = torch.rand(3, H, W, generator=torch.Generator().manual_seed(70)).to(dev)
+    for _ in range(2):
+        it.step(cam, bg, gt)
+    n = lambda t: t.detach().cpu().numpy().copy()
+    grads = n(it.bc_gradient_accum / it.denom)
+    grads[np.isnan(grads)] = 0.0
+    thr = float(np.quantile(grads[grads > 0], 0.7))
+    before = {"bc": n(model._bc), "distance": n(model._distance), "f_dc": n(model._features[:, :1]),
+              "f_rest": n(model._features[:, 1:]), "opacity": n(model._opacity), "scaling": n(model._scaling),
+              "rotation": n(model._rotation), "vertex1": n(model.vertex1), "vertex2": n(model.vertex2),
+              "vertex3": n(model.vertex3), "normal": n(model.normal), "r": n(model.r), "fid": n(model.fid),
+              "vertex_index": n(model.vertex_index), "v": n(model.v)}
+    st = lambda attr: it.optimizer.state[id(getattr(model, attr))]
+    feat_m, feat_v = n(st("_features")["exp_avg"]), n(st("_features")["exp_avg_sq"])
+    moments = {"bc": (n(st("_bc")["exp_avg"]), n(st("_bc")["exp_avg_sq"])),
+               "distance": (n(st("_distance")["exp_avg"]), n(st("_distance")["exp_avg_sq"])),
+               "f_dc": (feat_m[:, :1], feat_v[:, :1]), "f_rest": (feat_m[:, 1:], feat_v[:, 1:]),
+               "opacity": (n(st("_opacity")["exp_avg"]), n(st("_opacity")["exp_avg_sq"])),
+               "scaling": (n(st("_scaling")["exp_avg"]), n(st("_scaling")["exp_avg_sq"])),
+               "rotation": (n(st("_rotation")["exp_avg"]), n(st("_rotation")["exp_avg_sq"]))}
+    want, want_mom, sel = train_np.densify_and_split(before, moments, grads, thr, N)
+    S = it.densify_and_split(it.bc_gradient_accum / it.denom, thr, 0.0, N)
+    assert S == int(sel.sum()) and 0 < S < P
+    newP = P - S + S * N
+    assert it.P == newP == model._bc.shape[0] and model.v.shape[0] == V.shape[0] + 3 * S
+    eq = lambda a, b: np.array_equal(n(a), b)
+    assert eq(model._bc, want["bc"]) and eq(model._distance, want["distance"]) and eq(model._opacity, want["opacity"])
+    assert eq(model._rotation, want["rotation"]) and eq(model._features[:, :1], want["f_dc"]) and eq(model._features[:, 1:], want["f_rest"])
+    assert np.abs(n(model._scaling) - want["scaling"]).max() <= 1e-6
+    for k in ("vertex1", "vertex2", "vertex3", "normal", "r", "fid", "vertex_index", "v"):
+        assert eq(getattr(model, k), want[k]), k
+    fm, fv = n(st("_features")["exp_avg"]), n(st("_features")["exp_avg_sq"])
+    assert np.array_equal(fm[:, :1], want_mom["f_dc"][0]) and np.array_equal(fv[:, 1:], want_mom["f_rest"][1])
+    assert eq(st("_bc")["exp_avg"], want_mom["bc"][0]) and eq(st("_scaling")["exp_avg_sq"], want_mom["scaling"][1])
+    assert float(it.denom.abs().max()) == 0.0 and it.max_radii2D.shape[0] == newP and it.optimizer.n_step == 2
+    # children sit on their parent's face: the split triangles tile it
+    area = lambda a, b, c: np.linalg.norm(np.cross(b - a, c - a), axis=1)
+    kids = area(want["vertex1"][P - S:], want["vertex2"][P - S:], want["vertex3"][P - S:]).reshape(S, N)[:, :4].sum(axis=1)
+    parents = area(before["vertex1"][sel], before["vertex2"][sel], before["vertex3"][sel])
+    assert np.allclose(kids, parents, rtol=1e-4)
+    # training continues on the new set
+    losses = it.step(cam, bg, gt).cpu().numpy()
+    assert np.isfinite(losses).all() and it.optimizer.n_step == 3
+    # opacity reset (:334-339)
+    want_op = train_np.reset_opacity(n(model._opacity))
+    it.reset_opacity()
+    assert np.abs(n(model._opacity) - want_op).max() <= 1e-5 and float(st("_opacity")["exp_avg"].abs().max()) == 0.0
