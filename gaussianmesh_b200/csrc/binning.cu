@@ -226,7 +226,6 @@ constexpr int kSortThreads = 256;
 constexpr int kSortWarps = kSortThreads / 32;
 constexpr int kSortSmem = 4096;       // keys; 32 KB -- block-wide path for oversized buckets
 constexpr int kWarpSortMax = 256;     // largest bucket one warp sorts in registers (8 keys per lane)
-constexpr int kMidMax = 1024;         // largest bucket one warp sorts through sub-buckets in its shared-memory slice
 
 __device__ __forceinline__ uint64_t shfl_xor_u64(uint64_t v, int lane_mask)
 {
@@ -363,97 +362,7 @@ bucket_sort_pack_kernel(GeometryState g, BinningState b, uint32_t capacity, int 
 	else if (n <= 64) warp_sort_pack<2>(g, b, b.keys + s0, s0, n, lane);
 	else if (n <= 128) warp_sort_pack<4>(g, b, b.keys + s0, s0, n, lane);
 	else if (n <= kWarpSortMax) warp_sort_pack<8>(g, b, b.keys + s0, s0, n, lane);
-	else if (lane == 0) {
-		// left to mid_bucket_sort_pack_kernel (one warp each) or big_bucket_sort_pack_kernel (one block each)
-		if (n <= (uint32_t)kMidMax) g.big_list[kMaxBucketEntries - 1 - atomicAdd(&g.header->num_mid, 1u)] = gw;
-		else g.big_list[atomicAdd(&g.header->num_big, 1u)] = gw;
-	}
-}
-
-// Buckets of kWarpSortMax+1 .. kMidMax instances -- what a surface-bound scene produces by the thousand: a tile sees
-// one or two thin depth layers, so most of its instances share one or two of the global depth buckets.  ONE WARP per
-// bucket, no block barrier: the warp splits the bucket into up to 32 sub-buckets by linear interpolation of the depth
-// bits between the bucket's own minimum and maximum (monotone in depth, equal depths share a sub-bucket, so the
-// concatenation of the sorted sub-buckets is the sorted bucket), scatters the keys through its private slice of shared
-// memory and sorts the sub-buckets in registers one after the other.  A sub-bucket that still exceeds kWarpSortMax
-// (many equal depths) hands the whole bucket to the block-wide kernel.
-constexpr int kMidThreads = 128;
-constexpr int kMidWarps = kMidThreads / 32;
-constexpr int kMidTarget = 40;        // aimed-at keys per sub-bucket
-
-__global__ void __launch_bounds__(kMidThreads)
-mid_bucket_sort_pack_kernel(GeometryState g, BinningState b, uint32_t capacity, int bucket_log2)
-{
-	__shared__ uint64_t s_part_all[kMidWarps][kMidMax];
-	__shared__ uint32_t s_cnt_all[kMidWarps][32], s_off_all[kMidWarps][33];
-	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	uint64_t* const s_part = s_part_all[warp];
-	uint32_t* const s_cnt = s_cnt_all[warp];
-	uint32_t* const s_off = s_off_all[warp];
-	const uint32_t num_mid = g.header->num_mid;
-	for (uint32_t e = blockIdx.x * kMidWarps + warp; e < num_mid; e += gridDim.x * kMidWarps) {
-		const uint32_t gw = g.big_list[kMaxBucketEntries - 1 - e];
-		const uint32_t bk = gw & ((1u << bucket_log2) - 1u);
-		const uint32_t s0 = (bk == 0) ? g.tile_start[gw >> bucket_log2] : g.bucket_cursor[gw - 1];
-		const uint32_t n = min(g.bucket_cursor[gw], capacity) - s0;
-		const uint64_t* keys = b.keys + s0;
-		// depth range of the bucket (the keys were just written by emit: the three passes over them hit L2)
-		uint32_t lo = 0xffffffffu, hi = 0u;
-		for (uint32_t i = lane; i < n; i += 32) {
-			const uint32_t d = (uint32_t)(keys[i] >> 32);
-			lo = min(lo, d);
-			hi = max(hi, d);
-		}
-#pragma unroll
-		for (int o = 16; o > 0; o >>= 1) {
-			lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
-			hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
-		}
-		uint32_t S = 1;
-		while (S < 32u && S * kMidTarget < n) S <<= 1;
-		// float arithmetic is monotone (conversion, multiplication by a positive constant, truncation)
-		const float scale = (float)S / ((float)(hi - lo) + 1.0f);
-		auto sub_of = [&](uint64_t k) {
-			return min(S - 1u, (uint32_t)((float)((uint32_t)(k >> 32) - lo) * scale));
-		};
-		s_cnt[lane] = 0u;
-		__syncwarp();
-		for (uint32_t i = lane; i < n; i += 32)
-			atomicAdd(&s_cnt[sub_of(keys[i])], 1u);
-		__syncwarp();
-		{
-			const uint32_t c = s_cnt[lane];
-			uint32_t incl = c;
-#pragma unroll
-			for (int o = 1; o < 32; o <<= 1) {
-				const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
-				if (lane >= o) incl += v;
-			}
-			s_off[lane] = incl - c;
-			if (lane == 31) s_off[32] = incl;
-			__syncwarp();
-			s_cnt[lane] = incl - c;                    // becomes the scatter cursor
-		}
-		__syncwarp();
-		for (uint32_t i = lane; i < n; i += 32) {
-			const uint64_t k = keys[i];
-			s_part[atomicAdd(&s_cnt[sub_of(k)], 1u)] = k;
-		}
-		__syncwarp();
-		bool fallback = false;
-		for (uint32_t sb = 0; sb < S; sb++) {
-			const uint32_t o0 = s_off[sb], m = s_off[sb + 1] - o0;
-			if (m == 0) continue;
-			if (m <= 32) warp_sort_pack<1>(g, b, s_part + o0, s0 + o0, m, lane);
-			else if (m <= 64) warp_sort_pack<2>(g, b, s_part + o0, s0 + o0, m, lane);
-			else if (m <= 128) warp_sort_pack<4>(g, b, s_part + o0, s0 + o0, m, lane);
-			else if (m <= kWarpSortMax) warp_sort_pack<8>(g, b, s_part + o0, s0 + o0, m, lane);
-			else fallback = true;
-		}
-		if (fallback && lane == 0)
-			g.big_list[atomicAdd(&g.header->num_big, 1u)] = gw;   // re-packed as a whole by the block kernel (idempotent)
-		__syncwarp();   // the shared slices are reused by the next bucket
-	}
+	else if (lane == 0) g.big_list[atomicAdd(&g.header->num_big, 1u)] = gw;   // left to big_bucket_sort_pack_kernel
 }
 
 // The buckets the warp kernel skipped (more than kWarpSortMax instances), one BLOCK per bucket, taken from the
@@ -608,7 +517,6 @@ int launch_sort_pack(int num_tiles, const GeometryState& g, const BinningState& 
 	const uint32_t total = (uint32_t)num_tiles << vp.bucket_log2;
 	bucket_sort_pack_kernel<<<(total + kSortWarps - 1) / kSortWarps, kSortThreads, 0, stream>>>(
 		g, b, capacity, vp.bucket_log2, total);
-	mid_bucket_sort_pack_kernel<<<148 * 6, kMidThreads, 0, stream>>>(g, b, capacity, vp.bucket_log2);
 	// 32 KB of dynamic shared memory, 48 registers: six blocks per SM
 	big_bucket_sort_pack_kernel<<<148 * 6, kSortThreads, kBigSmemBytes, stream>>>(g, b, capacity, vp.bucket_log2);
 	return GM_OK;

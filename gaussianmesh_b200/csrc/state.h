@@ -46,8 +46,7 @@ struct FrameHeader {
 	uint32_t bucket_log2;
 	uint32_t num_large;      // Gaussians whose tile rectangle exceeds 64 tiles (walked by large_tiles_kernel)
 	uint32_t num_big;        // (tile, bucket) ranges too long for the register sort (big_bucket_sort_pack_kernel)
-	uint32_t num_mid;        // ranges of 257..1024 instances, one warp each (mid_bucket_sort_pack_kernel)
-	uint32_t pad[23];
+	uint32_t pad[24];
 };
 static_assert(sizeof(FrameHeader) == 128, "FrameHeader must be one 128-byte line");
 
@@ -64,8 +63,7 @@ struct GeometryState {
 	uint32_t* tile_count;     // [GM_MAX_TILES] instances per tile after exact tile culling
 	uint32_t* tile_start;     // [GM_MAX_TILES] first instance of the tile (multiple of kSegAlign)
 	uint32_t* bucket_cursor;  // [kMaxBucketEntries] per (tile, bucket): count -> start -> end (see binning.cu)
-	uint32_t* big_list;       // [kMaxBucketEntries] flat (tile, bucket) ids of the oversized buckets: the block-sorted
-	                          //   ones from the front, the warp-sorted (mid) ones from the back
+	uint32_t* big_list;       // [kMaxBucketEntries] flat (tile, bucket) ids of the oversized buckets
 	unsigned long long* scan_state;  // [kMaxScanBlocks + 1] chained-scan descriptors (flag << 32 | value) + ticket
 	uint32_t* depth_hist;     // [kDepthBins] visible-depth histogram of this frame
 	uint8_t* depth_lut;       // [kDepthBins] fine depth bin -> bucket (monotone)
