@@ -251,7 +251,7 @@ __device__ __forceinline__ void warp_bitonic(uint64_t (&key)[E], int lane)
 					if (pr > r) {
 						const bool up = (((r << 5) & k) == 0);
 						const uint64_t a = key[r], c = key[pr];
-						const bool swap = up ? (a > c) : (a < c);
+						const bool swap = ((a > c) == up);          // distinct keys: a < c is !(a > c)
 						key[r] = swap ? c : a;
 						key[pr] = swap ? a : c;
 					}
@@ -264,8 +264,10 @@ __device__ __forceinline__ void warp_bitonic(uint64_t (&key)[E], int lane)
 					const bool lower = ((lane & j) == 0);
 					const uint64_t mine = key[r];
 					const uint64_t other = shfl_xor_u64(mine, j);
+					// keys are distinct (the Gaussian id is part of them; equal padding keys may go either way), so
+					// "keep the smaller" is "keep mine iff mine < other": one 64-bit compare and one select
 					const bool take_min = (lower == up);
-					key[r] = take_min ? (mine < other ? mine : other) : (mine > other ? mine : other);
+					key[r] = ((mine < other) == take_min) ? mine : other;
 				}
 			}
 		}
