@@ -285,3 +285,38 @@ def test_densify_and_split_matches_oracle(cuda_device, N):
     want_op = train_np.reset_opacity(n(model._opacity))
     it.reset_opacity()
     assert np.abs(n(model._opacity) - want_op).max() <= 1e-5 and float(st("_opacity")["exp_avg"].abs().max()) == 0.0
+
+
+def test_densification_schedule_inside_the_loop(cuda_device):
+    """train_mesh_gaussian.py:114-139 through step(densify=True): statistics every iteration, densify_and_prune when
+    iteration > densify_from_iter and iteration % densification_interval == 0 (that iteration skips the optimizer
+    step, `update_flag`), opacity reset every opacity_reset_interval."""
+    from gaussianmesh_b200 import synthetic
+    from gaussianmesh_b200.renderer import MeshGaussianModel
+    from gaussianmesh_b200.training import OptimizationParams, TrainingIteration
+    dev = cuda_device
+    P, W, H = 4_000, 160, 120
+    V, F = synthetic.icosphere(2)
+    arrays = synthetic.mesh_bound_scene(P, V, F, seed=8)
+    arrays["mesh_vertices"] = V.astype(np.float32)
+    opt = OptimizationParams(densify_from_iter=1, densification_interval=2, densify_grad_threshold=1e-7,
+                             opacity_reset_interval=3)
+    model = MeshGaussianModel(arrays, dev, requires_grad=False)
+    it = TrainingIteration(model, opt, W, H)
+    cam = scenes.camera(dev, W, H, index=0)
+    bg = torch.zeros(3, device=dev)
+    gt = torch.rand(3, H, W, generator=torch.Generator().manual_seed(80)).to(dev)
+    it.step(cam, bg, gt, densify=True)                       # iteration 1: plain step
+    assert it.P == P and it.optimizer.n_step == 1
+    seen = int((it.denom > 0).sum())
+    assert seen > 0
+    it.step(cam, bg, gt, densify=True)                       # iteration 2: densify, no optimizer step
+    assert it.optimizer.n_step == 1
+    grown = it.P
+    assert grown > P and (grown - P) % 4 == 0 and grown <= 5 * P   # the Gaussians seen so far split into five (N = 5, :126)
+    assert model._bc.shape[0] == grown and float(it.denom.abs().max()) == 0.0
+    it.step(cam, bg, gt, densify=True)                       # iteration 3: plain step + opacity reset
+    assert it.optimizer.n_step == 2 and it.P == grown
+    # reset to <= 0.01, then this iteration's Adam step (moments zeroed: at most one learning rate, 0.05, in the logit)
+    assert float(model._opacity.max()) <= math.log(0.01 / 0.99) + opt.opacity_lr * 1.01
+    assert np.isfinite(it.losses.cpu().numpy()).all()
