@@ -24,6 +24,7 @@ way its Jittor glue drives it, on the same workload, every rank on its own view 
 from __future__ import annotations
 
 import argparse
+import gc
 import json
 import math
 import os
@@ -260,7 +261,18 @@ class ReferenceIteration:
 
 def timed(fn, steps, warmup, barrier, pre=None, post=None):
     """W untimed + K timed calls of fn(i); CUDA-event time in ms (this rank).  pre/post fork and join side streams
-    inside the timed region (multi-lane forward rendering)."""
+    inside the timed region (multi-lane forward rendering).  The cyclic garbage collector is paused for the region
+    (as timeit does): a generation-2 pass of a torch process takes tens of milliseconds of host time, during which the
+    launch queue drains and the device idles -- observed as a rare 2x outlier of one section."""
+    gc.collect()
+    gc.disable()
+    try:
+        return _timed(fn, steps, warmup, barrier, pre, post)
+    finally:
+        gc.enable()
+
+
+def _timed(fn, steps, warmup, barrier, pre=None, post=None):
     if pre:
         pre()
     for i in range(warmup):
@@ -498,6 +510,7 @@ def main():
 
     it_prof = None
     ms_it, _ = timed(train_iteration, K, Wm, barrier)
+    it_enqueue_ms = timed.last_enqueue_ms
     if args.impl == "ours":
         from gaussianmesh_b200 import _lib
         _lib.profile_begin()
@@ -628,6 +641,7 @@ def main():
             st["achieved_gbs"] = it_alg[k] / (st["ms_per_launch"] * 1e-3) / 1e9
             st["frac_of_hbm_peak"] = st["achieved_gbs"] / peak
     out["train_iteration"]["stages"] = it_stages
+    out["train_iteration"]["host_enqueue_ms_per_iteration"] = it_enqueue_ms / K
     out["train_iteration"]["instances_per_frame"] = it_info[0]
     out["train_iteration"]["visible_gaussians"] = it_info[1]
     kernels_per_stage = {"depth_buckets": 2, "preprocess": 2, "emit": 2, "sort_pack": 2}    # the rest launch one kernel
