@@ -26,8 +26,22 @@ __device__ __forceinline__ float3 dnormvdv3(float3 v, float3 dv)   // auxiliary.
 
 // kOverwrite: the five per-Gaussian output rows need not be pre-zeroed -- this kernel writes every element of
 // them (zeros for Gaussians that were not rendered and for SH coefficients above the active degree).
-template <bool kVecSH, bool kOverwrite>
-__global__ void __launch_bounds__(kThreads)
+// kCoop (needs kVecSH, M == 16, and kOverwrite or degree 3): the SH rows are not read / written by their owner
+// thread with twelve 128-bit accesses at a 192-byte lane stride -- one request then touches 32 cache lines and the
+// L1 tag stage, not HBM, sets the pace (ncu: l1tex 50 %) -- but staged per WARP through shared memory: the 32 rows of
+// a warp are one contiguous 6 KB block, copied with fully coalesced cp.async while the covariance part runs, read and
+// overwritten in place by their owners (row pitch 13 float4: conflict-free LDS.128 / STS.128), and stored back the
+// same way.
+constexpr int kRowF4 = 12;         // float4 per SH row (M == 16)
+constexpr int kRowPitchF4 = 13;
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
+{
+	asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
+
+template <bool kVecSH, bool kOverwrite, bool kCoop>
+__global__ void __launch_bounds__(kThreads, 2)
 geometry_backward_kernel(int P,
                          const float* __restrict__ means3D,
                          const int* __restrict__ radii,
@@ -58,15 +72,32 @@ geometry_backward_kernel(int P,
 	__syncthreads();
 
 	const int idx = blockIdx.x * kThreads + threadIdx.x;
-	if (idx >= P)
-		return;
-	if (!(radii[idx] > 0)) {
-		if (kOverwrite) {
+	const bool valid = idx < P;
+	const bool visible = valid && radii[idx] > 0;
+	const int lane = threadIdx.x & 31;
+	extern __shared__ float4 s_rows_all[];
+	float4* const s_rows = s_rows_all + (threadIdx.x >> 5) * (32 * kRowPitchF4);
+	const int row0 = idx - lane;                                   // first Gaussian of this warp
+	const int warp_floats4 = max(0, min(32, P - row0)) * kRowF4;
+	if (kCoop) {
+		const float4* src = reinterpret_cast<const float4*>(shs) + (size_t)row0 * kRowF4;
+#pragma unroll
+		for (int i = 0; i < kRowF4; i++) {
+			const int f = lane + 32 * i;
+			if (f < warp_floats4) {
+				const int r = f / kRowF4, c = f - r * kRowF4;
+				cp_async16(&s_rows[r * kRowPitchF4 + c], src + f);
+			}
+		}
+		asm volatile("cp.async.commit_group;" ::: "memory");
+	}
+	if (!visible) {
+		if (kOverwrite && valid) {
 #pragma unroll
 			for (int i = 0; i < 3; i++) dL_dmean3D[3 * idx + i] = 0.0f;
 #pragma unroll
 			for (int i = 0; i < 6; i++) dL_dcov3D[6 * idx + i] = 0.0f;
-			if (shs != nullptr) {
+			if (shs != nullptr && !kCoop) {
 				float* dsh = dL_dsh + (size_t)idx * vp.M * 3;
 				if (kVecSH) {
 					for (int j4 = 0; j4 < (vp.M * 3) / 4; j4++)
@@ -81,10 +112,14 @@ geometry_backward_kernel(int P,
 				reinterpret_cast<float4*>(dL_drot)[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
 			}
 		}
-		return;
+		if (!kCoop)
+			return;
 	}
 
-	const float3 mean = make_float3(means3D[3 * idx], means3D[3 * idx + 1], means3D[3 * idx + 2]);
+	float3 mean = make_float3(0.f, 0.f, 0.f), dmean = make_float3(0.f, 0.f, 0.f);
+	float dcov[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+	if (visible) {
+	mean = make_float3(means3D[3 * idx], means3D[3 * idx + 1], means3D[3 * idx + 2]);
 
 	// ------------------------------------------------------------------ backward.cu:157-273
 	float cov6[6];
@@ -117,7 +152,6 @@ geometry_backward_kernel(int P,
 	float dL_da = 0, dL_db = 0, dL_dc = 0;
 	const float denom2inv = 1.0f / ((denom * denom) + 0.0000001f);
 
-	float dcov[6];
 	if (denom2inv != 0) {
 		dL_da = denom2inv * (-c * c * dL_dconic.x + 2 * b * c * dL_dconic.y + (denom - a * c) * dL_dconic.z);
 		dL_dc = denom2inv * (-a * a * dL_dconic.z + 2 * a * b * dL_dconic.y + (denom - a * c) * dL_dconic.x);
@@ -165,7 +199,7 @@ geometry_backward_kernel(int P,
 	const float dL_dtz = -h_x * tz2 * dL_dJ00 - h_y * tz2 * dL_dJ11 + (2 * h_x * t.x) * tz3 * dL_dJ02 + (2 * h_y * t.y) * tz3 * dL_dJ12;
 
 	// backward.cu:269-273: first part of dL/dmean3D (assignment in the reference)
-	float3 dmean = transform_vec_4x3_transpose(make_float3(dL_dtx, dL_dty, dL_dtz), s_view);
+	dmean = transform_vec_4x3_transpose(make_float3(dL_dtx, dL_dty, dL_dtz), s_view);
 
 	// ------------------------------------------------------------------ backward.cu:370-387
 	{
@@ -187,7 +221,15 @@ geometry_backward_kernel(int P,
 	// dL/dsh[k] = basis_k(dir) * dL/dRGB (clamp-masked, :31-34), dL/ddir = sum_k grad basis_k * (sh_k . dL/dRGB),
 	// then through the normalisation of dir (dnormvdv, :128-138).  The row of SH coefficients is read and the
 	// row of gradients written with 128-bit accesses.
+	}   // visible
+
 	if (shs != nullptr) {
+		if (kCoop) {
+			asm volatile("cp.async.wait_all;" ::: "memory");
+			__syncwarp();
+		}
+		float4* const my_row = s_rows + lane * kRowPitchF4;
+		if (visible) {
 		const int deg = vp.D;
 		const float3 dir_orig = make_float3(mean.x - s_cam[0], mean.y - s_cam[1], mean.z - s_cam[2]);
 		const float len = sqrtf(dir_orig.x * dir_orig.x + dir_orig.y * dir_orig.y + dir_orig.z * dir_orig.z);
@@ -196,7 +238,15 @@ geometry_backward_kernel(int P,
 
 		const int n_floats = 3 * (deg + 1) * (deg + 1);
 		float sh[48];
-		load_sh<kVecSH>(shs + (size_t)idx * vp.M * 3, n_floats, sh);
+		if (kCoop) {
+#pragma unroll
+			for (int j = 0; j < kRowF4; j++) {
+				const float4 t = my_row[j];
+				sh[4 * j + 0] = t.x; sh[4 * j + 1] = t.y; sh[4 * j + 2] = t.z; sh[4 * j + 3] = t.w;
+			}
+		} else {
+			load_sh<kVecSH>(shs + (size_t)idx * vp.M * 3, n_floats, sh);
+		}
 		const uint32_t clamp_bits = __float_as_uint(g.rgb_clamp[idx].w);
 		float dRGB[3];
 #pragma unroll
@@ -247,6 +297,12 @@ geometry_backward_kernel(int P,
 			out[3 * k] = B[k] * dRGB[0]; out[3 * k + 1] = B[k] * dRGB[1]; out[3 * k + 2] = B[k] * dRGB[2];
 		}
 		// only coefficients up to `deg` are written (the caller's zeros stay above it, as in the reference)
+		if (kCoop) {
+			// `out` is zero above the active degree (B[k] == 0 there)
+#pragma unroll
+			for (int j = 0; j < kRowF4; j++)
+				my_row[j] = make_float4(out[4 * j], out[4 * j + 1], out[4 * j + 2], out[4 * j + 3]);
+		} else {
 		float* dsh = dL_dsh + (size_t)idx * vp.M * 3;
 		if (kOverwrite) {
 			// `out` is zero above the active degree (B[k] == 0 there); rows longer than 16 coefficients get zeros
@@ -281,9 +337,32 @@ geometry_backward_kernel(int P,
 			for (int i = 0; i < 48; i++)
 				if (i < n_floats) dsh[i] = out[i];
 		}
+		}
 		const float3 d = dnormvdv3(dir_orig, dL_ddir);
 		dmean.x += d.x; dmean.y += d.y; dmean.z += d.z;
+		} else if (kCoop && kOverwrite) {
+#pragma unroll
+			for (int j = 0; j < kRowF4; j++)
+				my_row[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+		}
+		if (kCoop) {
+			// rows of Gaussians that were not rendered: zeros when overwriting, untouched otherwise
+			const uint32_t row_mask = kOverwrite ? 0xffffffffu : __ballot_sync(0xffffffffu, visible);
+			__syncwarp();
+			float4* dst = reinterpret_cast<float4*>(dL_dsh) + (size_t)row0 * kRowF4;
+#pragma unroll
+			for (int i = 0; i < kRowF4; i++) {
+				const int f = lane + 32 * i;
+				if (f < warp_floats4) {
+					const int r = f / kRowF4, c = f - r * kRowF4;
+					if ((row_mask >> r) & 1u)
+						dst[f] = s_rows[r * kRowPitchF4 + c];
+				}
+			}
+		}
 	}
+	if (!visible)
+		return;
 
 	dL_dmean3D[3 * idx + 0] = dmean.x;
 	dL_dmean3D[3 * idx + 1] = dmean.y;
@@ -351,13 +430,19 @@ int launch_geometry_backward(int P, const float* means3D, const int* radii, cons
 	const dim3 grid((P + kThreads - 1) / kThreads);
 	const bool vec = sh_rows_vectorizable(shs, vp.M) && sh_rows_vectorizable(dL_dsh, vp.M) &&
 	                 vp.M * 3 >= 3 * (vp.D + 1) * (vp.D + 1);
-#define GM_LAUNCH_GEOM(V, O) geometry_backward_kernel<V, O><<<grid, kThreads, 0, stream>>>( \
-		P, means3D, radii, shs, scales, rotations, cov3Ds, vp, g, dL_dmean2D, dL_dconic, dL_dcolor, \
-		dL_dmean3D, dL_dcov3D, dL_dsh, dL_dscale, dL_drot)
-	if (vec && overwrite) GM_LAUNCH_GEOM(true, true);
-	else if (vec) GM_LAUNCH_GEOM(true, false);
-	else if (overwrite) GM_LAUNCH_GEOM(false, true);
-	else GM_LAUNCH_GEOM(false, false);
+	const bool coop = vec && shs != nullptr && vp.M == 16 && (overwrite || vp.D == 3);
+	constexpr size_t kCoopSmem = (size_t)(kThreads / 32) * 32 * kRowPitchF4 * sizeof(float4);
+#define GM_LAUNCH_GEOM(V, O, C) do { \
+		if (C) cudaFuncSetAttribute(geometry_backward_kernel<V, O, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCoopSmem); \
+		geometry_backward_kernel<V, O, C><<<grid, kThreads, (C) ? kCoopSmem : 0, stream>>>( \
+			P, means3D, radii, shs, scales, rotations, cov3Ds, vp, g, dL_dmean2D, dL_dconic, dL_dcolor, \
+			dL_dmean3D, dL_dcov3D, dL_dsh, dL_dscale, dL_drot); } while (0)
+	if (coop && overwrite) GM_LAUNCH_GEOM(true, true, true);
+	else if (coop) GM_LAUNCH_GEOM(true, false, true);
+	else if (vec && overwrite) GM_LAUNCH_GEOM(true, true, false);
+	else if (vec) GM_LAUNCH_GEOM(true, false, false);
+	else if (overwrite) GM_LAUNCH_GEOM(false, true, false);
+	else GM_LAUNCH_GEOM(false, false, false);
 #undef GM_LAUNCH_GEOM
 	return GM_OK;
 }
