@@ -140,7 +140,12 @@ class RenderArena:
                                        int(prefiltered), tmp_radii.data_ptr(), int(debug), stream), "gm_forward_0")
             self.high_water = max(self.high_water, n)
             self._want = int(n * self.headroom) + 1024
-        want = max(self._want, int(self.high_water * self.headroom) + 1024 if self.high_water else 0)
+        # grow when the largest frame seen so far comes within 8 % of the capacity -- not whenever a new high-water
+        # mark dents the headroom: a re-allocation is a cudaMalloc of hundreds of MB (milliseconds of host time during
+        # which the launch queue drains), and in training every parameter update moves the instance counts a little
+        want = self._want
+        if self.high_water and self.high_water * 1.08 + 1024 > self.capacity:
+            want = max(want, int(self.high_water * self.headroom) + 1024)
         if want > self.capacity:
             self.reserve(want)
 

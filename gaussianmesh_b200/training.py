@@ -271,7 +271,7 @@ class TrainingIteration:
         self.radii = torch.empty(P, dtype=torch.int32, device=dev)
         self.losses = torch.zeros(4, dtype=torch.float32, device=dev)     # loss w/o mrloss, L1, SSIM, mrloss
         self.scratch = torch.empty(lib.gm_photometric_scratch_bytes(3, H, W), dtype=torch.uint8, device=dev)
-        self.arena = RenderArena(dev, strict=False)
+        self.arena = RenderArena(dev, headroom=1.5, strict=False)     # the parameters move: instance counts drift
         # gradient slab: the atomically accumulated part first (zeroed per step), overwritten rows behind it
         sizes = {"means2D": 3 * P, "conic": 4 * P, "opacity": P, "colors": 3 * P,
                  "means3D": 3 * P, "cov3D": 6 * P, "scales": 3 * P, "rotations": 4 * P}
