@@ -246,6 +246,41 @@ preprocess_kernel(int P,
 					// too many tiles for a 64-bit mask (and for one thread): large_tiles_kernel walks this rectangle
 					// with a whole warp, once to count and once to place, in ONE kernel binary so both passes agree
 					g.large_list[atomicAdd(&g.header->num_large, 1u)] = (uint32_t)idx;
+				} else if (tight && conic.x * conic.z - conic.y * conic.y > 0.0f) {
+					// Row by row in closed form.  A tile [px0,px1] x [py0,py1] can receive alpha >= 1/255 only if it meets
+					// the ellipse q(d) = a dx^2 + 2 b dx dy + c dy^2 <= Lq; within one tile row the ellipse cut by the row's
+					// band is convex, so the tiles it meets are exactly those whose pixel span overlaps the band's
+					// x-interval [xmin, xmax] -- one interval per row instead of one quadratic minimisation per tile (the
+					// per-tile loop ran at the pace of the warp's largest splat).  Lq carries the margins of
+					// rect_cannot_contribute (2e-3 in the exponent, 32 ulp of the largest term over the walked box); the
+					// blend kernels cull exactly per 8x4 block again, so a spare tile costs time, never a bit.
+					const float a = conic.x, b = conic.y, c = conic.z;
+					const float det_c = a * c - b * b;
+					const float bx = fmaxf(fabsf((float)(tx_lo * kTile) - point_image.x), fabsf((float)(tx_hi * kTile) - point_image.x));
+					const float by = fmaxf(fabsf((float)(ty_lo * kTile) - point_image.y), fabsf((float)(ty_hi * kTile) - point_image.y));
+					const float Lq = 2.0f * thr + 2.0e-3f + 4.0e-6f * (a * bx * bx + 2.0f * fabsf(b) * bx * by + c * by * by);
+					const float inv_a = 1.0f / a;
+					const float dx_ext = sqrtf(Lq * c / det_c);          // largest |dx| on the ellipse, reached at dy = -/+ (b/c) dx_ext
+					const float dy_at = b / c * dx_ext;
+					const float aL = a * Lq;
+					for (int ty = ty_lo; ty < ty_hi; ty++) {
+						const float y0b = (float)(ty * kTile) - point_image.y;
+						const float y1b = fminf((float)(ty * kTile + (kTile - 1)), (float)(vp.H - 1)) - point_image.y;
+						const float dyM = fminf(y1b, fmaxf(y0b, -dy_at));     // band point nearest to the dx-maximiser
+						const float dym = fminf(y1b, fmaxf(y0b, dy_at));      // ... and to the dx-minimiser
+						const float DM = aL - det_c * dyM * dyM, Dm = aL - det_c * dym * dym;
+						if (DM < 0.0f && Dm < 0.0f)
+							continue;                                       // the band lies outside the ellipse's dy range
+						const float xmax = (-b * dyM + sqrtf(fmaxf(DM, 0.0f))) * inv_a;
+						const float xmin = (-b * dym - sqrtf(fmaxf(Dm, 0.0f))) * inv_a;
+						const int ta = max(tx_lo, (int)ceilf((point_image.x + xmin - (float)(kTile - 1)) * (1.0f / kTile) - 1.0e-3f));
+						const int tb = min(tx_hi - 1, (int)floorf((point_image.x + xmax) * (1.0f / kTile) + 1.0e-3f));
+						uint32_t* const row = g.bucket_cursor + (((size_t)ty * vp.tiles_x) << vp.bucket_log2) + bucket;
+						for (int tx = ta; tx <= tb; tx++) {
+							atomicAdd(&row[(size_t)tx << vp.bucket_log2], 1u);
+							kept |= 1ull << ((ty - y0) * w + (tx - x0));
+						}
+					}
 				} else {
 					for (int ty = ty_lo; ty < ty_hi; ty++) {
 						const float py0 = (float)(ty * kTile);
