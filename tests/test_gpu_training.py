@@ -146,7 +146,8 @@ def test_densify_stats_match_oracle(cuda_device):
     assert np.abs(dacc.cpu().numpy() - eacc).max() <= 1e-7
 
 
-def test_training_iteration_matches_autograd_composition(cuda_device):
+@pytest.mark.parametrize("degree", [3, 1])
+def test_training_iteration_matches_autograd_composition(cuda_device, degree):
     """Two iterations of TrainingIteration (fused, no tape) against the same iterations written the way
     train_mesh_gaussian.py:85-147 writes them: render() -> l1 / ssim / mesh_restrict_loss -> autograd backward ->
     densification statistics -> Adam, with the OPTIMIZER taken from the oracle."""
@@ -159,8 +160,8 @@ def test_training_iteration_matches_autograd_composition(cuda_device):
     V, F = synthetic.icosphere(3)
     arrays = synthetic.mesh_bound_scene(P, V, F, seed=2)
     opt = OptimizationParams(alpha_mrloss=0.05)              # many Gaussians larger than weight * sqrt(area): mrloss active
-    fused_model = MeshGaussianModel(arrays, dev, requires_grad=False)
-    ref_model = MeshGaussianModel(arrays, dev)
+    fused_model = MeshGaussianModel(arrays, dev, sh_degree=degree, requires_grad=False)
+    ref_model = MeshGaussianModel(arrays, dev, sh_degree=degree)
     it = TrainingIteration(fused_model, opt, W, H)
     cams = [scenes.camera(dev, W, H, index=i) for i in range(2)]
     bg = torch.zeros(3, device=dev)
