@@ -280,3 +280,64 @@ def test_adam_shard_ranges_partition_the_flat_vector(built_lib):
             assert lo.value == at and hi.value >= lo.value and (lo.value % 32 == 0 or lo.value == total)
             at = hi.value
         assert at == total
+
+
+def test_row_interval_tile_walk_keeps_every_contributing_tile():
+    """The closed-form tile walk of preprocess (csrc/preprocess.cu: per tile row, the x-interval of the threshold
+    ellipse cut by the row's band) restated in numpy float32 and held against brute force: every tile that contains a
+    pixel centre with q(d) <= 2 log(255 o) -- the blend kernels' alpha >= 1/255 test (forward.cu:336-345) -- must be
+    kept; and the walk must not keep more than a thin rim beyond the exact set of tiles the ellipse touches."""
+    f = np.float32
+    rng = np.random.default_rng(21)
+    T, W, H = 16, 640, 480
+    kept_total = exact_total = 0
+    for _ in range(400):
+        # a random conic from a random 2-D covariance (as preprocess builds it) and a random centre / opacity
+        s1, s2 = np.exp(rng.normal(1.2, 0.8)), np.exp(rng.normal(1.2, 0.8))
+        th = rng.uniform(0, np.pi)
+        R = np.array([[np.cos(th), -np.sin(th)], [np.sin(th), np.cos(th)]])
+        cov = R @ np.diag([s1 ** 2, s2 ** 2]) @ R.T + 0.3 * np.eye(2)
+        det = cov[0, 0] * cov[1, 1] - cov[0, 1] ** 2
+        a, b, c = f(cov[1, 1] / det), f(-cov[0, 1] / det), f(cov[0, 0] / det)
+        mx, my = f(rng.uniform(-20, W + 20)), f(rng.uniform(-20, H + 20))
+        o = f(rng.uniform(0.01, 1.0))
+        thr = f(max(0.0, np.log(f(255.0) * o)) + 1e-4)
+        # brute force over pixel centres
+        ys, xs = np.mgrid[0:H, 0:W]
+        dx, dy = (xs - mx).astype(f), (ys - my).astype(f)
+        q = a * dx * dx + f(2) * b * dx * dy + c * dy * dy
+        hit = q <= f(2) * thr
+        exact = {(int(y) // T, int(x) // T) for y, x in zip(*np.nonzero(hit))}
+        # the walk (float32, same expressions as the kernel)
+        lvl = f(2) * thr + f(0.05)
+        ex, ey = f(1.01) * np.sqrt(lvl * f(cov[0, 0])) + f(1), f(1.01) * np.sqrt(lvl * f(cov[1, 1])) + f(1)
+        tiles_x, tiles_y = (W + T - 1) // T, (H + T - 1) // T
+        tx_lo, tx_hi = max(0, int(np.floor((mx - ex) / T))), min(tiles_x, int(np.floor((mx + ex) / T)) + 1)
+        ty_lo, ty_hi = max(0, int(np.floor((my - ey) / T))), min(tiles_y, int(np.floor((my + ey) / T)) + 1)
+        kept = set()
+        if tx_lo < tx_hi and ty_lo < ty_hi:
+            det_c = a * c - b * b
+            bx = max(abs(f(tx_lo * T) - mx), abs(f(tx_hi * T) - mx))
+            by = max(abs(f(ty_lo * T) - my), abs(f(ty_hi * T) - my))
+            Lq = f(2) * thr + f(2e-3) + f(4e-6) * (a * bx * bx + f(2) * abs(b) * bx * by + c * by * by)
+            inv_a = f(1) / a
+            dx_ext = np.sqrt(Lq * c / det_c)
+            dy_at = b / c * dx_ext
+            aL = a * Lq
+            for ty in range(ty_lo, ty_hi):
+                y0b, y1b = f(ty * T) - my, f(min(ty * T + T - 1, H - 1)) - my
+                dyM, dym = min(y1b, max(y0b, -dy_at)), min(y1b, max(y0b, dy_at))
+                DM, Dm = aL - det_c * dyM * dyM, aL - det_c * dym * dym
+                if DM < 0 and Dm < 0:
+                    continue
+                xmax = (-b * dyM + np.sqrt(max(DM, f(0)))) * inv_a
+                xmin = (-b * dym - np.sqrt(max(Dm, f(0)))) * inv_a
+                ta = max(tx_lo, int(np.ceil((mx + xmin - f(T - 1)) / T - 1e-3)))
+                tb = min(tx_hi - 1, int(np.floor((mx + xmax) / T + 1e-3)))
+                kept |= {(ty, tx) for tx in range(ta, tb + 1)}
+        assert exact <= kept, (exact - kept, (a, b, c, mx, my, o))
+        kept_total += len(kept)
+        exact_total += len(exact)
+    assert exact_total > 1000
+    # tiles the continuous ellipse touches without covering a pixel centre: a thin rim only
+    assert kept_total <= 1.35 * exact_total
