@@ -796,3 +796,54 @@ def test_cxx_abi_drop_in_program(cuda_device, tmp_path):
     from gaussianmesh_b200.diff_gaussian_rasterizater import GaussianRasterizer
     vis = GaussianRasterizer(_settings(cam, bgt, D)).markVisible(sc["means3D"].detach())
     assert np.array_equal(vis.cpu().numpy().astype(np.uint8), present)
+
+
+_SCALAR_PROBE = r"""
+import sys, math, json, torch
+sys.path.insert(0, {root!r}); sys.path.insert(0, {root!r} + "/tests")
+import scenes, refcuda
+from gaussianmesh_b200.diff_gaussian_rasterizater import GaussianRasterizer
+from gaussianmesh_b200.renderer import make_settings
+dev = torch.device("cuda:0")
+P, W, H = 6000, 200, 136
+sc = scenes.free_scene(P, dev, seed=12)
+for k in ("means3D", "opacities", "shs", "scales", "rotations"):
+    sc[k].requires_grad_(True)
+cam = scenes.camera(dev, W, H, index=1)
+bg = torch.tensor([0.3, 0.1, 0.2], device=dev)
+m2d = torch.zeros(P, 3, device=dev, requires_grad=True)
+color, radii = GaussianRasterizer(make_settings(cam, bg, 3))(sc["means3D"], m2d, sc["opacities"], shs=sc["shs"],
+                                                             scales=sc["scales"], rotations=sc["rotations"])
+dL = torch.rand(3, H, W, generator=torch.Generator().manual_seed(13)).to(dev) - 0.5
+color.backward(dL)
+ref = refcuda.RefFrame(bg, sc["means3D"].detach(), sc["opacities"].detach(), cam.world_view_transform.contiguous(),
+                       cam.full_proj_transform.contiguous(), cam.camera_center.contiguous(), math.tan(cam.FoVx * 0.5),
+                       math.tan(cam.FoVy * 0.5), H, W, 3, shs=sc["shs"].detach(), scales=sc["scales"].detach(),
+                       rotations=sc["rotations"].detach())
+rg = ref.backward(dL)
+out = {{"fwd": float((color.detach() - ref.color).abs().max()), "radii": bool(torch.equal(radii, ref.radii))}}
+for k, rk in (("means3D", "means3D"), ("shs", "sh"), ("opacities", "opacity"), ("scales", "scales"), ("rotations", "rotations")):
+    out[k] = scenes.rel_err(sc[k].grad, rg[rk].view_as(sc[k].grad))
+out["means2D"] = scenes.rel_err(m2d.grad, rg["means2D"])
+print(json.dumps(out))
+"""
+
+
+def test_scalar_blend_kernels_still_match(cuda_device, tmp_path):
+    """GM_BLEND_SCALAR=1 selects the one-splat-per-iteration blend kernels kept for A/B measurements (the library reads
+    the variable once, hence the subprocess): same parity bar as the packed kernels."""
+    import json
+    import os
+    import subprocess
+    import sys
+    _need_ref()
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = tmp_path / "scalar_probe.py"
+    script.write_text(_SCALAR_PROBE.format(root=root))
+    run = subprocess.run([sys.executable, str(script)], capture_output=True, text=True, timeout=300,
+                         env=dict(os.environ, GM_BLEND_SCALAR="1"))
+    assert run.returncode == 0, run.stderr[-2000:]
+    res = json.loads([l for l in run.stdout.splitlines() if l.startswith("{")][-1])
+    assert res["radii"] and res["fwd"] <= FWD_TOL
+    for k in ("means3D", "shs", "opacities", "scales", "rotations", "means2D"):
+        assert res[k] <= BWD_TOL, (k, res[k])
