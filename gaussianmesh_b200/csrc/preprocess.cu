@@ -112,7 +112,17 @@ bucket_lut_kernel(const uint32_t* __restrict__ hist, uint8_t* __restrict__ lut, 
 }
 
 // 4 resident blocks per SM (64 registers, a 32-byte spill): measured faster than 3 blocks at 79 registers
-template <bool kVecSH>
+// kCoop (SH path, M == 16, degree 3, 16-byte aligned rows): the SH rows are not fetched by their owner thread with
+// twelve 128-bit loads at a 192-byte lane stride (one request = 32 cache lines: the L1 tag stage becomes the limit)
+// but staged per WARP: its 32 rows are one contiguous 6 KB block, copied into shared memory with coalesced cp.async
+// issued before anything else, and read by the owners after the geometry part.  Rows are kept at their natural
+// 12-float4 pitch (48 KB per block, so four blocks still fit an SM) with the column index XOR-swizzled by
+// (row >> 1) & 3, which makes the owners' LDS.128 conflict-free.
+constexpr int kRowF4 = 12;
+
+__device__ __forceinline__ int row_slot(int r, int c) { return r * kRowF4 + (c ^ ((r >> 1) & 3)); }
+
+template <bool kVecSH, bool kCoop>
 __global__ void __launch_bounds__(kThreads, 4)
 preprocess_kernel(int P,
                   const float* __restrict__ means3D,
@@ -143,6 +153,24 @@ preprocess_kernel(int P,
 
 	const int idx = blockIdx.x * kThreads + threadIdx.x;
 	bool visible = false;
+	extern __shared__ float4 s_rows_all[];
+	float4* const s_rows = s_rows_all + (threadIdx.x >> 5) * (32 * kRowF4);
+	if (kCoop) {
+		const int lane = threadIdx.x & 31;
+		const int row0 = idx - lane;
+		const int n4 = max(0, min(32, P - row0)) * kRowF4;
+		const float4* src = reinterpret_cast<const float4*>(shs) + (size_t)row0 * kRowF4;
+#pragma unroll
+		for (int i = 0; i < kRowF4; i++) {
+			const int f = lane + 32 * i;
+			if (f < n4) {
+				const int r = f / kRowF4;
+				asm volatile("cp.async.cg.shared.global [%0], [%1], 16;"
+				             ::"r"(smem_u32(&s_rows[row_slot(r, f - r * kRowF4)])), "l"(src + f) : "memory");
+			}
+		}
+		asm volatile("cp.async.commit_group;" ::: "memory");
+	}
 
 	if (idx < P) {
 		// forward.cu:186-187: a Gaussian that exits early keeps radius 0 (and touches no tile).
@@ -194,8 +222,10 @@ preprocess_kernel(int P,
 				break;
 
 			// forward.cu:239-247 (SH -> RGB with clamp mask) or precomputed colours
-			float4 rgbc;
-			if (colors_precomp == nullptr) {
+			float4 rgbc = make_float4(0.f, 0.f, 0.f, 0.f);
+			if (kCoop) {
+				// evaluated after the do-block, once the warp's rows have landed
+			} else if (colors_precomp == nullptr) {
 				// forward.cu:25-27: dir = (pos - campos) / length
 				float dx = p_orig.x - s_cam[0], dy = p_orig.y - s_cam[1], dz = p_orig.z - s_cam[2];
 				const float len = sqrtf(dx * dx + dy * dy + dz * dz);
@@ -219,7 +249,8 @@ preprocess_kernel(int P,
 			g.depths[idx] = p_view.z;
 			g.means2D[idx] = point_image;
 			g.conic_opacity[idx] = make_float4(conic.x, conic.y, conic.z, opacity);
-			g.rgb_clamp[idx] = rgbc;
+			if (!kCoop)
+				g.rgb_clamp[idx] = rgbc;
 			my_radius_i = (int)my_radius;
 			visible = true;
 
@@ -305,6 +336,31 @@ preprocess_kernel(int P,
 		radii[idx] = my_radius_i;
 	}
 
+	if (kCoop) {
+		asm volatile("cp.async.wait_all;" ::: "memory");
+		__syncwarp();
+		if (visible) {
+			// forward.cu:239-247 (SH -> RGB with clamp mask); forward.cu:25-27: dir = (pos - campos) / length
+			const int lane = threadIdx.x & 31;
+			float dx = means3D[3 * idx] - s_cam[0], dy = means3D[3 * idx + 1] - s_cam[1], dz = means3D[3 * idx + 2] - s_cam[2];
+			const float len = sqrtf(dx * dx + dy * dy + dz * dz);
+			dx = dx / len; dy = dy / len; dz = dz / len;
+			const ShDir d = sh_dir(dx, dy, dz);
+			float sh[48];
+#pragma unroll
+			for (int j = 0; j < kRowF4; j++) {
+				const float4 t = s_rows[row_slot(lane, j)];
+				sh[4 * j + 0] = t.x; sh[4 * j + 1] = t.y; sh[4 * j + 2] = t.z; sh[4 * j + 3] = t.w;
+			}
+			float r = sh_channel(vp.D, d, [&sh](int k) { return sh[3 * k + 0]; });
+			float gch = sh_channel(vp.D, d, [&sh](int k) { return sh[3 * k + 1]; });
+			float b = sh_channel(vp.D, d, [&sh](int k) { return sh[3 * k + 2]; });
+			r += 0.5f; gch += 0.5f; b += 0.5f;
+			const uint32_t bits = (r < 0 ? 1u : 0u) | (gch < 0 ? 2u : 0u) | (b < 0 ? 4u : 0u);
+			g.rgb_clamp[idx] = make_float4(max(r, 0.0f), max(gch, 0.0f), max(b, 0.0f), __uint_as_float(bits));
+		}
+	}
+
 	const uint32_t vis_mask = __ballot_sync(0xffffffffu, visible);
 	if ((threadIdx.x & 31) == 0 && vis_mask != 0)
 		atomicAdd(&g.header->num_visible, (uint32_t)__popc(vis_mask));
@@ -343,11 +399,17 @@ int launch_preprocess(int P, const float* means3D, const float* scales, const fl
 	if (P <= 0)
 		return GM_OK;
 	const dim3 grid((P + kThreads - 1) / kThreads);
-	if (colors_precomp == nullptr && sh_rows_vectorizable(shs, vp.M) && vp.M * 3 >= 3 * (vp.D + 1) * (vp.D + 1))
-		preprocess_kernel<true><<<grid, kThreads, 0, stream>>>(
+	const bool vec = colors_precomp == nullptr && sh_rows_vectorizable(shs, vp.M) && vp.M * 3 >= 3 * (vp.D + 1) * (vp.D + 1);
+	constexpr size_t kCoopSmem = (size_t)(kThreads / 32) * 32 * kRowF4 * sizeof(float4);      // 48 KB
+	if (vec && vp.M == 16 && vp.D == 3) {
+		cudaFuncSetAttribute(preprocess_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCoopSmem);
+		preprocess_kernel<true, true><<<grid, kThreads, kCoopSmem, stream>>>(
+			P, means3D, scales, rotations, opacities, shs, cov3D_precomp, colors_precomp, vp, radii, g, prefiltered);
+	} else if (vec)
+		preprocess_kernel<true, false><<<grid, kThreads, 0, stream>>>(
 			P, means3D, scales, rotations, opacities, shs, cov3D_precomp, colors_precomp, vp, radii, g, prefiltered);
 	else
-		preprocess_kernel<false><<<grid, kThreads, 0, stream>>>(
+		preprocess_kernel<false, false><<<grid, kThreads, 0, stream>>>(
 			P, means3D, scales, rotations, opacities, shs, cov3D_precomp, colors_precomp, vp, radii, g, prefiltered);
 	launch_large_tiles(0, radii, g, nullptr, 0, vp, stream);      // count pass for rectangles of more than 64 tiles
 	return GM_OK;
