@@ -341,3 +341,18 @@ def test_row_interval_tile_walk_keeps_every_contributing_tile():
     assert exact_total > 1000
     # tiles the continuous ellipse touches without covering a pixel centre: a thin rim only
     assert kept_total <= 1.35 * exact_total
+
+
+def test_header_is_plain_c(tmp_path):
+    """include/gm_rasterizer.h is the C-ABI contract: it must compile as C99 (no C++ in the signatures) and the two
+    structs passed by pointer must have the layout the ctypes mirror assumes."""
+    import ctypes as C
+    src = tmp_path / "hdr.c"
+    src.write_text('#include <stdio.h>\n#include "gm_rasterizer.h"\n'
+                   'int main(void) { printf("%zu %zu\\n", sizeof(gm_adam_tensor), sizeof(gm_adam_segment)); return 0; }\n')
+    exe = tmp_path / "hdr"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"),
+                    str(src), "-o", str(exe)], check=True, capture_output=True)
+    sizes = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()
+    from gaussianmesh_b200._lib import AdamTensor, AdamSegment
+    assert [int(x) for x in sizes] == [C.sizeof(AdamTensor), C.sizeof(AdamSegment)]
