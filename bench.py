@@ -146,9 +146,8 @@ def build_edit_workload(device, rank, world):
     with torch.no_grad():
         pos, scales, rots, opac = mesh_bind(t["bc_logits"], torch.zeros_like(t["distance"]), t["log_scales"], t["rot_raw"],
                                             t["opacity_logit"], t["vertex1"], t["vertex2"], t["vertex3"], t["normal"], t["r"])
-    weights = synthetic.barycentric_weights(pos.cpu().numpy(), V, a["triangles"]).astype(np.float32)
     cov6 = torch.from_numpy(synthetic.packed_covariance(scales.cpu().numpy(), rots.cpu().numpy())).to(device)
-    obj = DeformedObject(pos, cov6, opac, t["shs"], a["triangles"], weights, V, device)
+    obj = DeformedObject.load_mesh(pos, cov6, opac, t["shs"], pos, a["face_id"], V.astype(np.float64), F, device)
     Vd, _, _ = synthetic.twist_bend_deformation(V)
     # per-vertex rotation / shear of the deformation: ACAP GetRS on the GPU (the reference calls pyACAP on the CPU)
     from gaussianmesh_b200.acap import pyACAP

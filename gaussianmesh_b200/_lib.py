@@ -71,11 +71,18 @@ SIGNATURES = {
                                    _p, _p, _p, _p, _p, _p]),
     "gm_deform_gaussians": (_i, [_i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _i, _p, _p, _p, _p]),
     "gm_sh_to_rgb_rotated": (_i, [_i, _i, _i, _p, _p, _p, _p, _p, _p]),
+    "gm_sh_to_rgb_rotated_backward": (_i, [_i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "gm_cov3d_from_scale_rot": (_i, [_i, _p, _f, _p, _p, _p]),
+    "gm_cov3d_from_scale_rot_backward": (_i, [_i, _p, _f, _p, _p, _p, _p, _p]),
+    "gm_load_mesh": (_i, [_i, _i, _i, _p, _p, _p, _p, _p, _p, _p]),
     "gm_l1_loss": (_i, [_z, _p, _p, _p, _p, _p]),
     "gm_photometric_scratch_bytes": (_z, [_i, _i, _i]),
     "gm_photometric_loss": (_i, [_i, _i, _i, _p, _p, _f, _p, _p, _p, _p]),
     "gm_mesh_restrict_loss": (_i, [_i, _p, _p, _p, _p, _f, _p, _p, _i, _p]),
     "gm_adam_step": (_i, [_i, C.POINTER(AdamTensor), _i, _f, _f, _f, _p]),
+    "gm_adam_step_gated": (_i, [_i, C.POINTER(AdamTensor), _i, _f, _f, _f, _p, _p]),
+    "gm_frame_overflow_flag": (_p, [_p]),
+    "gm_densify_stats_gated": (_i, [_i, _p, _p, _p, _p, _p, _p, _p, _p]),
     "gm_adam_shard_range": (None, [_z, _i, _i, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
     "gm_adam_step_sharded_p2p": (_i, [_i, _i, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), _i, C.POINTER(AdamSegment), _z,
                                       _p, _p, _i, _f, _f, _f, _p]),

@@ -47,12 +47,12 @@ int check_stage(const char* what, bool debug, cudaStream_t stream)
 // dominant kernel; off by default (no events, no overhead).
 enum Stage { kStDepthBuckets, kStPreprocess, kStTileScan, kStEmit, kStSortPack, kStBlendFwd, kStBlendBwd, kStGeomBwd, kStL1,
              kStMeshBindFwd, kStMeshBindBwd, kStDeform, kStShRotated, kStMarkVisible, kStAcapRest, kStAcapGetRS,
-             kStPhotometric, kStMeshRestrict, kStAdam, kStDensifyStats,
+             kStPhotometric, kStMeshRestrict, kStAdam, kStDensifyStats, kStCov3dPython, kStLoadMesh,
              kNumStages };
 static const char* const kStageNames[kNumStages] = {
 	"depth_buckets", "preprocess", "tile_scan", "emit", "sort_pack", "blend_forward", "blend_backward", "geometry_backward",
 	"l1_loss", "mesh_bind_forward", "mesh_bind_backward", "deform", "sh_to_rgb_rotated", "mark_visible", "acap_rest",
-	"acap_get_rs", "photometric_loss", "mesh_restrict_loss", "adam", "densify_stats"};
+	"acap_get_rs", "photometric_loss", "mesh_restrict_loss", "adam", "densify_stats", "cov3d_python", "load_mesh"};
 
 struct StageRecord { int stage; cudaEvent_t start, stop; };
 static std::mutex g_profile_mutex;
@@ -464,6 +464,51 @@ int gm_sh_to_rgb_rotated(int P, int D, int M, const float* pos, const float* cam
 	return check_stage("sh_to_rgb_rotated", false, (cudaStream_t)stream);
 }
 
+int gm_sh_to_rgb_rotated_backward(int P, int D, int M, const float* pos, const float* campos, const float* rot,
+                                  const float* shs, const float* dL_drgb, float* dL_dshs, float* dL_dpos, gm_stream_t stream)
+{
+	if (P < 0 || D < 0 || D > 3 || M < (D + 1) * (D + 1))
+		return GM_ERR_BAD_ARGUMENT;
+	if (P > 0 && (!pos || !campos || !shs || !dL_drgb || (!dL_dshs && !dL_dpos)))
+		return GM_ERR_BAD_ARGUMENT;
+	{ StageScope scope_(kStShRotated, (cudaStream_t)stream);
+	  launch_sh_rotated_backward(P, D, M, pos, campos, rot, shs, dL_drgb, dL_dshs, dL_dpos, (cudaStream_t)stream); }
+	return check_stage("sh_to_rgb_rotated_backward", false, (cudaStream_t)stream);
+}
+
+int gm_cov3d_from_scale_rot(int P, const float* scales, float scale_modifier, const float* rotations, float* cov6,
+                            gm_stream_t stream)
+{
+	if (P < 0 || (P > 0 && (!scales || !rotations || !cov6)))
+		return GM_ERR_BAD_ARGUMENT;
+	{ StageScope scope_(kStCov3dPython, (cudaStream_t)stream);
+	  launch_cov3d_python(P, scales, scale_modifier, rotations, cov6, (cudaStream_t)stream); }
+	return check_stage("cov3d_from_scale_rot", false, (cudaStream_t)stream);
+}
+
+int gm_cov3d_from_scale_rot_backward(int P, const float* scales, float scale_modifier, const float* rotations,
+                                     const float* dL_dcov6, float* dL_dscale, float* dL_drot, gm_stream_t stream)
+{
+	if (P < 0 || (P > 0 && (!scales || !rotations || !dL_dcov6 || !dL_dscale || !dL_drot)))
+		return GM_ERR_BAD_ARGUMENT;
+	{ StageScope scope_(kStCov3dPython, (cudaStream_t)stream);
+	  launch_cov3d_python_backward(P, scales, scale_modifier, rotations, dL_dcov6, dL_dscale, dL_drot, (cudaStream_t)stream); }
+	return check_stage("cov3d_from_scale_rot_backward", false, (cudaStream_t)stream);
+}
+
+int gm_load_mesh(int P, int num_vertices, int num_faces, const double* vertex, const int32_t* faces, const int64_t* face_id,
+                 const float* proj_pos, int32_t* gaussian_triangles, double* weights, gm_stream_t stream)
+{
+	if (P < 0 || num_vertices < 0 || num_faces < 0)
+		return GM_ERR_BAD_ARGUMENT;
+	if (P > 0 && (num_faces == 0 || !vertex || !faces || !face_id || !proj_pos || !gaussian_triangles || !weights))
+		return GM_ERR_BAD_ARGUMENT;
+	{ StageScope scope_(kStLoadMesh, (cudaStream_t)stream);
+	  launch_load_mesh(P, num_faces, vertex, faces, reinterpret_cast<const long long*>(face_id), proj_pos, gaussian_triangles,
+	                   weights, (cudaStream_t)stream); }
+	return check_stage("load_mesh", false, (cudaStream_t)stream);
+}
+
 int gm_acap_build_rings(int num_vertices, int num_faces, const int32_t* faces_host, int32_t* ring_offsets_host,
                         int32_t* ring_neighbours_host, int32_t* face_offsets_host, int32_t* face_list_host)
 {
@@ -538,8 +583,8 @@ int gm_mesh_restrict_loss(int P, const float* scale, const float* vertex1, const
 	return check_stage("mesh_restrict_loss", false, (cudaStream_t)stream);
 }
 
-int gm_adam_step(int num_tensors, const gm_adam_tensor* tensors_host, int step, float beta1, float beta2, float eps,
-                 gm_stream_t stream)
+int gm_adam_step_gated(int num_tensors, const gm_adam_tensor* tensors_host, int step, float beta1, float beta2, float eps,
+                       const uint32_t* skip_flag, gm_stream_t stream)
 {
 	if (num_tensors < 0 || step < 1 || (num_tensors > 0 && tensors_host == nullptr))
 		return GM_ERR_BAD_ARGUMENT;
@@ -551,8 +596,23 @@ int gm_adam_step(int num_tensors, const gm_adam_tensor* tensors_host, int step, 
 			return GM_ERR_BAD_ARGUMENT;
 	}
 	{ StageScope scope_(kStAdam, (cudaStream_t)stream);
-	  launch_adam(num_tensors, tensors_host, step, beta1, beta2, eps, (cudaStream_t)stream); }
+	  launch_adam(num_tensors, tensors_host, step, beta1, beta2, eps, skip_flag, (cudaStream_t)stream); }
 	return check_stage("adam", false, (cudaStream_t)stream);
+}
+
+int gm_adam_step(int num_tensors, const gm_adam_tensor* tensors_host, int step, float beta1, float beta2, float eps,
+                 gm_stream_t stream)
+{
+	return gm_adam_step_gated(num_tensors, tensors_host, step, beta1, beta2, eps, nullptr, stream);
+}
+
+const uint32_t* gm_frame_overflow_flag(const char* geom_buffer)
+{
+	if (geom_buffer == nullptr)
+		return nullptr;
+	char* p = const_cast<char*>(geom_buffer);
+	GeometryState geom = GeometryState::fromChunk(p, 0);
+	return &geom.header->overflow;
 }
 
 void gm_adam_shard_range(size_t total, int world, int rank, size_t* lo, size_t* hi)
@@ -593,14 +653,20 @@ int gm_adam_step_sharded_p2p(int world, int rank, const float* const* grads_host
 	return check_stage("adam_sharded_p2p", false, (cudaStream_t)stream);
 }
 
-int gm_densify_stats(int P, const int32_t* radii, const float* dL_dmean2D, float* max_radii2D, float* grad_accum,
-                     float* denom, gm_stream_t stream)
+int gm_densify_stats_gated(int P, const int32_t* radii, const float* dL_dmean2D, float* max_radii2D, float* grad_accum,
+                           float* denom, const uint32_t* skip_flag, gm_stream_t stream)
 {
 	if (P < 0 || (P > 0 && (!radii || !dL_dmean2D || !max_radii2D || !grad_accum || !denom)))
 		return GM_ERR_BAD_ARGUMENT;
 	{ StageScope scope_(kStDensifyStats, (cudaStream_t)stream);
-	  launch_densify_stats(P, radii, dL_dmean2D, max_radii2D, grad_accum, denom, (cudaStream_t)stream); }
+	  launch_densify_stats(P, radii, dL_dmean2D, max_radii2D, grad_accum, denom, skip_flag, (cudaStream_t)stream); }
 	return check_stage("densify_stats", false, (cudaStream_t)stream);
+}
+
+int gm_densify_stats(int P, const int32_t* radii, const float* dL_dmean2D, float* max_radii2D, float* grad_accum,
+                     float* denom, gm_stream_t stream)
+{
+	return gm_densify_stats_gated(P, radii, dL_dmean2D, max_radii2D, grad_accum, denom, nullptr, stream);
 }
 
 } // extern "C"

@@ -610,6 +610,403 @@ blend_backward_pairs_kernel(GeometryState g, BinningState b, ImageState img, uin
 	}
 }
 
+
+// ---- tensor-core reduction over the warp's 32 pixels ----------------------------------------------
+// The per-(pixel, splat) work above ends in nine sums over the 32 pixels of the warp.  With q = G dL/dalpha and
+// w = alpha T those sums are two small matrix products over the pixel index p:
+//     M[s, k] = sum_p q[s, p] * Phi[p, k]      Phi[p, :] = (1, u, v, u^2, u v, v^2),  u, v = pixel offset from the block centre
+//     C[s, c] = sum_p w[s, p] * dL/dpixel[p, c]
+// (backward.cu:523,537-554 sum q dx, q dx^2, ... with dx = x_s - px: the splat-centred moments follow from the
+// pixel-centred ones by a shift applied once per (warp, splat), see `flush`).  Each lane parks (q, w) of its pixel in a
+// warp-private shared-memory slab, 16 splats deep, and the two products run on the tensor cores
+// (mma.sync.m16n8k8, TF32 inputs, FP32 accumulation): q and w are split into a TF32 head and tail (two MMAs, 21+ mantissa
+// bits), Phi is exact in TF32 (multiples of 1/4 below 16), dL/dpixel is split head/tail across two columns of the B
+// operand.  This replaces the 18-value transposing butterfly (37 % of the pairs kernel's instructions) with two 64-bit
+// shared-memory stores per pair of splats and ~12 instructions per splat at flush time.
+//
+// The splat queue is a warp-private RING of pair slots: survivors of the 32-wide cull are appended (an odd survivor
+// waits for the next chunk instead of being padded), evaluated pair by pair, and stay in the ring until the 16 slab rows
+// that hold their (q, w) have been reduced.  The record stages are released per warp (a counter per stage; the warp that
+// arrives last refills the stage), so there is no block-wide barrier in the loop.
+constexpr int kBatchM = 128;      // records per stage
+constexpr int kStagesM = 3;
+constexpr int kRing = 24;         // pair slots: <= 7 pending + <= 17 new
+constexpr int kRowPairs = 8;      // slab depth in pairs (16 MMA rows)
+constexpr int kSlabPitch = 80;    // floats per slab row pair: 32 pixels x (A, B) + 16 pad (conflict-free LDS.128 fragments)
+
+struct WarpRingM {
+	// [field][slot][4]: 0: xA xB yA yB   1: aA aB -bA -bB   2: cA cB oA oB   3: rA rB gA gB   4: bA bB posA posB
+	float v[5][kRing][4];
+	uint32_t id[kRing * 2];
+	float slabQ[kRowPairs][kSlabPitch];   // [row pair][pixel][A, B]
+	float slabW[kRowPairs][kSlabPitch];
+};
+
+struct __align__(128) BwdSmemM {
+	float4 conic[kStagesM][kBatchM];
+	float4 xyrg[kStagesM][kBatchM];
+	float2 bid[kStagesM][kBatchM];
+	WarpRingM ring[kWarps];
+	uint64_t full[kStagesM];
+	uint32_t released[kStagesM];
+	uint32_t warp_max[kWarps];
+};
+
+__device__ __forceinline__ uint32_t tf32_rna(float x)
+{
+	uint32_t r;
+	asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+	return r;
+}
+
+// x = head + tail with head the nearest TF32 value; the tail is exact in fp32 and the tensor core reads its top 19 bits
+__device__ __forceinline__ void tf32_split(float x, uint32_t& head, uint32_t& tail)
+{
+	head = tf32_rna(x);
+	tail = __float_as_uint(x - __uint_as_float(head));
+}
+
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1)
+{
+	asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+	             : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+	             : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+__global__ void __launch_bounds__(kThreads, 3)
+blend_backward_mma_kernel(GeometryState g, BinningState b, ImageState img, uint32_t capacity,
+                          int W, int H, int tiles_x, const float* __restrict__ bg_color,
+                          const float* __restrict__ dL_dpixels,
+                          float* __restrict__ dL_dmean2D,   // [P,3]
+                          float* __restrict__ dL_dconic2D,  // [P,4]
+                          float* __restrict__ dL_dopacity,  // [P]
+                          float* __restrict__ dL_dcolors)   // [P,3]
+{
+	extern __shared__ __align__(128) unsigned char smem_raw[];
+	BwdSmemM& s = *reinterpret_cast<BwdSmemM*>(smem_raw);
+
+	const int tile = blockIdx.x;
+	const int tile_x = tile % tiles_x, tile_y = tile / tiles_x;
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+	const int bx0 = tile_x * kTile + (warp & 1) * 8;
+	const int by0 = tile_y * kTile + (warp >> 1) * 4;
+	const int px = bx0 + (lane & 7), py = by0 + (lane >> 3);
+	const bool inside = px < W && py < H;
+	const uint32_t pix_id = (uint32_t)W * py + px;
+	const f2 npx = pk1(-(float)px), npy = pk1(-(float)py);
+	const float wx0 = (float)bx0, wy0 = (float)by0;
+	const float wx1 = (float)min(bx0 + 7, W - 1), wy1 = (float)min(by0 + 3, H - 1);
+
+	const uint32_t start = g.tile_start[tile];
+	uint32_t n = 0;
+	if (start < capacity)
+		n = min(g.tile_count[tile], capacity - start);
+
+	// backward.cu:430-448
+	const float T_final = inside ? img.accum_alpha[pix_id] : 0.0f;
+	float T = T_final;
+	const uint32_t last_contributor = inside ? min(img.n_contrib[pix_id], n) : 0u;
+
+	uint32_t warp_last = last_contributor;
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1)
+		warp_last = max(warp_last, __shfl_xor_sync(0xffffffffu, warp_last, o));
+	if (lane == 0)
+		s.warp_max[warp] = warp_last;
+	if (tid == 0) {
+#pragma unroll
+		for (int st = 0; st < kStagesM; st++) {
+			mbar_init(&s.full[st], 1);
+			s.released[st] = 0;
+		}
+		fence_mbar_init();
+	}
+	__syncthreads();
+	uint32_t tile_last = 0;
+#pragma unroll
+	for (int w = 0; w < kWarps; w++)
+		tile_last = max(tile_last, s.warp_max[w]);
+	if (tile_last == 0)
+		return;
+
+	float dL_dpixel0 = 0.0f, dL_dpixel1 = 0.0f, dL_dpixel2 = 0.0f;
+	if (inside) {
+		const size_t HW = (size_t)H * W;
+		dL_dpixel0 = dL_dpixels[0 * HW + pix_id];
+		dL_dpixel1 = dL_dpixels[1 * HW + pix_id];
+		dL_dpixel2 = dL_dpixels[2 * HW + pix_id];
+	}
+
+	// B operands of the two products, constant per warp.  Fragment layout of mma.m16n8k8 (row.col): this thread holds
+	// B[k = tg][n = gid] and B[k = tg + 4][n = gid]; k-step i maps k = tg, tg + 4 to the pixels 8 i + 2 tg, 8 i + 2 tg + 1
+	// of the warp's block (lane index = pixel index), the order in which the A fragments are read from the slab.
+	const int gid = lane >> 2, tg = lane & 3;
+	uint32_t phi[4][2], dfr[4][2];
+#pragma unroll
+	for (int i = 0; i < 4; i++)
+#pragma unroll
+		for (int j = 0; j < 2; j++) {
+			const int p = 8 * i + 2 * tg + j;
+			const float u = (float)(p & 7) - 3.5f, v = (float)(p >> 3) - 1.5f;
+			const float mono = gid == 0 ? 1.0f : gid == 1 ? u : gid == 2 ? v : gid == 3 ? u * u : gid == 4 ? u * v
+			                   : gid == 5 ? v * v : 0.0f;
+			phi[i][j] = __float_as_uint(mono);
+			const float d0 = __shfl_sync(0xffffffffu, dL_dpixel0, p);
+			const float d1 = __shfl_sync(0xffffffffu, dL_dpixel1, p);
+			const float d2 = __shfl_sync(0xffffffffu, dL_dpixel2, p);
+			const float d = (gid >> 1) == 0 ? d0 : (gid >> 1) == 1 ? d1 : (gid >> 1) == 2 ? d2 : 0.0f;
+			uint32_t head, tail;
+			tf32_split(d, head, tail);
+			dfr[i][j] = (gid & 1) ? tail : head;   // columns 2c, 2c + 1 = head, tail of channel c; columns 6, 7 = 0
+		}
+
+	// accum_rec and the pending (last_alpha * last_color, 1 - last_alpha) term of backward.cu:509-515
+	float acc0 = 0.0f, acc1 = 0.0f, acc2 = 0.0f;
+	float pend0 = 0.0f, pend1 = 0.0f, pend2 = 0.0f, keep_prev = 1.0f;
+
+	// backward.cu:455-461: d(pixel offset)/d(NDC mean); applied once per (warp, splat) in flush
+	const float ddelx_dx = 0.5 * W;
+	const float ddely_dy = 0.5 * H;
+	// backward.cu:531-534: dL/dalpha += (-T_final / (1 - alpha)) * (bg . dL/dpixel)
+	const f2 bg_term = pk1(-T_final * (bg_color[0] * dL_dpixel0 + bg_color[1] * dL_dpixel1 + bg_color[2] * dL_dpixel2));
+	const f2 dLp0 = pk1(dL_dpixel0), dLp1 = pk1(dL_dpixel1), dLp2 = pk1(dL_dpixel2);
+	const f2 neg_half = pk1(-0.5f), neg_one = pk1(-1.0f), one = pk1(1.0f);
+
+	auto issue = [&](int batch, int st) {
+		const uint32_t off = start + (uint32_t)batch * kBatchM;
+		const uint32_t cnt = min((uint32_t)kBatchM, n - (uint32_t)batch * kBatchM);
+		const uint32_t cnt4 = (cnt + 3u) & ~3u;
+		mbar_arrive_expect_tx(&s.full[st], cnt4 * 40u);
+		bulk_g2s(s.conic[st], b.rec_conic + off, cnt4 * 16u, &s.full[st]);
+		bulk_g2s(s.xyrg[st], b.rec_xyrg + off, cnt4 * 16u, &s.full[st]);
+		bulk_g2s(s.bid[st], b.rec_bid + off, cnt4 * 8u, &s.full[st]);
+	};
+
+	WarpRingM& r = s.ring[warp];
+	const float cx = (float)bx0 + 3.5f, cy = (float)by0 + 1.5f;
+
+	// Reduce the slab (up to 8 row pairs starting at ring slot `tail`) on the tensor cores and send every touched splat's
+	// gradients to global memory: lanes 0-7 own splat A of row pair (lane & 7), lanes 8-15 splat B.
+	auto flush = [&](int tail, uint32_t touched) {
+		__syncwarp();
+		float mq[4] = {0.0f, 0.0f, 0.0f, 0.0f}, mw[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll
+		for (int i = 0; i < 4; i++) {
+			// A fragment of k-step i: rows gid (splat A of pair gid) and gid + 8 (splat B), pixels 8 i + 2 tg, + 1
+			const float4 aq = *reinterpret_cast<const float4*>(&r.slabQ[gid][16 * i + 4 * tg]);
+			const float4 aw = *reinterpret_cast<const float4*>(&r.slabW[gid][16 * i + 4 * tg]);
+			uint32_t qh[4], ql[4], wh[4], wl[4];
+			tf32_split(aq.x, qh[0], ql[0]); tf32_split(aq.y, qh[1], ql[1]);
+			tf32_split(aq.z, qh[2], ql[2]); tf32_split(aq.w, qh[3], ql[3]);
+			tf32_split(aw.x, wh[0], wl[0]); tf32_split(aw.y, wh[1], wl[1]);
+			tf32_split(aw.z, wh[2], wl[2]); tf32_split(aw.w, wh[3], wl[3]);
+			mma_tf32(mq, qh, phi[i][0], phi[i][1]);
+			mma_tf32(mq, ql, phi[i][0], phi[i][1]);
+			mma_tf32(mw, wh, dfr[i][0], dfr[i][1]);
+			mma_tf32(mw, wl, dfr[i][0], dfr[i][1]);
+		}
+		__syncwarp();   // every fragment has been read: the slab is reused to transpose the results
+		// C fragment: (row gid, columns 2 tg, 2 tg + 1), (row gid + 8, same columns)
+		float* const park = &r.slabQ[0][0];   // [16 rows][12]: Sq Su Sv Suu Suv Svv | colour 0 1 2
+		if (tg < 3) {
+			*reinterpret_cast<float2*>(park + gid * 12 + 2 * tg) = make_float2(mq[0], mq[1]);
+			*reinterpret_cast<float2*>(park + (gid + 8) * 12 + 2 * tg) = make_float2(mq[2], mq[3]);
+			park[gid * 12 + 6 + tg] = mw[0] + mw[1];
+			park[(gid + 8) * 12 + 6 + tg] = mw[2] + mw[3];
+		}
+		__syncwarp();
+		if (lane < 16 && ((touched >> (lane & 7)) & 1u)) {
+			const float4 m0 = *reinterpret_cast<const float4*>(park + lane * 12);
+			const float4 m1 = *reinterpret_cast<const float4*>(park + lane * 12 + 4);
+			const float c2 = park[lane * 12 + 8];
+			const float Sq = m0.x, Su = m0.y, Sv = m0.z, Suu = m0.w, Suv = m1.x, Svv = m1.y, c0 = m1.z, c1 = m1.w;
+			const uint32_t any = (__float_as_uint(c0) | __float_as_uint(c1) | __float_as_uint(c2) | __float_as_uint(Sq) |
+			                      __float_as_uint(Su) | __float_as_uint(Sv) | __float_as_uint(Suu) | __float_as_uint(Suv) |
+			                      __float_as_uint(Svv)) << 1;
+			if (any != 0) {
+				int slot = tail + (lane & 7);
+				slot = slot >= kRing ? slot - kRing : slot;
+				const int h = lane >> 3;
+				const float a = r.v[1][slot][h], bb = -r.v[1][slot][2 + h], c = r.v[2][slot][h], o = r.v[2][slot][2 + h];
+				const uint32_t id = r.id[2 * slot + h];
+				// dx = x_s - px = X - u with X = x_s - (block centre): shift the pixel-centred moments to the splat
+				const float X = r.v[0][slot][h] - cx, Y = r.v[0][slot][2 + h] - cy;
+				const float Sx = fmaf(X, Sq, -Su), Sy = fmaf(Y, Sq, -Sv);
+				const float Sxx = fmaf(X, fmaf(X, Sq, -2.0f * Su), Suu);
+				const float Sxy = fmaf(X, fmaf(Y, Sq, -Sv), fmaf(-Y, Su, Suv));
+				const float Syy = fmaf(Y, fmaf(Y, Sq, -2.0f * Sv), Svv);
+				atomicAdd(&dL_dcolors[3 * (size_t)id + 0], c0);
+				atomicAdd(&dL_dcolors[3 * (size_t)id + 1], c1);
+				atomicAdd(&dL_dcolors[3 * (size_t)id + 2], c2);
+				// dL/dG = o dL/dalpha;  dG/ddelx = -G (a dx + b dy);  dG/ddely = -G (c dy + b dx)
+				atomicAdd(&dL_dmean2D[3 * (size_t)id + 0], -o * ddelx_dx * (a * Sx + bb * Sy));
+				atomicAdd(&dL_dmean2D[3 * (size_t)id + 1], -o * ddely_dy * (c * Sy + bb * Sx));
+				const float hh = -0.5f * o;
+				atomicAdd(&dL_dconic2D[4 * (size_t)id + 0], hh * Sxx);
+				atomicAdd(&dL_dconic2D[4 * (size_t)id + 1], hh * Sxy);
+				atomicAdd(&dL_dconic2D[4 * (size_t)id + 3], hh * Syy);
+				atomicAdd(&dL_dopacity[id], Sq);
+			}
+		}
+		__syncwarp();   // slab rows and ring slots are rewritten from here on
+	};
+
+	// warp-uniform ring state: `head` = slot the next survivor goes to (its A half is occupied when carry == 1),
+	// `tail` = slot of slab row pair 0, `npend` = row pairs filled, `touched` = row pairs some pixel contributed to
+	int head = 0, tail = 0, npend = 0, carry = 0;
+	uint32_t touched = 0;
+
+	// Evaluate n_pairs ring slots starting at `head` for this lane's pixel and park (q, w) in the slab.
+	auto run_pairs = [&](int n_pairs) {
+		int slot = head;
+		for (int k = 0; k < n_pairs; k++) {
+			const ulonglong2 XY = *reinterpret_cast<const ulonglong2*>(r.v[0][slot]);
+			const ulonglong2 AB = *reinterpret_cast<const ulonglong2*>(r.v[1][slot]);
+			const ulonglong2 CO = *reinterpret_cast<const ulonglong2*>(r.v[2][slot]);
+			const float4 BP = *reinterpret_cast<const float4*>(r.v[4][slot]);
+			// backward.cu:487-501, the forward's instruction sequence
+			const f2 dx = add2(XY.x, npx), dy = add2(XY.y, npy);
+			f2 t = mul2(dy, CO.x);
+			const f2 u = mul2(dx, AB.x);
+			t = mul2(dy, t);
+			const f2 sq = fma2(dx, u, t);
+			const f2 vv = mul2(dx, AB.y);
+			const f2 ww = mul2(dy, vv);
+			const f2 power = fma2(sq, neg_half, ww);
+			const f2 G = exp2x(power);
+			const f2 al = mul2(CO.y, G);
+			const float aA = fminf(lo(al), 0.99f), aB = fminf(hi(al), 0.99f);
+			const bool skipA = (__float_as_uint(BP.z) >= last_contributor) | (lo(power) > 0.0f) | (aA < 1.0f / 255.0f);
+			const bool skipB = (__float_as_uint(BP.w) >= last_contributor) | (hi(power) > 0.0f) | (aB < 1.0f / 255.0f);
+			if (!__all_sync(0xffffffffu, skipA & skipB)) {
+				touched |= 1u << npend;
+				const f2 e2 = pk(skipA ? 0.0f : aA, skipB ? 0.0f : aB);
+				const f2 Ge = pk(skipA ? 0.0f : lo(G), skipB ? 0.0f : hi(G));
+				// backward.cu:503-507: T <- T / (1 - alpha).  MUFU.RCP: 1 ulp, far inside the 1e-3 gradient tolerance
+				const f2 om = fma2(e2, neg_one, one);
+				const float rcpA = rcp_approx_ftz(lo(om)), rcpB = rcp_approx_ftz(hi(om));
+				const float TA = T * rcpA, TB = TA * rcpB;
+				T = TB;
+				const f2 T2 = pk(TA, TB), rcp2 = pk(rcpA, rcpB);
+				// backward.cu:509-521: accum_rec, walked A then B
+				const ulonglong2 RG = *reinterpret_cast<const ulonglong2*>(r.v[3][slot]);
+				const f2 col0 = RG.x, col1 = RG.y, col2 = pk(BP.x, BP.y);
+				const f2 ac0 = mul2(e2, col0), ac1 = mul2(e2, col1), ac2 = mul2(e2, col2);
+				const float accA0 = fmaf(keep_prev, acc0, pend0), accA1 = fmaf(keep_prev, acc1, pend1),
+				            accA2 = fmaf(keep_prev, acc2, pend2);
+				acc0 = fmaf(lo(om), accA0, lo(ac0));
+				acc1 = fmaf(lo(om), accA1, lo(ac1));
+				acc2 = fmaf(lo(om), accA2, lo(ac2));
+				pend0 = hi(ac0); pend1 = hi(ac1); pend2 = hi(ac2);
+				keep_prev = hi(om);
+				const f2 d0 = fma2(pk(accA0, acc0), neg_one, col0);
+				const f2 d1 = fma2(pk(accA1, acc1), neg_one, col1);
+				const f2 d2 = fma2(pk(accA2, acc2), neg_one, col2);
+				f2 dL_dalpha = fma2(d2, dLp2, fma2(d1, dLp1, mul2(d0, dLp0)));
+				// backward.cu:526-534
+				dL_dalpha = fma2(dL_dalpha, T2, mul2(bg_term, rcp2));
+				// w = alpha T (backward.cu:523) and q = G dL/dalpha (backward.cu:537-554) of this pixel, splats (A, B)
+				*reinterpret_cast<f2*>(&r.slabW[npend][2 * lane]) = mul2(e2, T2);
+				*reinterpret_cast<f2*>(&r.slabQ[npend][2 * lane]) = mul2(Ge, dL_dalpha);
+			}
+			npend++;
+			slot = (slot + 1 == kRing) ? 0 : slot + 1;
+			if (npend == kRowPairs) {
+				flush(tail, touched);
+				tail = slot;
+				npend = 0;
+				touched = 0;
+			}
+		}
+		head = slot;
+	};
+
+	const int batch_hi = (int)((tile_last - 1) / kBatchM);
+	if (tid == 0) {
+#pragma unroll
+		for (int st = 0; st < kStagesM; st++)
+			if (batch_hi - st >= 0)
+				issue(batch_hi - st, st);
+	}
+
+	int st = 0;
+	uint32_t parity = 0;
+	for (int batch = batch_hi; batch >= 0; batch--) {
+		mbar_wait(&s.full[st], parity);
+
+		const int batch_base = batch * kBatchM;
+		// positions >= warp_last are behind every pixel of this warp (backward.cu:487-489)
+		const int cnt = min(min(kBatchM, (int)n - batch_base), (int)warp_last - batch_base);
+		for (int base = (cnt > 0) ? ((cnt - 1) & ~31) : -1; base >= 0; base -= 32) {
+			// cull 32 splats in parallel against the warp's 8x4 pixel block; append the survivors back to front
+			const int j = base + lane;
+			bool keep = false;
+			float4 co, xr;
+			if (j < cnt) {
+				co = s.conic[st][j];
+				xr = s.xyrg[st][j];
+				keep = !rect_cannot_contribute(xr.x, xr.y, co.x, co.y, co.z, cull_threshold(co.w),
+				                               wx0, wy0, wx1, wy1);
+			}
+			const uint32_t mask = __ballot_sync(0xffffffffu, keep);
+			if (mask == 0)
+				continue;
+			if (keep) {
+				const int at = carry + __popc(mask >> lane) - 1;   // highest list position first
+				int slot = head + (at >> 1);
+				slot = slot >= kRing ? slot - kRing : slot;
+				const int h = at & 1;
+				const float2 bi = s.bid[st][j];
+				r.v[0][slot][h] = xr.x;
+				r.v[0][slot][2 + h] = xr.y;
+				r.v[1][slot][h] = co.x;
+				r.v[1][slot][2 + h] = -co.y;
+				r.v[2][slot][h] = co.z;
+				r.v[2][slot][2 + h] = co.w;
+				r.v[3][slot][h] = xr.z;
+				r.v[3][slot][2 + h] = xr.w;
+				r.v[4][slot][h] = bi.x;
+				r.v[4][slot][2 + h] = __uint_as_float((uint32_t)(batch_base + j));
+				r.id[2 * slot + h] = __float_as_uint(bi.y);
+			}
+			const int total = carry + __popc(mask);
+			carry = total & 1;
+			__syncwarp();
+			run_pairs(total >> 1);
+		}
+
+		// release the stage; the warp that arrives last refills it with the batch kStagesM further on
+		__syncwarp();
+		if (lane == 0) {
+			__threadfence_block();
+			const uint32_t old = atomicAdd(&s.released[st], 1u);
+			if ((old & (kWarps - 1)) == kWarps - 1 && batch - kStagesM >= 0)
+				issue(batch - kStagesM, st);
+		}
+		if (++st == kStagesM) {
+			st = 0;
+			parity ^= 1u;
+		}
+	}
+
+	// the odd survivor left over at the end is paired with a splat that no pixel accepts (position 2^32 - 1)
+	if (carry) {
+		if (lane == 0) {
+			r.v[0][head][1] = 0.0f; r.v[0][head][3] = 0.0f;
+			r.v[1][head][1] = 0.0f; r.v[1][head][3] = 0.0f;
+			r.v[2][head][1] = 0.0f; r.v[2][head][3] = 0.0f;
+			r.v[3][head][1] = 0.0f; r.v[3][head][3] = 0.0f;
+			r.v[4][head][1] = 0.0f; r.v[4][head][3] = __uint_as_float(0xffffffffu);
+			r.id[2 * head + 1] = 0u;
+		}
+		__syncwarp();
+		run_pairs(1);
+	}
+	if (npend > 0)
+		flush(tail, touched);
+}
+
 } // namespace
 
 int launch_blend_backward(const GeometryState& g, const BinningState& b, const ImageState& img, uint32_t capacity,
@@ -619,14 +1016,34 @@ int launch_blend_backward(const GeometryState& g, const BinningState& b, const I
 	const int num_tiles = vp.tiles_x * vp.tiles_y;
 	if (num_tiles <= 0)
 		return GM_OK;
-	// GM_BLEND_SCALAR=1 selects the one-splat-per-iteration kernel (kept for A/B measurements)
+	// GM_BLEND_SCALAR=1 selects the one-splat-per-iteration kernel, GM_BLEND_BWD=pairs the packed-pair kernel with the
+	// shuffle butterfly (both kept for A/B measurements); the default reduces on the tensor cores
 	static const bool scalar = std::getenv("GM_BLEND_SCALAR") != nullptr && std::getenv("GM_BLEND_SCALAR")[0] == '1';
+	static const bool pairs = std::getenv("GM_BLEND_BWD") != nullptr && std::getenv("GM_BLEND_BWD")[0] == 'p';
 	if (scalar)
 		blend_backward_kernel<<<num_tiles, kThreads, 0, stream>>>(
 			g, b, img, capacity, vp.W, vp.H, vp.tiles_x, vp.bg, dL_dpix, dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolor);
-	else
+	else if (pairs)
 		blend_backward_pairs_kernel<<<num_tiles, kThreads, 0, stream>>>(
 			g, b, img, capacity, vp.W, vp.H, vp.tiles_x, vp.bg, dL_dpix, dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolor);
+	else {
+		// the opt-in shared-memory size is a per-device function attribute
+		static bool opted_in[64] = {};
+		int dev = 0;
+		cudaGetDevice(&dev);
+		if (dev < 0 || dev >= 64 || !opted_in[dev]) {
+			const cudaError_t attr = cudaFuncSetAttribute(blend_backward_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+			                                              (int)sizeof(BwdSmemM));
+			if (attr != cudaSuccess) {
+				set_last_error("blend_backward shared memory", attr);
+				return GM_ERR_CUDA;
+			}
+			if (dev >= 0 && dev < 64)
+				opted_in[dev] = true;
+		}
+		blend_backward_mma_kernel<<<num_tiles, kThreads, sizeof(BwdSmemM), stream>>>(
+			g, b, img, capacity, vp.W, vp.H, vp.tiles_x, vp.bg, dL_dpix, dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolor);
+	}
 	return GM_OK;
 }
 

@@ -58,6 +58,14 @@ int launch_deform(int P, const float* V, const float* Vd, const float* VR, const
 int launch_sh_rotated(int P, int D, int M, const float* pos, const float* campos, const float* rot, const float* shs,
                       float* rgb, cudaStream_t stream);
 
+int launch_cov3d_python(int P, const float* scales, float mod, const float* rotations, float* cov6, cudaStream_t stream);
+int launch_cov3d_python_backward(int P, const float* scales, float mod, const float* rotations, const float* dL_dcov6,
+                                 float* dL_dscale, float* dL_drot, cudaStream_t stream);
+int launch_sh_rotated_backward(int P, int D, int M, const float* pos, const float* campos, const float* rot, const float* shs,
+                               const float* dL_drgb, float* dL_dshs, float* dL_dpos, cudaStream_t stream);
+int launch_load_mesh(int P, int num_faces, const double* vertex, const int* faces, const long long* face_id,
+                     const float* proj_pos, int* gaussian_triangles, double* weights, cudaStream_t stream);
+
 int launch_acap_rest(int Vn, const double* V, const int* F, const int* ring_off, const int* ring, const int* face_off,
                      const int* face_list, double* sqrt_w, double* normals, double* ata_inv, cudaStream_t stream);
 
@@ -75,11 +83,11 @@ int launch_photometric(int C, int H, int W, const float* img, const float* gt, f
 int launch_mesh_restrict(int P, const float* scale, const float* v1, const float* v2, const float* v3, float weight,
                          float* loss, float* dL_dscale, int accumulate, cudaStream_t stream);
 int launch_adam(int n, const gm_adam_tensor* tensors, int step, float beta1, float beta2, float eps,
-                cudaStream_t stream);
+                const uint32_t* skip_flag, cudaStream_t stream);
 int launch_adam_sharded_p2p(int world, int rank, const float* const* grads, float* const* params, int num_segments,
                             const gm_adam_segment* segments, size_t total, float* exp_avg, float* exp_avg_sq, int step,
                             float beta1, float beta2, float eps, cudaStream_t stream);
 int launch_densify_stats(int P, const int* radii, const float* dL_dmean2D, float* max_radii2D, float* grad_accum,
-                         float* denom, cudaStream_t stream);
+                         float* denom, const uint32_t* skip_flag, cudaStream_t stream);
 
 } // namespace gm

@@ -258,6 +258,209 @@ l1_kernel(size_t numel, const float* __restrict__ img, const float* __restrict__
 	}
 }
 
+
+// ---- the reference's "Python" pipeline variants (gaussian_renderer/__init__.py:78-94) ------------------------
+// compute_cov3D_python: pc.get_covariance(scaling_modifier) = strip_symmetric(L L^T), L = R(q / |q|) diag(mod * s)
+// (utils/general_utils.py:64-109).  Unlike the CUDA branch (forward.cu:127) the quaternion IS normalised here.
+__device__ __forceinline__ void quat_to_rot(float r, float x, float y, float z, float (&R)[9])
+{
+	// utils/general_utils.py:75-94, row-major R[3 * row + col]
+	R[0] = 1.0f - 2.0f * (y * y + z * z); R[1] = 2.0f * (x * y - r * z); R[2] = 2.0f * (x * z + r * y);
+	R[3] = 2.0f * (x * y + r * z); R[4] = 1.0f - 2.0f * (x * x + z * z); R[5] = 2.0f * (y * z - r * x);
+	R[6] = 2.0f * (x * z - r * y); R[7] = 2.0f * (y * z + r * x); R[8] = 1.0f - 2.0f * (x * x + y * y);
+}
+
+__global__ void __launch_bounds__(kThreads)
+cov3d_python_forward_kernel(int P, const float* __restrict__ scales, float mod, const float* __restrict__ rotations,
+                            float* __restrict__ cov6)
+{
+	const int i = blockIdx.x * kThreads + threadIdx.x;
+	if (i >= P)
+		return;
+	const float3 s = load3(scales, i);
+	const float4 q = make_float4(rotations[4 * i], rotations[4 * i + 1], rotations[4 * i + 2], rotations[4 * i + 3]);
+	const float norm = sqrtf(q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w);
+	float R[9];
+	quat_to_rot(q.x / norm, q.y / norm, q.z / norm, q.w / norm, R);
+	const float sc[3] = {mod * s.x, mod * s.y, mod * s.z};
+	float L[9];
+#pragma unroll
+	for (int a = 0; a < 3; a++)
+#pragma unroll
+		for (int b = 0; b < 3; b++)
+			L[3 * a + b] = R[3 * a + b] * sc[b];
+	float* o = cov6 + 6 * (size_t)i;
+	// actual_covariance = L @ L^T, then (0,0) (0,1) (0,2) (1,1) (1,2) (2,2)
+	const int ra[6] = {0, 0, 0, 1, 1, 2}, rb[6] = {0, 1, 2, 1, 2, 2};
+#pragma unroll
+	for (int e = 0; e < 6; e++)
+		o[e] = L[3 * ra[e] + 0] * L[3 * rb[e] + 0] + L[3 * ra[e] + 1] * L[3 * rb[e] + 1] + L[3 * ra[e] + 2] * L[3 * rb[e] + 2];
+}
+
+__global__ void __launch_bounds__(kThreads)
+cov3d_python_backward_kernel(int P, const float* __restrict__ scales, float mod, const float* __restrict__ rotations,
+                             const float* __restrict__ dL_dcov6, float* __restrict__ dL_dscale, float* __restrict__ dL_drot)
+{
+	const int i = blockIdx.x * kThreads + threadIdx.x;
+	if (i >= P)
+		return;
+	const float3 s = load3(scales, i);
+	const float4 qr = make_float4(rotations[4 * i], rotations[4 * i + 1], rotations[4 * i + 2], rotations[4 * i + 3]);
+	const float norm = sqrtf(qr.x * qr.x + qr.y * qr.y + qr.z * qr.z + qr.w * qr.w);
+	const float r = qr.x / norm, x = qr.y / norm, y = qr.z / norm, z = qr.w / norm;
+	float R[9];
+	quat_to_rot(r, x, y, z, R);
+	const float sc[3] = {mod * s.x, mod * s.y, mod * s.z};
+	const float* g = dL_dcov6 + 6 * (size_t)i;
+	// the six packed entries are read from the upper triangle only: dL/dSigma = G (upper), dL/dL = (G + G^T) L
+	const float Gs[9] = {2.0f * g[0], g[1], g[2], g[1], 2.0f * g[3], g[4], g[2], g[4], 2.0f * g[5]};
+	float dR[9], ds[3] = {0.0f, 0.0f, 0.0f};
+#pragma unroll
+	for (int a = 0; a < 3; a++)
+#pragma unroll
+		for (int b = 0; b < 3; b++) {
+			const float dLab = Gs[3 * a + 0] * R[0 + b] * sc[b] + Gs[3 * a + 1] * R[3 + b] * sc[b] + Gs[3 * a + 2] * R[6 + b] * sc[b];
+			dR[3 * a + b] = dLab * sc[b];
+			ds[b] += dLab * R[3 * a + b];
+		}
+	dL_dscale[3 * i + 0] = mod * ds[0];
+	dL_dscale[3 * i + 1] = mod * ds[1];
+	dL_dscale[3 * i + 2] = mod * ds[2];
+	// dR/dq of utils/general_utils.py:86-94
+	const float dr = 2.0f * (-z * dR[1] + y * dR[2] + z * dR[3] - x * dR[5] - y * dR[6] + x * dR[7]);
+	const float dx = 2.0f * (y * dR[1] + z * dR[2] + y * dR[3] - 2.0f * x * dR[4] - r * dR[5] + z * dR[6] + r * dR[7] - 2.0f * x * dR[8]);
+	const float dy = 2.0f * (-2.0f * y * dR[0] + x * dR[1] + r * dR[2] + x * dR[3] + z * dR[5] - r * dR[6] + z * dR[7] - 2.0f * y * dR[8]);
+	const float dz = 2.0f * (-2.0f * z * dR[0] - r * dR[1] + x * dR[2] + r * dR[3] - 2.0f * z * dR[4] + y * dR[5] + x * dR[6] + y * dR[7]);
+	// q = raw / |raw|
+	const float dot = r * dr + x * dx + y * dy + z * dz;
+	dL_drot[4 * i + 0] = (dr - r * dot) / norm;
+	dL_drot[4 * i + 1] = (dx - x * dot) / norm;
+	dL_drot[4 * i + 2] = (dy - y * dot) / norm;
+	dL_drot[4 * i + 3] = (dz - z * dot) / norm;
+}
+
+// convert_SHs_python (gaussian_renderer/__init__.py:87-92) and its edit-time twin (edittool/__init__.py:442-448) are
+// sh_rotated_kernel above; this is their backward: dL/dshs and, through the normalised direction, dL/dpos.
+// The chain is the one of eval_sh (utils/sh_utils.py:57-112) written per channel.
+__global__ void __launch_bounds__(kThreads)
+sh_rotated_backward_kernel(int P, int D, int M, const float* __restrict__ pos, const float* __restrict__ campos,
+                           const float* __restrict__ rot, const float* __restrict__ shs, const float* __restrict__ dL_drgb,
+                           float* __restrict__ dL_dshs, float* __restrict__ dL_dpos)
+{
+	const int i = blockIdx.x * kThreads + threadIdx.x;
+	if (i >= P)
+		return;
+	const float3 p = load3(pos, i);
+	const float ox = p.x - campos[0], oy = p.y - campos[1], oz = p.z - campos[2];
+	const float len = sqrtf(ox * ox + oy * oy + oz * oz);
+	const float dx = ox / len, dy = oy / len, dz = oz / len;
+	float x = dx, y = dy, z = dz;
+	const float* R = rot != nullptr ? rot + 9 * (size_t)i : nullptr;
+	if (R != nullptr) {
+		x = R[0] * dx + R[3] * dy + R[6] * dz;
+		y = R[1] * dx + R[4] * dy + R[7] * dz;
+		z = R[2] * dx + R[5] * dy + R[8] * dz;
+	}
+	const ShDir d = sh_dir(x, y, z);
+	const float* sh = shs + (size_t)i * M * 3;
+	float* dsh = dL_dshs != nullptr ? dL_dshs + (size_t)i * M * 3 : nullptr;
+	const float xx = d.xx, yy = d.yy, zz = d.zz, xy = d.xy, yz = d.yz, xz = d.xz;
+	// basis values b_k(dir) and their gradients
+	float bk[16], bx[16], by[16], bz[16];
+#pragma unroll
+	for (int k = 0; k < 16; k++) { bk[k] = 0.0f; bx[k] = 0.0f; by[k] = 0.0f; bz[k] = 0.0f; }
+	bk[0] = GM_SH_C0;
+	if (D > 0) {
+		bk[1] = -GM_SH_C1 * y; by[1] = -GM_SH_C1;
+		bk[2] = GM_SH_C1 * z;  bz[2] = GM_SH_C1;
+		bk[3] = -GM_SH_C1 * x; bx[3] = -GM_SH_C1;
+	}
+	if (D > 1) {
+		bk[4] = GM_SH_C2_0 * xy; bx[4] = GM_SH_C2_0 * y; by[4] = GM_SH_C2_0 * x;
+		bk[5] = GM_SH_C2_1 * yz; by[5] = GM_SH_C2_1 * z; bz[5] = GM_SH_C2_1 * y;
+		bk[6] = GM_SH_C2_2 * (2.0f * zz - xx - yy); bx[6] = GM_SH_C2_2 * -2.0f * x; by[6] = GM_SH_C2_2 * -2.0f * y; bz[6] = GM_SH_C2_2 * 4.0f * z;
+		bk[7] = GM_SH_C2_3 * xz; bx[7] = GM_SH_C2_3 * z; bz[7] = GM_SH_C2_3 * x;
+		bk[8] = GM_SH_C2_4 * (xx - yy); bx[8] = GM_SH_C2_4 * 2.0f * x; by[8] = GM_SH_C2_4 * -2.0f * y;
+	}
+	if (D > 2) {
+		bk[9] = GM_SH_C3_0 * y * (3.0f * xx - yy); bx[9] = GM_SH_C3_0 * 6.0f * xy; by[9] = GM_SH_C3_0 * 3.0f * (xx - yy);
+		bk[10] = GM_SH_C3_1 * xy * z; bx[10] = GM_SH_C3_1 * yz; by[10] = GM_SH_C3_1 * xz; bz[10] = GM_SH_C3_1 * xy;
+		bk[11] = GM_SH_C3_2 * y * (4.0f * zz - xx - yy); bx[11] = GM_SH_C3_2 * -2.0f * xy;
+		by[11] = GM_SH_C3_2 * (4.0f * zz - xx - 3.0f * yy); bz[11] = GM_SH_C3_2 * 8.0f * yz;
+		bk[12] = GM_SH_C3_3 * z * (2.0f * zz - 3.0f * xx - 3.0f * yy); bx[12] = GM_SH_C3_3 * -6.0f * xz;
+		by[12] = GM_SH_C3_3 * -6.0f * yz; bz[12] = GM_SH_C3_3 * (6.0f * zz - 3.0f * xx - 3.0f * yy);
+		bk[13] = GM_SH_C3_4 * x * (4.0f * zz - xx - yy); bx[13] = GM_SH_C3_4 * (4.0f * zz - 3.0f * xx - yy);
+		by[13] = GM_SH_C3_4 * -2.0f * xy; bz[13] = GM_SH_C3_4 * 8.0f * xz;
+		bk[14] = GM_SH_C3_5 * z * (xx - yy); bx[14] = GM_SH_C3_5 * 2.0f * xz; by[14] = GM_SH_C3_5 * -2.0f * yz; bz[14] = GM_SH_C3_5 * (xx - yy);
+		bk[15] = GM_SH_C3_6 * x * (xx - 3.0f * yy); bx[15] = GM_SH_C3_6 * 3.0f * (xx - yy); by[15] = GM_SH_C3_6 * -6.0f * xy;
+	}
+	const int n = (D + 1) * (D + 1);
+	float gx = 0.0f, gy = 0.0f, gz = 0.0f;
+#pragma unroll
+	for (int ch = 0; ch < 3; ch++) {
+		// forward value of the channel decides the clamp (max(v + 0.5, 0) has zero slope below)
+		const float v = sh_channel(D, d, [sh, ch](int k) { return sh[3 * k + ch]; });
+		const float gch = (v + 0.5f < 0.0f) ? 0.0f : dL_drgb[3 * i + ch];
+		for (int k = 0; k < M; k++) {
+			const float c = (k < n) ? sh[3 * k + ch] : 0.0f;
+			if (dsh != nullptr)
+				dsh[3 * k + ch] = (k < n) ? gch * bk[k & 15] : 0.0f;
+			if (k < n) {
+				gx += gch * c * bx[k & 15];
+				gy += gch * c * by[k & 15];
+				gz += gch * c * bz[k & 15];
+			}
+		}
+	}
+	if (dL_dpos == nullptr)
+		return;
+	// dir' = R^T dir: d/d dir = R (d/d dir')
+	float hx = gx, hy = gy, hz = gz;
+	if (R != nullptr) {
+		hx = R[0] * gx + R[1] * gy + R[2] * gz;
+		hy = R[3] * gx + R[4] * gy + R[5] * gz;
+		hz = R[6] * gx + R[7] * gy + R[8] * gz;
+	}
+	// dir = o / |o|
+	const float dot = dx * hx + dy * hy + dz * hz;
+	dL_dpos[3 * i + 0] = (hx - dx * dot) / len;
+	dL_dpos[3 * i + 1] = (hy - dy * dot) / len;
+	dL_dpos[3 * i + 2] = (hz - dz * dot) / len;
+}
+
+// SingleObjectDeform.load_mesh (edittool/__init__.py:65-101, the face-id branch): the Gaussian's face -> its three
+// vertex ids, and the area-ratio barycentric weights of the projected point (edittool/general_utils.py:73-88),
+// evaluated in float64 as numpy does.
+__global__ void __launch_bounds__(kThreads)
+load_mesh_kernel(int P, int num_faces, const double* __restrict__ vertex, const int* __restrict__ faces,
+                 const long long* __restrict__ face_id, const float* __restrict__ proj_pos,
+                 int* __restrict__ gaussian_triangles, double* __restrict__ weights)
+{
+	const int i = blockIdx.x * kThreads + threadIdx.x;
+	if (i >= P)
+		return;
+	long long f = face_id[i];
+	f = f < 0 ? 0 : (f >= num_faces ? num_faces - 1 : f);
+	const int t0 = faces[3 * f], t1 = faces[3 * f + 1], t2 = faces[3 * f + 2];
+	gaussian_triangles[3 * i + 0] = t0; gaussian_triangles[3 * i + 1] = t1; gaussian_triangles[3 * i + 2] = t2;
+	const double gx = proj_pos[3 * i], gy = proj_pos[3 * i + 1], gz = proj_pos[3 * i + 2];
+	double e[3][3];
+	const int tv[3] = {t0, t1, t2};
+#pragma unroll
+	for (int k = 0; k < 3; k++) {
+		e[k][0] = gx - vertex[3 * (size_t)tv[k]];
+		e[k][1] = gy - vertex[3 * (size_t)tv[k] + 1];
+		e[k][2] = gz - vertex[3 * (size_t)tv[k] + 2];
+	}
+	auto cross_norm = [](const double (&a)[3], const double (&b)[3]) {
+		const double cx = a[1] * b[2] - a[2] * b[1], cy = a[2] * b[0] - a[0] * b[2], cz = a[0] * b[1] - a[1] * b[0];
+		return sqrt(cx * cx + cy * cy + cz * cz);
+	};
+	const double s1 = cross_norm(e[1], e[2]), s2 = cross_norm(e[0], e[2]), s3 = cross_norm(e[0], e[1]);
+	const double sum = s1 + s2 + s3;
+	weights[3 * i + 0] = s1 / sum; weights[3 * i + 1] = s2 / sum; weights[3 * i + 2] = s3 / sum;
+}
+
 } // namespace
 
 int launch_mesh_bind_forward(int P, const float* bc_logits, const float* distance, const float* v1, const float* v2,
@@ -301,6 +504,40 @@ int launch_sh_rotated(int P, int D, int M, const float* pos, const float* campos
 {
 	if (P <= 0) return GM_OK;
 	sh_rotated_kernel<<<(P + kThreads - 1) / kThreads, kThreads, 0, stream>>>(P, D, M, pos, campos, rot, shs, rgb);
+	return GM_OK;
+}
+
+int launch_cov3d_python(int P, const float* scales, float mod, const float* rotations, float* cov6, cudaStream_t stream)
+{
+	if (P <= 0) return GM_OK;
+	cov3d_python_forward_kernel<<<(P + kThreads - 1) / kThreads, kThreads, 0, stream>>>(P, scales, mod, rotations, cov6);
+	return GM_OK;
+}
+
+int launch_cov3d_python_backward(int P, const float* scales, float mod, const float* rotations, const float* dL_dcov6,
+                                 float* dL_dscale, float* dL_drot, cudaStream_t stream)
+{
+	if (P <= 0) return GM_OK;
+	cov3d_python_backward_kernel<<<(P + kThreads - 1) / kThreads, kThreads, 0, stream>>>(P, scales, mod, rotations, dL_dcov6,
+	                                                                                  dL_dscale, dL_drot);
+	return GM_OK;
+}
+
+int launch_sh_rotated_backward(int P, int D, int M, const float* pos, const float* campos, const float* rot, const float* shs,
+                               const float* dL_drgb, float* dL_dshs, float* dL_dpos, cudaStream_t stream)
+{
+	if (P <= 0) return GM_OK;
+	sh_rotated_backward_kernel<<<(P + kThreads - 1) / kThreads, kThreads, 0, stream>>>(P, D, M, pos, campos, rot, shs, dL_drgb,
+	                                                                                dL_dshs, dL_dpos);
+	return GM_OK;
+}
+
+int launch_load_mesh(int P, int num_faces, const double* vertex, const int* faces, const long long* face_id,
+                     const float* proj_pos, int* gaussian_triangles, double* weights, cudaStream_t stream)
+{
+	if (P <= 0) return GM_OK;
+	load_mesh_kernel<<<(P + kThreads - 1) / kThreads, kThreads, 0, stream>>>(P, num_faces, vertex, faces, face_id, proj_pos,
+	                                                                      gaussian_triangles, weights);
 	return GM_OK;
 }
 

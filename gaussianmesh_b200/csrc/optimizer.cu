@@ -51,8 +51,13 @@ __device__ __forceinline__ void adam_one(float& p, float g, float& m, float& v, 
 }
 
 __global__ void __launch_bounds__(kThreads)
-adam_kernel(const __grid_constant__ AdamTable tab, float b0, float b1, float bias, float eps)
+adam_kernel(const __grid_constant__ AdamTable tab, float b0, float b1, float bias, float eps,
+            const uint32_t* __restrict__ skip_flag)
 {
+	// gated update: a frame whose binning chunk overflowed rendered only part of its tiles, so its gradients are
+	// partial -- the update is dropped on the device, without a host round trip (FrameHeader::overflow)
+	if (skip_flag != nullptr && *skip_flag != 0u)
+		return;
 	int k = 0;
 #pragma unroll
 	for (int i = 1; i < kAdamMaxTensors; i++)
@@ -154,10 +159,11 @@ adam_sharded_p2p_kernel(const __grid_constant__ ShardedAdamArgs a, float b0, flo
 
 __global__ void __launch_bounds__(kThreads)
 densify_stats_kernel(int P, const int* __restrict__ radii, const float* __restrict__ dL_dmean2D,
-                     float* __restrict__ max_radii2D, float* __restrict__ grad_accum, float* __restrict__ denom)
+                     float* __restrict__ max_radii2D, float* __restrict__ grad_accum, float* __restrict__ denom,
+                     const uint32_t* __restrict__ skip_flag)
 {
 	const int i = blockIdx.x * kThreads + threadIdx.x;
-	if (i >= P)
+	if (i >= P || (skip_flag != nullptr && *skip_flag != 0u))
 		return;
 	const int r = radii[i];
 	if (r <= 0)                                                    // visibility_filter = radii > 0
@@ -170,7 +176,8 @@ densify_stats_kernel(int P, const int* __restrict__ radii, const float* __restri
 
 } // namespace
 
-int launch_adam(int n, const gm_adam_tensor* tensors, int step, float beta1, float beta2, float eps, cudaStream_t stream)
+int launch_adam(int n, const gm_adam_tensor* tensors, int step, float beta1, float beta2, float eps,
+                const uint32_t* skip_flag, cudaStream_t stream)
 {
 	// Python-float arithmetic of the reference optimiser: double, rounded once
 	const double bias = sqrt(1.0 - pow((double)beta2, (double)step)) / (1.0 - pow((double)beta1, (double)step));
@@ -188,7 +195,7 @@ int launch_adam(int n, const gm_adam_tensor* tensors, int step, float beta1, flo
 		}
 		tab.first_block[tab.count] = blocks;
 		if (blocks > 0)
-			adam_kernel<<<blocks, kThreads, 0, stream>>>(tab, beta1, beta2, (float)bias, eps);
+			adam_kernel<<<blocks, kThreads, 0, stream>>>(tab, beta1, beta2, (float)bias, eps, skip_flag);
 	}
 	return GM_OK;
 }
@@ -223,11 +230,11 @@ int launch_adam_sharded_p2p(int world, int rank, const float* const* grads, floa
 }
 
 int launch_densify_stats(int P, const int* radii, const float* dL_dmean2D, float* max_radii2D, float* grad_accum,
-                         float* denom, cudaStream_t stream)
+                         float* denom, const uint32_t* skip_flag, cudaStream_t stream)
 {
 	if (P <= 0) return GM_OK;
 	densify_stats_kernel<<<(P + kThreads - 1) / kThreads, kThreads, 0, stream>>>(P, radii, dL_dmean2D, max_radii2D,
-	                                                                               grad_accum, denom);
+	                                                                               grad_accum, denom, skip_flag);
 	return GM_OK;
 }
 

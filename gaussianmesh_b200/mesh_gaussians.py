@@ -137,14 +137,86 @@ def deform_gaussians(vertex_rest, vertex_deformed, vertex_R, vertex_S, gaussian_
     return pos_out, cov_out, rot_out
 
 
+class _ShToRgb(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pos, shs, campos, rot, degree):
+        pos, campos, rot, shs = map(_c, (pos, campos, rot, shs))
+        P = pos.shape[0]
+        rgb = torch.empty(P, 3, dtype=torch.float32, device=pos.device)
+        check(lib.gm_sh_to_rgb_rotated(P, int(degree), int(shs.shape[1]), _p(pos), _p(campos), _p(rot), _p(shs), _p(rgb),
+                                       _stream()), "gm_sh_to_rgb_rotated")
+        ctx.save_for_backward(pos, shs, campos, rot if rot is not None else torch.empty(0, device=pos.device))
+        ctx.degree, ctx.has_rot = int(degree), rot is not None
+        return rgb
+
+    @staticmethod
+    def backward(ctx, g_rgb):
+        pos, shs, campos, rot = ctx.saved_tensors
+        rot = rot if ctx.has_rot else None
+        g_rgb = _c(g_rgb)
+        P = pos.shape[0]
+        need_pos, need_shs = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        d_pos = torch.empty_like(pos) if need_pos else None
+        d_shs = torch.empty_like(shs) if need_shs else None
+        if need_pos or need_shs:
+            check(lib.gm_sh_to_rgb_rotated_backward(P, ctx.degree, int(shs.shape[1]), _p(pos), _p(campos), _p(rot), _p(shs),
+                                                    _p(g_rgb), _p(d_shs), _p(d_pos), _stream()),
+                  "gm_sh_to_rgb_rotated_backward")
+        return d_pos, d_shs, None, None, None
+
+
 def sh_to_rgb_rotated(pos, campos, rot, shs, degree: int = 3) -> torch.Tensor:
-    """clamp(eval_sh(degree, shs, R_g^T normalize(pos - campos)) + 0.5, 0); rot may be None."""
-    pos, campos, rot, shs = map(_c, (pos, campos, rot, shs))
-    P = pos.shape[0]
-    rgb = torch.empty(P, 3, dtype=torch.float32, device=pos.device)
-    check(lib.gm_sh_to_rgb_rotated(P, int(degree), int(shs.shape[1]), _p(pos), _p(campos), _p(rot), _p(shs), _p(rgb),
-                                   _stream()), "gm_sh_to_rgb_rotated")
-    return rgb
+    """clamp(eval_sh(degree, shs, R_g^T normalize(pos - campos)) + 0.5, 0); rot may be None (then this is the
+    reference's convert_SHs_python branch, gaussian_renderer/__init__.py:87-92).  Differentiable w.r.t. pos and shs."""
+    return _ShToRgb.apply(pos, shs, campos, rot, degree)
+
+
+class _Cov3DPython(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, scales, rotations, modifier):
+        scales, rotations = _c(scales), _c(rotations)
+        P = scales.shape[0]
+        cov6 = torch.empty(P, 6, dtype=torch.float32, device=scales.device)
+        check(lib.gm_cov3d_from_scale_rot(P, _p(scales), float(modifier), _p(rotations), _p(cov6), _stream()),
+              "gm_cov3d_from_scale_rot")
+        ctx.save_for_backward(scales, rotations)
+        ctx.modifier = float(modifier)
+        return cov6
+
+    @staticmethod
+    def backward(ctx, g_cov6):
+        scales, rotations = ctx.saved_tensors
+        g_cov6 = _c(g_cov6)
+        d_s, d_r = torch.empty_like(scales), torch.empty_like(rotations)
+        check(lib.gm_cov3d_from_scale_rot_backward(scales.shape[0], _p(scales), ctx.modifier, _p(rotations), _p(g_cov6),
+                                                   _p(d_s), _p(d_r), _stream()), "gm_cov3d_from_scale_rot_backward")
+        return d_s, d_r, None
+
+
+def covariance_from_scaling_rotation(scaling, scaling_modifier: float, rotation) -> torch.Tensor:
+    """pc.get_covariance(scaling_modifier) of the compute_cov3D_python branch: strip_symmetric(L L^T) with
+    L = R(rotation / |rotation|) diag(scaling_modifier * scaling) (scene/mesh_based_gaussian_model.py:24-29,
+    utils/general_utils.py:64-109) -> [P,6].  Differentiable w.r.t. scaling and the RAW rotation."""
+    return _Cov3DPython.apply(scaling, rotation, scaling_modifier)
+
+
+def load_mesh(vertex, faces, face_id, proj_pos) -> Tuple[torch.Tensor, torch.Tensor]:
+    """SingleObjectDeform.load_mesh, face-id branch (edittool/__init__.py:87-101): (gaussian_triangles [P,3] int32,
+    barycentric weights [P,3] float64) on the device.  vertex [Vn,3] (float64 like igl.read_triangle_mesh), faces [Fn,3],
+    face_id [P] or [P,1], proj_pos [P,3] = get_proj_xyz."""
+    proj_pos = _c(proj_pos)
+    dev = proj_pos.device
+    vertex = torch.as_tensor(vertex, dtype=torch.float64).contiguous().to(dev)
+    faces = torch.as_tensor(faces).to(torch.int32).contiguous().to(dev)
+    face_id = torch.as_tensor(face_id).to(torch.int64).reshape(-1).contiguous().to(dev)
+    P = proj_pos.shape[0]
+    if face_id.shape[0] != P:
+        raise RasterizerError("load_mesh", GM_ERR_BAD_ARGUMENT, "one face id per Gaussian expected")
+    tri = torch.empty(P, 3, dtype=torch.int32, device=dev)
+    w = torch.empty(P, 3, dtype=torch.float64, device=dev)
+    check(lib.gm_load_mesh(P, int(vertex.shape[0]), int(faces.shape[0]), _p(vertex), _p(faces), _p(face_id), _p(proj_pos),
+                           _p(tri), _p(w), _stream()), "gm_load_mesh")
+    return tri, w
 
 
 class _L1(torch.autograd.Function):

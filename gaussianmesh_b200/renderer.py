@@ -161,29 +161,84 @@ class GaussianModel:
 
 @dataclass
 class PipelineParams:
-    """arguments/__init__.py:64-69; only the CUDA branches are implemented on this path."""
+    """arguments/__init__.py:64-69.  The two *_python flags select the reference's "Python" pipeline variants
+    (gaussian_renderer/__init__.py:78-94); here they run as one kernel each instead of a Jittor op chain."""
     convert_SHs_python: bool = False
     compute_cov3D_python: bool = False
     debug: bool = False
 
 
+def _fresh_screenspace_points(pc, P: int, device) -> torch.Tensor:
+    """reference gaussian_renderer/__init__.py:34 + reset_viewspace_point: a zero tensor whose gradient is the 2-D mean
+    gradient of THIS render.  Models that did not opt into gradients (requires_grad=False) share their buffer."""
+    pts = getattr(pc, "screenspace_points", None)
+    if pts is not None and not pts.requires_grad:
+        return pts
+    return torch.zeros(P, 3, dtype=torch.float32, device=device, requires_grad=True)
+
+
+def _python_color_and_cov(pc, pipe: PipelineParams, campos, scaling_modifier: float, means3D, scales, override_color):
+    """The branch logic of gaussian_renderer/__init__.py:74-96 -> (shs, colors_precomp, scales, rotations, cov3D_precomp)."""
+    cov3D_precomp = None
+    rotations = None
+    if pipe.compute_cov3D_python:
+        # pc.get_covariance(scaling_modifier): the RAW rotation parameter, normalised inside (:79)
+        cov3D_precomp = mg.covariance_from_scaling_rotation(scales, scaling_modifier, pc._rotation)
+        scales_out = None
+    else:
+        scales_out = scales
+    shs = colors_precomp = None
+    if override_color is None:
+        if pipe.convert_SHs_python:
+            colors_precomp = mg.sh_to_rgb_rotated(means3D, campos, None, pc.get_features, pc.active_sh_degree)   # :87-92
+        else:
+            shs = pc.get_features
+    else:
+        colors_precomp = override_color
+    return shs, colors_precomp, scales_out, rotations, cov3D_precomp
+
+
 def render(viewpoint_camera, pc: MeshGaussianModel, pipe: PipelineParams, bg_color: torch.Tensor,
            scaling_modifier: float = 1.0, override_color: Optional[torch.Tensor] = None,
-           arena: Optional[RenderArena] = None) -> Dict[str, torch.Tensor]:
-    """reference gaussian_renderer/__init__.py:26-143 (without the optional bg_gaussian concat)."""
-    if pipe.convert_SHs_python or pipe.compute_cov3D_python:
-        raise NotImplementedError("the Python SH / covariance fallbacks are the reference's slow path; "
-                                  "this renderer always uses the CUDA branches")
-    screenspace_points = pc.screenspace_points
+           bg_gaussian: Optional["GaussianModel"] = None, arena: Optional[RenderArena] = None) -> Dict[str, torch.Tensor]:
+    """reference gaussian_renderer/__init__.py:26-143, every branch: CUDA or Python SH colours, CUDA or Python
+    covariance, and the optional frozen `bg_gaussian` set appended as precomputed covariance (+ precomputed colours
+    when the foreground has them), :100-121 -- which, as in the reference, needs compute_cov3D_python."""
+    means3D, scales, rotations, opacity = pc.activate()
+    P = means3D.shape[0]
+    screenspace_points = _fresh_screenspace_points(pc, P, means3D.device)
+    pc.screenspace_points = screenspace_points
+    shs, colors_precomp, scales_r, _, cov3D_precomp = _python_color_and_cov(
+        pc, pipe, viewpoint_camera.camera_center, scaling_modifier, means3D, scales, override_color)
+    rotations_r = None if pipe.compute_cov3D_python else rotations
+    if bg_gaussian is not None:
+        if cov3D_precomp is None:
+            # the reference concatenates onto cov3D_precomp = None here and fails inside jt.concat (:117)
+            raise Exception("render(bg_gaussian=...) needs pipe.compute_cov3D_python: the background set is appended "
+                            "as precomputed 3D covariance")
+        with torch.no_grad():
+            b_xyz, b_scale, b_rot, b_opacity = bg_gaussian.activate()
+            b_cov = mg.covariance_from_scaling_rotation(b_scale, 1.0, b_rot)              # :101-104
+            b_shs = bg_gaussian.get_features.detach()
+        screenspace_points = torch.cat([screenspace_points, torch.zeros_like(b_xyz)], dim=0)      # :35-37
+        if shs is not None:
+            shs = torch.cat([shs, b_shs], dim=0)                                                  # :118-119
+        else:
+            with torch.no_grad():
+                b_colors = mg.sh_to_rgb_rotated(b_xyz, viewpoint_camera.camera_center, None, b_shs, 3)   # :109-113
+            colors_precomp = torch.cat([colors_precomp, b_colors], dim=0)                          # :121
+        means3D = torch.cat([means3D, b_xyz.detach()], dim=0)
+        opacity = torch.cat([opacity, b_opacity], dim=0)
+        cov3D_precomp = torch.cat([cov3D_precomp, b_cov], dim=0)
+        screenspace_points.retain_grad()
     raster_settings = make_settings(viewpoint_camera, bg_color, pc.active_sh_degree, scaling_modifier, pipe.debug)
     rasterizer = GaussianRasterizer(raster_settings=raster_settings, arena=arena)
-    means3D, scales, rotations, opacity = pc.activate()
-    shs, colors_precomp = (pc.get_features, None) if override_color is None else (None, override_color)
     rendered_image, radii = rasterizer(means3D=means3D, means2D=screenspace_points, shs=shs,
-                                       colors_precomp=colors_precomp, opacities=opacity, scales=scales,
-                                       rotations=rotations, cov3D_precomp=None)
+                                       colors_precomp=colors_precomp, opacities=opacity, scales=scales_r,
+                                       rotations=rotations_r, cov3D_precomp=cov3D_precomp)
     return {"render": rendered_image, "viewspace_points": screenspace_points, "visibility_filter": radii > 0,
-            "radii": radii, "vertex1": pc.vertex1, "vertex2": pc.vertex2, "vertex3": pc.vertex3, "scale": scales}
+            "radii": radii, "vertex1": pc.vertex1, "vertex2": pc.vertex2, "vertex3": pc.vertex3,
+            "scale": scales_r}
 
 
 def bg_render(viewpoint_camera, pc: GaussianModel, pipe: PipelineParams, bg_color: torch.Tensor,
@@ -192,29 +247,31 @@ def bg_render(viewpoint_camera, pc: GaussianModel, pipe: PipelineParams, bg_colo
               ) -> Dict[str, torch.Tensor]:
     """reference gaussian_renderer/__init__.py:146-260: the background model is trainable, the mesh-bound
     Gaussians (if given) are appended with their gradients stopped (:223-234)."""
-    if pipe.convert_SHs_python or pipe.compute_cov3D_python:
-        raise NotImplementedError("the Python SH / covariance fallbacks are the reference's slow path; "
-                                  "this renderer always uses the CUDA branches")
-    screenspace_points = pc.screenspace_points
     means3D, scales, rotations, opacity = pc.activate()
-    shs, colors_precomp = (pc.get_features, None) if override_color is None else (None, override_color)
+    screenspace_points = _fresh_screenspace_points(pc, means3D.shape[0], means3D.device)
+    pc.screenspace_points = screenspace_points
+    shs, colors_precomp, scales_r, _, cov3D_precomp = _python_color_and_cov(
+        pc, pipe, viewpoint_camera.camera_center, scaling_modifier, means3D, scales, override_color)
+    rotations_r = None if pipe.compute_cov3D_python else rotations
     if mesh_gaussians is not None:
-        if shs is None:
-            raise Exception("override_color cannot be combined with mesh_gaussians (the reference concatenates SHs)")
-        screenspace_points = torch.cat([screenspace_points, mesh_gaussians.screenspace_points], dim=0)
+        if shs is None or cov3D_precomp is not None:
+            raise Exception("mesh_gaussians can only be combined with the CUDA SH / covariance branches "
+                            "(the reference concatenates SHs, scales and rotations, :229-233)")
         with torch.no_grad():
             m_xyz, m_scale, m_rot, m_opacity = mesh_gaussians.activate()
             m_shs = mesh_gaussians.get_features.detach()
+        screenspace_points = torch.cat([screenspace_points, torch.zeros_like(m_xyz)], dim=0)
+        screenspace_points.retain_grad()
         means3D = torch.cat([means3D, m_xyz], dim=0)
-        scales = torch.cat([scales, m_scale], dim=0)
-        rotations = torch.cat([rotations, m_rot], dim=0)
+        scales_r = torch.cat([scales_r, m_scale], dim=0)
+        rotations_r = torch.cat([rotations_r, m_rot], dim=0)
         shs = torch.cat([shs, m_shs], dim=0)
         opacity = torch.cat([opacity, m_opacity], dim=0)
     raster_settings = make_settings(viewpoint_camera, bg_color, pc.active_sh_degree, scaling_modifier, pipe.debug)
     rasterizer = GaussianRasterizer(raster_settings=raster_settings, arena=arena)
     rendered_image, radii = rasterizer(means3D=means3D, means2D=screenspace_points, shs=shs,
-                                       colors_precomp=colors_precomp, opacities=opacity, scales=scales,
-                                       rotations=rotations, cov3D_precomp=None)
+                                       colors_precomp=colors_precomp, opacities=opacity, scales=scales_r,
+                                       rotations=rotations_r, cov3D_precomp=cov3D_precomp)
     return {"render": rendered_image, "viewspace_points": screenspace_points, "visibility_filter": radii > 0,
             "radii": radii}
 
@@ -246,6 +303,20 @@ class DeformedObject:
             [c[:, 0, 0], c[:, 0, 1], c[:, 0, 2], c[:, 1, 1], c[:, 1, 2], c[:, 2, 2]], dim=1).contiguous()
         self.deform_rot = torch.eye(3, device=dev).expand(P, 3, 3).contiguous()
         self.device = dev
+
+    @classmethod
+    def load_mesh(cls, pos, cov, opacity, shs, proj_pos, face_id, vertex, faces, device) -> "DeformedObject":
+        """SingleObjectDeform.load_gaussian + load_mesh (edittool/__init__.py:49-101, face-id branch): `face_id` [P] is the
+        face every Gaussian is bound to (the PLY's fid), `proj_pos` its projection onto that face (get_proj_xyz),
+        `vertex` / `faces` the rest mesh as igl.read_triangle_mesh returns it.  The per-Gaussian vertex ids and the
+        area-ratio barycentric weights are computed on the device in float64 (gm_load_mesh)."""
+        dev = torch.device(device)
+        proj = torch.as_tensor(proj_pos, dtype=torch.float32).contiguous().to(dev)
+        triangles, weights = mg.load_mesh(vertex, faces, face_id, proj)
+        obj = cls(pos, cov, opacity, shs, triangles, weights.float(), vertex, dev)
+        obj.coord = weights                      # float64, like self.coord in the reference
+        obj.index_tri = torch.as_tensor(face_id).reshape(-1, 1)
+        return obj
 
     def deform(self, vertex_deformed, vertex_R, vertex_S) -> None:
         f = lambda a: torch.as_tensor(a, dtype=torch.float32).contiguous().to(self.device)
@@ -304,9 +375,9 @@ class SceneRenderer:
         with torch.no_grad():
             image, _ = rasterizer(means3D=means3D, means2D=torch.zeros_like(means3D), shs=shs, colors_precomp=None,
                                   opacities=opacity, scales=None, rotations=None, cov3D_precomp=cov6)
-        bad = self.arena.overflowed
-        if bad:                      # first frames of a new view set: grow and render again
-            self.arena.verify()
+        # retire THIS frame before handing the image out (one sync per frame is fine for the viewer): a view that
+        # needs more instances than the arena held rendered only part of its tiles -- grow and render it again
+        if self.arena.verify():
             return self.render_gaussian(cam, bg)
         return image
 
@@ -445,6 +516,7 @@ class TrainStep:
         self.P, self.W, self.H, self.D, self.M = self.means3D.shape[0], W, H, sh_degree, self.shs.shape[1]
         P, M = self.P, self.M
         self.arena = RenderArena(self.device, strict=False)
+        self.overflowed_frames = 0          # frames whose gradients are partial (size the arena with reserve_for)
         self.image = torch.empty(3, H, W, dtype=torch.float32, device=self.device)
         self.dL_dimg = torch.empty_like(self.image)
         self.loss = torch.zeros(1, dtype=torch.float32, device=self.device)
@@ -471,12 +543,21 @@ class TrainStep:
         """Size the arena for these views up front (setup, not rendering)."""
         return self.arena.reserve_for_views(self.P, self.D, self.M, bg, self.W, self.H, [self._view_args(c) for c in cams])
 
+    def verify(self) -> int:
+        """Block until every submitted frame is done; returns how many frames overflowed the arena so far (their
+        gradients cover only the tiles that fit).  0 after reserve_for() on the views being trained."""
+        self.overflowed_frames += len(self.arena.verify())
+        return self.overflowed_frames
+
     def step(self, cam, bg: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
         """Enqueue one training step; returns the (device) loss tensor.  No host synchronisation."""
         stream = torch.cuda.current_stream(self.device).cuda_stream
         va = self._view_args(cam)
         cap, _, _, geom, binning, image_state = self.arena.forward(
             self.P, self.D, self.M, bg, self.W, self.H, va, False, False, stream, out_color=self.image, radii=self.radii)
+        if self.arena.overflowed:          # frames seen to have overflowed since the last step (arena already grown)
+            self.overflowed_frames += len(self.arena.overflowed)
+            self.arena.overflowed.clear()
         check(lib.gm_l1_loss(self.image.numel(), self.image.data_ptr(), target.data_ptr(), self.loss.data_ptr(),
                              self.dL_dimg.data_ptr(), stream), "gm_l1_loss")
         self._accum.zero_()

@@ -224,20 +224,6 @@ def twist_bend_deformation(V: np.ndarray) -> Tuple[np.ndarray, np.ndarray, np.nd
     S = np.swapaxes(Vt, 1, 2) @ (sig[:, :, None] * Vt)
     return Vd.astype(np.float32), R.astype(np.float32), S.astype(np.float32)
 
-
-def barycentric_weights(points: np.ndarray, V: np.ndarray, tri: np.ndarray) -> np.ndarray:
-    """Area-ratio barycentric weights of `points` in their triangles: s_k / (s_1 + s_2 + s_3)
-    (get_barycentric_coordinate, edittool/general_utils.py:73-88; float64 as numpy computes it)."""
-    p = points.astype(np.float64)
-    p1, p2, p3 = (V[tri[:, k]].astype(np.float64) for k in range(3))
-    e1, e2, e3 = p - p1, p - p2, p - p3
-    s1 = np.linalg.norm(np.cross(e2, e3), axis=1)[:, None]
-    s2 = np.linalg.norm(np.cross(e1, e3), axis=1)[:, None]
-    s3 = np.linalg.norm(np.cross(e1, e2), axis=1)[:, None]
-    s = s1 + s2 + s3
-    return np.concatenate([s1 / s, s2 / s, s3 / s], axis=1)
-
-
 def packed_covariance(scales: np.ndarray, rotations: np.ndarray, modifier: float = 1.0) -> np.ndarray:
     """strip_symmetric(L L^T), L = R(normalize(q)) diag(modifier * s): build_covariance_from_scaling_rotation
     (utils/general_utils.py:64-109); fp64 internally, returned as [P,6] float32 (xx,xy,xz,yy,yz,zz)."""

@@ -185,9 +185,11 @@ class Adam:
             for p in g["params"]:
                 p.grad = None
 
-    def step(self, grads: Optional[Dict[int, torch.Tensor]] = None) -> None:
+    def step(self, grads: Optional[Dict[int, torch.Tensor]] = None, skip_flag: Optional[int] = None) -> None:
         """`grads` maps id(param) -> gradient tensor; default is param.grad.  Parameters without a gradient are
-        skipped (a stop_grad parameter in the reference)."""
+        skipped (a stop_grad parameter in the reference).  `skip_flag` is the device address of a uint32 that, when
+        non-zero at execution time, turns the launch into a no-op (gm_frame_overflow_flag: a frame that overflowed its
+        arena must not reach the parameters)."""
         self.n_step += 1
         rows, keep = [], []
         for g in self.param_groups:
@@ -207,8 +209,8 @@ class Adam:
         if not rows:
             return
         table = (AdamTensor * len(rows))(*rows)
-        check(lib.gm_adam_step(len(rows), table, self.n_step, float(self.betas[0]), float(self.betas[1]), float(self.eps),
-                               _stream()), "gm_adam_step")
+        check(lib.gm_adam_step_gated(len(rows), table, self.n_step, float(self.betas[0]), float(self.betas[1]),
+                                     float(self.eps), skip_flag, _stream()), "gm_adam_step")
 
 
 # ---------------------------------------------------------------------------------------------
@@ -236,6 +238,7 @@ class TrainingIteration:
         self.spatial_lr_scale = spatial_lr_scale
         self._alloc, self._flat = alloc, flat_params
         self.iteration = 0
+        self.skipped_iterations = 0       # iterations whose frame overflowed the arena (update dropped on the device)
         self._allocate()
 
     def _allocate(self) -> None:
@@ -374,7 +377,8 @@ class TrainingIteration:
             setattr(m, attr, torch.cat([old.detach()[keep], new[attr]], dim=0).contiguous())
         for name, val in const.items():
             setattr(m, name, torch.cat([getattr(m, name)[keep], val], dim=0).contiguous())
-        m.screenspace_points = torch.zeros(m._bc.shape[0], 3, device=dev)
+        m.screenspace_points = torch.zeros(m._bc.shape[0], 3, device=dev,
+                                           requires_grad=bool(getattr(m.screenspace_points, "requires_grad", False)))
         n_step, lr_groups = self.optimizer.n_step, {g["name"]: g["lr"] for g in self.optimizer.param_groups}
         persistent = {k: getattr(self, k) for k in ("arena", "losses", "image", "dL_dimg", "scratch")}
         self._allocate()                                 # buffers for the new size, statistics restart at zero (:499-501)
@@ -469,6 +473,13 @@ class TrainingIteration:
         va = self._view_args(cam)
         cap, _, _, geom, binning, image_state = self.arena.forward(
             self.P, D, self.M, bg, self.W, self.H, va, False, False, stream, out_color=self.image, radii=self.radii)
+        # An overflowed frame (tiles past the arena's capacity not rendered) must not reach the parameters: the
+        # statistics and the optimizer are gated on the frame's device-side overflow word, the host sees the overflow
+        # one or two iterations later (arena.poll in forward), counts the dropped iteration, and the arena has grown.
+        gate = lib.gm_frame_overflow_flag(geom.data_ptr())
+        if self.arena.overflowed:
+            self.skipped_iterations += len(self.arena.overflowed)
+            self.arena.overflowed.clear()
         check(lib.gm_photometric_loss(3, self.H, self.W, _p(self.image), _p(gt_image), float(opt.lambda_dssim),
                                       _p(self.scratch), _p(self.losses), _p(self.dL_dimg), stream), "gm_photometric_loss")
         self._accum.zero_()
@@ -489,10 +500,10 @@ class TrainingIteration:
                                         _p(g["opacity"]), _p(g["bc"]), _p(g["distance"]), _p(g["log_scale"]),
                                         _p(g["rot_raw"]), _p(g["opacity_logit"]), stream), "gm_mesh_bind_backward")
         if it < opt.densify_until_iter:                                       # train_mesh_gaussian.py:114-121
-            check(lib.gm_densify_stats(self.P, _p(self.radii), _p(g["means2D"]), _p(self.max_radii2D),
-                                       _p(self.bc_gradient_accum), _p(self.denom), stream), "gm_densify_stats")
+            check(lib.gm_densify_stats_gated(self.P, _p(self.radii), _p(g["means2D"]), _p(self.max_radii2D),
+                                             _p(self.bc_gradient_accum), _p(self.denom), gate, stream), "gm_densify_stats")
         if densify and self.after_backward():                                  # train_mesh_gaussian.py:123-131,139
             return self.losses
         if optimizer_step and it < opt.iterations:                            # train_mesh_gaussian.py:136-147
-            self.optimizer.step(self._grad_of)
+            self.optimizer.step(self._grad_of, skip_flag=gate)
         return self.losses

@@ -204,6 +204,33 @@ int gm_sh_to_rgb_rotated(int P, int D, int M, const float* pos /*[P,3]*/, const 
                          const float* rot /*[P,3,3] or NULL*/, const float* shs,
                          float* rgb /*[P,3]*/, gm_stream_t stream);
 
+/* ---- backward of gm_sh_to_rgb_rotated: dL/dshs [P,M,3] (zero above degree D) and dL/dpos [P,3] through the
+ *      normalised (and, with rot, rotated) view direction; either output may be NULL.  With rot == NULL this is the
+ *      autograd of the reference's convert_SHs_python branch (gaussian_renderer/__init__.py:87-92,
+ *      utils/sh_utils.py:57-112), clamp included. */
+int gm_sh_to_rgb_rotated_backward(int P, int D, int M, const float* pos, const float* campos, const float* rot,
+                                  const float* shs, const float* dL_drgb /*[P,3]*/, float* dL_dshs, float* dL_dpos,
+                                  gm_stream_t stream);
+
+/* ---- the compute_cov3D_python branch (gaussian_renderer/__init__.py:78-79): pc.get_covariance(scaling_modifier) =
+ *      strip_symmetric(L L^T), L = R(q / |q|) diag(modifier * s) (utils/general_utils.py:64-109,
+ *      scene/mesh_based_gaussian_model.py:24-29,176-177).  The quaternion is normalised here, unlike the CUDA
+ *      branch (forward.cu:127).  cov6 is [P,6] packed xx,xy,xz,yy,yz,zz.  The backward takes dL/dcov6 as the
+ *      rasterizer returns it (six independent inputs) and writes dL/dscale [P,3], dL/drot [P,4]. */
+int gm_cov3d_from_scale_rot(int P, const float* scales, float scale_modifier, const float* rotations, float* cov6,
+                            gm_stream_t stream);
+int gm_cov3d_from_scale_rot_backward(int P, const float* scales, float scale_modifier, const float* rotations,
+                                     const float* dL_dcov6, float* dL_dscale, float* dL_drot, gm_stream_t stream);
+
+/* ---- SingleObjectDeform.load_mesh, face-id branch (edittool/__init__.py:87-101): gaussian_triangles[i] =
+ *      faces[face_id[i]] and the area-ratio barycentric weights of the projected point
+ *      (get_barycentric_coordinate, edittool/general_utils.py:73-88), float64 like numpy.
+ *      vertex [Vn,3] float64, faces [Fn,3] int32, face_id [P] int64, proj_pos [P,3] float32 (get_proj_xyz);
+ *      outputs gaussian_triangles [P,3] int32, weights [P,3] float64. */
+int gm_load_mesh(int P, int num_vertices, int num_faces, const double* vertex, const int32_t* faces,
+                 const int64_t* face_id, const float* proj_pos, int32_t* gaussian_triangles, double* weights,
+                 gm_stream_t stream);
+
 /* ---- ACAP rotation / shear per vertex; replaces pyACAP.pyACAP(mesh).GetRS(ref_V, def_V, _R = 1, ncpu)
  *      (edittool/__init__.py:102,109; ACAP/pyACAPv1.zip: mainpy.cpp:60-64, src/FeatureVector.cpp:81-173,428-590,
  *      src/Align.cpp:31-100).  float64 arithmetic like the reference.
@@ -272,6 +299,15 @@ typedef struct gm_adam_tensor {
 int gm_adam_step(int num_tensors, const gm_adam_tensor* tensors_host, int step, float beta1, float beta2, float eps,
                  gm_stream_t stream);
 
+/*  Device-side gate for the sync-free training loop: gm_forward never reads the instance count back
+ *  (rasterizer_impl.cu:411 does), so a frame that outgrew its binning chunk is only known on the device when the
+ *  optimizer runs.  gm_frame_overflow_flag returns the address of that frame's overflow word inside the geometry chunk;
+ *  the _gated variants read it (NULL = ungated) and drop the update / the statistics when it is set -- a partially
+ *  rendered frame never reaches the parameters.  The host learns of the overflow from gm_forward's frame_info_host. */
+const uint32_t* gm_frame_overflow_flag(const char* geom_buffer);
+int gm_adam_step_gated(int num_tensors, const gm_adam_tensor* tensors_host, int step, float beta1, float beta2, float eps,
+                       const uint32_t* skip_flag, gm_stream_t stream);
+
 /*  View-parallel training (no counterpart in the reference, which is single-GPU): every rank holds
  *  the whole model in ONE flat float vector of `total` floats (tensors at 32-float aligned offsets, described by
  *  `segments_host`), renders its own view, and leaves its gradient in a flat buffer of the same layout.
@@ -301,6 +337,8 @@ int gm_adam_step_sharded_p2p(int world, int rank, const float* const* grads_host
  *  with radii > 0:  max_radii2D = max(max_radii2D, radii);  grad_accum += |dL_dmean2D.xy|;  denom += 1. */
 int gm_densify_stats(int P, const int32_t* radii, const float* dL_dmean2D /*[P,3]*/, float* max_radii2D /*[P]*/,
                      float* grad_accum /*[P]*/, float* denom /*[P]*/, gm_stream_t stream);
+int gm_densify_stats_gated(int P, const int32_t* radii, const float* dL_dmean2D, float* max_radii2D, float* grad_accum,
+                           float* denom, const uint32_t* skip_flag, gm_stream_t stream);
 
 #ifdef __cplusplus
 }

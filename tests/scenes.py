@@ -64,3 +64,40 @@ def rel_err(a: torch.Tensor, b: torch.Tensor) -> float:
     if denom == 0.0:
         return float(a.abs().max())
     return float((a - b).abs().max()) / denom
+
+
+# Element-wise gradient measure ("norm-wise, plus element-wise with an absolute floor").  The max-norm
+# measure above lets a gradient 100x below the tensor's largest entry be completely wrong; this one bounds every
+# element: |a - b| <= rtol |b| + floor max|b|.  The reference's own gradients come out of float atomics in
+# scheduling order, so a small fraction of heavily cancelling elements may differ between two runs of the reference
+# itself; `min_frac` of the elements must pass and the worst offender is reported.
+GRAD_RTOL = 1e-3
+GRAD_FLOOR = 1e-5
+GRAD_MIN_FRAC = 0.999
+
+
+def grad_report(a: torch.Tensor, b: torch.Tensor, rtol: float = GRAD_RTOL, floor: float = GRAD_FLOOR) -> Dict[str, float]:
+    a = a.detach().reshape(-1).double()
+    b = b.detach().reshape(-1).double()
+    scale = float(b.abs().max())
+    diff = (a - b).abs()
+    bound = rtol * b.abs() + floor * scale
+    ok = diff <= bound
+    excess = diff / bound.clamp_min(1e-300)
+    worst = int(excess.argmax()) if a.numel() else 0
+    return {"rel": float(diff.max()) / scale if scale > 0 else float(a.abs().max()) if a.numel() else 0.0,
+            "frac_ok": float(ok.double().mean()) if a.numel() else 1.0,
+            "worst": worst, "worst_got": float(a[worst]) if a.numel() else 0.0,
+            "worst_want": float(b[worst]) if a.numel() else 0.0, "worst_excess": float(excess[worst]) if a.numel() else 0.0,
+            "scale": scale}
+
+
+def assert_grad(a: torch.Tensor, b: torch.Tensor, name: str, tol: float = 1e-3, min_frac: float = GRAD_MIN_FRAC) -> Dict[str, float]:
+    """Both gradient gates: max-norm relative error <= tol AND the element-wise bound for >= min_frac of the elements."""
+    rep = grad_report(a, b)
+    assert rep["rel"] <= tol, f"grad {name}: max-norm rel err {rep['rel']:.3e} > {tol}"
+    assert rep["frac_ok"] >= min_frac, (
+        f"grad {name}: only {100 * rep['frac_ok']:.4f}% of the elements within {GRAD_RTOL}*|ref| + {GRAD_FLOOR}*max|ref|; "
+        f"worst element {rep['worst']}: got {rep['worst_got']:.6e}, want {rep['worst_want']:.6e} "
+        f"({rep['worst_excess']:.1f}x the bound, tensor scale {rep['scale']:.3e})")
+    return rep
