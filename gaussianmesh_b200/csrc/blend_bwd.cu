@@ -618,51 +618,100 @@ blend_backward_pairs_kernel(GeometryState g, BinningState b, ImageState img, uin
 //     C[s, c] = sum_p w[s, p] * dL/dpixel[p, c]
 // (backward.cu:523,537-554 sum q dx, q dx^2, ... with dx = x_s - px: the splat-centred moments follow from the
 // pixel-centred ones by a shift applied once per (warp, splat), see `flush`).  Each lane parks (q, w) of its pixel in a
-// warp-private shared-memory slab, 16 splats deep, and the two products run on the tensor cores
-// (mma.sync.m16n8k8, TF32 inputs, FP32 accumulation): q and w are split into a TF32 head and tail (two MMAs, 21+ mantissa
-// bits), Phi is exact in TF32 (multiples of 1/4 below 16), dL/dpixel is split head/tail across two columns of the B
-// operand.  This replaces the 18-value transposing butterfly (37 % of the pairs kernel's instructions) with two 64-bit
-// shared-memory stores per pair of splats and ~12 instructions per splat at flush time.
+// warp-private shared-memory slab, 8 splats deep, and both products run on the tensor cores as ONE 16 x 32 A operand
+// (rows 0-7: q of the eight splats, rows 8-15: their w) against the two B operands (mma.sync.m16n8k8, TF32 inputs, FP32
+// accumulation): q and w are split into a TF32 head and an exact fp32 tail (two MMAs, 21+ mantissa bits), Phi is exact
+// in TF32 (multiples of 1/4 below 16), dL/dpixel is split head / tail across two columns of its B operand.  This
+// replaces the 18-value transposing butterfly (37 % of the pairs kernel's instructions) with two 64-bit shared-memory
+// stores per pair of splats and ~20 instructions per splat at flush time.
 //
-// The splat queue is a warp-private RING of pair slots: survivors of the 32-wide cull are appended (an odd survivor
-// waits for the next chunk instead of being padded), evaluated pair by pair, and stay in the ring until the 16 slab rows
-// that hold their (q, w) have been reduced.  The record stages are released per warp (a counter per stage; the warp that
-// arrives last refills the stage), so there is no block-wide barrier in the loop.
-constexpr int kBatchM = 128;      // records per stage
-constexpr int kStagesM = 3;
-constexpr int kRing = 24;         // pair slots: <= 7 pending + <= 17 new
-constexpr int kRowPairs = 8;      // slab depth in pairs (16 MMA rows)
-constexpr int kSlabPitch = 80;    // floats per slab row pair: 32 pixels x (A, B) + 16 pad (conflict-free LDS.128 fragments)
+// The record stages are released per warp (a counter per stage; the warp that arrives last refills the stage), so there
+// is no block-wide barrier in the loop and a warp with few surviving splats runs ahead of its neighbours.
+//
+// All shared-memory traffic of the inner loops goes through 32-bit shared-window addresses kept in registers (inline
+// ld.shared / st.shared): left to itself ptxas re-derives them from %tid and %cgaid in every iteration (S2R, a
+// ~100-cycle instruction) when registers are short.
+constexpr int kBatchM = 64;       // records per stage
+constexpr int kStagesM = 4;
+constexpr int kFlushPairs = 4;    // slab depth in pairs (8 splats = the 8 + 8 rows of one MMA)
+constexpr int kSlabPitch = 80;    // floats per slab row: 32 pixels x (q, w) + 16 pad (conflict-free LDS.128 fragments)
 
-struct WarpRingM {
-	// [field][slot][4]: 0: xA xB yA yB   1: aA aB -bA -bB   2: cA cB oA oB   3: rA rB gA gB   4: bA bB posA posB
-	float v[5][kRing][4];
-	uint32_t id[kRing * 2];
-	float slabQ[kRowPairs][kSlabPitch];   // [row pair][pixel][A, B]
-	float slabW[kRowPairs][kSlabPitch];
+struct WarpQueueM {
+	// [field][slot][4]: slot k holds splats 2k (A) and 2k+1 (B) of the compacted chunk, back to front
+	//   0: xA xB yA yB   1: aA aB -bA -bB   2: cA cB oA oB   3: rA rB gA gB   4: bA bB posA posB (0-based, as bits)
+	float v[5][16][4];
+	uint32_t id[32];
+	float slab[2 * kFlushPairs][kSlabPitch];   // [splat row][pixel][q, w]; reused as the 8 x 12 transpose buffer of a flush
+	uint32_t dfr[32][8];                       // this warp's B fragments of dL/dpixel, per lane
 };
 
 struct __align__(128) BwdSmemM {
 	float4 conic[kStagesM][kBatchM];
 	float4 xyrg[kStagesM][kBatchM];
 	float2 bid[kStagesM][kBatchM];
-	WarpRingM ring[kWarps];
+	WarpQueueM queue[kWarps];
+	uint32_t phi[32][8];                       // B fragments of the pixel monomials, per lane (same for every warp)
 	uint64_t full[kStagesM];
 	uint32_t released[kStagesM];
 	uint32_t warp_max[kWarps];
 };
 
-__device__ __forceinline__ uint32_t tf32_rna(float x)
+__device__ __forceinline__ float4 lds128(uint32_t addr)
 {
-	uint32_t r;
-	asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-	return r;
+	float4 v;
+	asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+	return v;
 }
 
-// x = head + tail with head the nearest TF32 value; the tail is exact in fp32 and the tensor core reads its top 19 bits
+__device__ __forceinline__ uint4 lds128u(uint32_t addr)
+{
+	uint4 v;
+	asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+	return v;
+}
+
+__device__ __forceinline__ uint2 lds64u(uint32_t addr)
+{
+	uint2 v;
+	asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr) : "memory");
+	return v;
+}
+
+__device__ __forceinline__ ulonglong2 lds128p(uint32_t addr)   // two packed fp32 pairs
+{
+	ulonglong2 v;
+	asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(v.x), "=l"(v.y) : "r"(addr) : "memory");
+	return v;
+}
+
+__device__ __forceinline__ float lds32(uint32_t addr)
+{
+	float v;
+	asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+	return v;
+}
+
+__device__ __forceinline__ void sts64(uint32_t addr, float a, float b)
+{
+	asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(a), "f"(b) : "memory");
+}
+
+__device__ __forceinline__ void sts32(uint32_t addr, float a)
+{
+	asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(a) : "memory");
+}
+
+// fire-and-forget global float add (SASS REDG: no return value, nothing for a later instruction to wait on)
+__device__ __forceinline__ void red_add(float* addr, float v)
+{
+	asm volatile("red.global.add.f32 [%0], %1;" ::"l"(addr), "f"(v) : "memory");
+}
+
+// x = head + tail: head = x with the 13 low mantissa bits cleared (a TF32 value), tail exact in fp32 (the tensor core
+// reads its top 19 bits): together 21+ mantissa bits of x enter the product
 __device__ __forceinline__ void tf32_split(float x, uint32_t& head, uint32_t& tail)
 {
-	head = tf32_rna(x);
+	head = __float_as_uint(x) & 0xffffe000u;
 	tail = __float_as_uint(x - __uint_as_float(head));
 }
 
@@ -673,7 +722,7 @@ __device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], 
 	             : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
-__global__ void __launch_bounds__(kThreads, 3)
+__global__ void __launch_bounds__(kThreads, 4)
 blend_backward_mma_kernel(GeometryState g, BinningState b, ImageState img, uint32_t capacity,
                           int W, int H, int tiles_x, const float* __restrict__ bg_color,
                           const float* __restrict__ dL_dpixels,
@@ -722,6 +771,23 @@ blend_backward_mma_kernel(GeometryState g, BinningState b, ImageState img, uint3
 		}
 		fence_mbar_init();
 	}
+	// B fragments of mma.m16n8k8 (row.col): this thread holds B[k = tg][n = gid] and B[k = tg + 4][n = gid]; k-step i maps
+	// k = tg, tg + 4 to the pixels 8 i + 2 tg, 8 i + 2 tg + 1 of the warp's block (lane index = pixel index), the order in
+	// which the A fragments are read from the slab.  Column n of Phi is the n-th monomial of the pixel's offset from the
+	// block centre (columns 6, 7 are zero); it is the same for every warp.
+	const int gid = lane >> 2, tg = lane & 3;
+	if (warp == 0) {
+#pragma unroll
+		for (int i = 0; i < 4; i++)
+#pragma unroll
+			for (int j = 0; j < 2; j++) {
+				const int p = 8 * i + 2 * tg + j;
+				const float u = (float)(p & 7) - 3.5f, v = (float)(p >> 3) - 1.5f;
+				const float mono = gid == 0 ? 1.0f : gid == 1 ? u : gid == 2 ? v : gid == 3 ? u * u : gid == 4 ? u * v
+				                   : gid == 5 ? v * v : 0.0f;
+				s.phi[lane][2 * i + j] = __float_as_uint(mono);
+			}
+	}
 	__syncthreads();
 	uint32_t tile_last = 0;
 #pragma unroll
@@ -738,28 +804,26 @@ blend_backward_mma_kernel(GeometryState g, BinningState b, ImageState img, uint3
 		dL_dpixel2 = dL_dpixels[2 * HW + pix_id];
 	}
 
-	// B operands of the two products, constant per warp.  Fragment layout of mma.m16n8k8 (row.col): this thread holds
-	// B[k = tg][n = gid] and B[k = tg + 4][n = gid]; k-step i maps k = tg, tg + 4 to the pixels 8 i + 2 tg, 8 i + 2 tg + 1
-	// of the warp's block (lane index = pixel index), the order in which the A fragments are read from the slab.
-	const int gid = lane >> 2, tg = lane & 3;
-	uint32_t phi[4][2], dfr[4][2];
+	WarpQueueM& q = s.queue[warp];
+	// the warp's dL/dpixel as B fragments: columns 2 c, 2 c + 1 = TF32 head and fp32 tail of channel c, columns 6, 7 zero.
+	// The 3 x 32 values are exchanged through the (not yet used) slab.
+	q.slab[0][lane] = dL_dpixel0;
+	q.slab[0][32 + lane] = dL_dpixel1;
+	q.slab[1][lane] = dL_dpixel2;
+	__syncwarp();
+	{
+		const int c = gid >> 1;
+		const float* src = c == 0 ? &q.slab[0][0] : c == 1 ? &q.slab[0][32] : &q.slab[1][0];
 #pragma unroll
-	for (int i = 0; i < 4; i++)
+		for (int i = 0; i < 4; i++)
 #pragma unroll
-		for (int j = 0; j < 2; j++) {
-			const int p = 8 * i + 2 * tg + j;
-			const float u = (float)(p & 7) - 3.5f, v = (float)(p >> 3) - 1.5f;
-			const float mono = gid == 0 ? 1.0f : gid == 1 ? u : gid == 2 ? v : gid == 3 ? u * u : gid == 4 ? u * v
-			                   : gid == 5 ? v * v : 0.0f;
-			phi[i][j] = __float_as_uint(mono);
-			const float d0 = __shfl_sync(0xffffffffu, dL_dpixel0, p);
-			const float d1 = __shfl_sync(0xffffffffu, dL_dpixel1, p);
-			const float d2 = __shfl_sync(0xffffffffu, dL_dpixel2, p);
-			const float d = (gid >> 1) == 0 ? d0 : (gid >> 1) == 1 ? d1 : (gid >> 1) == 2 ? d2 : 0.0f;
-			uint32_t head, tail;
-			tf32_split(d, head, tail);
-			dfr[i][j] = (gid & 1) ? tail : head;   // columns 2c, 2c + 1 = head, tail of channel c; columns 6, 7 = 0
-		}
+			for (int j = 0; j < 2; j++) {
+				uint32_t head, tail;
+				tf32_split(src[8 * i + 2 * tg + j], head, tail);
+				q.dfr[lane][2 * i + j] = gid >= 6 ? 0u : (gid & 1) ? tail : head;
+			}
+	}
+	__syncwarp();
 
 	// accum_rec and the pending (last_alpha * last_color, 1 - last_alpha) term of backward.cu:509-515
 	float acc0 = 0.0f, acc1 = 0.0f, acc2 = 0.0f;
@@ -783,143 +847,74 @@ blend_backward_mma_kernel(GeometryState g, BinningState b, ImageState img, uint3
 		bulk_g2s(s.bid[st], b.rec_bid + off, cnt4 * 8u, &s.full[st]);
 	};
 
-	WarpRingM& r = s.ring[warp];
+	// shared-window addresses, made opaque so that they stay in registers
+	uint32_t q_base = smem_u32(&q);
+	uint32_t frag_base = q_base + (uint32_t)offsetof(WarpQueueM, slab) + (uint32_t)(gid * kSlabPitch + 4 * tg) * 4u;
+	uint32_t slab_lane = q_base + (uint32_t)offsetof(WarpQueueM, slab) + (uint32_t)lane * 8u;
+	asm volatile("" : "+r"(q_base), "+r"(frag_base), "+r"(slab_lane));
+	const uint32_t phi_lane = smem_u32(&s.phi[lane][0]);
 	const float cx = (float)bx0 + 3.5f, cy = (float)by0 + 1.5f;
+	constexpr uint32_t kField = 16 * 16;   // bytes per queue field
 
-	// Reduce the slab (up to 8 row pairs starting at ring slot `tail`) on the tensor cores and send every touched splat's
-	// gradients to global memory: lanes 0-7 own splat A of row pair (lane & 7), lanes 8-15 splat B.
-	auto flush = [&](int tail, uint32_t touched) {
+	// Reduce the slab (up to 4 pairs = 8 splats, queue slots first .. first + 3) on the tensor cores and send every touched
+	// splat's gradients to global memory: lane l < 8 owns splat l of the group (pair l >> 1, half l & 1).
+	auto flush = [&](int first, uint32_t touched) {
 		__syncwarp();
-		float mq[4] = {0.0f, 0.0f, 0.0f, 0.0f}, mw[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+		float pm[4] = {0.0f, 0.0f, 0.0f, 0.0f}, dm[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+		const uint32_t dfr_lane = q_base + (uint32_t)offsetof(WarpQueueM, dfr) + (uint32_t)lane * 32u;
 #pragma unroll
 		for (int i = 0; i < 4; i++) {
-			// A fragment of k-step i: rows gid (splat A of pair gid) and gid + 8 (splat B), pixels 8 i + 2 tg, + 1
-			const float4 aq = *reinterpret_cast<const float4*>(&r.slabQ[gid][16 * i + 4 * tg]);
-			const float4 aw = *reinterpret_cast<const float4*>(&r.slabW[gid][16 * i + 4 * tg]);
-			uint32_t qh[4], ql[4], wh[4], wl[4];
-			tf32_split(aq.x, qh[0], ql[0]); tf32_split(aq.y, qh[1], ql[1]);
-			tf32_split(aq.z, qh[2], ql[2]); tf32_split(aq.w, qh[3], ql[3]);
-			tf32_split(aw.x, wh[0], wl[0]); tf32_split(aw.y, wh[1], wl[1]);
-			tf32_split(aw.z, wh[2], wl[2]); tf32_split(aw.w, wh[3], wl[3]);
-			mma_tf32(mq, qh, phi[i][0], phi[i][1]);
-			mma_tf32(mq, ql, phi[i][0], phi[i][1]);
-			mma_tf32(mw, wh, dfr[i][0], dfr[i][1]);
-			mma_tf32(mw, wl, dfr[i][0], dfr[i][1]);
+			// A fragment of k-step i: row gid = q of splat gid, row gid + 8 = its w; pixels 8 i + 2 tg and + 1
+			const float4 a = lds128(frag_base + 64u * i);
+			const uint2 bp = lds64u(phi_lane + 8u * i), bd = lds64u(dfr_lane + 8u * i);
+			uint32_t hi[4], lo[4];
+			tf32_split(a.x, hi[0], lo[0]); tf32_split(a.y, hi[1], lo[1]);
+			tf32_split(a.z, hi[2], lo[2]); tf32_split(a.w, hi[3], lo[3]);
+			mma_tf32(pm, hi, bp.x, bp.y);
+			mma_tf32(dm, hi, bd.x, bd.y);
+			mma_tf32(pm, lo, bp.x, bp.y);
+			mma_tf32(dm, lo, bd.x, bd.y);
 		}
 		__syncwarp();   // every fragment has been read: the slab is reused to transpose the results
-		// C fragment: (row gid, columns 2 tg, 2 tg + 1), (row gid + 8, same columns)
-		float* const park = &r.slabQ[0][0];   // [16 rows][12]: Sq Su Sv Suu Suv Svv | colour 0 1 2
+		// C fragments: (row gid, columns 2 tg, 2 tg + 1) of q x Phi; (row gid + 8, same columns) of w x dL/dpixel
+		const uint32_t park = q_base + (uint32_t)offsetof(WarpQueueM, slab);   // [8 splats][12]: Sq Su Sv Suu Suv Svv | colour 0 1 2
 		if (tg < 3) {
-			*reinterpret_cast<float2*>(park + gid * 12 + 2 * tg) = make_float2(mq[0], mq[1]);
-			*reinterpret_cast<float2*>(park + (gid + 8) * 12 + 2 * tg) = make_float2(mq[2], mq[3]);
-			park[gid * 12 + 6 + tg] = mw[0] + mw[1];
-			park[(gid + 8) * 12 + 6 + tg] = mw[2] + mw[3];
+			sts64(park + (uint32_t)(gid * 12 + 2 * tg) * 4u, pm[0], pm[1]);
+			sts32(park + (uint32_t)(gid * 12 + 6 + tg) * 4u, dm[2] + dm[3]);
 		}
 		__syncwarp();
-		if (lane < 16 && ((touched >> (lane & 7)) & 1u)) {
-			const float4 m0 = *reinterpret_cast<const float4*>(park + lane * 12);
-			const float4 m1 = *reinterpret_cast<const float4*>(park + lane * 12 + 4);
-			const float c2 = park[lane * 12 + 8];
+		if (lane < 8 && ((touched >> (lane >> 1)) & 1u)) {
+			const float4 m0 = lds128(park + (uint32_t)lane * 48u);
+			const float4 m1 = lds128(park + (uint32_t)lane * 48u + 16u);
+			const float c2 = lds32(park + (uint32_t)lane * 48u + 32u);
 			const float Sq = m0.x, Su = m0.y, Sv = m0.z, Suu = m0.w, Suv = m1.x, Svv = m1.y, c0 = m1.z, c1 = m1.w;
 			const uint32_t any = (__float_as_uint(c0) | __float_as_uint(c1) | __float_as_uint(c2) | __float_as_uint(Sq) |
 			                      __float_as_uint(Su) | __float_as_uint(Sv) | __float_as_uint(Suu) | __float_as_uint(Suv) |
 			                      __float_as_uint(Svv)) << 1;
 			if (any != 0) {
-				int slot = tail + (lane & 7);
-				slot = slot >= kRing ? slot - kRing : slot;
-				const int h = lane >> 3;
-				const float a = r.v[1][slot][h], bb = -r.v[1][slot][2 + h], c = r.v[2][slot][h], o = r.v[2][slot][2 + h];
-				const uint32_t id = r.id[2 * slot + h];
+				const int slot = first + (lane >> 1), h = lane & 1;
+				const float a = q.v[1][slot][h], bb = -q.v[1][slot][2 + h], c = q.v[2][slot][h], o = q.v[2][slot][2 + h];
+				const uint32_t id = q.id[2 * slot + h];
 				// dx = x_s - px = X - u with X = x_s - (block centre): shift the pixel-centred moments to the splat
-				const float X = r.v[0][slot][h] - cx, Y = r.v[0][slot][2 + h] - cy;
+				const float X = q.v[0][slot][h] - cx, Y = q.v[0][slot][2 + h] - cy;
 				const float Sx = fmaf(X, Sq, -Su), Sy = fmaf(Y, Sq, -Sv);
 				const float Sxx = fmaf(X, fmaf(X, Sq, -2.0f * Su), Suu);
 				const float Sxy = fmaf(X, fmaf(Y, Sq, -Sv), fmaf(-Y, Su, Suv));
 				const float Syy = fmaf(Y, fmaf(Y, Sq, -2.0f * Sv), Svv);
-				atomicAdd(&dL_dcolors[3 * (size_t)id + 0], c0);
-				atomicAdd(&dL_dcolors[3 * (size_t)id + 1], c1);
-				atomicAdd(&dL_dcolors[3 * (size_t)id + 2], c2);
+				red_add(&dL_dcolors[3 * (size_t)id + 0], c0);
+				red_add(&dL_dcolors[3 * (size_t)id + 1], c1);
+				red_add(&dL_dcolors[3 * (size_t)id + 2], c2);
 				// dL/dG = o dL/dalpha;  dG/ddelx = -G (a dx + b dy);  dG/ddely = -G (c dy + b dx)
-				atomicAdd(&dL_dmean2D[3 * (size_t)id + 0], -o * ddelx_dx * (a * Sx + bb * Sy));
-				atomicAdd(&dL_dmean2D[3 * (size_t)id + 1], -o * ddely_dy * (c * Sy + bb * Sx));
+				red_add(&dL_dmean2D[3 * (size_t)id + 0], -o * ddelx_dx * (a * Sx + bb * Sy));
+				red_add(&dL_dmean2D[3 * (size_t)id + 1], -o * ddely_dy * (c * Sy + bb * Sx));
 				const float hh = -0.5f * o;
-				atomicAdd(&dL_dconic2D[4 * (size_t)id + 0], hh * Sxx);
-				atomicAdd(&dL_dconic2D[4 * (size_t)id + 1], hh * Sxy);
-				atomicAdd(&dL_dconic2D[4 * (size_t)id + 3], hh * Syy);
-				atomicAdd(&dL_dopacity[id], Sq);
+				red_add(&dL_dconic2D[4 * (size_t)id + 0], hh * Sxx);
+				red_add(&dL_dconic2D[4 * (size_t)id + 1], hh * Sxy);
+				red_add(&dL_dconic2D[4 * (size_t)id + 3], hh * Syy);
+				red_add(&dL_dopacity[id], Sq);
 			}
 		}
-		__syncwarp();   // slab rows and ring slots are rewritten from here on
-	};
-
-	// warp-uniform ring state: `head` = slot the next survivor goes to (its A half is occupied when carry == 1),
-	// `tail` = slot of slab row pair 0, `npend` = row pairs filled, `touched` = row pairs some pixel contributed to
-	int head = 0, tail = 0, npend = 0, carry = 0;
-	uint32_t touched = 0;
-
-	// Evaluate n_pairs ring slots starting at `head` for this lane's pixel and park (q, w) in the slab.
-	auto run_pairs = [&](int n_pairs) {
-		int slot = head;
-		for (int k = 0; k < n_pairs; k++) {
-			const ulonglong2 XY = *reinterpret_cast<const ulonglong2*>(r.v[0][slot]);
-			const ulonglong2 AB = *reinterpret_cast<const ulonglong2*>(r.v[1][slot]);
-			const ulonglong2 CO = *reinterpret_cast<const ulonglong2*>(r.v[2][slot]);
-			const float4 BP = *reinterpret_cast<const float4*>(r.v[4][slot]);
-			// backward.cu:487-501, the forward's instruction sequence
-			const f2 dx = add2(XY.x, npx), dy = add2(XY.y, npy);
-			f2 t = mul2(dy, CO.x);
-			const f2 u = mul2(dx, AB.x);
-			t = mul2(dy, t);
-			const f2 sq = fma2(dx, u, t);
-			const f2 vv = mul2(dx, AB.y);
-			const f2 ww = mul2(dy, vv);
-			const f2 power = fma2(sq, neg_half, ww);
-			const f2 G = exp2x(power);
-			const f2 al = mul2(CO.y, G);
-			const float aA = fminf(lo(al), 0.99f), aB = fminf(hi(al), 0.99f);
-			const bool skipA = (__float_as_uint(BP.z) >= last_contributor) | (lo(power) > 0.0f) | (aA < 1.0f / 255.0f);
-			const bool skipB = (__float_as_uint(BP.w) >= last_contributor) | (hi(power) > 0.0f) | (aB < 1.0f / 255.0f);
-			if (!__all_sync(0xffffffffu, skipA & skipB)) {
-				touched |= 1u << npend;
-				const f2 e2 = pk(skipA ? 0.0f : aA, skipB ? 0.0f : aB);
-				const f2 Ge = pk(skipA ? 0.0f : lo(G), skipB ? 0.0f : hi(G));
-				// backward.cu:503-507: T <- T / (1 - alpha).  MUFU.RCP: 1 ulp, far inside the 1e-3 gradient tolerance
-				const f2 om = fma2(e2, neg_one, one);
-				const float rcpA = rcp_approx_ftz(lo(om)), rcpB = rcp_approx_ftz(hi(om));
-				const float TA = T * rcpA, TB = TA * rcpB;
-				T = TB;
-				const f2 T2 = pk(TA, TB), rcp2 = pk(rcpA, rcpB);
-				// backward.cu:509-521: accum_rec, walked A then B
-				const ulonglong2 RG = *reinterpret_cast<const ulonglong2*>(r.v[3][slot]);
-				const f2 col0 = RG.x, col1 = RG.y, col2 = pk(BP.x, BP.y);
-				const f2 ac0 = mul2(e2, col0), ac1 = mul2(e2, col1), ac2 = mul2(e2, col2);
-				const float accA0 = fmaf(keep_prev, acc0, pend0), accA1 = fmaf(keep_prev, acc1, pend1),
-				            accA2 = fmaf(keep_prev, acc2, pend2);
-				acc0 = fmaf(lo(om), accA0, lo(ac0));
-				acc1 = fmaf(lo(om), accA1, lo(ac1));
-				acc2 = fmaf(lo(om), accA2, lo(ac2));
-				pend0 = hi(ac0); pend1 = hi(ac1); pend2 = hi(ac2);
-				keep_prev = hi(om);
-				const f2 d0 = fma2(pk(accA0, acc0), neg_one, col0);
-				const f2 d1 = fma2(pk(accA1, acc1), neg_one, col1);
-				const f2 d2 = fma2(pk(accA2, acc2), neg_one, col2);
-				f2 dL_dalpha = fma2(d2, dLp2, fma2(d1, dLp1, mul2(d0, dLp0)));
-				// backward.cu:526-534
-				dL_dalpha = fma2(dL_dalpha, T2, mul2(bg_term, rcp2));
-				// w = alpha T (backward.cu:523) and q = G dL/dalpha (backward.cu:537-554) of this pixel, splats (A, B)
-				*reinterpret_cast<f2*>(&r.slabW[npend][2 * lane]) = mul2(e2, T2);
-				*reinterpret_cast<f2*>(&r.slabQ[npend][2 * lane]) = mul2(Ge, dL_dalpha);
-			}
-			npend++;
-			slot = (slot + 1 == kRing) ? 0 : slot + 1;
-			if (npend == kRowPairs) {
-				flush(tail, touched);
-				tail = slot;
-				npend = 0;
-				touched = 0;
-			}
-		}
-		head = slot;
+		__syncwarp();   // the slab is rewritten from here on
 	};
 
 	const int batch_hi = (int)((tile_last - 1) / kBatchM);
@@ -939,7 +934,7 @@ blend_backward_mma_kernel(GeometryState g, BinningState b, ImageState img, uint3
 		// positions >= warp_last are behind every pixel of this warp (backward.cu:487-489)
 		const int cnt = min(min(kBatchM, (int)n - batch_base), (int)warp_last - batch_base);
 		for (int base = (cnt > 0) ? ((cnt - 1) & ~31) : -1; base >= 0; base -= 32) {
-			// cull 32 splats in parallel against the warp's 8x4 pixel block; append the survivors back to front
+			// cull 32 splats in parallel against the warp's 8x4 pixel block; compact the survivors back to front
 			const int j = base + lane;
 			bool keep = false;
 			float4 co, xr;
@@ -952,28 +947,94 @@ blend_backward_mma_kernel(GeometryState g, BinningState b, ImageState img, uint3
 			const uint32_t mask = __ballot_sync(0xffffffffu, keep);
 			if (mask == 0)
 				continue;
-			if (keep) {
-				const int at = carry + __popc(mask >> lane) - 1;   // highest list position first
-				int slot = head + (at >> 1);
-				slot = slot >= kRing ? slot - kRing : slot;
-				const int h = at & 1;
-				const float2 bi = s.bid[st][j];
-				r.v[0][slot][h] = xr.x;
-				r.v[0][slot][2 + h] = xr.y;
-				r.v[1][slot][h] = co.x;
-				r.v[1][slot][2 + h] = -co.y;
-				r.v[2][slot][h] = co.z;
-				r.v[2][slot][2 + h] = co.w;
-				r.v[3][slot][h] = xr.z;
-				r.v[3][slot][2 + h] = xr.w;
-				r.v[4][slot][h] = bi.x;
-				r.v[4][slot][2 + h] = __uint_as_float((uint32_t)(batch_base + j));
-				r.id[2 * slot + h] = __float_as_uint(bi.y);
+			const int n_keep = __popc(mask);
+			{
+				// one non-surviving lane pads an odd queue with a splat that no pixel accepts (position 2^32 - 1)
+				const bool pad = !keep && (n_keep & 1) && lane == (__ffs(~mask) - 1);
+				if (keep || pad) {
+					const int at = keep ? __popc(mask >> lane) - 1 : n_keep;   // highest list position first
+					const int slot = at >> 1, h = at & 1;
+					const float2 bi = keep ? s.bid[st][j] : make_float2(0.0f, 0.0f);
+					q.v[0][slot][h] = keep ? xr.x : 0.0f;
+					q.v[0][slot][2 + h] = keep ? xr.y : 0.0f;
+					q.v[1][slot][h] = keep ? co.x : 0.0f;
+					q.v[1][slot][2 + h] = keep ? -co.y : 0.0f;
+					q.v[2][slot][h] = keep ? co.z : 0.0f;
+					q.v[2][slot][2 + h] = keep ? co.w : 0.0f;
+					q.v[3][slot][h] = keep ? xr.z : 0.0f;
+					q.v[3][slot][2 + h] = keep ? xr.w : 0.0f;
+					q.v[4][slot][h] = bi.x;
+					q.v[4][slot][2 + h] = __uint_as_float(keep ? (uint32_t)(batch_base + j) : 0xffffffffu);
+					q.id[at] = __float_as_uint(bi.y);
+				}
 			}
-			const int total = carry + __popc(mask);
-			carry = total & 1;
 			__syncwarp();
-			run_pairs(total >> 1);
+			const int n_pairs = (n_keep + 1) >> 1;
+			uint32_t touched = 0, bit = 1u;
+			uint32_t slot_addr = q_base, st_addr = slab_lane;
+			for (int k = 0; k < n_pairs; k++, slot_addr += 16u) {
+				const ulonglong2 XY = lds128p(slot_addr);
+				const ulonglong2 AB = lds128p(slot_addr + kField);
+				const ulonglong2 CO = lds128p(slot_addr + 2 * kField);
+				const float4 BP = lds128(slot_addr + 4 * kField);
+				// backward.cu:487-501, the forward's instruction sequence
+				const f2 dx = add2(XY.x, npx), dy = add2(XY.y, npy);
+				f2 t = mul2(dy, CO.x);
+				const f2 u = mul2(dx, AB.x);
+				t = mul2(dy, t);
+				const f2 sq = fma2(dx, u, t);
+				const f2 vv = mul2(dx, AB.y);
+				const f2 ww = mul2(dy, vv);
+				const f2 power = fma2(sq, neg_half, ww);
+				const f2 G = exp2x(power);
+				const f2 al = mul2(CO.y, G);
+				const float aA = fminf(lo(al), 0.99f), aB = fminf(hi(al), 0.99f);
+				const bool skipA = (__float_as_uint(BP.z) >= last_contributor) | (lo(power) > 0.0f) | (aA < 1.0f / 255.0f);
+				const bool skipB = (__float_as_uint(BP.w) >= last_contributor) | (hi(power) > 0.0f) | (aB < 1.0f / 255.0f);
+				if (!__all_sync(0xffffffffu, skipA & skipB)) {
+					touched |= bit;
+					const f2 e2 = pk(skipA ? 0.0f : aA, skipB ? 0.0f : aB);
+					const f2 Ge = pk(skipA ? 0.0f : lo(G), skipB ? 0.0f : hi(G));
+					// backward.cu:503-507: T <- T / (1 - alpha).  MUFU.RCP: 1 ulp, far inside the 1e-3 gradient tolerance
+					const f2 om = fma2(e2, neg_one, one);
+					const float rcpA = rcp_approx_ftz(lo(om)), rcpB = rcp_approx_ftz(hi(om));
+					const float TA = T * rcpA, TB = TA * rcpB;
+					T = TB;
+					const f2 T2 = pk(TA, TB), rcp2 = pk(rcpA, rcpB);
+					// backward.cu:509-521: accum_rec, walked A then B
+					const ulonglong2 RG = lds128p(slot_addr + 3 * kField);
+					const f2 col0 = RG.x, col1 = RG.y, col2 = pk(BP.x, BP.y);
+					const f2 ac0 = mul2(e2, col0), ac1 = mul2(e2, col1), ac2 = mul2(e2, col2);
+					const float accA0 = fmaf(keep_prev, acc0, pend0), accA1 = fmaf(keep_prev, acc1, pend1),
+					            accA2 = fmaf(keep_prev, acc2, pend2);
+					acc0 = fmaf(lo(om), accA0, lo(ac0));
+					acc1 = fmaf(lo(om), accA1, lo(ac1));
+					acc2 = fmaf(lo(om), accA2, lo(ac2));
+					pend0 = hi(ac0); pend1 = hi(ac1); pend2 = hi(ac2);
+					keep_prev = hi(om);
+					const f2 d0 = fma2(pk(accA0, acc0), neg_one, col0);
+					const f2 d1 = fma2(pk(accA1, acc1), neg_one, col1);
+					const f2 d2 = fma2(pk(accA2, acc2), neg_one, col2);
+					f2 dL_dalpha = fma2(d2, dLp2, fma2(d1, dLp1, mul2(d0, dLp0)));
+					// backward.cu:526-534
+					dL_dalpha = fma2(dL_dalpha, T2, mul2(bg_term, rcp2));
+					// q = G dL/dalpha (backward.cu:537-554) and w = alpha T (backward.cu:523) of this pixel: rows 2 r (splat A)
+					// and 2 r + 1 (splat B) of the slab
+					const f2 qq = mul2(Ge, dL_dalpha), wt = mul2(e2, T2);
+					sts64(st_addr, lo(qq), lo(wt));
+					sts64(st_addr + kSlabPitch * 4u, hi(qq), hi(wt));
+				}
+				bit <<= 1;
+				st_addr += 2u * kSlabPitch * 4u;
+				if (bit == (1u << kFlushPairs) || k == n_pairs - 1) {
+					if (touched != 0)
+						flush(k & ~(kFlushPairs - 1), touched);
+					touched = 0;
+					bit = 1u;
+					st_addr = slab_lane;
+				}
+			}
+			__syncwarp();   // the queue is rewritten by the next chunk
 		}
 
 		// release the stage; the warp that arrives last refills it with the batch kStagesM further on
@@ -989,22 +1050,6 @@ blend_backward_mma_kernel(GeometryState g, BinningState b, ImageState img, uint3
 			parity ^= 1u;
 		}
 	}
-
-	// the odd survivor left over at the end is paired with a splat that no pixel accepts (position 2^32 - 1)
-	if (carry) {
-		if (lane == 0) {
-			r.v[0][head][1] = 0.0f; r.v[0][head][3] = 0.0f;
-			r.v[1][head][1] = 0.0f; r.v[1][head][3] = 0.0f;
-			r.v[2][head][1] = 0.0f; r.v[2][head][3] = 0.0f;
-			r.v[3][head][1] = 0.0f; r.v[3][head][3] = 0.0f;
-			r.v[4][head][1] = 0.0f; r.v[4][head][3] = __uint_as_float(0xffffffffu);
-			r.id[2 * head + 1] = 0u;
-		}
-		__syncwarp();
-		run_pairs(1);
-	}
-	if (npend > 0)
-		flush(tail, touched);
 }
 
 } // namespace
@@ -1016,10 +1061,11 @@ int launch_blend_backward(const GeometryState& g, const BinningState& b, const I
 	const int num_tiles = vp.tiles_x * vp.tiles_y;
 	if (num_tiles <= 0)
 		return GM_OK;
-	// GM_BLEND_SCALAR=1 selects the one-splat-per-iteration kernel, GM_BLEND_BWD=pairs the packed-pair kernel with the
-	// shuffle butterfly (both kept for A/B measurements); the default reduces on the tensor cores
+	// The default is the packed-pair kernel with the shuffle butterfly.  GM_BLEND_BWD=mma selects the variant that reduces
+	// over the pixels on the tensor cores (same parity, 14 % fewer instructions, measured 2 % slower on B200: DESIGN.md 8),
+	// GM_BLEND_SCALAR=1 the one-splat-per-iteration kernel; both are kept for A/B measurements.
 	static const bool scalar = std::getenv("GM_BLEND_SCALAR") != nullptr && std::getenv("GM_BLEND_SCALAR")[0] == '1';
-	static const bool pairs = std::getenv("GM_BLEND_BWD") != nullptr && std::getenv("GM_BLEND_BWD")[0] == 'p';
+	static const bool pairs = !(std::getenv("GM_BLEND_BWD") != nullptr && std::getenv("GM_BLEND_BWD")[0] == 'm');
 	if (scalar)
 		blend_backward_kernel<<<num_tiles, kThreads, 0, stream>>>(
 			g, b, img, capacity, vp.W, vp.H, vp.tiles_x, vp.bg, dL_dpix, dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolor);

@@ -675,7 +675,8 @@ def test_python_pipeline_kernels_match_the_op_chains(cuda_device):
         rgb.backward(d * away[:, None])
         want.backward(d * away[:, None])
         scenes.assert_grad(f1.grad, f2.grad, f"sh deg {deg} -> shs", 1e-5, min_frac=1.0)
-        scenes.assert_grad(x1.grad, x2.grad, f"sh deg {deg} -> xyz", 1e-4, min_frac=0.999)
+        want_x = x2.grad if x2.grad is not None else torch.zeros_like(x2)      # degree 0 does not depend on the position
+        scenes.assert_grad(x1.grad, want_x, f"sh deg {deg} -> xyz", 1e-4, min_frac=0.999)
     # the edit-time twin with a per-Gaussian rotation
     ang = torch.rand(P, generator=g).to(dev) * 6.28
     c, s_ = torch.cos(ang), torch.sin(ang)
@@ -1061,10 +1062,10 @@ print(json.dumps(out))
 """
 
 
-@pytest.mark.parametrize("env", [{"GM_BLEND_SCALAR": "1"}, {"GM_BLEND_BWD": "pairs"}], ids=["scalar", "bwd_pairs"])
+@pytest.mark.parametrize("env", [{"GM_BLEND_SCALAR": "1"}, {"GM_BLEND_BWD": "mma"}], ids=["scalar", "bwd_mma"])
 def test_alternative_blend_kernels_still_match(cuda_device, tmp_path, env):
-    """GM_BLEND_SCALAR=1 selects the one-splat-per-iteration blend kernels, GM_BLEND_BWD=pairs the packed-pair backward
-    with the shuffle butterfly -- both kept for A/B measurements (the library reads the variables once, hence the
+    """GM_BLEND_SCALAR=1 selects the one-splat-per-iteration blend kernels, GM_BLEND_BWD=mma the backward that reduces
+    over the pixels on the tensor cores (TF32 mma.sync) -- both kept for A/B measurements (the library reads the variables once, hence the
     subprocess): same parity bar as the default kernels."""
     import json
     import os
