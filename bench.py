@@ -116,7 +116,8 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------ workload
 def build_workload(device, P, rank, world):
     from gaussianmesh_b200 import synthetic
-    from gaussianmesh_b200.renderer import shard_views, upload_cameras
+    from gaussianmesh_b200.cameras import upload_cameras
+    from gaussianmesh_b200.view_shard import shard_views
     arrays = synthetic.gaussian_scene(P, seed=0)
     scene = {k: torch.from_numpy(arrays[k]).to(device) for k in ("means3D", "opacities", "shs", "scales", "rotations")}
     cams_host = synthetic.orbit_cameras(NUM_VIEWS, WIDTH, HEIGHT)
@@ -131,7 +132,59 @@ def build_workload(device, P, rank, world):
     return scene, cams_host, cams, targets_host, targets, cams_packed_host
 
 
+class RefHyper:
+    """arguments/__init__.py:71-91 defaults used by the reference-style iteration (kept here so that the reference arm
+    never imports gaussianmesh_b200.training, which maps libCudaRasterizer.so)."""
+    position_lr_init = 0.00016
+    feature_lr = 0.0025
+    opacity_lr = 0.05
+    scaling_lr = 0.005
+    rotation_lr = 0.001
+    lambda_dssim = 0.2
+    alpha_mrloss = 6
+
+
 EDIT_P, EDIT_VIEWS = 500_000, 200
+
+
+class RefEditObject:
+    """Config-5 object for the reference arm, built with tensor ops only (torch standing in for Jittor): bind on the
+    face, numpy barycentric weights (the reference's get_barycentric_coordinate), analytic per-vertex R / S (pyACAP is a
+    CPU library of the reference that cannot be installed), deform_gaussian as its op chain."""
+
+    def __init__(self, device, rank, world):
+        import refcuda
+        from gaussianmesh_b200 import synthetic
+        from gaussianmesh_b200.cameras import upload_cameras
+        from gaussianmesh_b200.view_shard import shard_views
+        from oracle import python_path
+        V, F = synthetic.icosphere(4)
+        a = synthetic.mesh_bound_scene(EDIT_P, V, F, seed=0)
+        t = {k: torch.from_numpy(np.ascontiguousarray(v)).to(device) for k, v in a.items()}
+        bc = torch.softmax(t["bc_logits"], dim=1)
+        pos = (bc[:, 0:1] * t["vertex1"] + bc[:, 1:2] * t["vertex2"] + bc[:, 2:3] * t["vertex3"]).contiguous()
+        scales = torch.exp(t["log_scales"])
+        rots = torch.nn.functional.normalize(t["rot_raw"], dim=1)
+        self.opacity = torch.sigmoid(t["opacity_logit"]).contiguous()
+        self.shs = t["shs"]
+        Vd64 = V.astype(np.float64)
+        tri = a["triangles"]
+        w = python_path.get_barycentric_coordinate(pos.cpu().numpy().astype(np.float64), Vd64[tri[:, 0]], Vd64[tri[:, 1]],
+                                                   Vd64[tri[:, 2]]).astype(np.float32)
+        cov6 = torch.from_numpy(synthetic.packed_covariance(scales.cpu().numpy(), rots.cpu().numpy())).to(device)
+        Vd, R, S = synthetic.twist_bend_deformation(V)
+        f = lambda x: torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32)).to(device)
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        args = (f(V), f(Vd), f(R), f(S), torch.from_numpy(tri).to(device), f(w), pos, cov6)
+        refcuda.deform_gaussians_torch(*args)
+        torch.cuda.synchronize()
+        ev0.record()
+        self.deform_pos, self.deform_cov6, self.deform_rot = refcuda.deform_gaussians_torch(*args)
+        ev1.record()
+        torch.cuda.synchronize()
+        self.deform_ms = ev0.elapsed_time(ev1)
+        cams_host = synthetic.orbit_cameras(EDIT_VIEWS, WIDTH, HEIGHT)
+        self.cams = upload_cameras([cams_host[i] for i in shard_views(EDIT_VIEWS, world, rank)], device)
 
 
 def build_edit_workload(device, rank, world):
@@ -202,7 +255,6 @@ class ReferenceIteration:
 
     def __init__(self, device, arrays, W, H):
         import refcuda
-        from gaussianmesh_b200.training import OptimizationParams
         self.rc, self.W, self.H = refcuda, W, H
         t = {k: torch.from_numpy(np.ascontiguousarray(v)).to(device) for k, v in arrays.items()}
         self.t = t
@@ -210,7 +262,7 @@ class ReferenceIteration:
         self.bc, self.distance = leaf(t["bc_logits"]), leaf(t["distance"])
         self.f_dc, self.f_rest = leaf(t["shs"][:, :1].contiguous()), leaf(t["shs"][:, 1:].contiguous())
         self.opacity, self.scaling, self.rotation = leaf(t["opacity_logit"]), leaf(t["log_scales"]), leaf(t["rot_raw"])
-        o = self.o = OptimizationParams()
+        o = self.o = RefHyper
         self.optimizer = torch.optim.Adam([
             {"params": [self.bc], "lr": o.position_lr_init}, {"params": [self.distance], "lr": o.position_lr_init},
             {"params": [self.f_dc], "lr": o.feature_lr}, {"params": [self.f_rest], "lr": o.feature_lr / 20.0},
@@ -281,21 +333,30 @@ def _timed(fn, steps, warmup, barrier, pre=None, post=None):
     torch.cuda.synchronize()
     barrier()
     torch.cuda.synchronize()
-    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    # one event per step boundary (a marker in the stream, no stall): total = first -> last, plus per-step statistics
+    marks = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
     t0 = time.perf_counter()
-    start.record()
+    marks[0].record()
     if pre:
         pre()
     for i in range(steps):
         fn(warmup + i)
+        if not post:
+            marks[i + 1].record()
     if post:
         post()
-    stop.record()
+        marks[steps].record()
     timed.last_enqueue_ms = (time.perf_counter() - t0) * 1e3      # host time to enqueue K steps (diagnostic)
     torch.cuda.synchronize()
     wall = (time.perf_counter() - t0) * 1e3
     barrier()
-    return start.elapsed_time(stop), wall
+    if not post:
+        per = sorted(marks[i].elapsed_time(marks[i + 1]) for i in range(steps))
+        q = lambda f: per[min(len(per) - 1, int(f * len(per)))]
+        timed.last_step_stats = {"median_ms": statistics.median(per), "p10_ms": q(0.10), "p90_ms": q(0.90), "max_ms": per[-1]}
+    else:
+        timed.last_step_stats = None        # frames in flight on side streams: no per-step boundary on this stream
+    return marks[0].elapsed_time(marks[steps]), wall
 
 
 class OursArm:
@@ -374,6 +435,26 @@ class ReferenceArm:
     def counters(self):
         return (self.last_R, None, 0, None)
 
+    # ---- variant (i) of BASELINE.md 2.1: single-call Rasterizer::forward over persistent pre-sized chunks
+    def best_setup(self, cams, bg):
+        worst = 0
+        for cam in cams:
+            worst = max(worst, self._frame(cam, bg).R)
+        torch.cuda.synchronize()
+        s = self.scene
+        self.arena = self.rc.RefArena(self.device, s["means3D"].shape[0], self.H, self.W, s["shs"].shape[1], int(worst * 1.05) + 1024)
+
+    def best_train(self, cam, bg, target):
+        s = self.scene
+        color = self.arena.forward(bg, s["means3D"], s["opacities"], cam.world_view_transform, cam.full_proj_transform,
+                                   cam.camera_center, math.tan(cam.FoVx * 0.5), math.tan(cam.FoVy * 0.5), 3, shs=s["shs"],
+                                   scales=s["scales"], rotations=s["rotations"])
+        diff = color - target
+        loss = diff.abs().mean()
+        dL = torch.sign(diff) / diff.numel()
+        self.arena.backward(dL)
+        return loss
+
 
 def main():
     args = parse_args()
@@ -407,6 +488,7 @@ def main():
     prof = None
     ms_dev, _ = timed(train_resident, K, Wm, barrier)            # the headline region: no stage events
     enqueue_ms = timed.last_enqueue_ms
+    step_stats = timed.last_step_stats
     ms_prof = None
     if args.impl == "ours":
         # the same K steps again with every stage bracketed by CUDA events (per-kernel times for the roofline)
@@ -419,7 +501,7 @@ def main():
     ms_dev = max_over_ranks(ms_dev)
 
     # ---------------------------------------------------------------- (2) end to end with host inputs
-    from gaussianmesh_b200.renderer import DeviceCamera
+    from gaussianmesh_b200.cameras import DeviceCamera
     from gaussianmesh_b200.feed import HostFrameFeed
     loss_host = torch.zeros(1, dtype=torch.float32).pin_memory()
     if args.impl == "ours":
@@ -451,6 +533,7 @@ def main():
             loss_host.copy_(loss.reshape(1), non_blocking=True)
 
     ms_e2e, wall_e2e = timed(train_e2e, K, Wm, barrier)
+    e2e_stats = timed.last_step_stats
     arm.check()
     ms_e2e = max_over_ranks(max(ms_e2e, wall_e2e))
     loss_value = float(loss_host[0])
@@ -464,18 +547,48 @@ def main():
     arm.check()
     ms_fwd = max_over_ranks(ms_fwd)
 
+    # ---------------------------------------------------------------- (3b) N-GPU == 1-GPU: every rank renders global view 0
+    # (BASELINE.md 3 gate 3): the image bits must not depend on the rank / shard that produced them
+    from gaussianmesh_b200 import synthetic as _syn
+    from gaussianmesh_b200.cameras import DeviceCamera as _DC
+    view0 = _DC.upload(_syn.orbit_cameras(NUM_VIEWS, WIDTH, HEIGHT)[0], device)
+    if vb:
+        vb.begin_batch()
+    img0 = arm.forward(view0, bg)
+    if vb:
+        vb.end_batch()
+    torch.cuda.synchronize()
+    bits = img0.contiguous().view(torch.int32).to(torch.int64)
+    checksum = (int(bits.sum().item()), int((bits * torch.arange(1, bits.numel() + 1, device=device).view_as(bits) % 1000003).sum().item()))
+    shard_checksums = ctx.gather_objects(checksum)
+    shard_identical = all(c == shard_checksums[0] for c in shard_checksums)
+    arm.check()
+
+    # ---------------------------------------------------------------- (3c) reference only: its best case (variant i)
+    ref_best = None
+    if args.impl == "reference":
+        arm.best_setup(cams, bg)
+        ms_best, _ = timed(lambda i: arm.best_train(cams[i % nv], bg, targets[i % TARGET_POOL]), K, Wm, barrier)
+        ms_best = max_over_ranks(ms_best)
+        ref_best = {"value": world * K / (ms_best * 1e-3), "unit": UNIT, "ms_per_step": ms_best / K,
+                    "step_ms": timed.last_step_stats,
+                    "what": "BASELINE.md 2.1 variant (i): Rasterizer::forward (single call, its own mid-frame host read) over "
+                            "persistent pre-sized chunks, no per-frame allocation or chunk memset; backward into one "
+                            "pre-allocated gradient slab zeroed once per frame; torch elementwise L1"}
+        del arm.arena
+
     # ---------------------------------------------------------------- (4) edit path (config 5): deform once, orbit render
-    obj, (Vd, Rv, Sv), edit_cams, acap_ms = build_edit_workload(device, rank, world)
     white = torch.ones(3, dtype=torch.float32, device=device)
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize()
-    ev0.record()
-    obj.deform(Vd, Rv, Sv)
-    ev1.record()
-    torch.cuda.synchronize()
-    deform_ms = ev0.elapsed_time(ev1)
-    ne = len(edit_cams)
     if args.impl == "ours":
+        obj, (Vd, Rv, Sv), edit_cams, acap_ms = build_edit_workload(device, rank, world)
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        ev0.record()
+        obj.deform(Vd, Rv, Sv)
+        ev1.record()
+        torch.cuda.synchronize()
+        deform_ms = ev0.elapsed_time(ev1)
+        ne = len(edit_cams)
         from gaussianmesh_b200.arena import RenderArena
         edit_arena = RenderArena(device, strict=False)
 
@@ -485,6 +598,9 @@ def main():
         edit_arena.reserve(int(edit_arena.high_water * 1.5))
     else:
         import refcuda
+        obj = RefEditObject(device, rank, world)          # torch ops only: the reference arm never maps our library
+        edit_cams, deform_ms, acap_ms = obj.cams, obj.deform_ms, None
+        ne = len(edit_cams)
 
         def edit_frame(i):
             cam = edit_cams[i % ne]
@@ -541,11 +657,22 @@ def main():
                 if vp.it.arena.verify():
                     raise RuntimeError("arena overflow inside the timed view-parallel region")
                 ms_vp = max_over_ranks(ms_vp)
-                view_parallel[mode] = {"ms_per_step": ms_vp / K, "views_per_s": world * K / (ms_vp * 1e-3)}
-                del vp, vp_model
+                # every replica must hold the same parameters after the same global steps
+                flat = torch.cat([p_.detach().reshape(-1) for p_ in vp_model.parameters()]).contiguous().view(torch.int32).to(torch.int64)
+                psum = (int(flat.sum().item()), int((flat[::97] * 31 % 1000003).sum().item()))
+                sums = ctx.gather_objects(psum)
+                view_parallel[mode] = {"ms_per_step": ms_vp / K, "views_per_s": world * K / (ms_vp * 1e-3),
+                                       "step_ms": timed.last_step_stats,
+                                       "replicas_identical": all(c == sums[0] for c in sums)}
+                del vp, vp_model, flat
             except Exception as ex:       # keep the headline numbers if symmetric memory is unavailable on a box
                 view_parallel[mode] = {"error": repr(ex)[:300]}
     clocks = sampler.stop() if sampler is not None else None
+    replicas_identical = None
+    if view_parallel is not None:
+        flags = [view_parallel[m].get("replicas_identical") for m in ("nccl", "p2p") if isinstance(view_parallel.get(m), dict)]
+        flags = [f for f in flags if f is not None]
+        replicas_identical = all(flags) if flags else None
 
     if rank != 0:
         ctx.close()
@@ -564,7 +691,10 @@ def main():
                    "l2": "inputs larger than L2 (scene 236 MB + 300 MB gradients + 150 MB binning per frame; a different "
                          "view every step)"},
         "e2e": {"value": N * K / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
-                "ms_per_step": ms_e2e / K, "loss": loss_value},
+                "ms_per_step": ms_e2e / K, "loss": loss_value, "step_ms": e2e_stats},
+        "step_ms": step_stats,
+        "shard_identical": shard_identical,
+        "replicas_identical": replicas_identical,
         "forward": {"value": N * K / (ms_fwd * 1e-3), "unit": UNIT, "ms_per_frame": ms_fwd / K,
                     "frames_in_flight": FORWARD_LANES if args.impl == "ours" else 1},
         "edit": {"value": N * K / (ms_edit * 1e-3), "unit": UNIT, "ms_per_frame": ms_edit / K, "deform_ms": deform_ms,
@@ -583,15 +713,36 @@ def main():
                                      "p2p": "gm_adam_step_sharded_p2p: reduce-scatter + Adam + all-gather in one kernel over "
                                             "NVLink peer memory (symmetric memory), optimizer state sharded"}
         out["view_parallel"] = view_parallel
+    # ---- cross-arm correctness guard: both arms run the same K + W steps on the same views / targets, so the loss of the
+    # last end-to-end step must agree.  Each arm leaves its value in a scratch file; the arm that runs second compares.
+    key = f"P{P}_N{N}_K{K}_W{Wm}"
+    guard_path = os.path.join(tempfile.gettempdir(), "gm_bench_e2e_loss.json")
+    try:
+        guard = json.load(open(guard_path)) if os.path.exists(guard_path) else {}
+    except (OSError, ValueError):
+        guard = {}
+    other = guard.get(key, {}).get("ours" if args.impl == "reference" else "reference")
+    if other is not None:
+        out["e2e"]["other_arm_loss"] = other
+        out["e2e"]["loss_matches_other_arm"] = bool(abs(other - loss_value) <= 1e-5)
+    guard.setdefault(key, {})[args.impl] = loss_value
+    try:
+        json.dump(guard, open(guard_path, "w"))
+    except OSError:
+        pass
+    if other is not None and not out["e2e"]["loss_matches_other_arm"]:
+        print(f"bench.py: e2e loss {loss_value!r} of arm {args.impl!r} differs from the other arm's {other!r}", file=sys.stderr)
+
     if args.impl == "reference":
         out["impl"] = "reference"
+        out["reference_best"] = ref_best
         out["gpu_launches"] = 0
         out["instances_per_frame"] = info[0]
         out["cpu_baseline"] = {"value": out["value"], "unit": UNIT, "cores": 0, "kind": "reference",
                                "sample": "the reference's own implementation of this path is CUDA: its unmodified "
                                          "cuda_rasterizer sources rebuilt for sm_100a (oracle/_ref), run on the same GPU "
                                          "with the call protocol of its rasterize_points.py, all K steps"}
-        out["e2e"] = {"value": out["e2e"]["value"], "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4}
+        out["e2e"] = {k: v for k, v in out["e2e"].items()}      # value, unit, copies, loss, step statistics, cross-arm guard
         print(json.dumps(out))
         ctx.close()
         return

@@ -25,41 +25,12 @@ from . import mesh_gaussians as mg
 from ._lib import lib, check, GM_BACKWARD_OVERWRITE
 from .arena import RenderArena
 from .diff_gaussian_rasterizater import (GaussianRasterizationSettings, GaussianRasterizer, NewGaussianRasterizer)
-from .synthetic import Camera
+from .cameras import DeviceCamera, upload_cameras  # noqa: F401  (re-exported)
+from .synthetic import Camera  # noqa: F401
 from .view_shard import shard_views, ShardContext  # noqa: F401  (re-exported)
 
 
-# ---------------------------------------------------------------------------------------------
-# views
-# ---------------------------------------------------------------------------------------------
-@dataclass
-class DeviceCamera:
-    """A view with its three small matrices resident on the device."""
-    image_width: int
-    image_height: int
-    FoVx: float
-    FoVy: float
-    world_view_transform: torch.Tensor
-    full_proj_transform: torch.Tensor
-    camera_center: torch.Tensor
-
-    @staticmethod
-    def from_packed(cam: Camera, packed: torch.Tensor) -> "DeviceCamera":
-        """`packed` is a [35] device tensor: viewmatrix | projmatrix | campos (Camera.packed())."""
-        return DeviceCamera(cam.image_width, cam.image_height, cam.FoVx, cam.FoVy,
-                            packed[0:16].view(4, 4), packed[16:32].view(4, 4), packed[32:35])
-
-    @staticmethod
-    def upload(cam: Camera, device) -> "DeviceCamera":
-        return DeviceCamera.from_packed(cam, torch.from_numpy(cam.packed()).to(device))
-
-
-def upload_cameras(cams: Sequence[Camera], device) -> List[DeviceCamera]:
-    """One H2D copy for the whole camera set."""
-    if not cams:
-        return []
-    packed = torch.from_numpy(np.stack([c.packed() for c in cams])).to(device)
-    return [DeviceCamera.from_packed(c, packed[i]) for i, c in enumerate(cams)]
+# views: DeviceCamera / upload_cameras live in cameras.py (no dependency on the library) and are re-exported here
 
 
 def make_settings(cam, bg: torch.Tensor, sh_degree: int, scaling_modifier: float = 1.0, debug: bool = False
@@ -203,7 +174,11 @@ def render(viewpoint_camera, pc: MeshGaussianModel, pipe: PipelineParams, bg_col
            bg_gaussian: Optional["GaussianModel"] = None, arena: Optional[RenderArena] = None) -> Dict[str, torch.Tensor]:
     """reference gaussian_renderer/__init__.py:26-143, every branch: CUDA or Python SH colours, CUDA or Python
     covariance, and the optional frozen `bg_gaussian` set appended as precomputed covariance (+ precomputed colours
-    when the foreground has them), :100-121 -- which, as in the reference, needs compute_cov3D_python."""
+    when the foreground has them), :100-121 -- which, as in the reference, needs compute_cov3D_python.
+
+    Reference quirk kept by the glue: rasterize_points.py:154-158 derives the SH row length M from the SH tensor only when
+    no precomputed covariance is passed, so compute_cov3D_python WITHOUT convert_SHs_python rasterizes with M = 0 (every
+    Gaussian evaluates SH row 0) -- in the reference and here alike."""
     means3D, scales, rotations, opacity = pc.activate()
     P = means3D.shape[0]
     screenspace_points = _fresh_screenspace_points(pc, P, means3D.device)

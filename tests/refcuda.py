@@ -111,8 +111,10 @@ class RefFrame:
         return {"final_T": self.image[o0:o0 + 4 * N].view(torch.float32).view(self.H, self.W).clone(),
                 "n_contrib": self.image[o1:o1 + 4 * N].view(torch.int32).view(self.H, self.W).clone()}
 
-    def backward(self, dL_dpix: torch.Tensor, sync=True) -> Dict[str, torch.Tensor]:
-        P, M = self.P, self.M
+    def backward(self, dL_dpix: torch.Tensor, sync=True, M: Optional[int] = None) -> Dict[str, torch.Tensor]:
+        """`M` overrides the SH row length of the forward: the reference's backward glue takes it from the SH tensor alone
+        (rasterize_points.py:301) even when its forward ran with M = 0 (:154-158)."""
+        P, M = self.P, (self.M if M is None else M)
         dev = dL_dpix.device
         i = self.inputs
         z = lambda *s: torch.zeros(*s, dtype=torch.float32, device=dev)
@@ -133,6 +135,78 @@ class RefFrame:
         if M == 0:
             g["sh"] = g["sh"][:, :0]
         return g
+
+
+class RefArena:
+    """The reference's best case (BASELINE.md 2.1 variant i, SURVEY.md 8d): its single-call Rasterizer::forward
+    (rasterizer_impl.cu:198-336) over PERSISTENT, pre-sized chunks -- no per-frame allocation, no memset of the chunks --
+    and its backward into one pre-allocated gradient slab (zeroed once per frame: the reference's backward accumulates
+    with atomics).  The mid-frame host read of num_rendered is inside Rasterizer::forward and stays."""
+
+    def __init__(self, device, P: int, H: int, W: int, M: int, binning_instances: int):
+        l = lib()
+        self.P, self.H, self.W, self.M = P, H, W, M
+        self.geom = torch.empty(l.ref_required_geom(P), dtype=torch.uint8, device=device)
+        self.image = torch.empty(l.ref_required_image(H * W), dtype=torch.uint8, device=device)
+        self.binning = torch.empty(l.ref_required_binning(int(binning_instances)), dtype=torch.uint8, device=device)
+        self.radii = torch.empty(P, dtype=torch.int32, device=device)
+        self.color = torch.empty(3, H, W, dtype=torch.float32, device=device)
+        self._needed = C.c_size_t(0)
+        sizes = {"means2D": 3 * P, "conic": 4 * P, "opacity": P, "colors": 3 * P, "means3D": 3 * P, "cov3D": 6 * P,
+                 "sh": 3 * max(M, 1) * P, "scales": 3 * P, "rotations": 4 * P}
+        total = sum(sizes.values())
+        self.slab = torch.empty(total, dtype=torch.float32, device=device)
+        self.grads, off = {}, 0
+        for k, n in sizes.items():
+            self.grads[k] = self.slab[off:off + n]
+            off += n
+        self.R = 0
+
+    def forward(self, bg, means3D, opacities, viewmatrix, projmatrix, campos, tanfovx, tanfovy, degree, shs=None, colors=None,
+                scales=None, rotations=None, cov3D=None, scale_modifier=1.0):
+        self._args = (means3D, shs, colors, opacities, scales, float(scale_modifier), rotations, cov3D, viewmatrix, projmatrix,
+                      campos, float(tanfovx), float(tanfovy), bg, degree)
+        va = (_ptr(means3D), _ptr(shs), _ptr(colors), _ptr(opacities), _ptr(scales), float(scale_modifier), _ptr(rotations),
+              _ptr(cov3D), _ptr(viewmatrix), _ptr(projmatrix), _ptr(campos), float(tanfovx), float(tanfovy))
+        R = lib().ref_forward(self.geom.data_ptr(), self.geom.numel(), self.binning.data_ptr(), self.binning.numel(),
+                              self.image.data_ptr(), self.image.numel(), self.P, degree, self.M, _ptr(bg), self.W, self.H, *va, 0,
+                              self.color.data_ptr(), self.radii.data_ptr(), 0, C.byref(self._needed))
+        if R == -2:
+            raise RuntimeError(f"reference arena too small: binning needs {self._needed.value} bytes")
+        assert R >= 0, "reference forward failed"
+        self.R = R
+        return self.color
+
+    def backward(self, dL_dpix: torch.Tensor) -> Dict[str, torch.Tensor]:
+        means3D, shs, colors, opacities, scales, mod, rotations, cov3D, viewmatrix, projmatrix, campos, tx, ty, bg, degree = self._args
+        self.slab.zero_()
+        g = self.grads
+        rc = lib().ref_backward(self.P, degree, self.M, self.R, _ptr(bg), self.W, self.H, _ptr(means3D), _ptr(shs), _ptr(colors),
+                                _ptr(scales), mod, _ptr(rotations), _ptr(cov3D), _ptr(viewmatrix), _ptr(projmatrix), _ptr(campos),
+                                tx, ty, self.radii.data_ptr(), self.geom.data_ptr(), self.binning.data_ptr(),
+                                self.image.data_ptr(), dL_dpix.data_ptr(), g["means2D"].data_ptr(), g["conic"].data_ptr(),
+                                g["opacity"].data_ptr(), g["colors"].data_ptr(), g["means3D"].data_ptr(), g["cov3D"].data_ptr(),
+                                g["sh"].data_ptr(), g["scales"].data_ptr(), g["rotations"].data_ptr(), 0)
+        assert rc == 0, "reference backward failed"
+        return g
+
+
+def deform_gaussians_torch(vertex, vertex_deformed, vertex_R, vertex_S, triangles, weights, pos, cov6):
+    """SingleObjectDeform.deform_gaussian (edittool/__init__.py:103-131) as the tensor-op chain the reference runs (torch
+    standing in for Jittor).  cov6 packed in / out; returns (pos', cov6', R_g)."""
+    tri = triangles.long()
+    w_pos = weights[:, :, None]
+    w_rs = weights[:, :, None, None]
+    g_delta_pos = (w_pos * (vertex_deformed - vertex)[tri]).sum(dim=1)
+    g_delta_r = (w_rs * vertex_R[tri]).sum(dim=1)
+    rot = g_delta_r.transpose(1, 2)
+    g_delta_s = (w_rs * vertex_S[tri]).sum(dim=1)
+    g_delta_rs = torch.matmul(rot, g_delta_s)
+    c = cov6
+    full = torch.stack([c[:, 0], c[:, 1], c[:, 2], c[:, 1], c[:, 3], c[:, 4], c[:, 2], c[:, 4], c[:, 5]], dim=1).view(-1, 3, 3)
+    d = torch.matmul(torch.matmul(g_delta_rs, full), g_delta_rs.transpose(1, 2))
+    cov_out = torch.stack([d[:, 0, 0], d[:, 0, 1], d[:, 0, 2], d[:, 1, 1], d[:, 1, 2], d[:, 2, 2]], dim=1).contiguous()
+    return (pos + g_delta_pos).contiguous(), cov_out, rot.contiguous()
 
 
 def edit_colors_torch(pos: torch.Tensor, campos: torch.Tensor, rot: torch.Tensor, shs: torch.Tensor, deg: int = 3) -> torch.Tensor:

@@ -700,6 +700,7 @@ def test_render_python_pipeline_variants(cuda_device, flags):
     _need_ref()
     from gaussianmesh_b200 import synthetic
     from gaussianmesh_b200.renderer import MeshGaussianModel, PipelineParams, render
+    from gaussianmesh_b200.mesh_gaussians import covariance_from_scaling_rotation, sh_to_rgb_rotated
     from oracle import python_path
     dev = cuda_device
     cov_py, sh_py = flags
@@ -727,11 +728,15 @@ def test_render_python_pipeline_variants(cuda_device, flags):
     else:
         ref_in["scales"] = torch.from_numpy(inp["scales"]).to(dev)
         ref_in["rotations"] = torch.from_numpy(inp["rotations"]).to(dev)
-    ref = _ref(ref_in, cam, bgt, 3, variant)
-    # the oracle's numpy activations differ from the kernels' by an ulp here and there: radii may flip for a handful
+    # rasterize_points.py:154-158 takes M from the SH tensor only when NO precomputed covariance is given: with CUDA SHs and
+    # a Python covariance the reference itself runs with M = 0 (every Gaussian reads SH row 0).  The glue keeps the quirk.
+    m_quirk = 0 if (cov_py and not sh_py) else None
+    ref = _ref(ref_in, cam, bgt, 3, variant, M=m_quirk)
+    # the oracle's numpy activations differ from the kernels' by an ulp here and there: a radius or an alpha < 1/255
+    # decision may flip for a handful of Gaussians (<= 1/255 per pixel each); the strict comparison follows below
     assert int((out["radii"] != ref.radii).sum()) <= 3
-    err = float((out["render"].detach() - ref.color).abs().max())
-    assert err <= 2e-4, f"forward L-inf {err:.3e}"
+    diff = (out["render"].detach() - ref.color).abs()
+    assert float(diff.max()) <= 5e-3 and float(diff.mean()) <= 1e-6, (float(diff.max()), float(diff.mean()))
 
     # gradients: reference backward on OUR activations, chained through the torch op chains
     with torch.no_grad():
@@ -743,17 +748,24 @@ def test_render_python_pipeline_variants(cuda_device, flags):
     rin = {"means3D": xyz, "opacities": opac}
     if sh_py:
         col_t = refcuda.edit_colors_torch(xyz_l, cam.camera_center, torch.eye(3, device=dev).expand(P, 3, 3), leaf["shs"], 3)
-        rin["colors"] = col_t.detach().contiguous()
+        with torch.no_grad():       # the reference gets OUR kernels' tensors (identical inputs); torch supplies the chain rule
+            rin["colors"] = sh_to_rgb_rotated(xyz, cam.camera_center, None, pc._features, 3)
+        assert float((rin["colors"] - col_t).abs().max()) <= 2e-5
     else:
         rin["shs"] = leaf["shs"].detach()
     if cov_py:
         cov_t = _cov_python_torch(sc_t, leaf["rot_raw"], 1.0)
-        rin["cov3D"] = cov_t.detach().contiguous()
+        with torch.no_grad():
+            rin["cov3D"] = covariance_from_scaling_rotation(scales, 1.0, pc._rotation)
+        assert float((rin["cov3D"] - cov_t).abs().max()) <= 2e-6 * float(cov_t.abs().max())
     else:
         rot_t = torch.nn.functional.normalize(leaf["rot_raw"], dim=1)
-        rin["scales"], rin["rotations"] = sc_t.detach(), rot_t.detach()
-    ref2 = _ref(rin, cam, bgt, 3, variant)
-    rg = ref2.backward(dL)
+        rin["scales"], rin["rotations"] = scales, rot
+    ref2 = _ref(rin, cam, bgt, 3, variant, M=m_quirk)
+    assert torch.equal(out["radii"], ref2.radii)
+    err = float((out["render"].detach() - ref2.color).abs().max())
+    assert err <= FWD_TOL, f"forward L-inf {err:.3e}"
+    rg = ref2.backward(dL, M=16 if m_quirk == 0 else None)      # rasterize_points.py:301: the backward always uses sh.size(1)
     outs, gs = [], []
     if sh_py:
         outs.append(col_t); gs.append(rg["colors"])
@@ -806,10 +818,10 @@ def test_render_with_frozen_background_gaussians(cuda_device):
             else:
                 rin["shs"] = torch.cat([pc._features, bgm._features]).contiguous()
         variant = ("colors" if sh_py else "sh") + "+cov"
-        ref = _ref(rin, cam, bgt, 3, variant)
+        ref = _ref(rin, cam, bgt, 3, variant, M=None if sh_py else 0)      # rasterize_points.py:154-158: M = 0 with a covariance
         assert torch.equal(out["radii"], ref.radii)
         assert float((out["render"].detach() - ref.color).abs().max()) <= FWD_TOL
-        rg = ref.backward(dL)
+        rg = ref.backward(dL, M=None if sh_py else 16)
         scenes.assert_grad(out["viewspace_points"].grad, rg["means2D"], "viewspace", BWD_TOL)
         if not sh_py:
             scenes.assert_grad(pc._features.grad, rg["sh"][:n], "features", BWD_TOL)
