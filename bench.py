@@ -9,8 +9,9 @@ independent views sharded over N GPUs (one process per GPU, no collective on the
 Rank 0 prints ONE JSON line.  Keys (see DESIGN.md "Measurement"):
   value / ms_per_step   training frames per second over all ranks, inputs resident in HBM, CUDA-event timed,
                         max over ranks
-  e2e                   the same step driven with HOST inputs: per step the camera (140 B) and the target image
-                        (24.9 MB) are copied from pinned host memory and the loss is read back
+  e2e                   the same step driven with HOST inputs: per step the camera (140 B) and the 8-bit target image
+                        (6.2 MB, as the reference's loader holds it before / 255.0) are copied from pinned host memory and
+                        the loss is read back
   forward               forward-only rendering of the rank's view shard (config 3), frames/s
   edit                  config 5: deform once, then rotated-direction SH colours + forward per orbit frame
   train_iteration       the whole iteration of train_mesh_gaussian.py:73-147 on mesh-bound Gaussians (bind, render,
@@ -124,10 +125,14 @@ def build_workload(device, P, rank, world):
     mine = list(shard_views(NUM_VIEWS, world, rank))
     cams_host = [cams_host[i] for i in mine]
     cams = upload_cameras(cams_host, device)
+    # targets are 8-bit images, as the reference's loader reads them (float = uint8 / 255.0, utils/general_utils.py:22-27):
+    # the host copies stay uint8 (6.2 MB each), the resident copies are uint8 as well as float32
     rng = np.random.default_rng(1)
-    targets_host = [torch.from_numpy(rng.uniform(0.0, 1.0, size=(3, HEIGHT, WIDTH)).astype(np.float32)).pin_memory()
+    targets_host = [torch.from_numpy(rng.integers(0, 256, size=(3, HEIGHT, WIDTH), dtype=np.uint8)).pin_memory()
                     for _ in range(TARGET_POOL)]
-    targets = [t.to(device) for t in targets_host]
+    targets_u8 = [t.to(device) for t in targets_host]
+    targets = [t.float() / 255.0 for t in targets_u8]
+    build_workload.targets_u8 = targets_u8
     cams_packed_host = torch.from_numpy(np.stack([c.packed() for c in cams_host])).pin_memory()
     return scene, cams_host, cams, targets_host, targets, cams_packed_host
 
@@ -482,8 +487,12 @@ def main():
         arm.setup(cams, bg)
 
     # ---------------------------------------------------------------- (1) device-resident training frames
+    # ours reads the resident 8-bit image directly (value / 255 inside the loss kernel); the reference's glue takes the
+    # float image its loader produced
+    train_targets = build_workload.targets_u8 if args.impl == "ours" else targets
+
     def train_resident(i):
-        arm.train(cams[i % nv], bg, targets[i % TARGET_POOL])
+        arm.train(cams[i % nv], bg, train_targets[i % TARGET_POOL])
 
     prof = None
     ms_dev, _ = timed(train_resident, K, Wm, barrier)            # the headline region: no stage events
@@ -507,7 +516,7 @@ def main():
     if args.impl == "ours":
         # frame i+1's camera and target upload on a copy stream while frame i renders (every copy is still
         # inside the timed region; the loop is primed with frame 0's upload)
-        feed = HostFrameFeed(device, [(35,), (3, HEIGHT, WIDTH)])
+        feed = HostFrameFeed(device, [(35,), (3, HEIGHT, WIDTH)], dtypes=[torch.float32, torch.uint8])
 
         def upload(i):
             feed.push(cams_packed_host[i % nv], targets_host[i % TARGET_POOL])
@@ -523,13 +532,13 @@ def main():
     else:
         # the reference's glue uploads on the compute stream
         cam_dev = torch.empty(35, dtype=torch.float32, device=device)
-        target_dev = torch.empty(3, HEIGHT, WIDTH, dtype=torch.float32, device=device)
+        target_dev = torch.empty(3, HEIGHT, WIDTH, dtype=torch.uint8, device=device)
         e2e_cam = DeviceCamera.from_packed(cams_host[0], cam_dev)
 
         def train_e2e(i):
             cam_dev.copy_(cams_packed_host[i % nv], non_blocking=True)
             target_dev.copy_(targets_host[i % TARGET_POOL], non_blocking=True)
-            loss = arm.train(e2e_cam, bg, target_dev)
+            loss = arm.train(e2e_cam, bg, target_dev.float() / 255.0)       # PILtoTorch: uint8 -> float / 255.0
             loss_host.copy_(loss.reshape(1), non_blocking=True)
 
     ms_e2e, wall_e2e = timed(train_e2e, K, Wm, barrier)
@@ -679,13 +688,13 @@ def main():
         return
 
     N = world
-    h2d = cams_packed_host[0].numel() * 4 + targets_host[0].numel() * 4
+    h2d = cams_packed_host[0].numel() * 4 + targets_host[0].numel() * targets_host[0].element_size()
     out = {
         "metric": METRIC, "value": N * K / (ms_dev * 1e-3), "unit": UNIT, "n_gpus": N, "steps": K, "warmup": Wm,
         "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{P} Gaussians (SH degree 3, scale/rotation path), {WIDTH}x{HEIGHT}, forward + L1 to a random "
-                               f"target + full backward per frame; {NUM_VIEWS}-view orbit sharded over {N} GPU(s) in contiguous "
+                               f"8-bit target image + full backward per frame; {NUM_VIEWS}-view orbit sharded over {N} GPU(s) in contiguous "
                                "blocks, no collective on the render path",
                    "gaussians": P, "width": WIDTH, "height": HEIGHT, "views": NUM_VIEWS, "views_per_rank": nv,
                    "l2": "inputs larger than L2 (scene 236 MB + 300 MB gradients + 150 MB binning per frame; a different "

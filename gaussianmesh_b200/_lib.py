@@ -76,6 +76,8 @@ SIGNATURES = {
     "gm_cov3d_from_scale_rot_backward": (_i, [_i, _p, _f, _p, _p, _p, _p, _p]),
     "gm_load_mesh": (_i, [_i, _i, _i, _p, _p, _p, _p, _p, _p, _p]),
     "gm_l1_loss": (_i, [_z, _p, _p, _p, _p, _p]),
+    "gm_l1_loss_u8": (_i, [_z, _p, _p, _p, _p, _p]),
+    "gm_image_u8_to_float": (_i, [_z, _p, _p, _p]),
     "gm_photometric_scratch_bytes": (_z, [_i, _i, _i]),
     "gm_photometric_loss": (_i, [_i, _i, _i, _p, _p, _f, _p, _p, _p, _p]),
     "gm_mesh_restrict_loss": (_i, [_i, _p, _p, _p, _p, _f, _p, _p, _i, _p]),

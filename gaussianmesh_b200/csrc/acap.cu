@@ -40,6 +40,7 @@ __global__ void __launch_bounds__(kThreads)
 acap_normals_kernel(int Vn, const double* __restrict__ V, const int* __restrict__ F, const int* __restrict__ face_off,
                     const int* __restrict__ face_list, double* __restrict__ normals)
 {
+	pdl_sync();
 	const int i = blockIdx.x * kThreads + threadIdx.x;
 	if (i >= Vn)
 		return;
@@ -78,6 +79,7 @@ __global__ void __launch_bounds__(kThreads)
 acap_rest_kernel(int Vn, const double* __restrict__ V, const int* __restrict__ ring_off, const int* __restrict__ ring,
                  const double* __restrict__ normals, double* __restrict__ sqrt_w, double* __restrict__ ata_inv)
 {
+	pdl_sync();
 	const int i = blockIdx.x * kThreads + threadIdx.x;
 	if (i >= Vn)
 		return;
@@ -159,6 +161,7 @@ acap_rs_kernel(int Vn, const double* __restrict__ V0, const double* __restrict__
                const double* __restrict__ n1, const double* __restrict__ ata_inv, float* __restrict__ R_out,
                float* __restrict__ S_out)
 {
+	pdl_sync();
 	const int i = blockIdx.x * kThreads + threadIdx.x;
 	if (i >= Vn)
 		return;
@@ -231,8 +234,8 @@ int launch_acap_rest(int Vn, const double* V, const int* F, const int* ring_off,
 {
 	if (Vn <= 0) return GM_OK;
 	const int blocks = (Vn + kThreads - 1) / kThreads;
-	acap_normals_kernel<<<blocks, kThreads, 0, stream>>>(Vn, V, F, face_off, face_list, normals);
-	acap_rest_kernel<<<blocks, kThreads, 0, stream>>>(Vn, V, ring_off, ring, normals, sqrt_w, ata_inv);
+	launch_k(acap_normals_kernel, dim3(blocks), dim3(kThreads), 0, stream, Vn, V, F, face_off, face_list, normals);
+	launch_k(acap_rest_kernel, dim3(blocks), dim3(kThreads), 0, stream, Vn, V, ring_off, ring, normals, sqrt_w, ata_inv);
 	return GM_OK;
 }
 
@@ -242,8 +245,8 @@ int launch_acap_get_rs(int Vn, const double* V0, const double* V1, const int* F,
 {
 	if (Vn <= 0) return GM_OK;
 	const int blocks = (Vn + kThreads - 1) / kThreads;
-	acap_normals_kernel<<<blocks, kThreads, 0, stream>>>(Vn, V1, F, face_off, face_list, n1_scratch);
-	acap_rs_kernel<<<blocks, kThreads, 0, stream>>>(Vn, V0, V1, ring_off, ring, sqrt_w, n0, n1_scratch, ata_inv, R_out, S_out);
+	launch_k(acap_normals_kernel, dim3(blocks), dim3(kThreads), 0, stream, Vn, V1, F, face_off, face_list, n1_scratch);
+	launch_k(acap_rs_kernel, dim3(blocks), dim3(kThreads), 0, stream, Vn, V0, V1, ring_off, ring, sqrt_w, n0, n1_scratch, ata_inv, R_out, S_out);
 	return GM_OK;
 }
 

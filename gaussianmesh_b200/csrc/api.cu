@@ -4,6 +4,7 @@
 //     (declared in csrc/cuda_rasterizer/rasterizer.h, mirroring dgr/cuda_rasterizer/rasterizer.h).
 // No device memory is allocated here; all scratch lives in the caller's three chunks.
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <stdexcept>
@@ -21,6 +22,12 @@ static thread_local std::string g_last_error;
 void set_last_error(const char* what, cudaError_t err)
 {
 	g_last_error = std::string(what) + ": " + cudaGetErrorString(err);
+}
+
+bool pdl_enabled()
+{
+	static const bool on = !(std::getenv("GM_PDL") != nullptr && std::getenv("GM_PDL")[0] == '0');
+	return on;
 }
 
 // The reference's CHECK_CUDA (auxiliary.h:165-172): synchronise + check only in debug mode.  Launch
@@ -555,8 +562,24 @@ int gm_l1_loss(size_t numel, const float* img, const float* target, float* loss,
 {
 	if (loss == nullptr || (numel > 0 && (!img || !target)))
 		return GM_ERR_BAD_ARGUMENT;
-	{ StageScope scope_(kStL1, (cudaStream_t)stream); launch_l1(numel, img, target, loss, dL_dimg, (cudaStream_t)stream); }
+	{ StageScope scope_(kStL1, (cudaStream_t)stream); launch_l1(numel, img, target, 0, loss, dL_dimg, (cudaStream_t)stream); }
 	return check_stage("l1_loss", false, (cudaStream_t)stream);
+}
+
+int gm_l1_loss_u8(size_t numel, const float* img, const uint8_t* target, float* loss, float* dL_dimg, gm_stream_t stream)
+{
+	if (loss == nullptr || (numel > 0 && (!img || !target)))
+		return GM_ERR_BAD_ARGUMENT;
+	{ StageScope scope_(kStL1, (cudaStream_t)stream); launch_l1(numel, img, target, 1, loss, dL_dimg, (cudaStream_t)stream); }
+	return check_stage("l1_loss", false, (cudaStream_t)stream);
+}
+
+int gm_image_u8_to_float(size_t numel, const uint8_t* src, float* dst, gm_stream_t stream)
+{
+	if (numel > 0 && (!src || !dst))
+		return GM_ERR_BAD_ARGUMENT;
+	launch_u8_to_float(numel, src, dst, (cudaStream_t)stream);
+	return check_stage("image_u8_to_float", false, (cudaStream_t)stream);
 }
 
 size_t gm_photometric_scratch_bytes(int C, int H, int W) { return photometric_scratch_bytes(C, H, W); }

@@ -35,6 +35,7 @@ constexpr unsigned long long kFlagAggregate = 1ull << 32, kFlagInclusive = 2ull 
 __global__ void __launch_bounds__(kScanThreads)
 tile_scan_kernel(int num_tiles, int bucket_log2, GeometryState g, uint32_t capacity)
 {
+	pdl_sync();
 	__shared__ uint32_t warp_sums[kScanThreads / 32];
 	__shared__ uint32_t s_block, s_base;
 	const int tid = threadIdx.x;
@@ -129,6 +130,7 @@ __global__ void __launch_bounds__(kEmitThreads)
 emit_kernel(int P, const int* __restrict__ radii, GeometryState g, BinningState b, uint32_t capacity,
             int W, int H, int tiles_x, int tiles_y, int bucket_log2)
 {
+	pdl_sync();
 	const int idx = blockIdx.x * kEmitThreads + threadIdx.x;
 	if (idx >= P)
 		return;
@@ -188,6 +190,7 @@ __global__ void __launch_bounds__(kLargeThreads)
 large_tiles_kernel(int phase, const int* __restrict__ radii, GeometryState g, uint64_t* __restrict__ keys,
                    uint32_t capacity, int W, int H, int tiles_x, int tiles_y, int bucket_log2)
 {
+	pdl_sync();
 	const int lane = threadIdx.x & 31;
 	const uint32_t warps = gridDim.x * (kLargeThreads / 32);
 	const uint32_t n = g.header->num_large;
@@ -348,6 +351,7 @@ __device__ __forceinline__ void block_bitonic(Ptr a, uint32_t n)
 __global__ void __launch_bounds__(kSortThreads)
 bucket_sort_pack_kernel(GeometryState g, BinningState b, uint32_t capacity, int bucket_log2, uint32_t num_buckets_total)
 {
+	pdl_sync();
 	const int lane = threadIdx.x & 31;
 	const uint32_t gw = blockIdx.x * kSortWarps + (threadIdx.x >> 5);
 	if (gw >= num_buckets_total)
@@ -383,6 +387,7 @@ constexpr size_t kBigSmemBytes = (size_t)kSortSmem * sizeof(uint64_t);
 __global__ void __launch_bounds__(kSortThreads)
 big_bucket_sort_pack_kernel(GeometryState g, BinningState b, uint32_t capacity, int bucket_log2)
 {
+	pdl_sync();
 	extern __shared__ __align__(16) unsigned char big_smem[];
 	uint64_t* const s_part = reinterpret_cast<uint64_t*>(big_smem);      // [kSortSmem] keys partitioned by sub-bucket
 	__shared__ uint32_t s_cnt[kSubMax], s_off[kSubMax + 1], s_lo[kSortWarps], s_hi[kSortWarps], s_fallback;
@@ -488,14 +493,14 @@ int launch_tile_scan(int num_tiles, const GeometryState& g, uint32_t capacity, c
 {
 	if (num_tiles <= 0)
 		return GM_OK;
-	tile_scan_kernel<<<(num_tiles + kScanTiles - 1) / kScanTiles, kScanThreads, 0, stream>>>(num_tiles, vp.bucket_log2, g, capacity);
+	launch_k(tile_scan_kernel, dim3((num_tiles + kScanTiles - 1) / kScanTiles), dim3(kScanThreads), 0, stream, num_tiles, vp.bucket_log2, g, capacity);
 	return GM_OK;
 }
 
 int launch_large_tiles(int phase, const int* radii, const GeometryState& g, const BinningState* b, uint32_t capacity,
                        const ViewParams& vp, cudaStream_t stream)
 {
-	large_tiles_kernel<<<148, kLargeThreads, 0, stream>>>(phase, radii, g, b ? b->keys : nullptr, capacity, vp.W, vp.H,
+	launch_k(large_tiles_kernel, dim3(148), dim3(kLargeThreads), 0, stream, phase, radii, g, b ? b->keys : nullptr, capacity, vp.W, vp.H,
 	                                                     vp.tiles_x, vp.tiles_y, vp.bucket_log2);
 	return GM_OK;
 }
@@ -505,7 +510,7 @@ int launch_emit(int P, const int* radii, const GeometryState& g, const BinningSt
 {
 	if (P <= 0)
 		return GM_OK;
-	emit_kernel<<<(P + kEmitThreads - 1) / kEmitThreads, kEmitThreads, 0, stream>>>(
+	launch_k(emit_kernel, dim3((P + kEmitThreads - 1) / kEmitThreads), dim3(kEmitThreads), 0, stream, 
 		P, radii, g, b, capacity, vp.W, vp.H, vp.tiles_x, vp.tiles_y, vp.bucket_log2);
 	launch_large_tiles(1, radii, g, &b, capacity, vp, stream);
 	return GM_OK;
@@ -517,10 +522,10 @@ int launch_sort_pack(int num_tiles, const GeometryState& g, const BinningState& 
 	if (num_tiles <= 0)
 		return GM_OK;
 	const uint32_t total = (uint32_t)num_tiles << vp.bucket_log2;
-	bucket_sort_pack_kernel<<<(total + kSortWarps - 1) / kSortWarps, kSortThreads, 0, stream>>>(
+	launch_k(bucket_sort_pack_kernel, dim3((total + kSortWarps - 1) / kSortWarps), dim3(kSortThreads), 0, stream, 
 		g, b, capacity, vp.bucket_log2, total);
 	// 32 KB of dynamic shared memory, 48 registers: six blocks per SM
-	big_bucket_sort_pack_kernel<<<148 * 6, kSortThreads, kBigSmemBytes, stream>>>(g, b, capacity, vp.bucket_log2);
+	launch_k(big_bucket_sort_pack_kernel, dim3(148 * 6), dim3(kSortThreads), kBigSmemBytes, stream, g, b, capacity, vp.bucket_log2);
 	return GM_OK;
 }
 

@@ -102,6 +102,7 @@ blend_backward_kernel(GeometryState g, BinningState b, ImageState img, uint32_t 
                       float* __restrict__ dL_dopacity,  // [P]
                       float* __restrict__ dL_dcolors)   // [P,3]
 {
+	pdl_sync();
 	__shared__ BwdSmem s;
 
 	const int tile = blockIdx.x;
@@ -379,6 +380,7 @@ blend_backward_pairs_kernel(GeometryState g, BinningState b, ImageState img, uin
                             float* __restrict__ dL_dopacity,  // [P]
                             float* __restrict__ dL_dcolors)   // [P,3]
 {
+	pdl_sync();
 	__shared__ BwdSmemP s;
 
 	const int tile = blockIdx.x;
@@ -731,6 +733,7 @@ blend_backward_mma_kernel(GeometryState g, BinningState b, ImageState img, uint3
                           float* __restrict__ dL_dopacity,  // [P]
                           float* __restrict__ dL_dcolors)   // [P,3]
 {
+	pdl_sync();
 	extern __shared__ __align__(128) unsigned char smem_raw[];
 	BwdSmemM& s = *reinterpret_cast<BwdSmemM*>(smem_raw);
 
@@ -1067,10 +1070,10 @@ int launch_blend_backward(const GeometryState& g, const BinningState& b, const I
 	static const bool scalar = std::getenv("GM_BLEND_SCALAR") != nullptr && std::getenv("GM_BLEND_SCALAR")[0] == '1';
 	static const bool pairs = !(std::getenv("GM_BLEND_BWD") != nullptr && std::getenv("GM_BLEND_BWD")[0] == 'm');
 	if (scalar)
-		blend_backward_kernel<<<num_tiles, kThreads, 0, stream>>>(
+		launch_k(blend_backward_kernel, dim3(num_tiles), dim3(kThreads), 0, stream, 
 			g, b, img, capacity, vp.W, vp.H, vp.tiles_x, vp.bg, dL_dpix, dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolor);
 	else if (pairs)
-		blend_backward_pairs_kernel<<<num_tiles, kThreads, 0, stream>>>(
+		launch_k(blend_backward_pairs_kernel, dim3(num_tiles), dim3(kThreads), 0, stream, 
 			g, b, img, capacity, vp.W, vp.H, vp.tiles_x, vp.bg, dL_dpix, dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolor);
 	else {
 		// the opt-in shared-memory size is a per-device function attribute
@@ -1087,7 +1090,7 @@ int launch_blend_backward(const GeometryState& g, const BinningState& b, const I
 			if (dev >= 0 && dev < 64)
 				opted_in[dev] = true;
 		}
-		blend_backward_mma_kernel<<<num_tiles, kThreads, sizeof(BwdSmemM), stream>>>(
+		launch_k(blend_backward_mma_kernel, dim3(num_tiles), dim3(kThreads), sizeof(BwdSmemM), stream, 
 			g, b, img, capacity, vp.W, vp.H, vp.tiles_x, vp.bg, dL_dpix, dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolor);
 	}
 	return GM_OK;

@@ -43,6 +43,7 @@ blend_forward_kernel(GeometryState g, BinningState b, ImageState img, uint32_t c
                      int W, int H, int tiles_x, const float* __restrict__ bg_color,
                      float* __restrict__ out_color)
 {
+	pdl_sync();
 	__shared__ FwdSmem s;
 
 	const int tile = blockIdx.x;
@@ -207,6 +208,7 @@ blend_forward_pairs_kernel(GeometryState g, BinningState b, ImageState img, uint
                            int W, int H, int tiles_x, const float* __restrict__ bg_color,
                            float* __restrict__ out_color)
 {
+	pdl_sync();
 	__shared__ FwdSmemP s;
 
 	const int tile = blockIdx.x;
@@ -389,9 +391,9 @@ int launch_blend_forward(const GeometryState& g, const BinningState& b, const Im
 	// GM_BLEND_SCALAR=1 selects the one-pixel-per-thread kernel (kept for A/B measurements)
 	static const bool scalar = std::getenv("GM_BLEND_SCALAR") != nullptr && std::getenv("GM_BLEND_SCALAR")[0] == '1';
 	if (scalar)
-		blend_forward_kernel<<<num_tiles, kThreads, 0, stream>>>(g, b, img, capacity, vp.W, vp.H, vp.tiles_x, vp.bg, out_color);
+		launch_k(blend_forward_kernel, dim3(num_tiles), dim3(kThreads), 0, stream, g, b, img, capacity, vp.W, vp.H, vp.tiles_x, vp.bg, out_color);
 	else
-		blend_forward_pairs_kernel<<<num_tiles, kThreads, 0, stream>>>(g, b, img, capacity, vp.W, vp.H, vp.tiles_x, vp.bg, out_color);
+		launch_k(blend_forward_pairs_kernel, dim3(num_tiles), dim3(kThreads), 0, stream, g, b, img, capacity, vp.W, vp.H, vp.tiles_x, vp.bg, out_color);
 	return GM_OK;
 }
 

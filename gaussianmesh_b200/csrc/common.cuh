@@ -326,6 +326,37 @@ __device__ __forceinline__ uint32_t depth_fine_bin(float z)
 	return min(d, (uint32_t)(kDepthBins - 1));
 }
 
+// ---- programmatic dependent launch (PDL) --------------------------------------------------------------
+// Every kernel of the per-frame chain is launched with cudaLaunchAttributeProgrammaticStreamSerialization and starts
+// with pdl_sync(): griddepcontrol.wait blocks until the previous kernel of the stream has completed and its writes are
+// visible (so nothing here relaxes the stream order of memory), griddepcontrol.launch_dependents then lets the NEXT
+// kernel's blocks become resident as soon as every block of this one has got past that point -- they fill the SM slots
+// the last wave leaves idle and sit at their own wait, so the launch latency and the block-scheduling ramp of each
+// kernel overlap the tail of its predecessor instead of following it.  GM_PDL=0 turns the attribute off (A/B).
+__device__ __forceinline__ void pdl_sync()
+{
+	asm volatile("griddepcontrol.wait;" ::: "memory");
+	asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
+bool pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args)
+{
+	cudaLaunchConfig_t cfg = {};
+	cfg.gridDim = grid;
+	cfg.blockDim = block;
+	cfg.dynamicSmemBytes = smem;
+	cfg.stream = stream;
+	cudaLaunchAttribute attr[1];
+	attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+	attr[0].val.programmaticStreamSerializationAllowed = 1;
+	cfg.attrs = attr;
+	cfg.numAttrs = pdl_enabled() ? 1 : 0;
+	return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // ---- small PTX wrappers: mbarrier + 1-D bulk copy (TMA, SASS UBLKCP) ----------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p)
 {

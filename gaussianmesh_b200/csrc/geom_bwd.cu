@@ -60,6 +60,7 @@ geometry_backward_kernel(int P,
                          float* __restrict__ dL_dscale,          // [P,3]
                          float* __restrict__ dL_drot)            // [P,4]
 {
+	pdl_sync();
 	__shared__ float s_view[16];
 	__shared__ float s_proj[16];
 	__shared__ float s_cam[3];
@@ -434,7 +435,7 @@ int launch_geometry_backward(int P, const float* means3D, const int* radii, cons
 	constexpr size_t kCoopSmem = (size_t)(kThreads / 32) * 32 * kRowPitchF4 * sizeof(float4);
 #define GM_LAUNCH_GEOM(V, O, C) do { \
 		if (C) cudaFuncSetAttribute(geometry_backward_kernel<V, O, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCoopSmem); \
-		geometry_backward_kernel<V, O, C><<<grid, kThreads, (C) ? kCoopSmem : 0, stream>>>( \
+		launch_k(geometry_backward_kernel<V, O, C>, dim3(grid), dim3(kThreads), (C) ? kCoopSmem : 0, stream,  \
 			P, means3D, radii, shs, scales, rotations, cov3Ds, vp, g, dL_dmean2D, dL_dconic, dL_dcolor, \
 			dL_dmean3D, dL_dcov3D, dL_dsh, dL_dscale, dL_drot); } while (0)
 	if (coop && overwrite) GM_LAUNCH_GEOM(true, true, true);

@@ -75,7 +75,9 @@ int launch_acap_get_rs(int Vn, const double* V0, const double* V1, const int* F,
 
 int acap_build_rings_host(int Vn, int Fn, const int* F, int* ring_off, int* ring, int* face_off, int* face_list);
 
-int launch_l1(size_t numel, const float* img, const float* target, float* loss, float* dL_dimg, cudaStream_t stream);
+int launch_l1(size_t numel, const float* img, const void* target, int target_is_u8, float* loss, float* dL_dimg,
+              cudaStream_t stream);
+int launch_u8_to_float(size_t numel, const uint8_t* src, float* dst, cudaStream_t stream);
 
 size_t photometric_scratch_bytes(int C, int H, int W);
 int launch_photometric(int C, int H, int W, const float* img, const float* gt, float lambda, char* scratch, float* out,

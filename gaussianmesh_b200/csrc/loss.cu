@@ -119,6 +119,7 @@ photometric_forward_kernel(int H, int W, const float* __restrict__ img1, const f
                            PhotoSums* __restrict__ sums, float* __restrict__ dmaps /* [3][C][H][W] or null */,
                            size_t plane_all, float lambda, float inv_numel, float* __restrict__ out /* [3] */)
 {
+	pdl_sync();
 	__shared__ float s_in[2][kIn][kIn + 1];
 	__shared__ float s_h[5][kIn][kT + 1];
 	__shared__ float warp_part[kPT / 32];
@@ -219,6 +220,7 @@ photometric_backward_kernel(int H, int W, const float* __restrict__ img1, const 
                             const float* __restrict__ dmaps, size_t plane_all, float l1_scale, float ssim_scale,
                             float* __restrict__ dL_dimg1)
 {
+	pdl_sync();
 	__shared__ float s_d[3][kIn][kIn + 1];
 	__shared__ float s_h[3][kIn][kT + 1];
 	const int ch = blockIdx.z;
@@ -273,6 +275,7 @@ mesh_restrict_kernel(int P, const float* __restrict__ scale, const float* __rest
                      const float* __restrict__ v3, float weight, float* __restrict__ loss, float* __restrict__ dL_dscale,
                      int accumulate)
 {
+	pdl_sync();
 	__shared__ float warp_part[kThreads / 32];
 	float part = 0.0f;
 	for (int i = blockIdx.x * kThreads + threadIdx.x; i < P; i += gridDim.x * kThreads) {
@@ -331,10 +334,10 @@ int launch_photometric(int C, int H, int W, const float* img, const float* gt, f
 	const size_t numel = (size_t)C * H * W;
 	const float inv_numel = 1.0f / (float)numel;
 	const dim3 grid((W + kT - 1) / kT, (H + kT - 1) / kT, C), block(kPT);
-	photometric_forward_kernel<<<grid, block, 0, stream>>>(H, W, img, gt, sums, dL_dimg ? dmaps : nullptr, numel, lambda,
+	launch_k(photometric_forward_kernel, dim3(grid), dim3(block), 0, stream, H, W, img, gt, sums, dL_dimg ? dmaps : nullptr, numel, lambda,
 	                                                       inv_numel, out);
 	if (dL_dimg != nullptr)
-		photometric_backward_kernel<<<grid, block, 0, stream>>>(H, W, img, gt, dmaps, numel, (1.0f - lambda) * inv_numel,
+		launch_k(photometric_backward_kernel, dim3(grid), dim3(block), 0, stream, H, W, img, gt, dmaps, numel, (1.0f - lambda) * inv_numel,
 		                                                        -lambda * inv_numel, dL_dimg);
 	return GM_OK;
 }
@@ -345,7 +348,7 @@ int launch_mesh_restrict(int P, const float* scale, const float* v1, const float
 	cudaMemsetAsync(loss, 0, sizeof(float), stream);
 	if (P <= 0) return GM_OK;
 	const int blocks = min(148 * 8, (P + kThreads - 1) / kThreads);
-	mesh_restrict_kernel<<<blocks, kThreads, 0, stream>>>(P, scale, v1, v2, v3, weight, loss, dL_dscale, accumulate);
+	launch_k(mesh_restrict_kernel, dim3(blocks), dim3(kThreads), 0, stream, P, scale, v1, v2, v3, weight, loss, dL_dscale, accumulate);
 	return GM_OK;
 }
 

@@ -40,6 +40,7 @@ mesh_bind_forward_kernel(int P, const float* __restrict__ bc_logits, const float
                          float* __restrict__ xyz, float* __restrict__ scale, float* __restrict__ rot,
                          float* __restrict__ opacity)
 {
+	pdl_sync();
 	const int i = blockIdx.x * kThreads + threadIdx.x;
 	if (i >= P)
 		return;
@@ -79,6 +80,7 @@ mesh_bind_backward_kernel(int P, const float* __restrict__ bc_logits, const floa
                           float* __restrict__ dL_dlog_scale, float* __restrict__ dL_drot_raw,
                           float* __restrict__ dL_dopacity_logit)
 {
+	pdl_sync();
 	const int i = blockIdx.x * kThreads + threadIdx.x;
 	if (i >= P)
 		return;
@@ -135,6 +137,7 @@ deform_kernel(int P, const float* __restrict__ V, const float* __restrict__ Vd, 
               const float* __restrict__ pos_in, const float* __restrict__ cov_in, int cov_full,
               float* __restrict__ pos_out, float* __restrict__ cov6_out, float* __restrict__ rot_out)
 {
+	pdl_sync();
 	const int i = blockIdx.x * kThreads + threadIdx.x;
 	if (i >= P)
 		return;
@@ -208,6 +211,7 @@ __global__ void __launch_bounds__(kThreads)
 sh_rotated_kernel(int P, int D, int M, const float* __restrict__ pos, const float* __restrict__ campos,
                   const float* __restrict__ rot, const float* __restrict__ shs, float* __restrict__ rgb)
 {
+	pdl_sync();
 	const int i = blockIdx.x * kThreads + threadIdx.x;
 	if (i >= P)
 		return;
@@ -232,15 +236,25 @@ sh_rotated_kernel(int P, int D, int M, const float* __restrict__ pos, const floa
 	}
 }
 
-// utils/loss_utils.py:17-18
+// utils/loss_utils.py:17-18.  TT = float, or uint8_t for a target kept as the 8-bit image the reference's loader reads
+// (utils/general_utils.py PILtoTorch: uint8 / 255.0, the same fp32 division here) -- a quarter of the upload.
+template <typename TT>
+__device__ __forceinline__ float target_value(const TT* t, size_t i);
+template <>
+__device__ __forceinline__ float target_value<float>(const float* t, size_t i) { return t[i]; }
+template <>
+__device__ __forceinline__ float target_value<uint8_t>(const uint8_t* t, size_t i) { return (float)t[i] / 255.0f; }
+
+template <typename TT>
 __global__ void __launch_bounds__(kThreads)
-l1_kernel(size_t numel, const float* __restrict__ img, const float* __restrict__ target, float inv_numel,
+l1_kernel(size_t numel, const float* __restrict__ img, const TT* __restrict__ target, float inv_numel,
           float* __restrict__ loss, float* __restrict__ dL_dimg)
 {
+	pdl_sync();
 	__shared__ float warp_part[kThreads / 32];
 	float part = 0.0f;
 	for (size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x; i < numel; i += (size_t)gridDim.x * kThreads) {
-		const float d = img[i] - target[i];
+		const float d = img[i] - target_value<TT>(target, i);
 		part += fabsf(d);
 		if (dL_dimg != nullptr)
 			dL_dimg[i] = (d > 0.0f ? inv_numel : (d < 0.0f ? -inv_numel : 0.0f));
@@ -258,6 +272,21 @@ l1_kernel(size_t numel, const float* __restrict__ img, const float* __restrict__
 	}
 }
 
+__global__ void __launch_bounds__(kThreads)
+u8_to_float_kernel(size_t numel, const uint8_t* __restrict__ src, float* __restrict__ dst)
+{
+	pdl_sync();
+	// four pixels per thread: one 32-bit load, one 128-bit store
+	const size_t i4 = ((size_t)blockIdx.x * kThreads + threadIdx.x) * 4;
+	if (i4 + 4 <= numel && (reinterpret_cast<uintptr_t>(src) & 3u) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15u) == 0) {
+		const uchar4 v = *reinterpret_cast<const uchar4*>(src + i4);
+		*reinterpret_cast<float4*>(dst + i4) = make_float4((float)v.x / 255.0f, (float)v.y / 255.0f, (float)v.z / 255.0f,
+		                                                   (float)v.w / 255.0f);
+	} else {
+		for (size_t i = i4; i < numel && i < i4 + 4; i++)
+			dst[i] = (float)src[i] / 255.0f;
+	}
+}
 
 // ---- the reference's "Python" pipeline variants (gaussian_renderer/__init__.py:78-94) ------------------------
 // compute_cov3D_python: pc.get_covariance(scaling_modifier) = strip_symmetric(L L^T), L = R(q / |q|) diag(mod * s)
@@ -274,6 +303,7 @@ __global__ void __launch_bounds__(kThreads)
 cov3d_python_forward_kernel(int P, const float* __restrict__ scales, float mod, const float* __restrict__ rotations,
                             float* __restrict__ cov6)
 {
+	pdl_sync();
 	const int i = blockIdx.x * kThreads + threadIdx.x;
 	if (i >= P)
 		return;
@@ -301,6 +331,7 @@ __global__ void __launch_bounds__(kThreads)
 cov3d_python_backward_kernel(int P, const float* __restrict__ scales, float mod, const float* __restrict__ rotations,
                              const float* __restrict__ dL_dcov6, float* __restrict__ dL_dscale, float* __restrict__ dL_drot)
 {
+	pdl_sync();
 	const int i = blockIdx.x * kThreads + threadIdx.x;
 	if (i >= P)
 		return;
@@ -347,6 +378,7 @@ sh_rotated_backward_kernel(int P, int D, int M, const float* __restrict__ pos, c
                            const float* __restrict__ rot, const float* __restrict__ shs, const float* __restrict__ dL_drgb,
                            float* __restrict__ dL_dshs, float* __restrict__ dL_dpos)
 {
+	pdl_sync();
 	const int i = blockIdx.x * kThreads + threadIdx.x;
 	if (i >= P)
 		return;
@@ -436,6 +468,7 @@ load_mesh_kernel(int P, int num_faces, const double* __restrict__ vertex, const 
                  const long long* __restrict__ face_id, const float* __restrict__ proj_pos,
                  int* __restrict__ gaussian_triangles, double* __restrict__ weights)
 {
+	pdl_sync();
 	const int i = blockIdx.x * kThreads + threadIdx.x;
 	if (i >= P)
 		return;
@@ -469,7 +502,7 @@ int launch_mesh_bind_forward(int P, const float* bc_logits, const float* distanc
                              float* scale, float* rot, float* opacity, cudaStream_t stream)
 {
 	if (P <= 0) return GM_OK;
-	mesh_bind_forward_kernel<<<(P + kThreads - 1) / kThreads, kThreads, 0, stream>>>(
+	launch_k(mesh_bind_forward_kernel, dim3((P + kThreads - 1) / kThreads), dim3(kThreads), 0, stream, 
 		P, bc_logits, distance, v1, v2, v3, normal, r, alpha_distance, log_scale, rot_raw, opacity_logit, xyz, scale,
 		rot, opacity);
 	return GM_OK;
@@ -483,7 +516,7 @@ int launch_mesh_bind_backward(int P, const float* bc_logits, const float* distan
                               float* dL_drot_raw, float* dL_dopacity_logit, cudaStream_t stream)
 {
 	if (P <= 0) return GM_OK;
-	mesh_bind_backward_kernel<<<(P + kThreads - 1) / kThreads, kThreads, 0, stream>>>(
+	launch_k(mesh_bind_backward_kernel, dim3((P + kThreads - 1) / kThreads), dim3(kThreads), 0, stream, 
 		P, bc_logits, distance, v1, v2, v3, normal, r, alpha_distance, log_scale, rot_raw, opacity_logit, dL_dxyz,
 		dL_dscale, dL_drot, dL_dopacity, dL_dbc, dL_ddist, dL_dlog_scale, dL_drot_raw, dL_dopacity_logit);
 	return GM_OK;
@@ -494,7 +527,7 @@ int launch_deform(int P, const float* V, const float* Vd, const float* VR, const
                   float* cov6_out, float* rot_out, cudaStream_t stream)
 {
 	if (P <= 0) return GM_OK;
-	deform_kernel<<<(P + kThreads - 1) / kThreads, kThreads, 0, stream>>>(P, V, Vd, VR, VS, tri, w, pos_in, cov_in,
+	launch_k(deform_kernel, dim3((P + kThreads - 1) / kThreads), dim3(kThreads), 0, stream, P, V, Vd, VR, VS, tri, w, pos_in, cov_in,
 	                                                                        cov_full, pos_out, cov6_out, rot_out);
 	return GM_OK;
 }
@@ -503,14 +536,14 @@ int launch_sh_rotated(int P, int D, int M, const float* pos, const float* campos
                       float* rgb, cudaStream_t stream)
 {
 	if (P <= 0) return GM_OK;
-	sh_rotated_kernel<<<(P + kThreads - 1) / kThreads, kThreads, 0, stream>>>(P, D, M, pos, campos, rot, shs, rgb);
+	launch_k(sh_rotated_kernel, dim3((P + kThreads - 1) / kThreads), dim3(kThreads), 0, stream, P, D, M, pos, campos, rot, shs, rgb);
 	return GM_OK;
 }
 
 int launch_cov3d_python(int P, const float* scales, float mod, const float* rotations, float* cov6, cudaStream_t stream)
 {
 	if (P <= 0) return GM_OK;
-	cov3d_python_forward_kernel<<<(P + kThreads - 1) / kThreads, kThreads, 0, stream>>>(P, scales, mod, rotations, cov6);
+	launch_k(cov3d_python_forward_kernel, dim3((P + kThreads - 1) / kThreads), dim3(kThreads), 0, stream, P, scales, mod, rotations, cov6);
 	return GM_OK;
 }
 
@@ -518,7 +551,7 @@ int launch_cov3d_python_backward(int P, const float* scales, float mod, const fl
                                  float* dL_dscale, float* dL_drot, cudaStream_t stream)
 {
 	if (P <= 0) return GM_OK;
-	cov3d_python_backward_kernel<<<(P + kThreads - 1) / kThreads, kThreads, 0, stream>>>(P, scales, mod, rotations, dL_dcov6,
+	launch_k(cov3d_python_backward_kernel, dim3((P + kThreads - 1) / kThreads), dim3(kThreads), 0, stream, P, scales, mod, rotations, dL_dcov6,
 	                                                                                  dL_dscale, dL_drot);
 	return GM_OK;
 }
@@ -527,7 +560,7 @@ int launch_sh_rotated_backward(int P, int D, int M, const float* pos, const floa
                                const float* dL_drgb, float* dL_dshs, float* dL_dpos, cudaStream_t stream)
 {
 	if (P <= 0) return GM_OK;
-	sh_rotated_backward_kernel<<<(P + kThreads - 1) / kThreads, kThreads, 0, stream>>>(P, D, M, pos, campos, rot, shs, dL_drgb,
+	launch_k(sh_rotated_backward_kernel, dim3((P + kThreads - 1) / kThreads), dim3(kThreads), 0, stream, P, D, M, pos, campos, rot, shs, dL_drgb,
 	                                                                                dL_dshs, dL_dpos);
 	return GM_OK;
 }
@@ -536,17 +569,30 @@ int launch_load_mesh(int P, int num_faces, const double* vertex, const int* face
                      const float* proj_pos, int* gaussian_triangles, double* weights, cudaStream_t stream)
 {
 	if (P <= 0) return GM_OK;
-	load_mesh_kernel<<<(P + kThreads - 1) / kThreads, kThreads, 0, stream>>>(P, num_faces, vertex, faces, face_id, proj_pos,
+	launch_k(load_mesh_kernel, dim3((P + kThreads - 1) / kThreads), dim3(kThreads), 0, stream, P, num_faces, vertex, faces, face_id, proj_pos,
 	                                                                      gaussian_triangles, weights);
 	return GM_OK;
 }
 
-int launch_l1(size_t numel, const float* img, const float* target, float* loss, float* dL_dimg, cudaStream_t stream)
+int launch_l1(size_t numel, const float* img, const void* target, int target_is_u8, float* loss, float* dL_dimg, cudaStream_t stream)
 {
 	cudaMemsetAsync(loss, 0, sizeof(float), stream);
 	if (numel == 0) return GM_OK;
 	const int blocks = (int)min((size_t)148 * 8, (numel + kThreads - 1) / kThreads);
-	l1_kernel<<<blocks, kThreads, 0, stream>>>(numel, img, target, 1.0f / (float)numel, loss, dL_dimg);
+	if (target_is_u8)
+		launch_k(l1_kernel<uint8_t>, dim3(blocks), dim3(kThreads), 0, stream, numel, img, static_cast<const uint8_t*>(target),
+		         1.0f / (float)numel, loss, dL_dimg);
+	else
+		launch_k(l1_kernel<float>, dim3(blocks), dim3(kThreads), 0, stream, numel, img, static_cast<const float*>(target),
+		         1.0f / (float)numel, loss, dL_dimg);
+	return GM_OK;
+}
+
+int launch_u8_to_float(size_t numel, const uint8_t* src, float* dst, cudaStream_t stream)
+{
+	if (numel == 0) return GM_OK;
+	const size_t threads = (numel + 3) / 4;
+	launch_k(u8_to_float_kernel, dim3((unsigned int)((threads + kThreads - 1) / kThreads)), dim3(kThreads), 0, stream, numel, src, dst);
 	return GM_OK;
 }
 

@@ -54,6 +54,7 @@ __global__ void __launch_bounds__(kThreads)
 adam_kernel(const __grid_constant__ AdamTable tab, float b0, float b1, float bias, float eps,
             const uint32_t* __restrict__ skip_flag)
 {
+	pdl_sync();
 	// gated update: a frame whose binning chunk overflowed rendered only part of its tiles, so its gradients are
 	// partial -- the update is dropped on the device, without a host round trip (FrameHeader::overflow)
 	if (skip_flag != nullptr && *skip_flag != 0u)
@@ -113,6 +114,7 @@ __global__ void __launch_bounds__(kThreads)
 adam_sharded_p2p_kernel(const __grid_constant__ ShardedAdamArgs a, float b0, float b1, float bias, float eps,
                         float inv_world)
 {
+	pdl_sync();
 	const size_t i = a.lo + ((size_t)blockIdx.x * kThreads + threadIdx.x) * 4;
 	if (i >= a.hi)
 		return;
@@ -162,6 +164,7 @@ densify_stats_kernel(int P, const int* __restrict__ radii, const float* __restri
                      float* __restrict__ max_radii2D, float* __restrict__ grad_accum, float* __restrict__ denom,
                      const uint32_t* __restrict__ skip_flag)
 {
+	pdl_sync();
 	const int i = blockIdx.x * kThreads + threadIdx.x;
 	if (i >= P || (skip_flag != nullptr && *skip_flag != 0u))
 		return;
@@ -195,7 +198,7 @@ int launch_adam(int n, const gm_adam_tensor* tensors, int step, float beta1, flo
 		}
 		tab.first_block[tab.count] = blocks;
 		if (blocks > 0)
-			adam_kernel<<<blocks, kThreads, 0, stream>>>(tab, beta1, beta2, (float)bias, eps, skip_flag);
+			launch_k(adam_kernel, dim3(blocks), dim3(kThreads), 0, stream, tab, beta1, beta2, (float)bias, eps, skip_flag);
 	}
 	return GM_OK;
 }
@@ -224,7 +227,7 @@ int launch_adam_sharded_p2p(int world, int rank, const float* const* grads, floa
 		return GM_OK;
 	const double bias = sqrt(1.0 - pow((double)beta2, (double)step)) / (1.0 - pow((double)beta1, (double)step));
 	const size_t vecs = (hi - lo + 3) / 4;
-	adam_sharded_p2p_kernel<<<(unsigned int)((vecs + kThreads - 1) / kThreads), kThreads, 0, stream>>>(
+	launch_k(adam_sharded_p2p_kernel, dim3((unsigned int)((vecs + kThreads - 1) / kThreads)), dim3(kThreads), 0, stream, 
 		a, beta1, beta2, (float)bias, eps, 1.0f / (float)world);
 	return GM_OK;
 }
@@ -233,7 +236,7 @@ int launch_densify_stats(int P, const int* radii, const float* dL_dmean2D, float
                          float* denom, const uint32_t* skip_flag, cudaStream_t stream)
 {
 	if (P <= 0) return GM_OK;
-	densify_stats_kernel<<<(P + kThreads - 1) / kThreads, kThreads, 0, stream>>>(P, radii, dL_dmean2D, max_radii2D,
+	launch_k(densify_stats_kernel, dim3((P + kThreads - 1) / kThreads), dim3(kThreads), 0, stream, P, radii, dL_dmean2D, max_radii2D,
 	                                                                               grad_accum, denom, skip_flag);
 	return GM_OK;
 }

@@ -35,6 +35,7 @@ __device__ __forceinline__ bool near_cull_passes(const float3& p_orig, const flo
 __global__ void __launch_bounds__(kThreads)
 mark_visible_kernel(int P, const float* __restrict__ means3D, const float* __restrict__ view, uint8_t* __restrict__ present)
 {
+	pdl_sync();
 	int idx = blockIdx.x * kThreads + threadIdx.x;
 	if (idx >= P)
 		return;
@@ -50,6 +51,7 @@ __global__ void __launch_bounds__(kHistThreads)
 depth_histogram_kernel(int P, const float* __restrict__ means3D, const float* __restrict__ view,
                        uint32_t* __restrict__ hist)
 {
+	pdl_sync();
 	__shared__ uint32_t s_hist[kDepthBins];
 	for (int i = threadIdx.x; i < kDepthBins; i += kHistThreads)
 		s_hist[i] = 0;
@@ -75,6 +77,7 @@ static_assert(kDepthBins % kLutThreads == 0, "bins per thread");
 __global__ void __launch_bounds__(kLutThreads)
 bucket_lut_kernel(const uint32_t* __restrict__ hist, uint8_t* __restrict__ lut, int bucket_log2)
 {
+	pdl_sync();
 	constexpr int kPer = kDepthBins / kLutThreads;
 	__shared__ uint32_t warp_sums[kLutThreads / 32];
 	const int tid = threadIdx.x;
@@ -137,6 +140,7 @@ preprocess_kernel(int P,
                   GeometryState g,
                   bool prefiltered)
 {
+	pdl_sync();
 	__shared__ float s_view[16];
 	__shared__ float s_proj[16];
 	__shared__ float s_cam[3];
@@ -372,18 +376,20 @@ int launch_mark_visible(int P, const float* means3D, const float* viewmatrix, ui
 {
 	if (P <= 0)
 		return GM_OK;
-	mark_visible_kernel<<<(P + kThreads - 1) / kThreads, kThreads, 0, stream>>>(P, means3D, viewmatrix, present);
+	launch_k(mark_visible_kernel, dim3((P + kThreads - 1) / kThreads), dim3(kThreads), 0, stream, P, means3D, viewmatrix, present);
 	return GM_OK;
 }
 
 int launch_depth_buckets(int P, const float* means3D, const ViewParams& vp, const GeometryState& g, cudaStream_t stream)
 {
-	cudaMemsetAsync(g.depth_hist, 0, sizeof(uint32_t) * kDepthBins, stream);
+	// one clear for every per-frame counter (frame header, scan descriptors, depth histogram, bucket cursors): a memset
+	// between two kernels would break the programmatic launch chain, so it comes first
+	cudaMemsetAsync(g.header, 0, frame_clear_bytes(g, (size_t)(vp.tiles_x * vp.tiles_y) << vp.bucket_log2), stream);
 	if (P > 0) {
 		const int hist_blocks = min((P + kHistThreads - 1) / kHistThreads, 148 * 4);
-		depth_histogram_kernel<<<hist_blocks, kHistThreads, 0, stream>>>(P, means3D, vp.view, g.depth_hist);
+		launch_k(depth_histogram_kernel, dim3(hist_blocks), dim3(kHistThreads), 0, stream, P, means3D, vp.view, g.depth_hist);
 	}
-	bucket_lut_kernel<<<1, kLutThreads, 0, stream>>>(g.depth_hist, g.depth_lut, vp.bucket_log2);
+	launch_k(bucket_lut_kernel, dim3(1), dim3(kLutThreads), 0, stream, g.depth_hist, g.depth_lut, vp.bucket_log2);
 	return GM_OK;
 }
 
@@ -393,9 +399,7 @@ int launch_preprocess(int P, const float* means3D, const float* scales, const fl
                       const GeometryState& g, bool prefiltered, cudaStream_t stream)
 {
 	const int num_tiles = vp.tiles_x * vp.tiles_y;
-	cudaMemsetAsync(g.header, 0, sizeof(FrameHeader), stream);
-	cudaMemsetAsync(g.bucket_cursor, 0, sizeof(uint32_t) * ((size_t)num_tiles << vp.bucket_log2), stream);
-	cudaMemsetAsync(g.scan_state, 0, sizeof(unsigned long long) * ((size_t)kMaxScanBlocks + 1), stream);
+	(void)num_tiles;      // the per-frame counters were cleared by launch_depth_buckets, the first stage of the frame
 	if (P <= 0)
 		return GM_OK;
 	const dim3 grid((P + kThreads - 1) / kThreads);
@@ -403,13 +407,13 @@ int launch_preprocess(int P, const float* means3D, const float* scales, const fl
 	constexpr size_t kCoopSmem = (size_t)(kThreads / 32) * 32 * kRowF4 * sizeof(float4);      // 48 KB
 	if (vec && vp.M == 16 && vp.D == 3) {
 		cudaFuncSetAttribute(preprocess_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCoopSmem);
-		preprocess_kernel<true, true><<<grid, kThreads, kCoopSmem, stream>>>(
+		launch_k(preprocess_kernel<true, true>, dim3(grid), dim3(kThreads), kCoopSmem, stream, 
 			P, means3D, scales, rotations, opacities, shs, cov3D_precomp, colors_precomp, vp, radii, g, prefiltered);
 	} else if (vec)
-		preprocess_kernel<true, false><<<grid, kThreads, 0, stream>>>(
+		launch_k(preprocess_kernel<true, false>, dim3(grid), dim3(kThreads), 0, stream, 
 			P, means3D, scales, rotations, opacities, shs, cov3D_precomp, colors_precomp, vp, radii, g, prefiltered);
 	else
-		preprocess_kernel<false, false><<<grid, kThreads, 0, stream>>>(
+		launch_k(preprocess_kernel<false, false>, dim3(grid), dim3(kThreads), 0, stream, 
 			P, means3D, scales, rotations, opacities, shs, cov3D_precomp, colors_precomp, vp, radii, g, prefiltered);
 	launch_large_tiles(0, radii, g, nullptr, 0, vp, stream);      // count pass for rectangles of more than 64 tiles
 	return GM_OK;

@@ -106,7 +106,12 @@ inline size_t required(size_t n)
 inline GeometryState GeometryState::fromChunk(char*& chunk, size_t P)
 {
 	GeometryState g;
+	// header | scan_state | depth_hist | bucket_cursor are contiguous: one memset clears the per-frame counters
+	// (frame_clear_bytes); the per-Gaussian arrays follow
 	obtain(chunk, g.header, 1);
+	obtain(chunk, g.scan_state, (size_t)kMaxScanBlocks + 1);
+	obtain(chunk, g.depth_hist, (size_t)kDepthBins);
+	obtain(chunk, g.bucket_cursor, kMaxBucketEntries);
 	obtain(chunk, g.depths, P);
 	obtain(chunk, g.internal_radii, P);
 	obtain(chunk, g.means2D, P);
@@ -117,12 +122,15 @@ inline GeometryState GeometryState::fromChunk(char*& chunk, size_t P)
 	obtain(chunk, g.large_list, P);
 	obtain(chunk, g.tile_count, (size_t)GM_MAX_TILES);
 	obtain(chunk, g.tile_start, (size_t)GM_MAX_TILES);
-	obtain(chunk, g.bucket_cursor, kMaxBucketEntries);
 	obtain(chunk, g.big_list, kMaxBucketEntries);
-	obtain(chunk, g.scan_state, (size_t)kMaxScanBlocks + 1);
-	obtain(chunk, g.depth_hist, (size_t)kDepthBins);
 	obtain(chunk, g.depth_lut, (size_t)kDepthBins);
 	return g;
+}
+
+// bytes from the frame header to the end of the bucket cursors in use (num_entries = tiles << bucket_log2)
+inline size_t frame_clear_bytes(const GeometryState& g, size_t num_entries)
+{
+	return (size_t)(reinterpret_cast<const char*>(g.bucket_cursor + num_entries) - reinterpret_cast<const char*>(g.header));
 }
 
 inline ImageState ImageState::fromChunk(char*& chunk, size_t N)

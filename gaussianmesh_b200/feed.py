@@ -13,11 +13,13 @@ import torch
 
 
 class HostFrameFeed:
-    def __init__(self, device, shapes: Sequence[Tuple[int, ...]], dtype=torch.float32, slots: int = 2):
+    def __init__(self, device, shapes: Sequence[Tuple[int, ...]], dtype=torch.float32, slots: int = 2, dtypes=None):
+        """`dtypes` gives one dtype per shape (default: `dtype` for all), e.g. float32 camera + uint8 target image."""
         self.device = torch.device(device)
         self.copy_stream = torch.cuda.Stream(self.device)
         self.slots = slots
-        self.buffers: List[List[torch.Tensor]] = [[torch.empty(s, dtype=dtype, device=self.device) for s in shapes]
+        dtypes = list(dtypes) if dtypes is not None else [dtype] * len(shapes)
+        self.buffers: List[List[torch.Tensor]] = [[torch.empty(s, dtype=dt, device=self.device) for s, dt in zip(shapes, dtypes)]
                                                   for _ in range(slots)]
         self.ready = [torch.cuda.Event() for _ in range(slots)]
         self.free = [None] * slots

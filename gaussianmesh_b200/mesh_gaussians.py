@@ -222,10 +222,13 @@ def load_mesh(vertex, faces, face_id, proj_pos) -> Tuple[torch.Tensor, torch.Ten
 class _L1(torch.autograd.Function):
     @staticmethod
     def forward(ctx, img, target):
-        img, target = _c(img), _c(target)
+        img = _c(img)
+        u8 = target.dtype == torch.uint8
+        target = _c(target, torch.uint8 if u8 else torch.float32)
         loss = torch.empty(1, dtype=torch.float32, device=img.device)
         grad = torch.empty_like(img)
-        check(lib.gm_l1_loss(img.numel(), _p(img), _p(target), _p(loss), _p(grad), _stream()), "gm_l1_loss")
+        fn = lib.gm_l1_loss_u8 if u8 else lib.gm_l1_loss
+        check(fn(img.numel(), _p(img), _p(target), _p(loss), _p(grad), _stream()), "gm_l1_loss")
         ctx.save_for_backward(grad)
         return loss.view(())
 
@@ -235,6 +238,15 @@ class _L1(torch.autograd.Function):
         return grad * g, None
 
 
+def image_u8_to_float(img_u8: torch.Tensor) -> torch.Tensor:
+    """uint8 image -> float32 / 255.0 (utils/general_utils.py:22-27, PILtoTorch), one kernel."""
+    img_u8 = _c(img_u8, torch.uint8)
+    out = torch.empty(img_u8.shape, dtype=torch.float32, device=img_u8.device)
+    check(lib.gm_image_u8_to_float(img_u8.numel(), _p(img_u8), _p(out), _stream()), "gm_image_u8_to_float")
+    return out
+
+
 def l1_loss(network_output: torch.Tensor, gt: torch.Tensor) -> torch.Tensor:
-    """mean(abs(network_output - gt)) (utils/loss_utils.py:17-18), fused with its gradient."""
+    """mean(abs(network_output - gt)) (utils/loss_utils.py:17-18), fused with its gradient.  `gt` may be the uint8 image
+    (value / 255 inside the kernel)."""
     return _L1.apply(network_output, gt)

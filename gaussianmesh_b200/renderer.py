@@ -533,8 +533,10 @@ class TrainStep:
         if self.arena.overflowed:          # frames seen to have overflowed since the last step (arena already grown)
             self.overflowed_frames += len(self.arena.overflowed)
             self.arena.overflowed.clear()
-        check(lib.gm_l1_loss(self.image.numel(), self.image.data_ptr(), target.data_ptr(), self.loss.data_ptr(),
-                             self.dL_dimg.data_ptr(), stream), "gm_l1_loss")
+        # a uint8 target is the 8-bit ground-truth image (value / 255 inside the kernel), a float32 one is used as it is
+        l1 = lib.gm_l1_loss_u8 if target.dtype == torch.uint8 else lib.gm_l1_loss
+        check(l1(self.image.numel(), self.image.data_ptr(), target.data_ptr(), self.loss.data_ptr(),
+                 self.dL_dimg.data_ptr(), stream), "gm_l1_loss")
         self._accum.zero_()
         g = self.grads
         check(lib.gm_backward_ex(self.P, self.D, self.M, cap, bg.data_ptr(), self.W, self.H, va[0], va[1], None, va[4], 1.0,

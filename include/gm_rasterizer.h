@@ -260,6 +260,13 @@ int gm_acap_get_rs(int num_vertices, const double* vertex_rest, const double* ve
 int gm_l1_loss(size_t numel, const float* img, const float* target, float* loss /*[1]*/,
                float* dL_dimg, gm_stream_t stream);
 
+/*  Ground-truth images stay 8-bit in the reference's loaders until utils/general_utils.py:22-27 (PILtoTorch) divides by
+ *  255.0; keeping the target as uint8 quarters the per-step upload.  gm_l1_loss_u8 is gm_l1_loss with target[i] =
+ *  (float)u8[i] / 255.0f evaluated inside the kernel; gm_image_u8_to_float writes that float image (for the losses that
+ *  take a float target). */
+int gm_l1_loss_u8(size_t numel, const float* img, const uint8_t* target, float* loss, float* dL_dimg, gm_stream_t stream);
+int gm_image_u8_to_float(size_t numel, const uint8_t* src, float* dst, gm_stream_t stream);
+
 /* ---- the rest of one training iteration around the op (train_mesh_gaussian.py:85-147) -------
  *
  *  gm_photometric_loss: out[0] = (1 - lambda) L1 + lambda (1 - SSIM), out[1] = L1 = mean|img - gt|,
