@@ -656,7 +656,7 @@ def main():
         view_parallel = {"global_batch_views": world,
                          "workload": "the section-5 iteration with one view per rank per step: gradients averaged over the "
                                      "ranks, one optimizer step per global batch"}
-        for mode in ("nccl", "p2p"):
+        for mode in ("nccl", "p2p", "mc"):
             try:
                 vp_model = MeshGaussianModel(it_arrays, device, requires_grad=False)
                 vp = ViewParallelTrainer(vp_model, OptimizationParams(), WIDTH, HEIGHT, mode=mode)
@@ -679,7 +679,7 @@ def main():
     clocks = sampler.stop() if sampler is not None else None
     replicas_identical = None
     if view_parallel is not None:
-        flags = [view_parallel[m].get("replicas_identical") for m in ("nccl", "p2p") if isinstance(view_parallel.get(m), dict)]
+        flags = [view_parallel[m].get("replicas_identical") for m in ("nccl", "p2p", "mc") if isinstance(view_parallel.get(m), dict)]
         flags = [f for f in flags if f is not None]
         replicas_identical = all(flags) if flags else None
 
@@ -720,7 +720,9 @@ def main():
     if view_parallel is not None:
         view_parallel["exchange"] = {"nccl": "ncclAllReduce of the flat gradient vector + replicated one-launch Adam",
                                      "p2p": "gm_adam_step_sharded_p2p: reduce-scatter + Adam + all-gather in one kernel over "
-                                            "NVLink peer memory (symmetric memory), optimizer state sharded"}
+                                            "NVLink peer memory (symmetric memory, P2P loads / stores), optimizer state sharded",
+                                     "mc": "gm_adam_step_sharded_mc: the same kernel over the NVSwitch multicast mapping: "
+                                           "multimem.ld_reduce (sum inside the switch) + multimem.st (store to all replicas)"}
         out["view_parallel"] = view_parallel
     # ---- cross-arm correctness guard: both arms run the same K + W steps on the same views / targets, so the loss of the
     # last end-to-end step must agree.  Each arm leaves its value in a scratch file; the arm that runs second compares.

@@ -88,6 +88,7 @@ SIGNATURES = {
     "gm_adam_shard_range": (None, [_z, _i, _i, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
     "gm_adam_step_sharded_p2p": (_i, [_i, _i, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), _i, C.POINTER(AdamSegment), _z,
                                       _p, _p, _i, _f, _f, _f, _p]),
+    "gm_adam_step_sharded_mc": (_i, [_i, _i, _p, _p, _p, _i, C.POINTER(AdamSegment), _z, _p, _p, _i, _f, _f, _f, _p]),
     "gm_densify_stats": (_i, [_i, _p, _p, _p, _p, _p, _p]),
     "gm_acap_build_rings": (_i, [_i, _i, _p, _p, _p, _p, _p]),
     "gm_acap_rest": (_i, [_i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),

@@ -676,6 +676,29 @@ int gm_adam_step_sharded_p2p(int world, int rank, const float* const* grads_host
 	return check_stage("adam_sharded_p2p", false, (cudaStream_t)stream);
 }
 
+int gm_adam_step_sharded_mc(int world, int rank, const float* grads_multicast, float* params_multicast,
+                            const float* params_local, int num_segments, const gm_adam_segment* segments_host, size_t total,
+                            float* exp_avg, float* exp_avg_sq, int step, float beta1, float beta2, float eps, gm_stream_t stream)
+{
+	if (world < 1 || world > GM_MAX_PEERS || rank < 0 || rank >= world || num_segments < 0 || num_segments > 8 || step < 1)
+		return GM_ERR_BAD_ARGUMENT;
+	if (!grads_multicast || !params_multicast || !params_local || (num_segments > 0 && !segments_host) || (total & 3) != 0)
+		return GM_ERR_BAD_ARGUMENT;
+	for (int s = 0; s < num_segments; s++) {
+		const gm_adam_segment& sg = segments_host[s];
+		if ((sg.offset & 31) != 0 || sg.offset + sg.numel > total || (sg.period > 0 && sg.split > sg.period))
+			return GM_ERR_BAD_ARGUMENT;
+	}
+	size_t lo, hi;
+	gm_adam_shard_range(total, world, rank, &lo, &hi);
+	if (hi > lo && (!exp_avg || !exp_avg_sq))
+		return GM_ERR_BAD_ARGUMENT;
+	{ StageScope scope_(kStAdam, (cudaStream_t)stream);
+	  launch_adam_sharded_mc(world, rank, grads_multicast, params_multicast, params_local, num_segments, segments_host, total,
+	                         exp_avg, exp_avg_sq, step, beta1, beta2, eps, (cudaStream_t)stream); }
+	return check_stage("adam_sharded_mc", false, (cudaStream_t)stream);
+}
+
 int gm_densify_stats_gated(int P, const int32_t* radii, const float* dL_dmean2D, float* max_radii2D, float* grad_accum,
                            float* denom, const uint32_t* skip_flag, gm_stream_t stream)
 {

@@ -380,6 +380,245 @@ blend_forward_pairs_kernel(GeometryState g, BinningState b, ImageState img, uint
 	}
 }
 
+
+// ---- the same packed-pair kernel without a block-wide barrier in the batch loop -------------------------
+// The staged records live in a ring of kStagesF stages.  A warp waits only for the stage it needs (mbarrier), and
+// when it is through with a stage it counts itself off; the warp that arrives last refills the stage with the batch
+// kStagesF further on.  A warp whose 32 pixels have all terminated (or whose block is culled) therefore never holds
+// the others back, and nobody waits at a barrier for the slowest warp of every batch (16 % of the stall samples of the
+// barrier version).  The reference's block-wide early exit (forward.cu:303-306) becomes: once all eight warps are
+// done, the refilling warp stops issuing copies and publishes the first batch that will never arrive (`stop_at`);
+// every warp drains the copies already in flight and leaves.
+constexpr int kBatchF = 128;
+constexpr int kStagesF = 3;
+
+struct __align__(128) FwdSmemR {
+	float4 conic[kStagesF][kBatchF];
+	float4 xyrg[kStagesF][kBatchF];
+	float2 bid[kStagesF][kBatchF];
+	WarpQueueP queue[kThreads / 32];
+	uint64_t full[kStagesF];
+	uint32_t released[kStagesF];
+	uint32_t done_warps;
+	int stop_at;
+};
+
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity)
+{
+	uint32_t ok;
+	asm volatile(
+		"{\n\t"
+		".reg .pred p;\n\t"
+		"mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+		"selp.u32 %0, 1, 0, p;\n\t"
+		"}" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+	return ok != 0;
+}
+
+__global__ void __launch_bounds__(kThreads)
+blend_forward_ring_kernel(GeometryState g, BinningState b, ImageState img, uint32_t capacity,
+                          int W, int H, int tiles_x, const float* __restrict__ bg_color,
+                          float* __restrict__ out_color)
+{
+	pdl_sync();
+	__shared__ FwdSmemR s;
+
+	const int tile = blockIdx.x;
+	const int tile_x = tile % tiles_x, tile_y = tile / tiles_x;
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+	// 8x4 pixel block per warp
+	const int bx0 = tile_x * kTile + (warp & 1) * 8;
+	const int by0 = tile_y * kTile + (warp >> 1) * 4;
+	const int px = bx0 + (lane & 7), py = by0 + (lane >> 3);
+	const bool inside = px < W && py < H;
+	const f2 npx = pk1(-(float)px), npy = pk1(-(float)py);
+	const float wx0 = (float)bx0, wy0 = (float)by0;
+	const float wx1 = (float)min(bx0 + 7, W - 1), wy1 = (float)min(by0 + 3, H - 1);
+
+	const uint32_t start = g.tile_start[tile];
+	uint32_t n = 0;
+	if (start < capacity)
+		n = min(g.tile_count[tile], capacity - start);
+	const int num_batches = (int)((n + kBatchF - 1) / kBatchF);
+
+	auto issue = [&](int batch, int st) {
+		const uint32_t off = start + (uint32_t)batch * kBatchF;
+		const uint32_t cnt = min((uint32_t)kBatchF, n - (uint32_t)batch * kBatchF);
+		const uint32_t cnt4 = (cnt + 3u) & ~3u;
+		mbar_arrive_expect_tx(&s.full[st], cnt4 * 40u);
+		bulk_g2s(s.conic[st], b.rec_conic + off, cnt4 * 16u, &s.full[st]);
+		bulk_g2s(s.xyrg[st], b.rec_xyrg + off, cnt4 * 16u, &s.full[st]);
+		bulk_g2s(s.bid[st], b.rec_bid + off, cnt4 * 8u, &s.full[st]);
+	};
+	if (tid == 0) {
+#pragma unroll
+		for (int st = 0; st < kStagesF; st++) {
+			mbar_init(&s.full[st], 1);
+			s.released[st] = 0;
+		}
+		s.done_warps = 0;
+		s.stop_at = num_batches;
+		fence_mbar_init();
+#pragma unroll
+		for (int st = 0; st < kStagesF; st++)
+			if (st < num_batches)
+				issue(st, st);
+	}
+	__syncthreads();
+
+	// forward.cu:294-298
+	const float kInf = __int_as_float(0x7f800000);
+	float thr = inside ? 1.0f / 255.0f : kInf;
+	float T = 1.0f;
+	uint32_t last_contributor = 0;
+	float C0 = 0.0f, C1 = 0.0f, C2 = 0.0f;
+	const f2 neg_half = pk1(-0.5f);
+	WarpQueueP& q = s.queue[warp];
+	bool warp_done = __all_sync(0xffffffffu, thr == kInf);
+	if (warp_done && lane == 0)
+		atomicAdd(&s.done_warps, 1u);
+
+	int st = 0;
+	uint32_t parity = 0;
+	for (int batch = 0; batch < num_batches; batch++) {
+		// wait for this batch -- or learn that it will never be issued (every warp of the tile is done)
+		bool stopped = false;
+		while (!mbar_try_wait(&s.full[st], parity)) {
+			if (*reinterpret_cast<volatile int*>(&s.stop_at) <= batch) {
+				stopped = true;
+				break;
+			}
+		}
+		if (stopped)
+			break;
+
+		if (!warp_done) {
+			const int cnt = (int)min((uint32_t)kBatchF, n - (uint32_t)batch * kBatchF);
+			for (int base = 0; base < cnt; base += 32) {
+				// cull 32 splats in parallel against the warp's 8x4 pixel block and compact the survivors
+				const int j = base + lane;
+				bool keep = false;
+				float4 co, xr;
+				if (j < cnt) {
+					co = s.conic[st][j];
+					xr = s.xyrg[st][j];
+					keep = !rect_cannot_contribute(xr.x, xr.y, co.x, co.y, co.z, cull_threshold(co.w),
+					                               wx0, wy0, wx1, wy1);
+				}
+				const uint32_t mask = __ballot_sync(0xffffffffu, keep);
+				if (mask == 0)
+					continue;
+				const int n_keep = __popc(mask);
+				{
+					// the lane behind the last survivor pads an odd queue with a splat of opacity 0 (alpha == 0: skipped)
+					const int pos = keep ? __popc(mask & ((1u << lane) - 1u)) : n_keep;
+					const bool pad = !keep && (n_keep & 1) && lane == (__ffs(~mask) - 1);
+					if (keep || pad) {
+						const int slot = pos >> 1, h = pos & 1;
+						q.v[0][slot][h] = keep ? xr.x : 0.0f;
+						q.v[0][slot][2 + h] = keep ? xr.y : 0.0f;
+						q.v[1][slot][h] = keep ? co.x : 0.0f;
+						q.v[1][slot][2 + h] = keep ? -co.y : 0.0f;
+						q.v[2][slot][h] = keep ? co.z : 0.0f;
+						q.v[2][slot][2 + h] = keep ? co.w : 0.0f;
+						q.v[3][slot][h] = keep ? xr.z : 0.0f;
+						q.v[3][slot][2 + h] = keep ? xr.w : 0.0f;
+						q.v[4][slot][h] = keep ? s.bid[st][j].x : 0.0f;
+						q.v[4][slot][2 + h] = __uint_as_float(keep ? (uint32_t)(batch * kBatchF + j + 1) : 0u);
+					}
+				}
+				__syncwarp();
+				const int n_pairs = (n_keep + 1) >> 1;
+#pragma unroll 2
+				for (int k = 0; k < n_pairs; k++) {
+					const ulonglong2 XY = *reinterpret_cast<const ulonglong2*>(q.v[0][k]);
+					const ulonglong2 AB = *reinterpret_cast<const ulonglong2*>(q.v[1][k]);
+					const ulonglong2 CO = *reinterpret_cast<const ulonglong2*>(q.v[2][k]);
+					// forward.cu:331-335: d = xy - pixf; power = -0.5 (a dx dx + c dy dy) - b dx dy
+					const f2 dx = add2(XY.x, npx), dy = add2(XY.y, npy);
+					f2 t = mul2(dy, CO.x);
+					const f2 u = mul2(dx, AB.x);
+					t = mul2(dy, t);
+					const f2 sq = fma2(dx, u, t);
+					const f2 v = mul2(dx, AB.y);
+					const f2 w = mul2(dy, v);
+					const f2 power = fma2(sq, neg_half, w);
+					// forward.cu:343: alpha = min(0.99, opacity * exp(power))
+					const f2 al = mul2(CO.y, exp2x(power));
+					const float aA = fminf(lo(al), 0.99f), aB = fminf(hi(al), 0.99f);
+					const float4 BP = *reinterpret_cast<const float4*>(q.v[4][k]);
+
+					// splat A -- forward.cu:336,344: the two `continue`s zero alpha; :346-351: test_T = T (1 - alpha), a
+					// skipped splat gives T back (T >= 1e-4 while the pixel is live), a terminating one freezes the pixel
+					const bool sA = (lo(power) > 0.0f) | (aA < thr);
+					const float eA = sA ? 0.0f : aA;
+					const float ttA = __fmul_rn(T, __fadd_rn(1.0f, -eA));
+					const bool tA = ttA < 0.0001f;
+					thr = tA ? kInf : thr;
+					const float wA = tA ? 0.0f : eA;
+					const float TA = T;
+					T = tA ? T : ttA;
+					last_contributor = (sA | tA) ? last_contributor : __float_as_uint(BP.z);
+					// splat B
+					const bool sB = (hi(power) > 0.0f) | (aB < thr);
+					const float eB = sB ? 0.0f : aB;
+					const float ttB = __fmul_rn(T, __fadd_rn(1.0f, -eB));
+					const bool tB = ttB < 0.0001f;
+					thr = tB ? kInf : thr;
+					const float wB = tB ? 0.0f : eB;
+					const float TB = T;
+					T = tB ? T : ttB;
+					last_contributor = (sB | tB) ? last_contributor : __float_as_uint(BP.w);
+
+					// forward.cu:354-355: C += (feature * alpha) * T
+					const ulonglong2 RG = *reinterpret_cast<const ulonglong2*>(q.v[3][k]);
+					const f2 w2 = pk(wA, wB);
+					const f2 cr = mul2(w2, RG.x), cg = mul2(w2, RG.y), cb = mul2(w2, pk(BP.x, BP.y));
+					C0 = __fmaf_rn(TB, hi(cr), __fmaf_rn(TA, lo(cr), C0));
+					C1 = __fmaf_rn(TB, hi(cg), __fmaf_rn(TA, lo(cg), C1));
+					C2 = __fmaf_rn(TB, hi(cb), __fmaf_rn(TA, lo(cb), C2));
+				}
+				__syncwarp();   // the queue is rewritten by the next chunk
+				if (__all_sync(0xffffffffu, thr == kInf)) {
+					warp_done = true;
+					if (lane == 0)
+						atomicAdd(&s.done_warps, 1u);
+					break;
+				}
+			}
+		}
+
+		// release the stage; the warp that arrives last refills it, unless every warp of the tile has finished
+		__syncwarp();
+		if (lane == 0) {
+			__threadfence_block();
+			const uint32_t old = atomicAdd(&s.released[st], 1u);
+			if ((old & (kThreads / 32 - 1)) == kThreads / 32 - 1 && batch + kStagesF < num_batches) {
+				if (*reinterpret_cast<volatile uint32_t*>(&s.done_warps) == kThreads / 32)
+					atomicMin(&s.stop_at, batch + kStagesF);
+				else
+					issue(batch + kStagesF, st);
+			}
+		}
+		if (++st == kStagesF) {
+			st = 0;
+			parity ^= 1u;
+		}
+	}
+
+	// forward.cu:366-373
+	if (inside) {
+		const uint32_t pix_id = (uint32_t)W * py + px;
+		img.accum_alpha[pix_id] = T;
+		img.n_contrib[pix_id] = last_contributor;
+		const size_t HW = (size_t)H * W;
+		out_color[0 * HW + pix_id] = C0 + T * bg_color[0];
+		out_color[1 * HW + pix_id] = C1 + T * bg_color[1];
+		out_color[2 * HW + pix_id] = C2 + T * bg_color[2];
+	}
+}
+
 } // namespace
 
 int launch_blend_forward(const GeometryState& g, const BinningState& b, const ImageState& img, uint32_t capacity,
@@ -388,8 +627,14 @@ int launch_blend_forward(const GeometryState& g, const BinningState& b, const Im
 	const int num_tiles = vp.tiles_x * vp.tiles_y;
 	if (num_tiles <= 0)
 		return GM_OK;
-	// GM_BLEND_SCALAR=1 selects the one-pixel-per-thread kernel (kept for A/B measurements)
+	// GM_BLEND_SCALAR=1 selects the one-pixel-per-thread kernel, GM_BLEND_FWD=barrier the packed-pair kernel with a
+	// block barrier per batch (both kept for A/B measurements); the default is the packed-pair kernel over the stage ring
 	static const bool scalar = std::getenv("GM_BLEND_SCALAR") != nullptr && std::getenv("GM_BLEND_SCALAR")[0] == '1';
+	static const bool barrier = std::getenv("GM_BLEND_FWD") != nullptr && std::getenv("GM_BLEND_FWD")[0] == 'b';
+	if (!scalar && !barrier) {
+		launch_k(blend_forward_ring_kernel, dim3(num_tiles), dim3(kThreads), 0, stream, g, b, img, capacity, vp.W, vp.H, vp.tiles_x, vp.bg, out_color);
+		return GM_OK;
+	}
 	if (scalar)
 		launch_k(blend_forward_kernel, dim3(num_tiles), dim3(kThreads), 0, stream, g, b, img, capacity, vp.W, vp.H, vp.tiles_x, vp.bg, out_color);
 	else

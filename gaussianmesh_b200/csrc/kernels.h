@@ -89,6 +89,9 @@ int launch_adam(int n, const gm_adam_tensor* tensors, int step, float beta1, flo
 int launch_adam_sharded_p2p(int world, int rank, const float* const* grads, float* const* params, int num_segments,
                             const gm_adam_segment* segments, size_t total, float* exp_avg, float* exp_avg_sq, int step,
                             float beta1, float beta2, float eps, cudaStream_t stream);
+int launch_adam_sharded_mc(int world, int rank, const float* grads_mc, float* params_mc, const float* params_local,
+                           int num_segments, const gm_adam_segment* segments, size_t total, float* exp_avg, float* exp_avg_sq,
+                           int step, float beta1, float beta2, float eps, cudaStream_t stream);
 int launch_densify_stats(int P, const int* radii, const float* dL_dmean2D, float* max_radii2D, float* grad_accum,
                          float* denom, const uint32_t* skip_flag, cudaStream_t stream);
 

@@ -159,6 +159,88 @@ adam_sharded_p2p_kernel(const __grid_constant__ ShardedAdamArgs a, float b0, flo
 			*reinterpret_cast<float4*>(a.params[q] + i) = out;
 }
 
+// ---- the same exchange through the NVSwitch multicast mapping (NVLS) -----------------------------------------------
+// With a multicast address over every rank's gradient vector, ONE multimem.ld_reduce returns the sum of the N copies --
+// the reduction happens inside the switch, so each rank pulls 1/N of the vector once instead of N-1 peer copies of it --
+// and ONE multimem.st writes the updated parameters into all N parameter vectors.  Per GPU and step the NVLink bytes
+// drop from 2 (N-1)/N * bytes(vector) to about 2/N * bytes(vector) in each direction.  Four 128-bit reductions are in
+// flight per thread before the first is consumed.
+struct ShardedAdamMcArgs {
+	const float* grads_mc;         // multicast address of the flat gradient vectors
+	float* params_mc;              // multicast address of the flat parameter vectors
+	const float* params_local;     // this rank's own parameter vector (unicast)
+	gm_adam_segment seg[kAdamMaxTensors];
+	int num_segments;
+	size_t lo, hi;
+	float* exp_avg;
+	float* exp_avg_sq;
+};
+
+__device__ __forceinline__ float4 multimem_ld_reduce_add(const float* mc_addr)
+{
+	float4 v;
+	asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+	             : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(mc_addr) : "memory");
+	return v;
+}
+
+__device__ __forceinline__ void multimem_st(float* mc_addr, float4 v)
+{
+	asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};"
+	             ::"l"(mc_addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+constexpr int kMcUnroll = 4;
+
+__global__ void __launch_bounds__(kThreads)
+adam_sharded_mc_kernel(const __grid_constant__ ShardedAdamMcArgs a, float b0, float b1, float bias, float eps,
+                       float inv_world)
+{
+	pdl_sync();
+	const size_t base = a.lo + (size_t)blockIdx.x * (kThreads * kMcUnroll * 4) + (size_t)threadIdx.x * 4;
+	float4 g[kMcUnroll];
+	bool live[kMcUnroll];
+	int seg_of[kMcUnroll];
+#pragma unroll
+	for (int u = 0; u < kMcUnroll; u++) {
+		const size_t i = base + (size_t)u * kThreads * 4;
+		int k = -1;
+#pragma unroll
+		for (int s = 0; s < kAdamMaxTensors; s++)
+			if (s < a.num_segments && i >= a.seg[s].offset && i < a.seg[s].offset + a.seg[s].numel)
+				k = s;
+		seg_of[u] = k;
+		live[u] = i < a.hi && k >= 0;                              // k < 0: alignment padding between tensors
+		if (live[u])
+			g[u] = multimem_ld_reduce_add(a.grads_mc + i);          // sum over the ranks, reduced in the switch
+	}
+#pragma unroll
+	for (int u = 0; u < kMcUnroll; u++) {
+		if (!live[u])
+			continue;
+		const size_t i = base + (size_t)u * kThreads * 4;
+		const gm_adam_segment& sg = a.seg[seg_of[u]];
+		const size_t rel = i - sg.offset;
+		float gv[4] = {g[u].x * inv_world, g[u].y * inv_world, g[u].z * inv_world, g[u].w * inv_world};
+		const float4 p4 = *reinterpret_cast<const float4*>(a.params_local + i);
+		float pv[4] = {p4.x, p4.y, p4.z, p4.w};
+		const float4 m4 = *reinterpret_cast<const float4*>(a.exp_avg + (i - a.lo));
+		const float4 v4 = *reinterpret_cast<const float4*>(a.exp_avg_sq + (i - a.lo));
+		float mv[4] = {m4.x, m4.y, m4.z, m4.w}, vv[4] = {v4.x, v4.y, v4.z, v4.w};
+		unsigned int r = sg.period > 0 ? (unsigned int)(rel % sg.period) : 0u;
+#pragma unroll
+		for (int c = 0; c < 4; c++) {
+			const float lr = (sg.period > 0 && r < sg.split) ? sg.lr_head : sg.lr;
+			r = (r + 1 == sg.period) ? 0u : r + 1;
+			if (rel + c < sg.numel)
+				adam_one(pv[c], gv[c], mv[c], vv[c], b0, b1, lr * bias, eps);
+		}
+		*reinterpret_cast<float4*>(a.exp_avg + (i - a.lo)) = make_float4(mv[0], mv[1], mv[2], mv[3]);
+		*reinterpret_cast<float4*>(a.exp_avg_sq + (i - a.lo)) = make_float4(vv[0], vv[1], vv[2], vv[3]);
+		multimem_st(a.params_mc + i, make_float4(pv[0], pv[1], pv[2], pv[3]));   // into every rank's parameter vector
+	}
+}
+
 __global__ void __launch_bounds__(kThreads)
 densify_stats_kernel(int P, const int* __restrict__ radii, const float* __restrict__ dL_dmean2D,
                      float* __restrict__ max_radii2D, float* __restrict__ grad_accum, float* __restrict__ denom,
@@ -229,6 +311,32 @@ int launch_adam_sharded_p2p(int world, int rank, const float* const* grads, floa
 	const size_t vecs = (hi - lo + 3) / 4;
 	launch_k(adam_sharded_p2p_kernel, dim3((unsigned int)((vecs + kThreads - 1) / kThreads)), dim3(kThreads), 0, stream, 
 		a, beta1, beta2, (float)bias, eps, 1.0f / (float)world);
+	return GM_OK;
+}
+
+int launch_adam_sharded_mc(int world, int rank, const float* grads_mc, float* params_mc, const float* params_local,
+                           int num_segments, const gm_adam_segment* segments, size_t total, float* exp_avg, float* exp_avg_sq,
+                           int step, float beta1, float beta2, float eps, cudaStream_t stream)
+{
+	ShardedAdamMcArgs a;
+	a.grads_mc = grads_mc;
+	a.params_mc = params_mc;
+	a.params_local = params_local;
+	a.num_segments = num_segments;
+	for (int s = 0; s < num_segments; s++)
+		a.seg[s] = segments[s];
+	size_t lo, hi;
+	gm_adam_shard_range(total, world, rank, &lo, &hi);
+	a.lo = lo;
+	a.hi = hi;
+	a.exp_avg = exp_avg;
+	a.exp_avg_sq = exp_avg_sq;
+	if (hi <= lo)
+		return GM_OK;
+	const double bias = sqrt(1.0 - pow((double)beta2, (double)step)) / (1.0 - pow((double)beta1, (double)step));
+	const size_t per_block = (size_t)kThreads * kMcUnroll * 4;
+	launch_k(adam_sharded_mc_kernel, dim3((unsigned int)((hi - lo + per_block - 1) / per_block)), dim3(kThreads), 0, stream,
+	         a, beta1, beta2, (float)bias, eps, 1.0f / (float)world);
 	return GM_OK;
 }
 

@@ -4,13 +4,17 @@ repository is the gradient average before the optimizer.  The reference has no c
 semantics are those of plain data parallelism over views: the loss is the mean over the batch's views, densification
 statistics are accumulated per view as train_mesh_gaussian.py:117-121 does for consecutive iterations.
 
-Two exchange modes:
+Three exchange modes:
 
   "p2p"   gm_adam_step_sharded_p2p: gradient reduce-scatter + Adam + parameter all-gather fused in ONE kernel over
           NVLink peer memory.  Parameters and gradients live in symmetric memory (torch.distributed._symmetric_memory:
           cuMem allocations mapped into every rank); rank r reads shard r of every rank's gradient vector, updates it
           with its shard of the Adam moments (optimizer state is sharded, ZeRO-1 style) and writes the new parameters
           into every rank's parameter vector.  Two device-side barriers bracket the kernel; no host synchronisation.
+  "mc"    gm_adam_step_sharded_mc: the same fused kernel over the NVSwitch MULTICAST mapping of the two vectors
+          (symmetric memory's multicast_ptr): multimem.ld_reduce sums the N gradient copies inside the switch,
+          multimem.st writes the new parameters to all N replicas -- about 2/N of the vector per GPU and direction instead
+          of 2 (N-1)/N.  Needs NVLS (an NVSwitch system); `mode="mc"` raises if the mapping is not available.
   "nccl"  the baseline the fused kernel is measured against: ncclAllReduce of the flat gradient vector followed by the
           replicated one-launch Adam (gm_adam_step) on every rank.
 
@@ -62,15 +66,16 @@ class ViewParallelTrainer:
     def __init__(self, model, opt: OptimizationParams, W: int, H: int, mode: str = "p2p", group=None,
                  spatial_lr_scale: float = 1.0):
         import torch.distributed as dist
-        if mode not in ("p2p", "nccl"):
-            raise ValueError("mode must be 'p2p' or 'nccl'")
+        if mode not in ("p2p", "mc", "nccl"):
+            raise ValueError("mode must be 'p2p', 'mc' or 'nccl'")
         self.mode = mode
         self.exchange = GradientExchange(group)
         self.world, self.rank = self.exchange.world, self.exchange.rank
         dev = model._bc.device
         self._handles = []
         alloc = None
-        if mode == "p2p" and self.world > 1:
+        fused = mode in ("p2p", "mc")
+        if fused and self.world > 1:
             import torch.distributed._symmetric_memory as symm_mem
             self._symm = symm_mem
             self._group = group if group is not None else dist.group.WORLD
@@ -79,13 +84,13 @@ class ViewParallelTrainer:
                 t = symm_mem.empty(n, dtype=torch.float32, device=dev)
                 self._handles.append((t, symm_mem.rendezvous(t, self._group)))
                 return t
-        self.it = TrainingIteration(model, opt, W, H, spatial_lr_scale, alloc=alloc, flat_params=(mode == "p2p"))
+        self.it = TrainingIteration(model, opt, W, H, spatial_lr_scale, alloc=alloc, flat_params=fused)
         it = self.it
         P = it.P
         self._inc_max = torch.zeros(P, dtype=torch.float32, device=dev)
         self._inc_sum = torch.zeros(2, P, dtype=torch.float32, device=dev)
         self.n_step = 0
-        if mode == "p2p":
+        if fused:
             lo, hi = C.c_size_t(), C.c_size_t()
             lib.gm_adam_shard_range(it.flat_numel, self.world, self.rank, C.byref(lo), C.byref(hi))
             self.shard = (lo.value, hi.value)
@@ -98,10 +103,19 @@ class ViewParallelTrainer:
                 self._grad_ptrs = (C.c_void_p * self.world)(*[int(x) for x in g_h.buffer_ptrs])
                 self._param_ptrs = (C.c_void_p * self.world)(*[int(x) for x in p_h.buffer_ptrs])
                 self._barrier = p_h
+                self._grad_mc = int(getattr(g_h, "multicast_ptr", 0) or 0)
+                self._param_mc = int(getattr(p_h, "multicast_ptr", 0) or 0)
+                if mode == "mc" and (self._grad_mc == 0 or self._param_mc == 0):
+                    raise RasterizerError("ViewParallelTrainer", GM_ERR_BAD_ARGUMENT,
+                                          "no multicast mapping for the symmetric allocations (NVLS unavailable): use mode='p2p'")
             else:
                 self._grad_ptrs = (C.c_void_p * 1)(it.param_grads.data_ptr())
                 self._param_ptrs = (C.c_void_p * 1)(it.flat_parameters.data_ptr())
                 self._barrier = None
+                self._grad_mc = self._param_mc = 0
+                if mode == "mc":
+                    raise RasterizerError("ViewParallelTrainer", GM_ERR_BAD_ARGUMENT,
+                                          "mode='mc' needs a process group of at least two ranks (multimem addresses)")
 
     def reserve_for(self, cams: Sequence, bg: torch.Tensor) -> int:
         return self.it.reserve_for(cams, bg)
@@ -132,9 +146,16 @@ class ViewParallelTrainer:
                 rows = it.adam_segments()
                 segs = (AdamSegment * len(rows))(*[AdamSegment(*r) for r in rows])
                 self._device_barrier(0)          # every rank's gradients are complete
-                check(lib.gm_adam_step_sharded_p2p(self.world, self.rank, self._grad_ptrs, self._param_ptrs, len(rows), segs,
-                                                   it.flat_numel, self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(),
-                                                   self.n_step, 0.9, 0.999, 1e-15, stream), "gm_adam_step_sharded_p2p")
+                if self.mode == "mc":
+                    check(lib.gm_adam_step_sharded_mc(self.world, self.rank, self._grad_mc, self._param_mc,
+                                                      it.flat_parameters.data_ptr(), len(rows), segs, it.flat_numel,
+                                                      self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(), self.n_step, 0.9,
+                                                      0.999, 1e-15, stream), "gm_adam_step_sharded_mc")
+                else:
+                    check(lib.gm_adam_step_sharded_p2p(self.world, self.rank, self._grad_ptrs, self._param_ptrs, len(rows),
+                                                       segs, it.flat_numel, self.exp_avg.data_ptr(),
+                                                       self.exp_avg_sq.data_ptr(), self.n_step, 0.9, 0.999, 1e-15, stream),
+                          "gm_adam_step_sharded_p2p")
                 self._device_barrier(1)          # every rank's parameter stores have landed
         if it.iteration < it.opt.densify_until_iter:
             self.exchange.merge_stats_(it.max_radii2D, it.bc_gradient_accum, it.denom, self._inc_max, self._inc_sum)

@@ -340,6 +340,16 @@ int gm_adam_step_sharded_p2p(int world, int rank, const float* const* grads_host
                              float* exp_avg, float* exp_avg_sq, int step, float beta1, float beta2, float eps,
                              gm_stream_t stream);
 
+/*  The same exchange through a MULTICAST mapping of the two vectors (NVSwitch / NVLS; torch symmetric memory exposes
+ *  it as handle.multicast_ptr): multimem.ld_reduce.add sums the N gradient copies inside the switch, multimem.st writes
+ *  the new parameters into all N parameter vectors.  grads_multicast / params_multicast are the multicast addresses,
+ *  params_local this rank's own (unicast) parameter vector; everything else as gm_adam_step_sharded_p2p.  Per GPU the
+ *  NVLink traffic drops from 2 (N-1)/N to about 2/N of the vector in each direction. */
+int gm_adam_step_sharded_mc(int world, int rank, const float* grads_multicast, float* params_multicast,
+                            const float* params_local, int num_segments, const gm_adam_segment* segments_host, size_t total,
+                            float* exp_avg, float* exp_avg_sq, int step, float beta1, float beta2, float eps,
+                            gm_stream_t stream);
+
 /*  gm_densify_stats (train_mesh_gaussian.py:117-121, scene/mesh_based_gaussian_model.py:587-589): for every Gaussian
  *  with radii > 0:  max_radii2D = max(max_radii2D, radii);  grad_accum += |dL_dmean2D.xy|;  denom += 1. */
 int gm_densify_stats(int P, const int32_t* radii, const float* dL_dmean2D /*[P,3]*/, float* max_radii2D /*[P]*/,

@@ -21,8 +21,10 @@ def test_view_parallel_training_two_ranks(cuda_device):
     per_rank = json.loads([l for l in out.stdout.splitlines() if l.startswith("[")][-1])
     assert len(per_rank) == 2
     for res in per_rank:
-        for mode in ("nccl", "p2p"):
+        for mode in ("nccl", "p2p", "mc"):
             r = res[mode]
+            if mode == "mc" and "error" in r and "NVLS unavailable" in r["error"]:
+                continue                  # no multicast mapping on this box (no NVSwitch): the P2P kernel is the fused path
             assert "error" not in r, r
             assert r["replicas_identical"] and r["max_radii_equal"] and r["denom_equal"] and r["accum_rel"] <= 1e-3
             for k in ("_features", "_bc", "_distance", "_scaling", "_rotation", "_opacity"):

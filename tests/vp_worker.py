@@ -62,7 +62,7 @@ def main():
     out = {"world": world}
     lr_max = {"_features": opt.feature_lr, "_bc": opt.position_lr_init, "_distance": opt.position_lr_init,
               "_scaling": opt.scaling_lr, "_rotation": opt.rotation_lr, "_opacity": opt.opacity_lr}
-    for mode in ("nccl", "p2p"):
+    for mode in ("nccl", "p2p", "mc"):
         try:
             got_p, got_s = run(mode)
         except Exception as ex:      # report, do not hang the other rank
