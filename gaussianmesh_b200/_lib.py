@@ -121,7 +121,9 @@ lib = _load()
 
 def check(rc: int, where: str) -> int:
     if rc < 0:
-        detail = lib.gm_last_error().decode() if rc == GM_ERR_CUDA else ""
+        detail = lib.gm_last_error().decode() if rc in (GM_ERR_CUDA, GM_ERR_BAD_ARGUMENT) else ""
+        if rc == GM_ERR_BAD_ARGUMENT and "aligned" not in detail:
+            detail = ""          # the library only describes alignment rejections; anything else in there is stale
         raise RasterizerError(where, rc, detail)
     return rc
 

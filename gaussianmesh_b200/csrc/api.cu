@@ -128,6 +128,18 @@ static uint32_t binning_capacity_instances(size_t bytes)
 	return (uint32_t)r;
 }
 
+// The kernels read a quaternion row with one 128-bit access: [P,4] float rows are 16 bytes, so only the base can be off.
+static bool misaligned16(const void* p)
+{
+	return p != nullptr && (reinterpret_cast<uintptr_t>(p) & 15u) != 0;
+}
+
+static int reject_misaligned(const char* what)
+{
+	g_last_error = std::string(what) + " must be 16-byte aligned (quaternion rows are read as float4)";
+	return GM_ERR_BAD_ARGUMENT;
+}
+
 static int forward_stage0(char* geom_buffer, int P, const ViewParams& vp, const float* means3D, const float* shs,
                           const float* colors_precomp, const float* opacities, const float* scales,
                           const float* rotations, const float* cov3D_precomp, bool prefiltered, int* radii,
@@ -139,6 +151,8 @@ static int forward_stage0(char* geom_buffer, int P, const ViewParams& vp, const 
 		return GM_ERR_BAD_ARGUMENT;
 	if (cov3D_precomp == nullptr && (scales == nullptr || rotations == nullptr))
 		return GM_ERR_BAD_ARGUMENT;
+	if (cov3D_precomp == nullptr && misaligned16(rotations))
+		return reject_misaligned("rotations");
 	const int num_tiles = vp.tiles_x * vp.tiles_y;
 	if (num_tiles > GM_MAX_TILES)
 		return GM_ERR_TOO_MANY_TILES;
@@ -371,6 +385,8 @@ int gm_backward_ex(int P, int D, int M, int R, const float* background, int widt
 		return GM_ERR_BAD_ARGUMENT;
 	if (vp.tiles_x * vp.tiles_y > GM_MAX_TILES)
 		return GM_ERR_TOO_MANY_TILES;
+	if (sr_path && (misaligned16(rotations) || misaligned16(dL_drot)))
+		return reject_misaligned("rotations / dL_drot");
 	if (P == 0)
 		return GM_OK;
 
@@ -418,6 +434,8 @@ int gm_mesh_bind_forward(int P, const float* bc_logits, const float* distance, c
 		return GM_ERR_BAD_ARGUMENT;
 	if ((scale != nullptr && !log_scale) || (rot != nullptr && !rot_raw) || (opacity != nullptr && !opacity_logit))
 		return GM_ERR_BAD_ARGUMENT;
+	if (rot != nullptr && (misaligned16(rot) || misaligned16(rot_raw)))
+		return reject_misaligned("rot / rot_raw");
 	{ StageScope scope_(kStMeshBindFwd, (cudaStream_t)stream); launch_mesh_bind_forward(P, bc_logits, distance, vertex1, vertex2, vertex3, normal, r, alpha_distance, log_scale,
 	                         rot_raw, opacity_logit, xyz, scale, rot, opacity, (cudaStream_t)stream); }
 	return check_stage("mesh_bind_forward", false, (cudaStream_t)stream);
@@ -439,6 +457,8 @@ int gm_mesh_bind_backward(int P, const float* bc_logits, const float* distance, 
 	if ((dL_dscale && dL_dlog_scale && !log_scale) || (dL_drot && dL_drot_raw && !rot_raw) ||
 	    (dL_dopacity && dL_dopacity_logit && !opacity_logit))
 		return GM_ERR_BAD_ARGUMENT;
+	if (dL_drot && dL_drot_raw && (misaligned16(dL_drot) || misaligned16(dL_drot_raw) || misaligned16(rot_raw)))
+		return reject_misaligned("rot_raw / dL_drot / dL_drot_raw");
 	{ StageScope scope_(kStMeshBindBwd, (cudaStream_t)stream); launch_mesh_bind_backward(P, bc_logits, distance, vertex1, vertex2, vertex3, normal, r, alpha_distance, log_scale,
 	                          rot_raw, opacity_logit, dL_dxyz, dL_dscale, dL_drot, dL_dopacity, dL_dbc_logits,
 	                          dL_ddistance, dL_dlog_scale, dL_drot_raw, dL_dopacity_logit, (cudaStream_t)stream); }

@@ -76,7 +76,13 @@ def read_ply_vertices(path: str) -> Dict[str, np.ndarray]:
 def load_mesh_gaussian_ply(path: str, max_sh_degree: int = 3) -> Dict[str, np.ndarray]:
     """MeshBasedGaussianModel.load_ply (scene/mesh_based_gaussian_model.py:341-409) -> the arrays
     `renderer.MeshGaussianModel` takes.  Note the reference stores f_dc / f_rest channel-major
-    ([P,3,K] flattened) and transposes to [P,K,3] on load; `shs` here is the concatenated [P,16,3]."""
+    ([P,3,K] flattened) and transposes to [P,K,3] on load; `shs` here is the concatenated [P,16,3].
+
+    One deliberate difference: the reference's load_ply assigns `self._bc = jt.array(xyz)` (:393) -- the saved barycentric
+    logits ca / cb / cc are read (:347-349) and dropped, so get_xyz of a reloaded model is meaningless there and the edit
+    tool only ever uses get_load_xyz.  Here `bc_logits` are the saved ca / cb / cc (what save_ply wrote, :321) and the
+    saved positions are returned separately as `xyz`, so a loaded model binds to its faces exactly as the trained one did.
+    `vertex_index` (v_index1..3) are the per-Gaussian vertex ids MeshGaussianModel carries through densification."""
     v = read_ply_vertices(path)
     stack = lambda *names: np.stack([v[n] for n in names], axis=1).astype(np.float32)
     P = v["x"].shape[0]

@@ -64,7 +64,9 @@ class MeshGaussianModel:
         self.vertex1, self.vertex2, self.vertex3 = t("vertex1"), t("vertex2"), t("vertex3")
         self.normal, self.r = t("normal"), t("r")
         # mesh bookkeeping carried through densification (scene/mesh_based_gaussian_model.py:59-66); optional
-        self.vertex_index = t("triangles").long() if "triangles" in arrays else None
+        # ("triangles" is the synthetic generator's name, "vertex_index" the PLY loader's -- io.load_mesh_gaussian_ply)
+        tri_key = "triangles" if "triangles" in arrays else ("vertex_index" if "vertex_index" in arrays else None)
+        self.vertex_index = t(tri_key).long() if tri_key else None
         self.fid = t("face_id").long().view(-1, 1) if "face_id" in arrays else None
         self.v = t("mesh_vertices") if "mesh_vertices" in arrays else None
         self.alpha_distance = alpha_distance
@@ -75,6 +77,20 @@ class MeshGaussianModel:
 
     def parameters(self) -> List[torch.Tensor]:
         return [self._bc, self._distance, self._scaling, self._rotation, self._opacity, self._features]
+
+    def to_arrays(self) -> Dict[str, np.ndarray]:
+        """The arrays io.save_mesh_gaussian_ply writes (scene/mesh_based_gaussian_model.py:305-334): parameters, per-Gaussian
+        face data and the mesh bookkeeping carried through densification."""
+        c = lambda x: x.detach().cpu().numpy()
+        P = self._bc.shape[0]
+        with torch.no_grad():
+            xyz = c(self.activate()[0]) if self._bc.is_cuda else np.zeros((P, 3), np.float32)
+        tri = c(self.vertex_index).astype(np.int32) if self.vertex_index is not None else np.zeros((P, 3), np.int32)
+        fid = c(self.fid).astype(np.int32).reshape(P, 1) if self.fid is not None else np.zeros((P, 1), np.int32)
+        return {"xyz": xyz, "normal": c(self.normal), "bc_logits": c(self._bc), "vertex1": c(self.vertex1),
+                "vertex2": c(self.vertex2), "vertex3": c(self.vertex3), "distance": c(self._distance), "vertex_index": tri,
+                "r": c(self.r), "face_id": fid, "shs": c(self._features), "opacity_logit": c(self._opacity),
+                "log_scales": c(self._scaling), "rot_raw": c(self._rotation)}
 
     def activate(self):
         """(xyz, scaling, rotation, opacity) -- one kernel, one autograd node."""

@@ -329,8 +329,10 @@ class TrainingIteration:
         mesh vertices; the survivors keep their Adam moments, children start at zero; statistics restart."""
         if N not in (4, 5):
             raise ValueError("N must be 4 or 5 (split_mesh_and_gaussian / split_mesh_and_gaussian_pro)")
-        if self._flat:
-            raise NotImplementedError("densification of a symmetric-memory (view-parallel) model is not implemented")
+        # with flat_params the new tensors are moved into a freshly allocated flat vector by _allocate() below (for a
+        # symmetric-memory model that is a collective: every rank must densify with the same `grads`, which the merged
+        # statistics of view_parallel guarantee); the sharded Adam moments of that mode are carried by
+        # ViewParallelTrainer.densify_and_prune, the ones handled here are the replicated optimizer's
         m = self.model
         sel = grads.reshape(-1) >= grad_threshold
         S = int(sel.sum().item())                       # the reference reads this back too (:514)

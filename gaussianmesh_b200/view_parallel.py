@@ -91,34 +91,105 @@ class ViewParallelTrainer:
         self._inc_sum = torch.zeros(2, P, dtype=torch.float32, device=dev)
         self.n_step = 0
         if fused:
-            lo, hi = C.c_size_t(), C.c_size_t()
-            lib.gm_adam_shard_range(it.flat_numel, self.world, self.rank, C.byref(lo), C.byref(hi))
-            self.shard = (lo.value, hi.value)
-            n = max(hi.value - lo.value, 4)
+            if mode == "mc" and self.world == 1:
+                raise RasterizerError("ViewParallelTrainer", GM_ERR_BAD_ARGUMENT,
+                                      "mode='mc' needs a process group of at least two ranks (multimem addresses)")
+            self._bind_flat_buffers()
+            lo, hi = self.shard
+            n = max(hi - lo, 4)
             self.exp_avg = torch.zeros(n, dtype=torch.float32, device=dev)          # this rank's shard only
             self.exp_avg_sq = torch.zeros(n, dtype=torch.float32, device=dev)
-            if self.world > 1:
-                (g_t, g_h), (p_t, p_h) = self._handles[0], self._handles[1]        # alloc order: param_grads, flat_parameters
-                assert g_t.data_ptr() == it.param_grads.data_ptr() and p_t.data_ptr() == it.flat_parameters.data_ptr()
-                self._grad_ptrs = (C.c_void_p * self.world)(*[int(x) for x in g_h.buffer_ptrs])
-                self._param_ptrs = (C.c_void_p * self.world)(*[int(x) for x in p_h.buffer_ptrs])
-                self._barrier = p_h
-                self._grad_mc = int(getattr(g_h, "multicast_ptr", 0) or 0)
-                self._param_mc = int(getattr(p_h, "multicast_ptr", 0) or 0)
-                if mode == "mc" and (self._grad_mc == 0 or self._param_mc == 0):
-                    raise RasterizerError("ViewParallelTrainer", GM_ERR_BAD_ARGUMENT,
-                                          "no multicast mapping for the symmetric allocations (NVLS unavailable): use mode='p2p'")
-            else:
-                self._grad_ptrs = (C.c_void_p * 1)(it.param_grads.data_ptr())
-                self._param_ptrs = (C.c_void_p * 1)(it.flat_parameters.data_ptr())
-                self._barrier = None
-                self._grad_mc = self._param_mc = 0
-                if mode == "mc":
-                    raise RasterizerError("ViewParallelTrainer", GM_ERR_BAD_ARGUMENT,
-                                          "mode='mc' needs a process group of at least two ranks (multimem addresses)")
+            if mode == "mc" and (self._grad_mc == 0 or self._param_mc == 0):
+                raise RasterizerError("ViewParallelTrainer", GM_ERR_BAD_ARGUMENT,
+                                      "no multicast mapping for the symmetric allocations (NVLS unavailable): use mode='p2p'")
 
     def reserve_for(self, cams: Sequence, bg: torch.Tensor) -> int:
         return self.it.reserve_for(cams, bg)
+
+    # ------------------------------------------------------------------------------------------
+    # densification of the replicated / symmetric-memory model (scene/mesh_based_gaussian_model.py:504-585,
+    # train_mesh_gaussian.py:119-132).  Every rank holds the same merged statistics, so every rank takes the same
+    # decisions; in the fused modes the flat vectors are re-created (a collective rendezvous) and the sharded Adam
+    # moments are re-partitioned for the new layout.
+    # ------------------------------------------------------------------------------------------
+    def _bind_flat_buffers(self) -> None:
+        """Shard range, peer / multicast addresses and the barrier handle of the CURRENT flat vectors."""
+        it = self.it
+        lo, hi = C.c_size_t(), C.c_size_t()
+        lib.gm_adam_shard_range(it.flat_numel, self.world, self.rank, C.byref(lo), C.byref(hi))
+        self.shard = (lo.value, hi.value)
+        if self.world > 1:
+            (g_t, g_h), (p_t, p_h) = self._handles[-2], self._handles[-1]             # alloc order: param_grads, flat_parameters
+            assert g_t.data_ptr() == it.param_grads.data_ptr() and p_t.data_ptr() == it.flat_parameters.data_ptr()
+            self._grad_ptrs = (C.c_void_p * self.world)(*[int(x) for x in g_h.buffer_ptrs])
+            self._param_ptrs = (C.c_void_p * self.world)(*[int(x) for x in p_h.buffer_ptrs])
+            self._barrier = p_h
+            self._grad_mc = int(getattr(g_h, "multicast_ptr", 0) or 0)
+            self._param_mc = int(getattr(p_h, "multicast_ptr", 0) or 0)
+        else:
+            self._grad_ptrs = (C.c_void_p * 1)(it.param_grads.data_ptr())
+            self._param_ptrs = (C.c_void_p * 1)(it.flat_parameters.data_ptr())
+            self._barrier = None
+            self._grad_mc = self._param_mc = 0
+
+    def _gather_moments(self):
+        """The full flat Adam moment vectors from the per-rank shards (once per densification)."""
+        it = self.it
+        full = [torch.zeros(it.flat_numel, dtype=torch.float32, device=it.device) for _ in range(2)]
+        for vec, mine in zip(full, (self.exp_avg, self.exp_avg_sq)):
+            parts = []
+            for r in range(self.world):
+                lo, hi = C.c_size_t(), C.c_size_t()
+                lib.gm_adam_shard_range(it.flat_numel, self.world, r, C.byref(lo), C.byref(hi))
+                parts.append(vec[lo.value:hi.value])
+            own = parts[self.rank]
+            own.copy_(mine[:own.numel()])
+            if self.world > 1:
+                self.exchange.dist.all_gather(parts, own.clone(), group=self.exchange.group)
+        return full
+
+    def densify_and_prune(self, max_grad: float, min_opacity: float = 0.005, extent: float = 0.0, max_screen_size=None,
+                          N: int = 4) -> int:
+        """TrainingIteration.densify_and_prune for the view-parallel trainer, every mode.  Returns the number of Gaussians
+        split (the same on every rank)."""
+        it = self.it
+        fused = self.mode in ("p2p", "mc")
+        if not fused:
+            return it.densify_and_prune(max_grad, min_opacity, extent, max_screen_size, N)
+        grads = it.bc_gradient_accum / it.denom
+        grads[grads.isnan()] = 0.0
+        sel = grads.reshape(-1) >= max_grad
+        S = int(sel.sum().item())
+        if S == 0:
+            return 0
+        keep = ~sel
+        old_layout = dict(it.layout)
+        old_rows = {gname: getattr(it.model, attr).shape[0] for attr, gname, _ in it.PARAMS}
+        full_m, full_v = self._gather_moments()
+        n_step = self.n_step
+        it.densify_and_split(grads, max_grad, extent, N)      # model surgery + new flat vectors (collective rendezvous)
+        self._bind_flat_buffers()
+        self._handles = self._handles[-2:]                    # the previous symmetric allocations can go
+        # moments of the survivors keep their values, children start at zero (:411-422, cat_tensors_to_optimizer)
+        new_m = torch.zeros(it.flat_numel, dtype=torch.float32, device=it.device)
+        new_v = torch.zeros_like(new_m)
+        kept = int(keep.sum().item())
+        for attr, gname, _ in it.PARAMS:
+            o_off, o_n = old_layout[gname]
+            n_off, _ = it.layout[gname]
+            width = o_n // old_rows[gname]
+            for src, dst in ((full_m, new_m), (full_v, new_v)):
+                dst[n_off:n_off + kept * width].view(kept, width).copy_(src[o_off:o_off + o_n].view(old_rows[gname], width)[keep])
+        lo, hi = self.shard
+        n = max(hi - lo, 4)
+        self.exp_avg = torch.zeros(n, dtype=torch.float32, device=it.device)
+        self.exp_avg_sq = torch.zeros(n, dtype=torch.float32, device=it.device)
+        self.exp_avg[:hi - lo].copy_(new_m[lo:hi])
+        self.exp_avg_sq[:hi - lo].copy_(new_v[lo:hi])
+        self._inc_max = torch.zeros(it.P, dtype=torch.float32, device=it.device)
+        self._inc_sum = torch.zeros(2, it.P, dtype=torch.float32, device=it.device)
+        self.n_step = n_step
+        return S
 
     def _device_barrier(self, channel: int) -> None:
         if self._barrier is not None:

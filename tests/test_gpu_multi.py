@@ -27,6 +27,11 @@ def test_view_parallel_training_two_ranks(cuda_device):
                 continue                  # no multicast mapping on this box (no NVSwitch): the P2P kernel is the fused path
             assert "error" not in r, r
             assert r["replicas_identical"] and r["max_radii_equal"] and r["denom_equal"] and r["accum_rel"] <= 1e-3
+            # densification of the view-parallel model: same Gaussians split as in the single process (up to a handful whose
+            # accumulated gradient sits within rounding of the threshold), replicas still identical after the next step
+            assert r["split"][0] > 0 and abs(r["split"][0] - r["split"][1]) <= 3, r["split"]
+            if r["split"][0] == r["split"][1]:
+                assert r["after_shapes_equal"] and r["after_replicas_identical"] and r["after_max_over_lr"] <= 2.002 * 3, r
             for k in ("_features", "_bc", "_distance", "_scaling", "_rotation", "_opacity"):
                 # Adam steps are ~ +-lr early on: elements with a ~0 gradient may step differently (see test_gpu_training)
                 assert r[k]["max_over_lr"] <= 2.002 * 2 and r[k]["frac_off"] <= 0.02, (mode, k, r[k])

@@ -1074,10 +1074,12 @@ print(json.dumps(out))
 """
 
 
-@pytest.mark.parametrize("env", [{"GM_BLEND_SCALAR": "1"}, {"GM_BLEND_BWD": "mma"}], ids=["scalar", "bwd_mma"])
+@pytest.mark.parametrize("env", [{"GM_BLEND_SCALAR": "1"}, {"GM_BLEND_BWD": "mma"}, {"GM_BLEND_FWD": "ring"}, {"GM_PDL": "0"}],
+                         ids=["scalar", "bwd_mma", "fwd_ring", "no_pdl"])
 def test_alternative_blend_kernels_still_match(cuda_device, tmp_path, env):
     """GM_BLEND_SCALAR=1 selects the one-splat-per-iteration blend kernels, GM_BLEND_BWD=mma the backward that reduces
-    over the pixels on the tensor cores (TF32 mma.sync) -- both kept for A/B measurements (the library reads the variables once, hence the
+    over the pixels on the tensor cores (TF32 mma.sync), GM_BLEND_FWD=ring the forward over a barrier-free stage ring, GM_PDL=0
+    plain stream-ordered launches -- all kept for A/B measurements (the library reads the variables once, hence the
     subprocess): same parity bar as the default kernels."""
     import json
     import os

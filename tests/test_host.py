@@ -211,6 +211,33 @@ def test_mesh_gaussian_ply_roundtrip_and_schema(tmp_path):
     assert np.array_equal(v["f_dc_2"], a["shs"][:, 0, 2])
 
 
+def test_loaded_ply_builds_a_model_that_saves_back(tmp_path, built_lib):
+    """load_mesh_gaussian_ply -> MeshGaussianModel -> to_arrays -> save_mesh_gaussian_ply keeps every column, including the
+    per-Gaussian vertex ids and face ids the densification bookkeeping needs (the loader names them vertex_index / face_id,
+    the synthetic generator triangles / face_id: the model takes either)."""
+    import torch
+    from gaussianmesh_b200 import io, synthetic
+    from gaussianmesh_b200.renderer import MeshGaussianModel
+    V, F = synthetic.icosphere(1)
+    a = synthetic.mesh_bound_scene(120, V, F, seed=5)
+    rec = {"xyz": np.zeros((120, 3), np.float32), "normal": a["normal"], "bc_logits": a["bc_logits"], "vertex1": a["vertex1"],
+           "vertex2": a["vertex2"], "vertex3": a["vertex3"], "distance": a["distance"], "vertex_index": a["triangles"], "r": a["r"],
+           "face_id": a["face_id"][:, None], "shs": a["shs"], "opacity_logit": a["opacity_logit"], "log_scales": a["log_scales"],
+           "rot_raw": a["rot_raw"]}
+    path = str(tmp_path / "in.ply")
+    io.save_mesh_gaussian_ply(path, rec)
+    model = MeshGaussianModel(io.load_mesh_gaussian_ply(path), torch.device("cpu"), requires_grad=False)
+    assert model.vertex_index is not None and torch.equal(model.vertex_index, torch.from_numpy(a["triangles"]).long())
+    assert model.fid is not None and torch.equal(model.fid.view(-1), torch.from_numpy(a["face_id"]).long())
+    out = str(tmp_path / "out.ply")
+    io.save_mesh_gaussian_ply(out, model.to_arrays())
+    back = io.load_mesh_gaussian_ply(out)
+    for k in ("bc_logits", "vertex1", "vertex2", "vertex3", "normal", "distance", "opacity_logit", "r", "shs", "log_scales",
+              "rot_raw", "vertex_index"):
+        assert np.array_equal(back[k], rec[k].astype(back[k].dtype)), k
+    assert np.array_equal(back["face_id"][:, 0], a["face_id"])
+
+
 def test_cameras_json_roundtrip(tmp_path):
     """camera_to_JSON (utils/camera_utils.py:64-84) <-> ObjectVisualTool.get_camera (edittool/__init__.py:547-584)."""
     import json

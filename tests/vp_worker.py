@@ -41,8 +41,15 @@ def main():
             tr.step(cams[s * world + rank], bg, gts[s * world + rank])
         torch.cuda.synchronize()
         dist.barrier()
-        return ({k: getattr(model, k).detach().clone() for k in names},
-                (tr.it.max_radii2D.clone(), tr.it.bc_gradient_accum.clone(), tr.it.denom.clone()))
+        before = ({k: getattr(model, k).detach().clone() for k in names},
+                  (tr.it.max_radii2D.clone(), tr.it.bc_gradient_accum.clone(), tr.it.denom.clone()))
+        # densification of the view-parallel model (every rank takes the same decisions), then one more global step
+        split = tr.densify_and_prune(run.threshold, N=5)
+        tr.step(cams[rank], bg, gts[rank])
+        torch.cuda.synchronize()
+        dist.barrier()
+        after = {k: getattr(model, k).detach().clone() for k in names}
+        return before[0], before[1], split, after
 
     def run_single():
         model = MeshGaussianModel(arrays, dev, requires_grad=False)
@@ -55,16 +62,30 @@ def main():
             it.param_grads.copy_(acc / world)
             it.optimizer.step(it._grad_of)
         torch.cuda.synchronize()
-        return ({k: getattr(model, k).detach().clone() for k in names},
-                (it.max_radii2D.clone(), it.bc_gradient_accum.clone(), it.denom.clone()))
+        before = ({k: getattr(model, k).detach().clone() for k in names},
+                  (it.max_radii2D.clone(), it.bc_gradient_accum.clone(), it.denom.clone()))
+        g = (it.bc_gradient_accum / it.denom).nan_to_num(0.0).reshape(-1)
+        thr = torch.quantile(g[g > 0], 0.97).reshape(1)
+        dist.broadcast(thr, src=0)
+        run.threshold = float(thr)
+        split = it.densify_and_prune(run.threshold, N=5)
+        acc = torch.zeros_like(it.param_grads)
+        for r in range(world):
+            it.step(cams[r], bg, gts[r], iteration=steps + 1, optimizer_step=False)
+            acc += it.param_grads
+        it.param_grads.copy_(acc / world)
+        it.optimizer.step(it._grad_of)
+        torch.cuda.synchronize()
+        after = {k: getattr(model, k).detach().clone() for k in names}
+        return before[0], before[1], split, after
 
-    ref_p, ref_s = run_single()
+    ref_p, ref_s, ref_split, ref_after = run_single()
     out = {"world": world}
     lr_max = {"_features": opt.feature_lr, "_bc": opt.position_lr_init, "_distance": opt.position_lr_init,
               "_scaling": opt.scaling_lr, "_rotation": opt.rotation_lr, "_opacity": opt.opacity_lr}
     for mode in ("nccl", "p2p", "mc"):
         try:
-            got_p, got_s = run(mode)
+            got_p, got_s, got_split, got_after = run(mode)
         except Exception as ex:      # report, do not hang the other rank
             out[mode] = {"error": repr(ex)[:500]}
             continue
@@ -80,6 +101,16 @@ def main():
         other = flat.clone()
         dist.broadcast(other, src=0)
         res["replicas_identical"] = bool(torch.equal(flat, other))
+        # after densify_and_prune + one more step: same split, same shapes, parameters within an Adam step of the single
+        # process, replicas still identical
+        res["split"] = [int(got_split), int(ref_split)]
+        res["after_shapes_equal"] = all(got_after[k].shape == ref_after[k].shape for k in names)
+        if res["after_shapes_equal"]:
+            res["after_max_over_lr"] = max(float((got_after[k] - ref_after[k]).abs().max()) / lr_max[k] for k in names)
+            flat2 = torch.cat([got_after[k].reshape(-1) for k in names])
+            other2 = flat2.clone()
+            dist.broadcast(other2, src=0)
+            res["after_replicas_identical"] = bool(torch.equal(flat2, other2))
         out[mode] = res
     gathered = [None] * world
     dist.all_gather_object(gathered, out)
