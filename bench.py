@@ -461,10 +461,28 @@ class ReferenceArm:
         return loss
 
 
+_JSON_FD = None
+
+
+def emit_json(obj) -> None:
+    """The ONE JSON line goes to the process's original stdout; everything else any library prints (NCCL's version banner
+    is a printf on stdout) was redirected to stderr at start-up."""
+    line = (json.dumps(obj) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(line.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, line)
+
+
 def main():
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)                      # C-level and Python-level stdout -> stderr from here on
     args = parse_args()
     if not torch.cuda.is_available():
-        print(json.dumps({"error": "no CUDA device: the hot path has no CPU fallback"}))
+        emit_json({"error": "no CUDA device: the hot path has no CPU fallback"})
         sys.exit(1)
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local_rank)
@@ -754,7 +772,7 @@ def main():
                                          "cuda_rasterizer sources rebuilt for sm_100a (oracle/_ref), run on the same GPU "
                                          "with the call protocol of its rasterize_points.py, all K steps"}
         out["e2e"] = {k: v for k, v in out["e2e"].items()}      # value, unit, copies, loss, step statistics, cross-arm guard
-        print(json.dumps(out))
+        emit_json(out)
         ctx.close()
         return
 
@@ -821,7 +839,7 @@ def main():
             out["cpu_baseline"] = cpu_oracle.timed_sample(P, WIDTH, HEIGHT, frames=args.cpu_sample_frames)
         except Exception as ex:   # the baseline is a reported number, never a dependency of the product
             out["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": f"failed: {ex!r}"}
-    print(json.dumps(out))
+    emit_json(out)
     ctx.close()
 
 

@@ -155,7 +155,11 @@ class ViewParallelTrainer:
         it = self.it
         fused = self.mode in ("p2p", "mc")
         if not fused:
-            return it.densify_and_prune(max_grad, min_opacity, extent, max_screen_size, N)
+            S = it.densify_and_prune(max_grad, min_opacity, extent, max_screen_size, N)
+            if S:
+                self._inc_max = torch.zeros(it.P, dtype=torch.float32, device=it.device)
+                self._inc_sum = torch.zeros(2, it.P, dtype=torch.float32, device=it.device)
+            return S
         grads = it.bc_gradient_accum / it.denom
         grads[grads.isnan()] = 0.0
         sel = grads.reshape(-1) >= max_grad
