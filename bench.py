@@ -114,6 +114,21 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def nvlink_bytes(gpu_index: int):
+    """(tx, rx) data bytes over all NVLink links of one GPU since driver load (`nvidia-smi nvlink -gt d`), or None."""
+    import re
+    try:
+        out = subprocess.run(["nvidia-smi", "nvlink", "-gt", "d", "-i", str(gpu_index)], capture_output=True, text=True,
+                             timeout=30).stdout
+    except (OSError, subprocess.SubprocessError):
+        return None
+    tx = [int(m) for m in re.findall(r"Data Tx:\s*(\d+)\s*KiB", out)]
+    rx = [int(m) for m in re.findall(r"Data Rx:\s*(\d+)\s*KiB", out)]
+    if not tx or not rx:
+        return None
+    return sum(tx) * 1024, sum(rx) * 1024
+
+
 # ------------------------------------------------------------------------------------------------ workload
 def build_workload(device, P, rank, world):
     from gaussianmesh_b200 import synthetic
@@ -680,7 +695,11 @@ def main():
                 vp = ViewParallelTrainer(vp_model, OptimizationParams(), WIDTH, HEIGHT, mode=mode)
                 if not args.no_presize:
                     vp.reserve_for(cams, bg)
+                torch.cuda.synchronize()
+                barrier()
+                nv0 = nvlink_bytes(local_rank) if rank == 0 else None
                 ms_vp, _ = timed(lambda i: vp.step(cams[i % nv], bg, targets[i % TARGET_POOL]), K, Wm, barrier)
+                nv1 = nvlink_bytes(local_rank) if rank == 0 else None
                 if vp.it.arena.verify():
                     raise RuntimeError("arena overflow inside the timed view-parallel region")
                 ms_vp = max_over_ranks(ms_vp)
@@ -691,6 +710,10 @@ def main():
                 view_parallel[mode] = {"ms_per_step": ms_vp / K, "views_per_s": world * K / (ms_vp * 1e-3),
                                        "step_ms": timed.last_step_stats,
                                        "replicas_identical": all(c == sums[0] for c in sums)}
+                if nv0 is not None and nv1 is not None:
+                    # hardware NVLink data counters of rank 0's GPU around the W + K steps of this mode
+                    view_parallel[mode]["nvlink_tx_mb_per_step"] = (nv1[0] - nv0[0]) / (K + Wm) / 1e6
+                    view_parallel[mode]["nvlink_rx_mb_per_step"] = (nv1[1] - nv0[1]) / (K + Wm) / 1e6
                 del vp, vp_model, flat
             except Exception as ex:       # keep the headline numbers if symmetric memory is unavailable on a box
                 view_parallel[mode] = {"error": repr(ex)[:300]}
