@@ -22,7 +22,7 @@ import numpy as np
 import torch
 
 from . import mesh_gaussians as mg
-from ._lib import lib, check, GM_BACKWARD_OVERWRITE
+from ._lib import lib, check, GM_BACKWARD_OVERWRITE, RasterizerError, GM_ERR_BAD_ARGUMENT
 from .arena import RenderArena
 from .diff_gaussian_rasterizater import (GaussianRasterizationSettings, GaussianRasterizer, NewGaussianRasterizer)
 from .cameras import DeviceCamera, upload_cameras  # noqa: F401  (re-exported)
@@ -538,7 +538,76 @@ class TrainStep:
         """Block until every submitted frame is done; returns how many frames overflowed the arena so far (their
         gradients cover only the tiles that fit).  0 after reserve_for() on the views being trained."""
         self.overflowed_frames += len(self.arena.verify())
+        if getattr(self, "_graph", None) is not None:
+            torch.cuda.synchronize(self.device)
+            self.overflowed_frames += int(self._graph_overflow.item())
+            self._graph_overflow.zero_()
         return self.overflowed_frames
+
+    # ------------------------------------------------------------------------------------------
+    # the same step as ONE CUDA graph launch
+    # ------------------------------------------------------------------------------------------
+    def capture(self, cam, bg: torch.Tensor, target: torch.Tensor) -> None:
+        """Capture step() into a CUDA graph (the programmatic-launch edges between the kernels are kept as graph edges).
+        The graph reads the camera from a static 35-float buffer and the target from a static buffer of `target`'s dtype
+        and shape; step_graph() copies a frame's camera / target into them and replays.  Intrinsics (FoV) are kernel
+        arguments and therefore fixed at capture time; the arena must already be sized (reserve_for)."""
+        if self.arena.capacity == 0:
+            raise RasterizerError("TrainStep.capture", GM_ERR_BAD_ARGUMENT, "size the arena first (reserve_for)")
+        self._g_cam = torch.zeros(35, dtype=torch.float32, device=self.device)
+        self._g_cam.copy_(torch.cat([cam.world_view_transform.reshape(-1), cam.full_proj_transform.reshape(-1),
+                                     cam.camera_center.reshape(-1)]))
+        self._g_target = torch.empty_like(target)
+        self._g_target.copy_(target)
+        self._g_fov = (float(cam.FoVx), float(cam.FoVy))
+        self._g_view = DeviceCamera(cam.image_width, cam.image_height, cam.FoVx, cam.FoVy, self._g_cam[0:16].view(4, 4),
+                                    self._g_cam[16:32].view(4, 4), self._g_cam[32:35])
+        self._graph_overflow = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self._g_bg = bg
+        self.step(self._g_view, bg, self._g_target)          # warm-up outside the capture (module loading, attributes)
+        torch.cuda.synchronize(self.device)
+        self._graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._graph):
+            self._step_captured(self._g_view, bg, self._g_target)
+
+    def _step_captured(self, cam, bg, target) -> None:
+        """step() without the arena's event bookkeeping (events recorded during capture cannot be queried): fixed capacity,
+        overflow accumulated on the device."""
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        va = self._view_args(cam)
+        a = self.arena
+        check(lib.gm_forward(a.geom.data_ptr(), a.binning.data_ptr(), a.binning.numel(), a.image.data_ptr(), self.P, self.D,
+                             self.M, bg.data_ptr(), self.W, self.H, *va, 0, self.image.data_ptr(), self.radii.data_ptr(), 0,
+                             None, stream), "gm_forward")
+        l1 = lib.gm_l1_loss_u8 if target.dtype == torch.uint8 else lib.gm_l1_loss
+        check(l1(self.image.numel(), self.image.data_ptr(), target.data_ptr(), self.loss.data_ptr(), self.dL_dimg.data_ptr(),
+                 stream), "gm_l1_loss")
+        self._accum.zero_()
+        g = self.grads
+        check(lib.gm_backward_ex(self.P, self.D, self.M, a.capacity, bg.data_ptr(), self.W, self.H, va[0], va[1], None, va[4], 1.0,
+                                 va[6], None, va[8], va[9], va[10], va[11], va[12], self.radii.data_ptr(), a.geom.data_ptr(),
+                                 a.binning.data_ptr(), a.image.data_ptr(), self.dL_dimg.data_ptr(), g["means2D"].data_ptr(),
+                                 g["conic"].data_ptr(), g["opacity"].data_ptr(), g["colors"].data_ptr(), g["means3D"].data_ptr(),
+                                 g["cov3D"].data_ptr(), g["sh"].data_ptr(), g["scales"].data_ptr(), g["rotations"].data_ptr(), 0,
+                                 GM_BACKWARD_OVERWRITE, stream), "gm_backward_ex")
+        # frame header word 2 = overflow flag of this frame (gm_frame_overflow_flag)
+        hdr = a.geom[:16].view(torch.int32)
+        self._graph_overflow.add_(hdr[2:3])
+
+    def step_graph(self, cam, bg: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
+        """One training step as a single graph launch: two small device copies (camera, target) + cudaGraphLaunch."""
+        if getattr(self, "_graph", None) is None:
+            self.capture(cam, bg, target)
+        if (float(cam.FoVx), float(cam.FoVy)) != self._g_fov or bg.data_ptr() != self._g_bg.data_ptr():
+            raise RasterizerError("TrainStep.step_graph", GM_ERR_BAD_ARGUMENT,
+                                  "the graph was captured for other intrinsics / another background tensor: capture() again")
+        self._g_cam[0:16].copy_(cam.world_view_transform.reshape(-1), non_blocking=True)
+        self._g_cam[16:32].copy_(cam.full_proj_transform.reshape(-1), non_blocking=True)
+        self._g_cam[32:35].copy_(cam.camera_center.reshape(-1), non_blocking=True)
+        if target.data_ptr() != self._g_target.data_ptr():
+            self._g_target.copy_(target, non_blocking=True)
+        self._graph.replay()
+        return self.loss
 
     def step(self, cam, bg: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
         """Enqueue one training step; returns the (device) loss tensor.  No host synchronisation."""

@@ -497,6 +497,40 @@ def test_train_step_matches_autograd_path(cuda_device):
         assert scenes.rel_err(ts.grads[k].view_as(a), a) <= 1e-5, k
 
 
+def test_train_step_cuda_graph_and_uint8_target(cuda_device):
+    """TrainStep.step_graph (the step as ONE CUDA graph launch, camera / target read from static buffers) against the
+    eager step on other views than the one captured, with the 8-bit target image (value / 255 inside the loss kernel)
+    against the float image the reference's loader would have produced."""
+    from gaussianmesh_b200.renderer import TrainStep
+    from gaussianmesh_b200.mesh_gaussians import image_u8_to_float
+    dev = cuda_device
+    P, W, H = 12_000, 256, 160
+    sc = _scene(dev, P, seed=14)
+    bgt = torch.zeros(3, device=dev)
+    cams = [scenes.camera(dev, W, H, index=i, n=9) for i in (0, 3, 6)]
+    g = torch.Generator().manual_seed(2)
+    targets_u8 = [torch.randint(0, 256, (3, H, W), generator=g, dtype=torch.uint8).to(dev) for _ in cams]
+    targets_f = [t.float() / 255.0 for t in targets_u8]
+    # IEEE division in the kernel; torch divides a float tensor by a scalar by multiplying with its reciprocal (1 ulp apart)
+    assert float((image_u8_to_float(targets_u8[0]) - targets_f[0]).abs().max()) <= 1.2e-7
+    assert torch.equal(image_u8_to_float(targets_u8[0]), (targets_u8[0].double() / 255.0).float())
+    targets_f = [image_u8_to_float(t) for t in targets_u8]
+    eager = TrainStep(dev, sc["means3D"], sc["opacities"], sc["shs"], sc["scales"], sc["rotations"], W, H)
+    graph = TrainStep(dev, sc["means3D"], sc["opacities"], sc["shs"], sc["scales"], sc["rotations"], W, H)
+    eager.reserve_for(cams, bgt)
+    graph.reserve_for(cams, bgt)
+    graph.capture(cams[0], bgt, targets_u8[0])
+    for cam, tu8, tf in zip(cams[::-1], targets_u8[::-1], targets_f[::-1]):
+        l_e = float(eager.step(cam, bgt, tf))
+        l_g = float(graph.step_graph(cam, bgt, tu8))
+        assert abs(l_e - l_g) <= 1e-6
+        assert torch.equal(eager.image, graph.image) and torch.equal(eager.radii, graph.radii)
+        assert torch.equal(eager.dL_dimg, graph.dL_dimg)
+        for k in ("means3D", "sh", "opacity", "scales", "rotations", "means2D"):
+            assert scenes.rel_err(graph.grads[k], eager.grads[k]) <= 1e-5, k
+    assert graph.verify() == 0 and eager.verify() == 0
+
+
 # ------------------------------------------------------------------------------------------------ mesh kernels
 def _eval_sh_torch(deg, sh, dirs):
     """edittool/sh_utils.py:34-89 with sh [P,3,16] and dirs [P,3]."""
