@@ -71,8 +71,6 @@ class pyACAP:
     def GetRS(self, ref_array, deformed_array, _R=1, cpunum=0) -> Tuple[torch.Tensor, torch.Tensor]:
         """(R [1, 9 Vn], S [1, 9 Vn]) float32 on the device.  `ref_array` must be the mesh the object was built from
         (the reference ignores it too: mainpy.cpp:60-64 only updates the deformed copy)."""
-        if not _R:
-            raise NotImplementedError("only _R = 1 (rotation matrices) is implemented; the reference never asks for log-rotations")
         V1 = torch.as_tensor(deformed_array, dtype=torch.float64).contiguous().to(self.device)
         if V1.shape != (self.Vn, 3):
             raise RasterizerError("pyACAP.GetRS", GM_ERR_BAD_ARGUMENT, f"deformed vertices must be [{self.Vn}, 3]")
@@ -83,4 +81,68 @@ class pyACAP:
                                  self.ring.data_ptr(), self.face_off.data_ptr(), self.face_list.data_ptr(),
                                  self.sqrt_w.data_ptr(), self.n0.data_ptr(), self.ata_inv.data_ptr(), self._n1.data_ptr(),
                                  R.data_ptr(), S.data_ptr(), stream), "gm_acap_get_rs")
+        if not _R:
+            # log-rotations with the branch (axis sign, multiples of 2 pi) propagated breadth-first over the mesh
+            # (RefMesh::bfscorrot, FeatureVector.cpp:269-318; logrot, Align.cpp:131-276).  A sequential walk over the
+            # vertices of a control mesh: host side, like the ring builder; no caller of the reference uses it.
+            logr = log_rotations_bfs(R.view(self.Vn, 3, 3).cpu().numpy(), self.ring_off.cpu().numpy(), self.ring.cpu().numpy())
+            R = torch.from_numpy(logr.reshape(1, -1).astype(np.float32)).to(self.device)
         return R, S
+
+
+def _skew(axis: np.ndarray, angle: float) -> np.ndarray:
+    """Rot::ToLogR (Align.cpp:112-122)"""
+    m = np.zeros((3, 3))
+    m[0, 1], m[0, 2], m[1, 2] = -axis[2], axis[1], -axis[0]
+    return angle * (m - m.T)
+
+
+def log_rotations_bfs(R_out: np.ndarray, ring_off: np.ndarray, ring: np.ndarray, root: int = 0) -> np.ndarray:
+    """GetRS(..., _R = 0): per-vertex log-rotation matrices [Vn,3,3] as the reference returns them (the transposed
+    log of the polar rotation, FeatureVector.cpp:531-545).  `R_out` [Vn,3,3] is what GetRS(_R = 1) returns (r^T).
+    The principal logarithm is ambiguous by the sign of the axis and by multiples of 2 pi; the reference fixes both
+    by walking the mesh breadth-first from `root` and keeping every vertex close to its BFS parent."""
+    r = np.swapaxes(np.asarray(R_out, np.float64), 1, 2)
+    Vn = r.shape[0]
+    axis = np.zeros((Vn, 3)); theta = np.zeros(Vn); circlek = np.zeros(Vn)
+    out = np.zeros((Vn, 3, 3))
+    visited = np.zeros(Vn, bool)
+    acos = np.arccos(np.clip((np.trace(r, axis1=1, axis2=2) - 1.0) / 2.0, -1.0, 1.0))
+
+    def raw_axis(j, th):
+        t = (r[j] - r[j].T) / (2.0 * np.sin(th))
+        return np.array([t[2, 1], t[0, 2], t[1, 0]])
+
+    for start in range(root, Vn):
+        if visited[start]:
+            continue
+        visited[start] = True
+        queue = [(start, -1)]
+        head = 0
+        while head < len(queue):
+            j, fa = queue[head]
+            head += 1
+            th = float(acos[j])
+            if fa < 0:                                    # logrot(r), Align.cpp:131-154
+                if abs(th) <= 1e-6:
+                    axis[j], theta[j], circlek[j] = 0.0, 0.0, 0.0
+                else:
+                    a = raw_axis(j, th)
+                    axis[j], theta[j], circlek[j] = a / np.linalg.norm(a), th, 0.0
+            else:                                         # logrot(r, parent), Align.cpp:180-276
+                if abs(th) <= 1e-6:
+                    axis[j], theta[j], circlek[j] = axis[fa], 0.0, circlek[fa]
+                else:
+                    a = axis[fa].copy() if abs(th - np.pi) <= 1e-6 else raw_axis(j, th)
+                    if float(a @ axis[fa]) < 0.0:
+                        a, th = -a, 2.0 * np.pi - th
+                    axis[j], theta[j], circlek[j] = a / np.linalg.norm(a), th, circlek[fa]
+                if abs(th - theta[fa]) > np.pi:
+                    circlek[j] += -1.0 if theta[fa] < np.pi else 1.0
+            out[j] = _skew(axis[j], circlek[j] * 2.0 * np.pi + theta[j]).T
+            for e in range(int(ring_off[j]), int(ring_off[j + 1])):
+                k = int(ring[e])
+                if not visited[k]:
+                    visited[k] = True
+                    queue.append((k, j))
+    return out

@@ -51,7 +51,8 @@ def main():
     logr = np.array([float(x) for x in z.read("test/LOGRNEW.txt").decode().splitlines()[1].split()]).reshape(-1, 3, 3)
     S = np.array([float(x) for x in z.read("test/S.txt").decode().splitlines()[1].split()]).reshape(-1, 3, 3)
     out = os.path.join(ROOT, "tests", "golden", "acap_1_to_2.npz")
-    np.savez_compressed(out, V_rest=V0, V_deformed=V1, F=F, R_gold=exp_r(logr), S_gold=S)
+    # logR_gold: the stored rows themselves = what GetRS(..., _R=0) returns (FeatureVector.cpp:531-557)
+    np.savez_compressed(out, V_rest=V0, V_deformed=V1, F=F, R_gold=exp_r(logr), S_gold=S, logR_gold=logr)
     print(out, os.path.getsize(out), "bytes;", V0.shape, F.shape)
 
 

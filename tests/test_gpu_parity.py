@@ -986,6 +986,10 @@ def test_acap_get_rs_matches_golden_and_oracle(cuda_device):
     R1, S1 = tool.GetRS(g["V_rest"], g["V_deformed"], 1, 8)
     R, S = R1.reshape(-1, 3, 3).cpu().numpy(), S1.reshape(-1, 3, 3).cpu().numpy()
     assert np.abs(R - g["R_gold"]).max() <= 3e-5 and np.abs(S - g["S_gold"]).max() <= 3e-5
+    # _R = 0: log-rotations with the reference's breadth-first branch selection, against test/LOGRNEW.txt itself
+    L0, S0 = tool.GetRS(g["V_rest"], g["V_deformed"], 0, 8)
+    errL = np.abs(L0.reshape(-1, 3, 3).cpu().numpy() - g["logR_gold"]).reshape(R.shape[0], -1).max(axis=1)
+    assert (errL <= 2e-4).mean() >= 0.995 and errL.max() <= 0.05 and torch.equal(S0, S1)
     rest = acap_np.rest_state(g["V_rest"], g["F"])
     Ro, So = acap_np.get_rs(rest, g["V_deformed"])
     assert np.abs(R - Ro).max() <= 1e-6 and np.abs(S - So).max() <= 1e-6          # float32 outputs of a float64 kernel

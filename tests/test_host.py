@@ -238,6 +238,28 @@ def test_loaded_ply_builds_a_model_that_saves_back(tmp_path, built_lib):
     assert np.array_equal(back["face_id"][:, 0], a["face_id"])
 
 
+def test_acap_log_rotations_follow_the_reference_branches(built_lib):
+    """GetRS(..., _R = 0): the breadth-first branch selection of the log-rotations (RefMesh::bfscorrot + logrot) against
+    the reference's own golden vector test/LOGRNEW.txt, whose angles run up to 5.97 rad -- far beyond the principal range."""
+    import ctypes as C
+    from gaussianmesh_b200._lib import lib, check
+    from gaussianmesh_b200.acap import log_rotations_bfs
+    d = np.load(os.path.join(ROOT, "tests", "golden", "acap_1_to_2.npz"))
+    V, F = d["V_rest"], np.ascontiguousarray(d["F"], np.int32)
+    Vn, Fn = V.shape[0], F.shape[0]
+    ring_off, ring = np.zeros(Vn + 1, np.int32), np.zeros(3 * Fn + Vn, np.int32)
+    face_off, face_list = np.zeros(Vn + 1, np.int32), np.zeros(3 * Fn, np.int32)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    check(lib.gm_acap_build_rings(Vn, Fn, p(F), p(ring_off), p(ring), p(face_off), p(face_list)), "gm_acap_build_rings")
+    gold = d["logR_gold"]
+    angle = np.sqrt(gold[:, 0, 1] ** 2 + gold[:, 0, 2] ** 2 + gold[:, 1, 2] ** 2)
+    assert angle.max() > np.pi                                    # the golden really leaves the principal branch
+    got = log_rotations_bfs(d["R_gold"], ring_off, ring)
+    err = np.abs(got - gold).reshape(Vn, -1).max(axis=1)
+    # two vertices sit on a branch point (exp of the stored logarithm is within rounding of a rotation by pi)
+    assert (err <= 1e-6).mean() >= 0.995 and err.max() <= 0.05, (float((err <= 1e-6).mean()), float(err.max()))
+
+
 def test_cameras_json_roundtrip(tmp_path):
     """camera_to_JSON (utils/camera_utils.py:64-84) <-> ObjectVisualTool.get_camera (edittool/__init__.py:547-584)."""
     import json
