@@ -168,5 +168,62 @@ def timed_sample(P: int, W: int, H: int, frames: int = 1) -> dict:
     pp.sh_to_rgb(3, inp["shs"], inp["means3D"], cams[0].camera_center)
     out["python_preprocess_ms"] = (time.perf_counter() - t0) * 1e3
     out["python_preprocess_note"] = ("numpy fp32 restatement of get_xyz/get_scaling/get_rotation/get_opacity + "
-                                     "build_covariance_from_scaling_rotation + eval_sh for the same P (one frame)")
+                                     "build_covariance_from_scaling_rotation + eval_sh for the same P (one frame), one thread")
+    # the same chain as multi-threaded tensor ops (torch CPU standing in for Jittor's CPU backend)
+    try:
+        out.update(_torch_cpu_preprocess(mesh, cams[0].camera_center))
+    except Exception as ex:      # a reported baseline, never a dependency
+        out["jittor_cpu_preprocess_note"] = f"torch CPU restatement failed: {ex!r}"
     return out
+
+
+def _torch_cpu_preprocess(mesh: dict, campos: np.ndarray) -> dict:
+    """get_xyz / get_scaling / get_rotation / get_opacity (scene/mesh_based_gaussian_model.py:122-174), get_covariance
+    (:24-29, utils/general_utils.py:64-109) and the convert_SHs_python colours (gaussian_renderer/__init__.py:87-92,
+    utils/sh_utils.py:57-112) as elementwise tensor ops on the host cores, all threads."""
+    import torch
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    t = {k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in mesh.items() if v.dtype == np.float32}
+    cam = torch.from_numpy(np.ascontiguousarray(campos, dtype=np.float32))
+    C0, C1 = 0.28209479177387814, 0.4886025119029199
+    C2 = [1.0925484305920792, -1.0925484305920792, 0.31539156525252005, -1.0925484305920792, 0.5462742152960396]
+    C3 = [-0.5900435899266435, 2.890611442640554, -0.4570457994644658, 0.3731763325901154, -0.4570457994644658,
+          1.445305721320277, -0.5900435899266435]
+
+    def chain():
+        bc = torch.softmax(t["bc_logits"], dim=1)
+        xyz = bc[:, 0:1] * t["vertex1"] + bc[:, 1:2] * t["vertex2"] + bc[:, 2:3] * t["vertex3"] \
+            + 4.0 * t["r"] * (torch.sigmoid(t["distance"]) - 0.5) * t["normal"]
+        scales = torch.exp(t["log_scales"])
+        torch.sigmoid(t["opacity_logit"])
+        q = t["rot_raw"] / torch.sqrt((t["rot_raw"] ** 2).sum(dim=1))[:, None]
+        r, x, y, z = q[:, 0], q[:, 1], q[:, 2], q[:, 3]
+        R = torch.stack([1 - 2 * (y * y + z * z), 2 * (x * y - r * z), 2 * (x * z + r * y), 2 * (x * y + r * z),
+                         1 - 2 * (x * x + z * z), 2 * (y * z - r * x), 2 * (x * z - r * y), 2 * (y * z + r * x),
+                         1 - 2 * (x * x + y * y)], dim=1).view(-1, 3, 3)
+        L = R * scales[:, None, :]
+        S = L @ L.transpose(1, 2)
+        torch.stack([S[:, 0, 0], S[:, 0, 1], S[:, 0, 2], S[:, 1, 1], S[:, 1, 2], S[:, 2, 2]], dim=1)
+        sh = t["shs"].transpose(1, 2)
+        d = xyz - cam.repeat(xyz.shape[0], 1)
+        d = d / d.norm(dim=1, keepdim=True)
+        x, y, z = d[:, 0:1], d[:, 1:2], d[:, 2:3]
+        xx, yy, zz, xy, yz, xz = x * x, y * y, z * z, x * y, y * z, x * z
+        res = C0 * sh[..., 0] - C1 * y * sh[..., 1] + C1 * z * sh[..., 2] - C1 * x * sh[..., 3]
+        res = (res + C2[0] * xy * sh[..., 4] + C2[1] * yz * sh[..., 5] + C2[2] * (2.0 * zz - xx - yy) * sh[..., 6]
+               + C2[3] * xz * sh[..., 7] + C2[4] * (xx - yy) * sh[..., 8])
+        res = (res + C3[0] * y * (3 * xx - yy) * sh[..., 9] + C3[1] * xy * z * sh[..., 10]
+               + C3[2] * y * (4 * zz - xx - yy) * sh[..., 11] + C3[3] * z * (2 * zz - 3 * xx - 3 * yy) * sh[..., 12]
+               + C3[4] * x * (4 * zz - xx - yy) * sh[..., 13] + C3[5] * z * (xx - yy) * sh[..., 14]
+               + C3[6] * x * (xx - 3 * yy) * sh[..., 15])
+        return torch.clamp(res + 0.5, min=0.0)
+
+    chain()                                           # warm-up (thread pool, allocator)
+    t0 = time.perf_counter()
+    chain()
+    ms = (time.perf_counter() - t0) * 1e3
+    return {"jittor_cpu_preprocess_ms": ms, "jittor_cpu_preprocess_cores": threads,
+            "jittor_cpu_preprocess_note": "the reference's Python preprocess chain (bind + activations + Python covariance + "
+                                          "Python SH colours) as multi-threaded tensor ops, torch CPU standing in for Jittor's "
+                                          "CPU backend (not installable here), one frame, same P"}

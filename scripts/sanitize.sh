@@ -55,8 +55,27 @@ vp = ViewParallelTrainer(MeshGaussianModel(arrays, dev, requires_grad=False), Op
 vp.step(cam, bg, target); vp.step(cam, bg, target)
 torch.cuda.synchronize()
 print("case iteration ok", losses.tolist())
+
+# round-2 kernels: Python pipeline variants (covariance / SH colours with their backward), load_mesh, uint8 target loss
+from gaussianmesh_b200.renderer import PipelineParams, render, GaussianModel
+from gaussianmesh_b200.mesh_gaussians import load_mesh, l1_loss as l1
+pc = MeshGaussianModel(arrays, dev)
+bgm = GaussianModel(synthetic.gaussian_scene(1500, seed=2, extent=3.0), dev)
+for flags in ((True, False), (False, True), (True, True)):
+    out = render(cam, pc, PipelineParams(convert_SHs_python=flags[1], compute_cov3D_python=flags[0]), bg,
+                 bg_gaussian=bgm if flags[0] else None)
+    tu8 = torch.randint(0, 256, (3, H, W), dtype=torch.uint8, device=dev)
+    l1(out["render"], tu8).backward()
+tri, w = load_mesh(V.astype("float64"), F, arrays["face_id"], pc.activate()[0].detach())
+torch.cuda.synchronize()
+print("case python pipeline ok", float(w.sum()))
 PY
 for tool in memcheck racecheck synccheck; do
   timeout 900 compute-sanitizer --tool $tool --print-limit 20 python /tmp/san_case.py > gpurun_out/sanitize_$tool.log 2>&1
-  echo "== $tool exit $?"; grep -E "ERROR SUMMARY|RACECHECK SUMMARY|case " gpurun_out/sanitize_$tool.log | tail -5
+  echo "== $tool exit $?"; grep -E "ERROR SUMMARY|RACECHECK SUMMARY|case " gpurun_out/sanitize_$tool.log | tail -6
+done
+# the selectable kernel variants (tensor-core backward, barrier-free forward ring)
+for tool in memcheck racecheck; do
+  GM_BLEND_BWD=mma GM_BLEND_FWD=ring timeout 900 compute-sanitizer --tool $tool --print-limit 20 python /tmp/san_case.py > gpurun_out/sanitize_variants_$tool.log 2>&1
+  echo "== variants $tool exit $?"; grep -E "ERROR SUMMARY|RACECHECK SUMMARY|case " gpurun_out/sanitize_variants_$tool.log | tail -6
 done
