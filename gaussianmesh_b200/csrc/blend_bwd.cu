@@ -654,7 +654,7 @@ struct __align__(128) BwdSmemM {
 	WarpQueueM queue[kWarps];
 	uint32_t phi[32][8];                       // B fragments of the pixel monomials, per lane (same for every warp)
 	uint64_t full[kStagesM];
-	uint64_t empty[kStagesM];                  // one arrival per warp that is through with the stage
+	uint64_t empty[kStagesM];                  // one arrival per thread that is through with the stage
 	uint32_t released[kStagesM];
 	uint32_t warp_max[kWarps];
 };
@@ -771,7 +771,7 @@ blend_backward_mma_kernel(GeometryState g, BinningState b, ImageState img, uint3
 #pragma unroll
 		for (int st = 0; st < kStagesM; st++) {
 			mbar_init(&s.full[st], 1);
-			mbar_init(&s.empty[st], kWarps);
+			mbar_init(&s.empty[st], kThreads);
 			s.released[st] = 0;
 		}
 		fence_mbar_init();
@@ -1044,11 +1044,11 @@ blend_backward_mma_kernel(GeometryState g, BinningState b, ImageState img, uint3
 
 		// release the stage; the warp that arrives last refills it with the batch kStagesM further on
 		__syncwarp();
+		mbar_arrive(&s.empty[st]);                                       // release: this thread's reads of the stage are done
 		if (lane == 0) {
-			mbar_arrive(&s.empty[st]);                                   // release: this warp's reads of the stage are done
 			const uint32_t old = atomicAdd(&s.released[st], 1u);
 			if ((old & (kWarps - 1)) == kWarps - 1 && batch - kStagesM >= 0) {
-				mbar_wait(&s.empty[st], parity);                          // acquire: all eight arrivals (returns at once)
+				mbar_wait(&s.empty[st], parity);                          // acquire: every thread's arrival (returns at once)
 				fence_proxy_async();
 				issue(batch - kStagesM, st);
 			}

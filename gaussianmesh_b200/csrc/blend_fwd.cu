@@ -398,7 +398,7 @@ struct __align__(128) FwdSmemR {
 	float2 bid[kStagesF][kBatchF];
 	WarpQueueP queue[kThreads / 32];
 	uint64_t full[kStagesF];
-	uint64_t empty[kStagesF];          // one arrival per warp that is through with the stage
+	uint64_t empty[kStagesF];          // one arrival per thread that is through with the stage
 	uint32_t released[kStagesF];
 	uint32_t done_warps;
 	int stop_at;
@@ -456,7 +456,7 @@ blend_forward_ring_kernel(GeometryState g, BinningState b, ImageState img, uint3
 #pragma unroll
 		for (int st = 0; st < kStagesF; st++) {
 			mbar_init(&s.full[st], 1);
-			mbar_init(&s.empty[st], kThreads / 32);
+			mbar_init(&s.empty[st], kThreads);
 			s.released[st] = 0;
 		}
 		s.done_warps = 0;
@@ -593,11 +593,11 @@ blend_forward_ring_kernel(GeometryState g, BinningState b, ImageState img, uint3
 
 		// release the stage; the warp that arrives last refills it, unless every warp of the tile has finished
 		__syncwarp();
+		mbar_arrive(&s.empty[st]);                                       // release: this thread's reads of the stage are done
 		if (lane == 0) {
-			mbar_arrive(&s.empty[st]);                                   // release: this warp's reads of the stage are done
 			const uint32_t old = atomicAdd(&s.released[st], 1u);
 			if ((old & (kThreads / 32 - 1)) == kThreads / 32 - 1 && batch + kStagesF < num_batches) {
-				mbar_wait(&s.empty[st], parity);                          // acquire: all eight arrivals (returns at once)
+				mbar_wait(&s.empty[st], parity);                          // acquire: every thread's arrival (returns at once)
 				if (*reinterpret_cast<volatile uint32_t*>(&s.done_warps) == kThreads / 32)
 					atomicMin(&s.stop_at, batch + kStagesF);
 				else {
