@@ -457,6 +457,30 @@ def test_view_batch_renderer_and_overflow_recovery(cuda_device):
     assert torch.equal(batch2, singles)
 
 
+def test_scene_renderer_rerenders_an_overflowed_frame(cuda_device):
+    """SceneRenderer.render_gaussian retires the frame it just submitted: a view that needs more instances than the arena
+    holds (a closer camera after the arena was sized by a far one) is detected on THIS call, the arena grows and the frame
+    is rendered again -- never a truncated image."""
+    _need_ref()
+    from gaussianmesh_b200.renderer import SceneRenderer
+    dev = cuda_device
+    W, H = 320, 200
+    bgs = scenes.free_scene(15_000, dev, seed=33, extent=2.0, log_scale_mean=math.log(0.03))
+    cov = scenes.packed_cov(bgs["scales"], bgs["rotations"])
+    scene = SceneRenderer(dev, bgs["means3D"], cov, bgs["opacities"], bgs["shs"])
+    far = scenes.camera(dev, W, H, index=0, n=8, radius=40.0)
+    near = scenes.camera(dev, W, H, index=3, n=8, radius=4.0)
+    scene.render_gaussian(far)
+    scene.arena.headroom = 1.0                   # no slack: the near view cannot fit what the far view needed
+    cap_before = scene.arena.capacity
+    img = scene.render_gaussian(near)
+    assert scene.arena.capacity > cap_before     # it overflowed, grew and re-rendered
+    white = torch.ones(3, device=dev)
+    ref = _ref({"means3D": bgs["means3D"], "opacities": bgs["opacities"], "shs": bgs["shs"], "cov3D": cov}, near, white, 3,
+               "sh+cov", M=16)
+    assert float((img - ref.color).abs().max()) <= FWD_TOL
+
+
 def test_strict_arena_raises_on_overflow(cuda_device):
     from gaussianmesh_b200.arena import RenderArena
     from gaussianmesh_b200 import RasterizerError

@@ -321,3 +321,39 @@ def test_densification_schedule_inside_the_loop(cuda_device):
     # reset to <= 0.01, then this iteration's Adam step (moments zeroed: at most one learning rate, 0.05, in the logit)
     assert float(model._opacity.max()) <= math.log(0.01 / 0.99) + opt.opacity_lr * 1.01
     assert np.isfinite(it.losses.cpu().numpy()).all()
+
+
+def test_overflowed_frame_never_reaches_the_parameters(cuda_device):
+    """An arena that is too small for a frame renders only the tiles that fit.  The sync-free iteration cannot see that on
+    the host before the optimizer is enqueued, so the statistics and Adam are gated on the frame's overflow word ON THE DEVICE
+    (gm_frame_overflow_flag, gm_adam_step_gated, gm_densify_stats_gated): the parameters and the statistics stay exactly as
+    they were, the host counts the dropped iteration one step later, and the grown arena lets the next iteration through."""
+    from gaussianmesh_b200 import synthetic
+    from gaussianmesh_b200.renderer import MeshGaussianModel, upload_cameras
+    from gaussianmesh_b200.training import OptimizationParams, TrainingIteration
+    dev = cuda_device
+    P, W, H = 8_000, 200, 136
+    V, F = synthetic.icosphere(2)
+    arrays = synthetic.mesh_bound_scene(P, V, F, seed=7)
+    cams = upload_cameras(synthetic.orbit_cameras(3, W, H), dev)
+    bg = torch.zeros(3, device=dev)
+    gt = torch.rand(3, H, W, generator=torch.Generator().manual_seed(9)).to(dev)
+    model = MeshGaussianModel(arrays, dev, requires_grad=False)
+    it = TrainingIteration(model, OptimizationParams(alpha_mrloss=0.05), W, H)
+    # an arena far too small, that will not be sized by the first frame
+    it.arena._want = 64
+    it.arena.headroom = 1.0
+    before = {k: getattr(model, k).clone() for k in ("_features", "_bc", "_distance", "_scaling", "_rotation", "_opacity")}
+    it.step(cams[0], bg, gt)
+    torch.cuda.synchronize()
+    need, visible, overflow, cap = it.arena._info[0].tolist()
+    assert overflow == 1 and need > cap
+    for k, v in before.items():
+        assert torch.equal(getattr(model, k), v), k                       # the update was dropped on the device
+    assert float(it.denom.sum()) == 0.0 and float(it.max_radii2D.max()) == 0.0
+    it.step(cams[1], bg, gt)                                              # the arena has grown: this one goes through
+    torch.cuda.synchronize()
+    assert it.skipped_iterations == 1 and it.arena.overflowed == []
+    assert not torch.equal(model._features, before["_features"])
+    assert float(it.denom.sum()) > 0.0
+    assert it.arena.verify() == []
