@@ -510,7 +510,13 @@ def main():
     P = args.gaussians
     scene, cams_host, cams, targets_host, targets, cams_packed_host = build_workload(device, P, rank, world)
     bg = torch.zeros(3, dtype=torch.float32, device=device)
-    arm = OursArm(device, scene, WIDTH, HEIGHT) if args.impl == "ours" else ReferenceArm(device, scene, WIDTH, HEIGHT)
+    try:
+        arm = OursArm(device, scene, WIDTH, HEIGHT) if args.impl == "ours" else ReferenceArm(device, scene, WIDTH, HEIGHT)
+    except FileNotFoundError as ex:          # oracle/_ref was not built (it is built by __graft_entry__.build() where the reference lives)
+        if rank == 0:
+            emit_json({"impl": "reference", "unavailable": f"{ex} is missing: run `make -C oracle ref` where /root/reference exists"})
+        ctx.close()
+        return
     K, Wm = args.steps, args.warmup
     nv = len(cams)
     # started before the sizing pass so that nvidia-smi's start-up (NVML initialisation) is over when the first timed
