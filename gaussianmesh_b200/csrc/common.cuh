@@ -276,37 +276,40 @@ __host__ __device__ __forceinline__ bool sh_rows_vectorizable(const void* shs, i
 __device__ __forceinline__ bool rect_cannot_contribute(float mx, float my, float a, float b, float c, float thr,
                                                        float px0, float py0, float px1, float py1)
 {
-	if (thr < 0.0f)
-		return true;
+	// Written without branches (every candidate is evaluated, the answer is selected): sort_pack runs this test for the
+	// eight warp blocks of a tile back to back, and straight-line code lets the eight evaluations overlap.  The values
+	// are those of the obvious early-out formulation; a division by a non-positive conic entry only feeds a discarded lane.
+	const bool dead = thr < 0.0f;
 	// offsets of the rectangle edges relative to the centre (d = mean - pixel, sign is irrelevant
 	// for the quadratic form as long as both axes use the same convention)
 	const float dx0 = px0 - mx, dx1 = px1 - mx;
 	const float dy0 = py0 - my, dy1 = py1 - my;
 	const bool in_x = (dx0 <= 0.0f) && (dx1 >= 0.0f);
 	const bool in_y = (dy0 <= 0.0f) && (dy1 >= 0.0f);
-	if (in_x && in_y)
-		return false;
-	if (!(a > 0.0f) || !(c > 0.0f))
-		return false;   // degenerate conic: leave it to the per-pixel test
+	const bool covers = in_x && in_y;                       // the centre lies inside the rectangle
+	const bool degenerate = !(a > 0.0f) || !(c > 0.0f);     // degenerate conic: leave it to the per-pixel test
 
 	// The edge minimiser only has to be near the true one: q is stationary there, so the few-ulp error of the
 	// approximate division moves q by a second-order amount, far below the margins kept at the end.
 	float qmin = 3.0e38f;
-	if (!in_x) {
+	{
 		const float dx = (dx0 > 0.0f) ? dx0 : dx1;                  // facing vertical edge
 		const float dy = fminf(dy1, fmaxf(dy0, __fdividef(-b * dx, c)));
-		qmin = fminf(qmin, a * dx * dx + 2.0f * b * dx * dy + c * dy * dy);
+		const float q = a * dx * dx + 2.0f * b * dx * dy + c * dy * dy;
+		qmin = in_x ? qmin : fminf(qmin, q);
 	}
-	if (!in_y) {
+	{
 		const float dy = (dy0 > 0.0f) ? dy0 : dy1;                  // facing horizontal edge
 		const float dx = fminf(dx1, fmaxf(dx0, __fdividef(-b * dy, a)));
-		qmin = fminf(qmin, a * dx * dx + 2.0f * b * dx * dy + c * dy * dy);
+		const float q = a * dx * dx + 2.0f * b * dx * dy + c * dy * dy;
+		qmin = in_y ? qmin : fminf(qmin, q);
 	}
 	const float ex = fmaxf(fabsf(dx0), fabsf(dx1));
 	const float ey = fmaxf(fabsf(dy0), fabsf(dy1));
 	const float mag = a * ex * ex + 2.0f * fabsf(b) * ex * ey + c * ey * ey;
 	// 32 ulp of the largest term covers the rounding of q here and of `power` in the blend kernels
-	return qmin - 4.0e-6f * mag > 2.0f * thr + 2.0e-3f;
+	const bool beyond = qmin - 4.0e-6f * mag > 2.0f * thr + 2.0e-3f;
+	return dead || (!covers && !degenerate && beyond);
 }
 
 __device__ __forceinline__ float cull_threshold(float opacity)
