@@ -37,6 +37,12 @@ class AdamTensor(C.Structure):
                 ("split", C.c_uint32)]
 
 
+class ForwardEpilogue(C.Structure):
+    """gm_forward_epilogue of include/gm_rasterizer.h"""
+    _fields_ = [("target", C.c_void_p), ("target_is_u8", C.c_int), ("loss", C.c_void_p), ("dL_dimg", C.c_void_p),
+                ("zero_ptr", C.c_void_p), ("zero_floats", C.c_size_t)]
+
+
 class AdamSegment(C.Structure):
     """gm_adam_segment of include/gm_rasterizer.h"""
     _fields_ = [("offset", C.c_size_t), ("numel", C.c_size_t), ("lr", C.c_float), ("lr_head", C.c_float),
@@ -60,6 +66,7 @@ SIGNATURES = {
     "gm_forward_0": (_i, [_p, _i, _i, _i, _p, _i, _i, *_VIEW_ARGS, _i, _p, _i, _p]),
     "gm_forward_1": (_i, [_p, _p, _p, _i, _i, _i, _i, _p, _i, _i, *_VIEW_ARGS, _i, _p, _p, _i, _p]),
     "gm_forward": (_i, [_p, _p, _z, _p, _i, _i, _i, _p, _i, _i, *_VIEW_ARGS, _i, _p, _p, _i, _p, _p]),
+    "gm_forward_ex": (_i, [_p, _p, _z, _p, _i, _i, _i, _p, _i, _i, *_VIEW_ARGS, _i, _p, _p, _i, _p, C.POINTER(ForwardEpilogue), _p]),
     "gm_forward_status": (_i, [_p, _p, _p, _p]),
     "gm_geom_view": (None, [_p, _z, _p]),
     "gm_backward": (_i, [_i, _i, _i, _i, _p, _i, _i, _p, _p, _p, _p, _f, _p, _p, _p, _p, _p, _f, _f, _p,

@@ -123,9 +123,10 @@ class RenderArena:
     # ------------------------------------------------------------------ forward
     def forward(self, P: int, D: int, M: int, background: torch.Tensor, W: int, H: int, view_args: tuple,
                 prefiltered: bool, debug: bool, stream: int, out_color: Optional[torch.Tensor] = None,
-                radii: Optional[torch.Tensor] = None):
+                radii: Optional[torch.Tensor] = None, epilogue=None):
         """gm_forward over the arena's chunks.  Returns the tuple RasterizeGaussiansCUDA returns, with
-        num_rendered = the arena capacity in instances (what gm_backward needs as R)."""
+        num_rendered = the arena capacity in instances (what gm_backward needs as R).  `epilogue` (a
+        _lib.ForwardEpilogue) folds the L1 loss and / or the clearing of the gradient accumulators into the blend kernel."""
         self._ensure(P, W * H)
         self.poll()
         if self.overflowed and self.strict:
@@ -158,10 +159,10 @@ class RenderArena:
             self._events[slot].synchronize()
             self._retire(slot)
         self._next = (slot + 1) % self.RING
-        check(lib.gm_forward(self.geom.data_ptr(), self.binning.data_ptr(), self.binning.numel(),
-                             self.image.data_ptr(), P, D, M, background.data_ptr(), W, H, *view_args,
-                             int(prefiltered), out_color.data_ptr(), radii.data_ptr(), int(debug),
-                             self._info[slot].data_ptr(), stream), "gm_forward")
+        check(lib.gm_forward_ex(self.geom.data_ptr(), self.binning.data_ptr(), self.binning.numel(),
+                                self.image.data_ptr(), P, D, M, background.data_ptr(), W, H, *view_args,
+                                int(prefiltered), out_color.data_ptr(), radii.data_ptr(), int(debug),
+                                self._info[slot].data_ptr(), epilogue, stream), "gm_forward")
         ev = torch.cuda.Event()
         ev.record(torch.cuda.current_stream(self.device))
         self._events[slot] = ev

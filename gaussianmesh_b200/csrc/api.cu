@@ -173,7 +173,7 @@ static int forward_stage0(char* geom_buffer, int P, const ViewParams& vp, const 
 
 static int forward_stage1(const GeometryState& geom, char* binning_buffer, char* image_buffer, int P,
                           const ViewParams& vp, uint32_t capacity, const int* radii, float* out_color, bool debug,
-                          cudaStream_t stream)
+                          cudaStream_t stream, const gm_forward_epilogue* epilogue = nullptr)
 {
 	if (out_color == nullptr || image_buffer == nullptr || (capacity > 0 && binning_buffer == nullptr))
 		return GM_ERR_BAD_ARGUMENT;
@@ -187,8 +187,19 @@ static int forward_stage1(const GeometryState& geom, char* binning_buffer, char*
 	if (int rc = check_stage("emit", debug, stream)) return rc;
 	{ StageScope scope_(kStSortPack, stream); launch_sort_pack(num_tiles, geom, binning, capacity, vp, stream); }
 	if (int rc = check_stage("sort_pack", debug, stream)) return rc;
-	{ StageScope scope_(kStBlendFwd, stream); launch_blend_forward(geom, binning, img, capacity, vp, out_color, stream); }
+	bool folded = false;
+	{ StageScope scope_(kStBlendFwd, stream); launch_blend_forward(geom, binning, img, capacity, vp, out_color, epilogue, &folded, stream); }
 	if (int rc = check_stage("blend_forward", debug, stream)) return rc;
+	if (epilogue != nullptr && !folded) {
+		// an A/B kernel variant that has no epilogue: the same work as separate launches
+		if (epilogue->loss != nullptr && epilogue->target != nullptr) {
+			StageScope scope_(kStL1, stream);
+			launch_l1((size_t)3 * vp.W * vp.H, out_color, epilogue->target, epilogue->target_is_u8, epilogue->loss, epilogue->dL_dimg, stream);
+		}
+		if (epilogue->zero_ptr != nullptr && epilogue->zero_floats > 0)
+			cudaMemsetAsync(epilogue->zero_ptr, 0, epilogue->zero_floats * sizeof(float), stream);
+		if (int rc = check_stage("forward epilogue", debug, stream)) return rc;
+	}
 	return GM_OK;
 }
 
@@ -302,13 +313,13 @@ int gm_forward_1(char* geom_buffer, char* binning_buffer, char* image_buffer, in
 	                      debug != 0, stream);
 }
 
-int gm_forward(char* geom_buffer, char* binning_buffer, size_t binning_capacity, char* image_buffer, int P,
-               int D, int M, const float* background, int width, int height, const float* means3D,
-               const float* shs, const float* colors_precomp, const float* opacities, const float* scales,
-               float scale_modifier, const float* rotations, const float* cov3D_precomp,
-               const float* viewmatrix, const float* projmatrix, const float* cam_pos, float tan_fovx,
-               float tan_fovy, int prefiltered, float* out_color, int* radii, int debug,
-               uint32_t* frame_info_host, gm_stream_t stream_)
+int gm_forward_ex(char* geom_buffer, char* binning_buffer, size_t binning_capacity, char* image_buffer, int P,
+                  int D, int M, const float* background, int width, int height, const float* means3D,
+                  const float* shs, const float* colors_precomp, const float* opacities, const float* scales,
+                  float scale_modifier, const float* rotations, const float* cov3D_precomp,
+                  const float* viewmatrix, const float* projmatrix, const float* cam_pos, float tan_fovx,
+                  float tan_fovy, int prefiltered, float* out_color, int* radii, int debug,
+                  uint32_t* frame_info_host, const gm_forward_epilogue* epilogue, gm_stream_t stream_)
 {
 	cudaStream_t stream = (cudaStream_t)stream_;
 	ViewParams vp;
@@ -316,6 +327,13 @@ int gm_forward(char* geom_buffer, char* binning_buffer, size_t binning_capacity,
 		return GM_ERR_BAD_ARGUMENT;
 	if (geom_buffer == nullptr)
 		return GM_ERR_BAD_ARGUMENT;
+	if (epilogue != nullptr) {
+		if ((reinterpret_cast<uintptr_t>(epilogue->zero_ptr) & 15u) != 0 || (epilogue->zero_floats & 3u) != 0)
+			return GM_ERR_BAD_ARGUMENT;
+		// the loss is accumulated per tile: cleared here, ahead of the whole launch chain
+		if (epilogue->loss != nullptr && cudaMemsetAsync(epilogue->loss, 0, sizeof(float), stream) != cudaSuccess)
+			return GM_ERR_CUDA;
+	}
 	const uint32_t capacity = binning_capacity_instances(binning_capacity);
 	GeometryState geom;
 	if (int rc = forward_stage0(geom_buffer, P, vp, means3D, shs, colors_precomp, opacities, scales, rotations,
@@ -330,7 +348,21 @@ int gm_forward(char* geom_buffer, char* binning_buffer, size_t binning_capacity,
 			return GM_ERR_CUDA;
 		}
 	}
-	return forward_stage1(geom, binning_buffer, image_buffer, P, vp, capacity, radii, out_color, debug != 0, stream);
+	return forward_stage1(geom, binning_buffer, image_buffer, P, vp, capacity, radii, out_color, debug != 0, stream, epilogue);
+}
+
+int gm_forward(char* geom_buffer, char* binning_buffer, size_t binning_capacity, char* image_buffer, int P,
+               int D, int M, const float* background, int width, int height, const float* means3D,
+               const float* shs, const float* colors_precomp, const float* opacities, const float* scales,
+               float scale_modifier, const float* rotations, const float* cov3D_precomp,
+               const float* viewmatrix, const float* projmatrix, const float* cam_pos, float tan_fovx,
+               float tan_fovy, int prefiltered, float* out_color, int* radii, int debug,
+               uint32_t* frame_info_host, gm_stream_t stream_)
+{
+	return gm_forward_ex(geom_buffer, binning_buffer, binning_capacity, image_buffer, P, D, M, background, width, height,
+	                     means3D, shs, colors_precomp, opacities, scales, scale_modifier, rotations, cov3D_precomp, viewmatrix,
+	                     projmatrix, cam_pos, tan_fovx, tan_fovy, prefiltered, out_color, radii, debug, frame_info_host,
+	                     nullptr, stream_);
 }
 
 int gm_forward_status(const char* geom_buffer, int* num_rendered, int* num_visible, gm_stream_t stream_)

@@ -203,13 +203,33 @@ struct __align__(128) FwdSmemP {
 	uint64_t full[2];
 };
 
+// Work folded into the kernel for the training step (gm_forward_ex): the L1 loss of the finished pixels and the
+// clearing of the gradient accumulators the backward adds into.  All-null = plain forward.
+struct FwdEpilogue {
+	const float* target_f;
+	const uint8_t* target_u8;
+	float* loss;
+	float* dL_dimg;
+	float4* zero_ptr;
+	size_t zero_vec4;
+	float inv_numel;
+};
+
 __global__ void __launch_bounds__(kThreads)
 blend_forward_pairs_kernel(GeometryState g, BinningState b, ImageState img, uint32_t capacity,
                            int W, int H, int tiles_x, const float* __restrict__ bg_color,
-                           float* __restrict__ out_color)
+                           float* __restrict__ out_color, FwdEpilogue epi)
 {
 	pdl_sync();
 	__shared__ FwdSmemP s;
+	__shared__ float s_loss[kThreads / 32];
+	if (epi.zero_ptr != nullptr) {
+		// this block's slice of the buffer to clear: plain stores, issued before the blend loop and retired behind it
+		const size_t per = (epi.zero_vec4 + gridDim.x - 1) / gridDim.x;
+		const size_t z0 = (size_t)blockIdx.x * per, z1 = min(z0 + per, epi.zero_vec4);
+		for (size_t i = z0 + threadIdx.x; i < z1; i += kThreads)
+			epi.zero_ptr[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+	}
 
 	const int tile = blockIdx.x;
 	const int tile_x = tile % tiles_x, tile_y = tile / tiles_x;
@@ -369,14 +389,44 @@ blend_forward_pairs_kernel(GeometryState g, BinningState b, ImageState img, uint
 	}
 
 	// forward.cu:366-373
+	float part = 0.0f;
 	if (inside) {
 		const uint32_t pix_id = (uint32_t)W * py + px;
 		img.accum_alpha[pix_id] = T;
 		img.n_contrib[pix_id] = last_contributor;
 		const size_t HW = (size_t)H * W;
-		out_color[0 * HW + pix_id] = C0 + T * bg_color[0];
-		out_color[1 * HW + pix_id] = C1 + T * bg_color[1];
-		out_color[2 * HW + pix_id] = C2 + T * bg_color[2];
+		const float o0 = C0 + T * bg_color[0], o1 = C1 + T * bg_color[1], o2 = C2 + T * bg_color[2];
+		out_color[0 * HW + pix_id] = o0;
+		out_color[1 * HW + pix_id] = o1;
+		out_color[2 * HW + pix_id] = o2;
+		if (epi.loss != nullptr) {
+			// utils/loss_utils.py:17-18 on the pixel just finished: |image - target| and its gradient
+			const float oc[3] = {o0, o1, o2};
+#pragma unroll
+			for (int ch = 0; ch < 3; ch++) {
+				const size_t at = ch * HW + pix_id;
+				const float t = epi.target_u8 != nullptr ? (float)epi.target_u8[at] / 255.0f : epi.target_f[at];
+				const float d = oc[ch] - t;
+				part += fabsf(d);
+				if (epi.dL_dimg != nullptr)
+					epi.dL_dimg[at] = (d > 0.0f ? epi.inv_numel : (d < 0.0f ? -epi.inv_numel : 0.0f));
+			}
+		}
+	}
+	if (epi.loss != nullptr) {
+#pragma unroll
+		for (int o = 16; o > 0; o >>= 1)
+			part += __shfl_xor_sync(0xffffffffu, part, o);
+		if (lane == 0)
+			s_loss[warp] = part;
+		__syncthreads();
+		if (tid == 0) {
+			float sum = 0.0f;
+#pragma unroll
+			for (int w = 0; w < kThreads / 32; w++)
+				sum += s_loss[w];
+			atomicAdd(epi.loss, sum * epi.inv_numel);
+		}
 	}
 }
 
@@ -627,8 +677,11 @@ blend_forward_ring_kernel(GeometryState g, BinningState b, ImageState img, uint3
 } // namespace
 
 int launch_blend_forward(const GeometryState& g, const BinningState& b, const ImageState& img, uint32_t capacity,
-                         const ViewParams& vp, float* out_color, cudaStream_t stream)
+                         const ViewParams& vp, float* out_color, const gm_forward_epilogue* epilogue, bool* epilogue_done,
+                         cudaStream_t stream)
 {
+	if (epilogue_done != nullptr)
+		*epilogue_done = false;
 	const int num_tiles = vp.tiles_x * vp.tiles_y;
 	if (num_tiles <= 0)
 		return GM_OK;
@@ -642,10 +695,27 @@ int launch_blend_forward(const GeometryState& g, const BinningState& b, const Im
 		launch_k(blend_forward_ring_kernel, dim3(num_tiles), dim3(kThreads), 0, stream, g, b, img, capacity, vp.W, vp.H, vp.tiles_x, vp.bg, out_color);
 		return GM_OK;
 	}
-	if (scalar)
+	if (scalar) {
 		launch_k(blend_forward_kernel, dim3(num_tiles), dim3(kThreads), 0, stream, g, b, img, capacity, vp.W, vp.H, vp.tiles_x, vp.bg, out_color);
-	else
-		launch_k(blend_forward_pairs_kernel, dim3(num_tiles), dim3(kThreads), 0, stream, g, b, img, capacity, vp.W, vp.H, vp.tiles_x, vp.bg, out_color);
+		return GM_OK;
+	}
+	FwdEpilogue e = {};
+	if (epilogue != nullptr) {
+		if (epilogue->loss != nullptr && epilogue->target != nullptr) {
+			e.target_f = epilogue->target_is_u8 ? nullptr : static_cast<const float*>(epilogue->target);
+			e.target_u8 = epilogue->target_is_u8 ? static_cast<const uint8_t*>(epilogue->target) : nullptr;
+			e.loss = epilogue->loss;
+			e.dL_dimg = epilogue->dL_dimg;
+			e.inv_numel = 1.0f / (3.0f * (float)vp.W * (float)vp.H);
+		}
+		if (epilogue->zero_ptr != nullptr && epilogue->zero_floats > 0) {
+			e.zero_ptr = reinterpret_cast<float4*>(epilogue->zero_ptr);
+			e.zero_vec4 = epilogue->zero_floats / 4;
+		}
+		if (epilogue_done != nullptr)
+			*epilogue_done = true;
+	}
+	launch_k(blend_forward_pairs_kernel, dim3(num_tiles), dim3(kThreads), 0, stream, g, b, img, capacity, vp.W, vp.H, vp.tiles_x, vp.bg, out_color, e);
 	return GM_OK;
 }
 

@@ -26,8 +26,10 @@ int launch_emit(int P, const int* radii, const GeometryState& g, const BinningSt
 int launch_sort_pack(int num_tiles, const GeometryState& g, const BinningState& b, uint32_t capacity,
                      const ViewParams& vp, cudaStream_t stream);
 
+// `epilogue` may be NULL; *epilogue_done tells the caller whether the selected kernel folded it in (the A/B variants do not)
 int launch_blend_forward(const GeometryState& g, const BinningState& b, const ImageState& img, uint32_t capacity,
-                         const ViewParams& vp, float* out_color, cudaStream_t stream);
+                         const ViewParams& vp, float* out_color, const gm_forward_epilogue* epilogue, bool* epilogue_done,
+                         cudaStream_t stream);
 
 int launch_blend_backward(const GeometryState& g, const BinningState& b, const ImageState& img, uint32_t capacity,
                           const ViewParams& vp, const float* dL_dpix, float* dL_dmean2D, float* dL_dconic,

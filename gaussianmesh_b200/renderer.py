@@ -22,7 +22,7 @@ import numpy as np
 import torch
 
 from . import mesh_gaussians as mg
-from ._lib import lib, check, GM_BACKWARD_OVERWRITE, RasterizerError, GM_ERR_BAD_ARGUMENT
+from ._lib import lib, check, GM_BACKWARD_OVERWRITE, RasterizerError, GM_ERR_BAD_ARGUMENT, ForwardEpilogue
 from .arena import RenderArena
 from .diff_gaussian_rasterizater import (GaussianRasterizationSettings, GaussianRasterizer, NewGaussianRasterizer)
 from .cameras import DeviceCamera, upload_cameras  # noqa: F401  (re-exported)
@@ -576,13 +576,9 @@ class TrainStep:
         stream = torch.cuda.current_stream(self.device).cuda_stream
         va = self._view_args(cam)
         a = self.arena
-        check(lib.gm_forward(a.geom.data_ptr(), a.binning.data_ptr(), a.binning.numel(), a.image.data_ptr(), self.P, self.D,
-                             self.M, bg.data_ptr(), self.W, self.H, *va, 0, self.image.data_ptr(), self.radii.data_ptr(), 0,
-                             None, stream), "gm_forward")
-        l1 = lib.gm_l1_loss_u8 if target.dtype == torch.uint8 else lib.gm_l1_loss
-        check(l1(self.image.numel(), self.image.data_ptr(), target.data_ptr(), self.loss.data_ptr(), self.dL_dimg.data_ptr(),
-                 stream), "gm_l1_loss")
-        self._accum.zero_()
+        check(lib.gm_forward_ex(a.geom.data_ptr(), a.binning.data_ptr(), a.binning.numel(), a.image.data_ptr(), self.P, self.D,
+                                self.M, bg.data_ptr(), self.W, self.H, *va, 0, self.image.data_ptr(), self.radii.data_ptr(), 0,
+                                None, self._epilogue(target), stream), "gm_forward")
         g = self.grads
         check(lib.gm_backward_ex(self.P, self.D, self.M, a.capacity, bg.data_ptr(), self.W, self.H, va[0], va[1], None, va[4], 1.0,
                                  va[6], None, va[8], va[9], va[10], va[11], va[12], self.radii.data_ptr(), a.geom.data_ptr(),
@@ -609,20 +605,22 @@ class TrainStep:
         self._graph.replay()
         return self.loss
 
+    def _epilogue(self, target: torch.Tensor) -> ForwardEpilogue:
+        """The L1 loss against `target` (uint8 = the 8-bit ground-truth image, value / 255 inside the kernel; float32 as it is)
+        and the clearing of the accumulated gradient buffers, both folded into the blend kernel (gm_forward_ex)."""
+        return ForwardEpilogue(target.data_ptr(), int(target.dtype == torch.uint8), self.loss.data_ptr(), self.dL_dimg.data_ptr(),
+                               self._accum.data_ptr(), self._accum.numel())
+
     def step(self, cam, bg: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
         """Enqueue one training step; returns the (device) loss tensor.  No host synchronisation."""
         stream = torch.cuda.current_stream(self.device).cuda_stream
         va = self._view_args(cam)
         cap, _, _, geom, binning, image_state = self.arena.forward(
-            self.P, self.D, self.M, bg, self.W, self.H, va, False, False, stream, out_color=self.image, radii=self.radii)
+            self.P, self.D, self.M, bg, self.W, self.H, va, False, False, stream, out_color=self.image, radii=self.radii,
+            epilogue=self._epilogue(target))
         if self.arena.overflowed:          # frames seen to have overflowed since the last step (arena already grown)
             self.overflowed_frames += len(self.arena.overflowed)
             self.arena.overflowed.clear()
-        # a uint8 target is the 8-bit ground-truth image (value / 255 inside the kernel), a float32 one is used as it is
-        l1 = lib.gm_l1_loss_u8 if target.dtype == torch.uint8 else lib.gm_l1_loss
-        check(l1(self.image.numel(), self.image.data_ptr(), target.data_ptr(), self.loss.data_ptr(),
-                 self.dL_dimg.data_ptr(), stream), "gm_l1_loss")
-        self._accum.zero_()
         g = self.grads
         check(lib.gm_backward_ex(self.P, self.D, self.M, cap, bg.data_ptr(), self.W, self.H, va[0], va[1], None, va[4], 1.0,
                               va[6], None, va[8], va[9], va[10], va[11], va[12], self.radii.data_ptr(),

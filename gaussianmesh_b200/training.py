@@ -22,7 +22,7 @@ from typing import Dict, List, Optional, Sequence
 import numpy as np
 import torch
 
-from ._lib import lib, check, AdamTensor, RasterizerError, GM_ERR_BAD_ARGUMENT, GM_BACKWARD_OVERWRITE
+from ._lib import lib, check, AdamTensor, RasterizerError, GM_ERR_BAD_ARGUMENT, GM_BACKWARD_OVERWRITE, ForwardEpilogue
 from .arena import RenderArena
 from .mesh_gaussians import _c, _p, _stream, l1_loss  # noqa: F401  (l1_loss re-exported)
 
@@ -473,8 +473,10 @@ class TrainingIteration:
         D = m.active_sh_degree
         self._bind(stream)
         va = self._view_args(cam)
+        # the accumulated gradient buffers are cleared inside the blend kernel (gm_forward_ex): one launch less per iteration
         cap, _, _, geom, binning, image_state = self.arena.forward(
-            self.P, D, self.M, bg, self.W, self.H, va, False, False, stream, out_color=self.image, radii=self.radii)
+            self.P, D, self.M, bg, self.W, self.H, va, False, False, stream, out_color=self.image, radii=self.radii,
+            epilogue=ForwardEpilogue(None, 0, None, None, self._accum.data_ptr(), self._accum.numel()))
         # An overflowed frame (tiles past the arena's capacity not rendered) must not reach the parameters: the
         # statistics and the optimizer are gated on the frame's device-side overflow word, the host sees the overflow
         # one or two iterations later (arena.poll in forward), counts the dropped iteration, and the arena has grown.
@@ -484,7 +486,6 @@ class TrainingIteration:
             self.arena.overflowed.clear()
         check(lib.gm_photometric_loss(3, self.H, self.W, _p(self.image), _p(gt_image), float(opt.lambda_dssim),
                                       _p(self.scratch), _p(self.losses), _p(self.dL_dimg), stream), "gm_photometric_loss")
-        self._accum.zero_()
         g = self.grads
         check(lib.gm_backward_ex(self.P, D, self.M, cap, bg.data_ptr(), self.W, self.H, va[0], va[1], None, va[4], 1.0,
                                  va[6], None, va[8], va[9], va[10], va[11], va[12], self.radii.data_ptr(),

@@ -113,6 +113,30 @@ int gm_forward(char* geom_buffer, char* binning_buffer, size_t binning_capacity,
                int prefiltered, float* out_color, int* radii, int debug,
                uint32_t* frame_info_host, gm_stream_t stream);
 
+/*  gm_forward with work folded into the epilogue of the blend kernel (the training step's next two launches):
+ *    target / loss / dL_dimg   L1 loss against `target` ([3,H,W]; float32, or uint8 when target_is_u8 -- value / 255.0f):
+ *                              *loss = mean |image - target| (zeroed by this call, accumulated per tile), dL_dimg = its
+ *                              gradient sign(image - target) / (3 H W) -- what gm_l1_loss computes (utils/loss_utils.py:17-18);
+ *    zero_ptr / zero_floats    a float buffer (16-byte aligned, a multiple of 4 floats) that is cleared: the accumulated
+ *                              gradient buffers gm_backward adds into (rasterize_points.py:302-305 allocates them zeroed).
+ *  Every field may be NULL / 0.  The blend kernel is issue-bound with the memory system idle, so both ride for free. */
+typedef struct gm_forward_epilogue {
+	const void* target;
+	int target_is_u8;
+	float* loss;
+	float* dL_dimg;
+	float* zero_ptr;
+	size_t zero_floats;
+} gm_forward_epilogue;
+int gm_forward_ex(char* geom_buffer, char* binning_buffer, size_t binning_capacity,
+                  char* image_buffer, int P, int D, int M, const float* background, int width,
+                  int height, const float* means3D, const float* shs, const float* colors_precomp,
+                  const float* opacities, const float* scales, float scale_modifier,
+                  const float* rotations, const float* cov3D_precomp, const float* viewmatrix,
+                  const float* projmatrix, const float* cam_pos, float tan_fovx, float tan_fovy,
+                  int prefiltered, float* out_color, int* radii, int debug,
+                  uint32_t* frame_info_host, const gm_forward_epilogue* epilogue, gm_stream_t stream);
+
 /*  Blocking: synchronises `stream`, reads the frame header of a geometry chunk and reports
  *  GM_OK / GM_ERR_BINNING_OVERFLOW; *num_rendered / *num_visible may be NULL. */
 int gm_forward_status(const char* geom_buffer, int* num_rendered, int* num_visible,

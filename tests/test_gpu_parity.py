@@ -521,6 +521,39 @@ def test_train_step_matches_autograd_path(cuda_device):
         assert scenes.rel_err(ts.grads[k].view_as(a), a) <= 1e-5, k
 
 
+def test_forward_epilogue_matches_separate_launches(cuda_device):
+    """gm_forward_ex folds the L1 loss (float or 8-bit target) and the clearing of a buffer into the blend kernel: same
+    image bits, same gradient image, same loss as gm_forward + gm_l1_loss; the A/B kernel variants take the fallback."""
+    from gaussianmesh_b200._lib import lib, check, ForwardEpilogue
+    from gaussianmesh_b200.arena import RenderArena
+    dev = cuda_device
+    P, W, H = 9_000, 250, 130                       # ragged size: partial tiles on both edges
+    sc = _scene(dev, P, seed=15)
+    cam = scenes.camera(dev, W, H, index=2)
+    bgt = torch.tensor([0.2, 0.3, 0.1], device=dev)
+    ref_img, _ = _ours(sc, cam, bgt, 3, "sh")
+    va = (sc["means3D"].data_ptr(), sc["shs"].data_ptr(), None, sc["opacities"].data_ptr(), sc["scales"].data_ptr(), 1.0,
+          sc["rotations"].data_ptr(), None, cam.world_view_transform.data_ptr(), cam.full_proj_transform.data_ptr(),
+          cam.camera_center.data_ptr(), math.tan(cam.FoVx * 0.5), math.tan(cam.FoVy * 0.5))
+    g = torch.Generator().manual_seed(4)
+    for tgt in (torch.rand(3, H, W, generator=g).to(dev), torch.randint(0, 256, (3, H, W), generator=g, dtype=torch.uint8).to(dev)):
+        arena = RenderArena(dev)
+        img = torch.empty(3, H, W, device=dev)
+        loss, dL = torch.full((1,), 7.0, device=dev), torch.full((3, H, W), 9.0, device=dev)
+        junk = torch.full((4096 + 4,), 5.0, device=dev)
+        epi = ForwardEpilogue(tgt.data_ptr(), int(tgt.dtype == torch.uint8), loss.data_ptr(), dL.data_ptr(), junk.data_ptr(), 4096)
+        arena.forward(P, 3, 16, bgt, W, H, va, False, False, torch.cuda.current_stream().cuda_stream, out_color=img, epilogue=epi)
+        torch.cuda.synchronize()
+        assert torch.equal(img, ref_img.detach())
+        want_loss, want_dL = torch.empty(1, device=dev), torch.empty(3, H, W, device=dev)
+        fn = lib.gm_l1_loss_u8 if tgt.dtype == torch.uint8 else lib.gm_l1_loss
+        check(fn(img.numel(), img.data_ptr(), tgt.data_ptr(), want_loss.data_ptr(), want_dL.data_ptr(),
+                 torch.cuda.current_stream().cuda_stream), "gm_l1_loss")
+        assert torch.equal(dL, want_dL) and abs(float(loss) - float(want_loss)) <= 1e-6
+        assert float(junk[:4096].abs().max()) == 0.0 and float(junk[4096:].min()) == 5.0
+        assert arena.verify() == []
+
+
 def test_train_step_cuda_graph_and_uint8_target(cuda_device):
     """TrainStep.step_graph (the step as ONE CUDA graph launch, camera / target read from static buffers) against the
     eager step on other views than the one captured, with the 8-bit target image (value / 255 inside the loss kernel)

@@ -394,14 +394,15 @@ def test_row_interval_tile_walk_keeps_every_contributing_tile():
 
 def test_header_is_plain_c(tmp_path):
     """include/gm_rasterizer.h is the C-ABI contract: it must compile as C99 (no C++ in the signatures) and the two
-    structs passed by pointer must have the layout the ctypes mirror assumes."""
+    three structs passed by pointer must have the layout the ctypes mirror assumes."""
     import ctypes as C
     src = tmp_path / "hdr.c"
     src.write_text('#include <stdio.h>\n#include "gm_rasterizer.h"\n'
-                   'int main(void) { printf("%zu %zu\\n", sizeof(gm_adam_tensor), sizeof(gm_adam_segment)); return 0; }\n')
+                   'int main(void) { printf("%zu %zu %zu\\n", sizeof(gm_adam_tensor), sizeof(gm_adam_segment), '
+                   'sizeof(gm_forward_epilogue)); return 0; }\n')
     exe = tmp_path / "hdr"
     subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"),
                     str(src), "-o", str(exe)], check=True, capture_output=True)
     sizes = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()
-    from gaussianmesh_b200._lib import AdamTensor, AdamSegment
-    assert [int(x) for x in sizes] == [C.sizeof(AdamTensor), C.sizeof(AdamSegment)]
+    from gaussianmesh_b200._lib import AdamTensor, AdamSegment, ForwardEpilogue
+    assert [int(x) for x in sizes] == [C.sizeof(AdamTensor), C.sizeof(AdamSegment), C.sizeof(ForwardEpilogue)]
