@@ -19,6 +19,25 @@ echo "Raw list: \`profiles/r2_launches.csv\`.  Times under ncu are cold-cache an
 echo
 python scripts/summarize_launches.py gpurun_out/launches_${tag}.csv 0
 echo
+python - <<PY
+import csv, json
+rows=[]
+with open('gpurun_out/launches_${tag}.csv', newline='') as f:
+    lines=[l for l in f if l.startswith('"')]
+for r in csv.DictReader(lines):
+    if r.get('Metric Name')!='gpu__time_duration.sum': continue
+    v=float(r['Metric Value'].replace(',','')); u=r['Metric Unit']
+    us = v/1e3 if u in ('ns','nsecond') else (v if u in ('us','usecond') else v*1e3)
+    rows.append((r['Kernel Name'], us))
+starts=[i for i,(n,_) in enumerate(rows) if 'depth_histogram_kernel' in n]
+frames=[rows[a:b] for a,b in zip(starts, starts[1:]) if any('blend_backward' in n for n,_ in rows[a:b]) and not any('photometric' in n or 'adam' in n for n,_ in rows[a:b])]
+if frames:
+    seg=frames[min(2,len(frames)-1)]
+    tot=sum(u for _,u in seg)
+    d=json.load(open('gpurun_out/bench_ours_${tag}.json')); x=json.load(open('gpurun_out/bench_ours_${tag}_GM_PDL_0.json'))
+    print(f"One training frame under ncu: {len(seg)} kernel launches, sum of kernel times {tot/1e3:.3f} ms (serialised, cold cache).  Measured step: {d['ms_per_step']:.3f} ms with programmatic dependent launch, {x['ms_per_step']:.3f} ms with plain stream-ordered launches (\`GM_PDL=0\`); sum of the CUDA-event stage times {sum(v['ms_per_launch'] for v in d['stages'].values()):.3f} ms.")
+PY
+echo
 echo "CUDA-event stage times inside the timed training region of bench.py (\`profiles/r2_bench_ours.json\`, 50 steps):"
 echo
 python - <<PY
