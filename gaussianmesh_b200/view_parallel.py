@@ -105,8 +105,8 @@ class ViewParallelTrainer:
             if mode == "mc" and (self._grad_mc == 0 or self._param_mc == 0):
                 raise RasterizerError("ViewParallelTrainer", GM_ERR_BAD_ARGUMENT,
                                       "no multicast mapping for the symmetric allocations (NVLS unavailable): use mode='p2p'")
-            # measured on 8 x B200: multicast 2.17 ms / global step against 2.25 ms for peer loads / stores; on 2 GPUs the
-            # peer version wins (1.88 against 2.15 ms): the switch-side reduction pays from four ranks up
+            # measured on 8 x B200: multicast 2.16 ms / global step against 2.23 ms for peer loads / stores; on 2 GPUs the
+            # peer version wins (1.87 against 2.15 ms): the switch-side reduction pays from four ranks up
             if auto and self.world >= 4 and self._grad_mc != 0 and self._param_mc != 0:
                 self.mode = "mc"
 
