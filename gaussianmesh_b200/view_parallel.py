@@ -140,19 +140,29 @@ class ViewParallelTrainer:
             self._grad_mc = self._param_mc = 0
 
     def _gather_moments(self):
-        """The full flat Adam moment vectors from the per-rank shards (once per densification)."""
+        """The full flat Adam moment vectors from the per-rank shards (once per densification).  Shards differ by at most
+        one 32-float block, so every rank contributes a buffer of the largest shard's size and the padding is dropped."""
         it = self.it
-        full = [torch.zeros(it.flat_numel, dtype=torch.float32, device=it.device) for _ in range(2)]
-        for vec, mine in zip(full, (self.exp_avg, self.exp_avg_sq)):
-            parts = []
-            for r in range(self.world):
-                lo, hi = C.c_size_t(), C.c_size_t()
-                lib.gm_adam_shard_range(it.flat_numel, self.world, r, C.byref(lo), C.byref(hi))
-                parts.append(vec[lo.value:hi.value])
-            own = parts[self.rank]
-            own.copy_(mine[:own.numel()])
+        ranges = []
+        for r in range(self.world):
+            lo, hi = C.c_size_t(), C.c_size_t()
+            lib.gm_adam_shard_range(it.flat_numel, self.world, r, C.byref(lo), C.byref(hi))
+            ranges.append((lo.value, hi.value))
+        width = max(hi - lo for lo, hi in ranges)
+        full = []
+        for mine in (self.exp_avg, self.exp_avg_sq):
+            lo, hi = ranges[self.rank]
+            send = torch.zeros(width, dtype=torch.float32, device=it.device)
+            send[:hi - lo].copy_(mine[:hi - lo])
+            recv = torch.empty(self.world * width, dtype=torch.float32, device=it.device)
             if self.world > 1:
-                self.exchange.dist.all_gather(parts, own.clone(), group=self.exchange.group)
+                self.exchange.dist.all_gather_into_tensor(recv, send, group=self.exchange.group)
+            else:
+                recv.copy_(send)
+            vec = torch.zeros(it.flat_numel, dtype=torch.float32, device=it.device)
+            for r, (a, b) in enumerate(ranges):
+                vec[a:b].copy_(recv[r * width:r * width + (b - a)])
+            full.append(vec)
         return full
 
     def densify_and_prune(self, max_grad: float, min_opacity: float = 0.005, extent: float = 0.0, max_screen_size=None,
