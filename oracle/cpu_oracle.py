@@ -223,7 +223,57 @@ def _torch_cpu_preprocess(mesh: dict, campos: np.ndarray) -> dict:
     t0 = time.perf_counter()
     chain()
     ms = (time.perf_counter() - t0) * 1e3
+
+    # the edit-time chain (a4-a6) for half as many Gaussians (config 5): deform_gaussian once per deformed mesh
+    # (edittool/__init__.py:103-131), then per frame the rotated-direction eval_sh and strip_symmetric (:442-448,
+    # edittool/general_utils.py:26-37) -- the reference recomputes strip_symmetric every frame
+    Pe = t["shs"].shape[0] // 2
+    g = torch.Generator().manual_seed(0)
+    Vn = 2562
+    V, Vd = torch.randn(Vn, 3, generator=g), torch.randn(Vn, 3, generator=g)
+    VR, VS = torch.randn(Vn, 3, 3, generator=g), torch.randn(Vn, 3, 3, generator=g)
+    tri = torch.randint(0, Vn, (Pe, 3), generator=g)
+    w = torch.rand(Pe, 3, generator=g)
+    pos = t["vertex1"][:Pe].clone()
+    cov = torch.randn(Pe, 3, 3, generator=g)
+    sh_e = t["shs"][:Pe]
+
+    def deform():
+        w_pos, w_rs = w[:, :, None], w[:, :, None, None]
+        g_delta_pos = (w_pos * (Vd - V)[tri]).sum(dim=1)
+        rot = (w_rs * VR[tri]).sum(dim=1).transpose(1, 2)
+        g_delta_rs = torch.matmul(rot, (w_rs * VS[tri]).sum(dim=1))
+        return pos + g_delta_pos, torch.matmul(torch.matmul(g_delta_rs, cov), g_delta_rs.transpose(1, 2)), rot
+
+    def edit_frame(dpos, dcov, rot):
+        sh = sh_e.transpose(1, 2)
+        d = dpos - cam.repeat(dpos.shape[0], 1)
+        d = d / d.norm(dim=1, keepdim=True)
+        d = torch.matmul(rot.transpose(1, 2), d.unsqueeze(2)).squeeze(2)
+        x, y, z = d[:, 0:1], d[:, 1:2], d[:, 2:3]
+        xx, yy, zz, xy, yz, xz = x * x, y * y, z * z, x * y, y * z, x * z
+        res = C0 * sh[..., 0] - C1 * y * sh[..., 1] + C1 * z * sh[..., 2] - C1 * x * sh[..., 3]
+        res = (res + C2[0] * xy * sh[..., 4] + C2[1] * yz * sh[..., 5] + C2[2] * (2.0 * zz - xx - yy) * sh[..., 6]
+               + C2[3] * xz * sh[..., 7] + C2[4] * (xx - yy) * sh[..., 8])
+        res = (res + C3[0] * y * (3 * xx - yy) * sh[..., 9] + C3[1] * xy * z * sh[..., 10]
+               + C3[2] * y * (4 * zz - xx - yy) * sh[..., 11] + C3[3] * z * (2 * zz - 3 * xx - 3 * yy) * sh[..., 12]
+               + C3[4] * x * (4 * zz - xx - yy) * sh[..., 13] + C3[5] * z * (xx - yy) * sh[..., 14]
+               + C3[6] * x * (xx - 3 * yy) * sh[..., 15])
+        torch.clamp(res + 0.5, min=0.0)
+        c6 = torch.zeros(dcov.shape[0], 6)
+        c6[:, 0], c6[:, 1], c6[:, 2] = dcov[:, 0, 0], dcov[:, 0, 1], dcov[:, 0, 2]
+        c6[:, 3], c6[:, 4], c6[:, 5] = dcov[:, 1, 1], dcov[:, 1, 2], dcov[:, 2, 2]
+
+    state = deform()
+    t0 = time.perf_counter()
+    state = deform()
+    deform_ms = (time.perf_counter() - t0) * 1e3
+    edit_frame(*state)
+    t0 = time.perf_counter()
+    edit_frame(*state)
+    edit_ms = (time.perf_counter() - t0) * 1e3
     return {"jittor_cpu_preprocess_ms": ms, "jittor_cpu_preprocess_cores": threads,
+            "jittor_cpu_edit_frame_ms": edit_ms, "jittor_cpu_deform_ms": deform_ms, "jittor_cpu_edit_gaussians": int(Pe),
             "jittor_cpu_preprocess_note": "the reference's Python preprocess chain (bind + activations + Python covariance + "
                                           "Python SH colours) as multi-threaded tensor ops, torch CPU standing in for Jittor's "
                                           "CPU backend (not installable here), one frame, same P"}
