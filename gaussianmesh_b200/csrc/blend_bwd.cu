@@ -371,6 +371,7 @@ __device__ __forceinline__ float butterfly18(const f2 (&v)[kComp], int lane)
 	return keep + __shfl_xor_sync(0xffffffffu, send, 1);
 }
 
+template <int EXP>
 __global__ void __launch_bounds__(kThreads, 4)
 blend_backward_pairs_kernel(GeometryState g, BinningState b, ImageState img, uint32_t capacity,
                             int W, int H, int tiles_x, const float* __restrict__ bg_color,
@@ -514,7 +515,7 @@ blend_backward_pairs_kernel(GeometryState g, BinningState b, ImageState img, uin
 			const int n_pairs = (n_keep + 1) >> 1;
 			uint32_t touched = 0, pair_bits = 3u;
 			float* park_at = park_lane;
-			for (int k = 0; k < n_pairs; k++, pair_bits <<= 2, park_at += 2 * kComp) {
+			for (int k = 0; k < (EXP == 3 ? 0 : n_pairs); k++, pair_bits <<= 2, park_at += 2 * kComp) {
 				const ulonglong2 XY = *reinterpret_cast<const ulonglong2*>(q.v[0][k]);
 				const ulonglong2 AB = *reinterpret_cast<const ulonglong2*>(q.v[1][k]);
 				const ulonglong2 CO = *reinterpret_cast<const ulonglong2*>(q.v[2][k]);
@@ -577,12 +578,17 @@ blend_backward_pairs_kernel(GeometryState g, BinningState b, ImageState img, uin
 				v[6] = mul2(qdx, dx);
 				v[7] = mul2(qdx, dy);
 				v[8] = mul2(qdy, dy);
-				const float total = butterfly18(v, lane);
-				if (park_writer)
-					*park_at = total;
+				if (EXP == 0) {
+					const float total = butterfly18(v, lane);
+					if (park_writer)
+						*park_at = total;
+				} else {
+					*reinterpret_cast<float2*>(q.park + 2 * lane) = make_float2(lo(v[3]), lo(dchannel_dcolor));
+					*reinterpret_cast<float2*>(q.park + 64 + 2 * lane) = make_float2(hi(v[3]), hi(dchannel_dcolor));
+				}
 			}
 			__syncwarp();
-			if ((touched >> lane) & 1u) {
+			if (EXP < 2 && ((touched >> lane) & 1u)) {
 				// this lane sends queue entry `lane` to global memory (unless no pixel accepted it)
 				const float* m = q.park + lane * kComp;
 				const float Sq = m[3], Sx = m[4], Sy = m[5], Sxx = m[6], Sxy = m[7], Syy = m[8];
@@ -1060,6 +1066,351 @@ blend_backward_mma_kernel(GeometryState g, BinningState b, ImageState img, uint3
 	}
 }
 
+
+// ---- column sums: lanes own splats when the sums leave the warp -------------------------------------
+// The nine sums over the warp's 32 pixels are not formed per splat with shuffles.  Each lane parks (q, w) = (G dL/dalpha,
+// alpha T) of its pixel in a warp-private slab, one row per evaluated splat, ACROSS the 32-splat culling chunks; when 16
+// rows are full the roles turn: lane l takes splat l & 15 and walks 16 of its 32 pixels (half l >> 4 of the block), forming
+//     sum_p q[s, p] * (1, u, v, u^2, u v, v^2)[p]      and      sum_p w[s, p] * dL/dpixel[p, :]
+// with u, v the pixel's offset from the block centre (compile-time constants of the unrolled loop; a row of eight pixels is
+// first reduced to three partial sums).  One exchange joins the two halves, and lanes 0-15 shift the pixel-centred moments
+// to their splat (dx = X - u), apply the splat-constant factors of backward.cu:537-554 and send nine REDs.  Against the
+// 18-value butterfly of the pairs kernel (about 37 instructions per splat) this costs about 14 per splat, and nothing in it
+// sits on the alpha / T recurrence.  The survivors of the culling are paired across chunk boundaries (an odd one is carried
+// to the next chunk instead of being padded).
+constexpr int kBatchC = 128;      // records per stage
+constexpr int kSlabRowsC = 16;
+constexpr int kSlabPitchC = 66;   // floats per slab row: 32 pixels x (q, w) + 2 (rows 8 bytes apart modulo 128: conflict-free column reads)
+
+struct WarpQueueC {
+	// [field][slot][4]: slot k holds entries 2k (A, further back) and 2k+1 (B) of the compacted survivors, back to front
+	//   0: xA xB yA yB   1: aA aB -bA -bB   2: cA cB oA oB   3: rA rB gA gB   4: bA bB posA posB (0-based, as bits)
+	//   5: idA idB - -   (33 entries: up to 32 survivors of a chunk behind one carried over)
+	float v[6][17][4];
+	float slab[kSlabRowsC * kSlabPitchC];
+	float table[kSlabRowsC / 2][16];   // per parked pair: fields 0, 1, 2, 5 of its queue slot (what the flush needs)
+	float4 dlp[32];                    // dL/dpixel of the warp's 32 pixels
+};
+
+struct __align__(128) BwdSmemC {
+	float4 conic[2][kBatchC];
+	float4 xyrg[2][kBatchC];
+	float2 bid[2][kBatchC];
+	WarpQueueC queue[kWarps];
+	uint64_t full[2];
+	uint32_t warp_max[kWarps];
+};
+
+__global__ void __launch_bounds__(kThreads, 3)
+blend_backward_cols_kernel(GeometryState g, BinningState b, ImageState img, uint32_t capacity,
+                           int W, int H, int tiles_x, const float* __restrict__ bg_color,
+                           const float* __restrict__ dL_dpixels,
+                           float* __restrict__ dL_dmean2D,   // [P,3]
+                           float* __restrict__ dL_dconic2D,  // [P,4]
+                           float* __restrict__ dL_dopacity,  // [P]
+                           float* __restrict__ dL_dcolors)   // [P,3]
+{
+	pdl_sync();
+	extern __shared__ __align__(128) unsigned char smem_raw[];
+	BwdSmemC& s = *reinterpret_cast<BwdSmemC*>(smem_raw);
+
+	const int tile = blockIdx.x;
+	const int tile_x = tile % tiles_x, tile_y = tile / tiles_x;
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+	const int bx0 = tile_x * kTile + (warp & 1) * 8;
+	const int by0 = tile_y * kTile + (warp >> 1) * 4;
+	const int px = bx0 + (lane & 7), py = by0 + (lane >> 3);
+	const bool inside = px < W && py < H;
+	const uint32_t pix_id = (uint32_t)W * py + px;
+	const f2 npx = pk1(-(float)px), npy = pk1(-(float)py);
+	const float wx0 = (float)bx0, wy0 = (float)by0;
+	const float wx1 = (float)min(bx0 + 7, W - 1), wy1 = (float)min(by0 + 3, H - 1);
+
+	const uint32_t start = g.tile_start[tile];
+	uint32_t n = 0;
+	if (start < capacity)
+		n = min(g.tile_count[tile], capacity - start);
+
+	// backward.cu:430-448
+	const float T_final = inside ? img.accum_alpha[pix_id] : 0.0f;
+	float T = T_final;
+	const uint32_t last_contributor = inside ? min(img.n_contrib[pix_id], n) : 0u;
+
+	uint32_t warp_last = last_contributor;
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1)
+		warp_last = max(warp_last, __shfl_xor_sync(0xffffffffu, warp_last, o));
+	if (lane == 0)
+		s.warp_max[warp] = warp_last;
+	if (tid == 0) {
+		mbar_init(&s.full[0], 1);
+		mbar_init(&s.full[1], 1);
+		fence_mbar_init();
+	}
+	__syncthreads();
+	uint32_t tile_last = 0;
+#pragma unroll
+	for (int w = 0; w < kWarps; w++)
+		tile_last = max(tile_last, s.warp_max[w]);
+	if (tile_last == 0)
+		return;
+
+	float dL_dpixel0 = 0.0f, dL_dpixel1 = 0.0f, dL_dpixel2 = 0.0f;
+	if (inside) {
+		const size_t HW = (size_t)H * W;
+		dL_dpixel0 = dL_dpixels[0 * HW + pix_id];
+		dL_dpixel1 = dL_dpixels[1 * HW + pix_id];
+		dL_dpixel2 = dL_dpixels[2 * HW + pix_id];
+	}
+	WarpQueueC& q = s.queue[warp];
+	q.dlp[lane] = make_float4(dL_dpixel0, dL_dpixel1, dL_dpixel2, 0.0f);
+
+	// accum_rec and the pending (last_alpha * last_color, 1 - last_alpha) term of backward.cu:509-515
+	float acc0 = 0.0f, acc1 = 0.0f, acc2 = 0.0f;
+	float pend0 = 0.0f, pend1 = 0.0f, pend2 = 0.0f, keep_prev = 1.0f;
+
+	// backward.cu:455-461: d(pixel offset)/d(NDC mean); applied once per (warp, splat) in flush
+	const float ddelx_dx = 0.5 * W;
+	const float ddely_dy = 0.5 * H;
+	// backward.cu:531-534: dL/dalpha += (-T_final / (1 - alpha)) * (bg . dL/dpixel)
+	const f2 bg_term = pk1(-T_final * (bg_color[0] * dL_dpixel0 + bg_color[1] * dL_dpixel1 + bg_color[2] * dL_dpixel2));
+	const f2 dLp0 = pk1(dL_dpixel0), dLp1 = pk1(dL_dpixel1), dLp2 = pk1(dL_dpixel2);
+	const f2 neg_half = pk1(-0.5f), neg_one = pk1(-1.0f), one = pk1(1.0f);
+
+	auto issue = [&](int batch, int buf) {
+		const uint32_t off = start + (uint32_t)batch * kBatchC;
+		const uint32_t cnt = min((uint32_t)kBatchC, n - (uint32_t)batch * kBatchC);
+		const uint32_t cnt4 = (cnt + 3u) & ~3u;
+		mbar_arrive_expect_tx(&s.full[buf], cnt4 * 40u);
+		bulk_g2s(s.conic[buf], b.rec_conic + off, cnt4 * 16u, &s.full[buf]);
+		bulk_g2s(s.xyrg[buf], b.rec_xyrg + off, cnt4 * 16u, &s.full[buf]);
+		bulk_g2s(s.bid[buf], b.rec_bid + off, cnt4 * 8u, &s.full[buf]);
+	};
+
+	// Shared-window addresses of everything the inner loops touch, made opaque so that they stay in registers: left to
+	// itself ptxas re-derives them from %tid and %cgaid in every iteration (S2R, a ~100-cycle instruction).
+	uint32_t q_base = smem_u32(&q);
+	// this lane's word of a queue slot that is copied to the table when the slot's pair is parked (lanes 0-15: fields 0, 1, 2, 5)
+	// (lanes 16-31 duplicate lanes 0-15: same word to the same place, which spares the loop a lane predicate)
+	uint32_t copy_src = q_base + (uint32_t)((((lane >> 2) & 3) == 3 ? 5 : ((lane >> 2) & 3)) * 17 * 16 + (lane & 3) * 4);
+	uint32_t slab_lane = q_base + (uint32_t)offsetof(WarpQueueC, slab) + (uint32_t)lane * 8u;
+	uint32_t table_lane = q_base + (uint32_t)offsetof(WarpQueueC, table) + (uint32_t)(lane & 15) * 4u;
+	asm volatile("" : "+r"(q_base), "+r"(copy_src), "+r"(slab_lane), "+r"(table_lane));
+	constexpr uint32_t kField = 17 * 16;   // bytes per queue field
+	const float cx = (float)bx0 + 3.5f, cy = (float)by0 + 1.5f;
+
+	// Sum the parked rows (rows 0 .. rows-1, `rows` even and warp-uniform) over the pixels and send each splat's gradients.
+	auto flush = [&](int rows) {
+		__syncwarp();
+		const int half = lane >> 4;
+		// row (lane & 15) of the slab, pixels 16 half .. 16 half + 15
+		const uint32_t row_addr = slab_lane + (uint32_t)(lane & 15) * (kSlabPitchC * 4u - 8u);
+		const uint32_t dl_addr = q_base + (uint32_t)offsetof(WarpQueueC, dlp) + (uint32_t)half * 256u;
+		float Sq = 0.0f, Su = 0.0f, Sv = 0.0f, Suu = 0.0f, Suv = 0.0f, Svv = 0.0f, c0 = 0.0f, c1 = 0.0f, c2 = 0.0f;
+#pragma unroll
+		for (int r = 0; r < 2; r++) {
+			float R0 = 0.0f, R1 = 0.0f, R2 = 0.0f;
+#pragma unroll
+			for (int u = 0; u < 8; u++) {
+				const uint2 qwb = lds64u(row_addr + 8u * (8 * r + u));
+				const float2 qw = make_float2(__uint_as_float(qwb.x), __uint_as_float(qwb.y));
+				const float4 d = lds128(dl_addr + 16u * (8 * r + u));
+				const float uu = (float)u - 3.5f;
+				R0 += qw.x;
+				R1 = fmaf(qw.x, uu, R1);
+				R2 = fmaf(qw.x, uu * uu, R2);
+				c0 = fmaf(qw.y, d.x, c0);
+				c1 = fmaf(qw.y, d.y, c1);
+				c2 = fmaf(qw.y, d.z, c2);
+			}
+			const float vv = (float)(2 * half + r) - 1.5f;
+			Sq += R0;
+			Su += R1;
+			Suu += R2;
+			Sv = fmaf(vv, R0, Sv);
+			Suv = fmaf(vv, R1, Suv);
+			Svv = fmaf(vv * vv, R0, Svv);
+		}
+		Sq += __shfl_xor_sync(0xffffffffu, Sq, 16);
+		Su += __shfl_xor_sync(0xffffffffu, Su, 16);
+		Sv += __shfl_xor_sync(0xffffffffu, Sv, 16);
+		Suu += __shfl_xor_sync(0xffffffffu, Suu, 16);
+		Suv += __shfl_xor_sync(0xffffffffu, Suv, 16);
+		Svv += __shfl_xor_sync(0xffffffffu, Svv, 16);
+		c0 += __shfl_xor_sync(0xffffffffu, c0, 16);
+		c1 += __shfl_xor_sync(0xffffffffu, c1, 16);
+		c2 += __shfl_xor_sync(0xffffffffu, c2, 16);
+		if (lane < rows) {
+			const uint32_t any = (__float_as_uint(c0) | __float_as_uint(c1) | __float_as_uint(c2) | __float_as_uint(Sq) |
+			                      __float_as_uint(Su) | __float_as_uint(Sv) | __float_as_uint(Suu) | __float_as_uint(Suv) |
+			                      __float_as_uint(Svv)) << 1;
+			if (any != 0) {
+				const uint32_t t = table_lane + (uint32_t)(lane >> 1) * 56u;   // table[lane >> 1] + (lane & 1)
+				const float a = lds32(t + 16u), bb = -lds32(t + 24u), c = lds32(t + 32u), o = lds32(t + 40u);
+				const uint32_t id = __float_as_uint(lds32(t + 48u));
+				// dx = x_s - px = X - u with X = x_s - (block centre): shift the pixel-centred moments to the splat
+				const float X = lds32(t) - cx, Y = lds32(t + 8u) - cy;
+				const float Sx = fmaf(X, Sq, -Su), Sy = fmaf(Y, Sq, -Sv);
+				const float Sxx = fmaf(X, fmaf(X, Sq, -2.0f * Su), Suu);
+				const float Sxy = fmaf(X, fmaf(Y, Sq, -Sv), fmaf(-Y, Su, Suv));
+				const float Syy = fmaf(Y, fmaf(Y, Sq, -2.0f * Sv), Svv);
+				red_add(&dL_dcolors[3 * (size_t)id + 0], c0);
+				red_add(&dL_dcolors[3 * (size_t)id + 1], c1);
+				red_add(&dL_dcolors[3 * (size_t)id + 2], c2);
+				// dL/dG = o dL/dalpha;  dG/ddelx = -G (a dx + b dy);  dG/ddely = -G (c dy + b dx)
+				red_add(&dL_dmean2D[3 * (size_t)id + 0], -o * ddelx_dx * (a * Sx + bb * Sy));
+				red_add(&dL_dmean2D[3 * (size_t)id + 1], -o * ddely_dy * (c * Sy + bb * Sx));
+				const float hh = -0.5f * o;
+				red_add(&dL_dconic2D[4 * (size_t)id + 0], hh * Sxx);
+				red_add(&dL_dconic2D[4 * (size_t)id + 1], hh * Sxy);
+				red_add(&dL_dconic2D[4 * (size_t)id + 3], hh * Syy);
+				red_add(&dL_dopacity[id], Sq);
+			}
+		}
+		__syncwarp();   // slab and table are rewritten from here on
+	};
+
+	const int batch_hi = (int)((tile_last - 1) / kBatchC);
+	if (tid == 0)
+		issue(batch_hi, 0);
+
+	int carry = 0;      // 1: queue entry 0 holds a survivor of an earlier chunk that has not been evaluated yet
+	int row = 0;        // parked slab rows
+	for (int it = 0, batch = batch_hi; batch >= 0; it++, batch--) {
+		const int buf = it & 1;
+		// every warp has finished batch+1 (buffer buf^1) before it is overwritten
+		if (it > 0)
+			__syncthreads();
+		if (tid == 0 && batch > 0)
+			issue(batch - 1, buf ^ 1);
+		mbar_wait(&s.full[buf], (uint32_t)(it >> 1) & 1u);
+
+		const int batch_base = batch * kBatchC;
+		// positions >= warp_last are behind every pixel of this warp (backward.cu:487-489)
+		const int cnt = min(min(kBatchC, (int)n - batch_base), (int)warp_last - batch_base);
+		for (int base = (cnt > 0) ? ((cnt - 1) & ~31) : -1; base >= 0; base -= 32) {
+			// cull 32 splats in parallel against the warp's 8x4 pixel block; append the survivors back to front
+			const int j = base + lane;
+			bool keep = false;
+			float4 co, xr;
+			if (j < cnt) {
+				co = s.conic[buf][j];
+				xr = s.xyrg[buf][j];
+				keep = !rect_cannot_contribute(xr.x, xr.y, co.x, co.y, co.z, cull_threshold(co.w),
+				                               wx0, wy0, wx1, wy1);
+			}
+			const uint32_t mask = __ballot_sync(0xffffffffu, keep);
+			const bool last_chunk = (batch | base) == 0;
+			const int n_keep = __popc(mask);
+			int total = carry + n_keep;
+			if (total == 0 || (n_keep == 0 && !last_chunk))
+				continue;
+			{
+				if (keep) {
+					const int at = carry + __popc(mask >> lane) - 1;   // highest list position first
+					const int slot = at >> 1, h = at & 1;
+					const float2 bi = s.bid[buf][j];
+					q.v[0][slot][h] = xr.x;
+					q.v[0][slot][2 + h] = xr.y;
+					q.v[1][slot][h] = co.x;
+					q.v[1][slot][2 + h] = -co.y;
+					q.v[2][slot][h] = co.z;
+					q.v[2][slot][2 + h] = co.w;
+					q.v[3][slot][h] = xr.z;
+					q.v[3][slot][2 + h] = xr.w;
+					q.v[4][slot][h] = bi.x;
+					q.v[4][slot][2 + h] = __uint_as_float((uint32_t)(batch_base + j));
+					q.v[5][slot][h] = bi.y;
+				}
+				if (last_chunk && (total & 1)) {
+					// the list's very last entry, if odd, is paired with a splat that no pixel accepts (position 2^32 - 1)
+					if (lane < 6) {
+						q.v[lane][total >> 1][1] = 0.0f;
+						q.v[lane][total >> 1][3] = lane == 4 ? __uint_as_float(0xffffffffu) : 0.0f;
+					}
+					total++;
+				}
+			}
+			__syncwarp();
+			const int n_pairs = total >> 1;
+			uint32_t slot_addr = q_base;
+			for (int k = 0; k < n_pairs; k++, slot_addr += 16u) {
+				const ulonglong2 XY = lds128p(slot_addr);
+				const ulonglong2 AB = lds128p(slot_addr + kField);
+				const ulonglong2 CO = lds128p(slot_addr + 2 * kField);
+				const float4 BP = lds128(slot_addr + 4 * kField);
+				// backward.cu:487-501, the forward's instruction sequence
+				const f2 dx = add2(XY.x, npx), dy = add2(XY.y, npy);
+				f2 t = mul2(dy, CO.x);
+				const f2 u = mul2(dx, AB.x);
+				t = mul2(dy, t);
+				const f2 sq = fma2(dx, u, t);
+				const f2 vv = mul2(dx, AB.y);
+				const f2 ww = mul2(dy, vv);
+				const f2 power = fma2(sq, neg_half, ww);
+				const f2 G = exp2x(power);
+				const f2 al = mul2(CO.y, G);
+				const float aA = fminf(lo(al), 0.99f), aB = fminf(hi(al), 0.99f);
+				const bool skipA = (__float_as_uint(BP.z) >= last_contributor) | (lo(power) > 0.0f) | (aA < 1.0f / 255.0f);
+				const bool skipB = (__float_as_uint(BP.w) >= last_contributor) | (hi(power) > 0.0f) | (aB < 1.0f / 255.0f);
+				if (__all_sync(0xffffffffu, skipA & skipB))
+					continue;
+
+				const f2 e2 = pk(skipA ? 0.0f : aA, skipB ? 0.0f : aB);
+				const f2 Ge = pk(skipA ? 0.0f : lo(G), skipB ? 0.0f : hi(G));
+				// backward.cu:503-507: T <- T / (1 - alpha).  MUFU.RCP: 1 ulp, far inside the 1e-3 gradient tolerance
+				const f2 om = fma2(e2, neg_one, one);
+				const float rcpA = rcp_approx_ftz(lo(om)), rcpB = rcp_approx_ftz(hi(om));
+				const float TA = T * rcpA, TB = TA * rcpB;
+				T = TB;
+				const f2 T2 = pk(TA, TB), rcp2 = pk(rcpA, rcpB);
+				// backward.cu:509-521: accum_rec, walked A then B
+				const ulonglong2 RG = lds128p(slot_addr + 3 * kField);
+				const f2 col0 = RG.x, col1 = RG.y, col2 = pk(BP.x, BP.y);
+				const f2 ac0 = mul2(e2, col0), ac1 = mul2(e2, col1), ac2 = mul2(e2, col2);
+				const float accA0 = fmaf(keep_prev, acc0, pend0), accA1 = fmaf(keep_prev, acc1, pend1),
+				            accA2 = fmaf(keep_prev, acc2, pend2);
+				acc0 = fmaf(lo(om), accA0, lo(ac0));
+				acc1 = fmaf(lo(om), accA1, lo(ac1));
+				acc2 = fmaf(lo(om), accA2, lo(ac2));
+				pend0 = hi(ac0); pend1 = hi(ac1); pend2 = hi(ac2);
+				keep_prev = hi(om);
+				const f2 d0 = fma2(pk(accA0, acc0), neg_one, col0);
+				const f2 d1 = fma2(pk(accA1, acc1), neg_one, col1);
+				const f2 d2 = fma2(pk(accA2, acc2), neg_one, col2);
+				f2 dL_dalpha = fma2(d2, dLp2, fma2(d1, dLp1, mul2(d0, dLp0)));
+				// backward.cu:526-534
+				dL_dalpha = fma2(dL_dalpha, T2, mul2(bg_term, rcp2));
+				// q = G dL/dalpha (backward.cu:537-554) and w = alpha T (backward.cu:523) of this pixel: slab rows `row` (splat A)
+				// and row + 1 (splat B); the lanes copy what the flush needs of the queue slot, one word each
+				const f2 qq = mul2(Ge, dL_dalpha), wt = mul2(e2, T2);
+				const uint32_t dst = slab_lane + (uint32_t)row * (kSlabPitchC * 4u);
+				sts64(dst, lo(qq), lo(wt));
+				sts64(dst + kSlabPitchC * 4u, hi(qq), hi(wt));
+				sts32(table_lane + (uint32_t)row * 32u, lds32(copy_src + (uint32_t)k * 16u));
+				row += 2;
+				if (row == kSlabRowsC) {
+					flush(kSlabRowsC);
+					row = 0;
+				}
+			}
+			__syncwarp();   // every lane is through with the queue
+			carry = total & 1;
+			if (carry) {
+				// the odd survivor (entry total - 1 = half A of slot n_pairs) becomes entry 0 of the next chunk's list
+				if (n_pairs > 0 && lane < 12) {
+					const int f = lane >> 1, e = (lane & 1) * 2;
+					q.v[f][0][e] = q.v[f][n_pairs][e];
+				}
+				__syncwarp();
+			}
+		}
+	}
+	if (row > 0)
+		flush(row);
+}
+
 } // namespace
 
 int launch_blend_backward(const GeometryState& g, const BinningState& b, const ImageState& img, uint32_t capacity,
@@ -1074,11 +1425,33 @@ int launch_blend_backward(const GeometryState& g, const BinningState& b, const I
 	// GM_BLEND_SCALAR=1 the one-splat-per-iteration kernel; both are kept for A/B measurements.
 	static const bool scalar = std::getenv("GM_BLEND_SCALAR") != nullptr && std::getenv("GM_BLEND_SCALAR")[0] == '1';
 	static const bool pairs = !(std::getenv("GM_BLEND_BWD") != nullptr && std::getenv("GM_BLEND_BWD")[0] == 'm');
+	static const bool cols = std::getenv("GM_BLEND_BWD") != nullptr && std::getenv("GM_BLEND_BWD")[0] == 'c';
 	if (scalar)
 		launch_k(blend_backward_kernel, dim3(num_tiles), dim3(kThreads), 0, stream, 
 			g, b, img, capacity, vp.W, vp.H, vp.tiles_x, vp.bg, dL_dpix, dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolor);
-	else if (pairs)
-		launch_k(blend_backward_pairs_kernel, dim3(num_tiles), dim3(kThreads), 0, stream, 
+	else if (cols) {
+		static bool opted_in_c[64] = {};
+		int dev = 0;
+		cudaGetDevice(&dev);
+		if (dev < 0 || dev >= 64 || !opted_in_c[dev]) {
+			const cudaError_t attr = cudaFuncSetAttribute(blend_backward_cols_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+			                                              (int)sizeof(BwdSmemC));
+			if (attr != cudaSuccess) {
+				set_last_error("blend_backward shared memory", attr);
+				return GM_ERR_CUDA;
+			}
+			if (dev >= 0 && dev < 64)
+				opted_in_c[dev] = true;
+		}
+		launch_k(blend_backward_cols_kernel, dim3(num_tiles), dim3(kThreads), sizeof(BwdSmemC), stream,
+			g, b, img, capacity, vp.W, vp.H, vp.tiles_x, vp.bg, dL_dpix, dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolor);
+	} else if (pairs && std::getenv("GM_EXP") != nullptr) {
+		const int e = std::atoi(std::getenv("GM_EXP"));
+		auto kern = e == 1 ? blend_backward_pairs_kernel<1> : e == 2 ? blend_backward_pairs_kernel<2> : blend_backward_pairs_kernel<3>;
+		launch_k(kern, dim3(num_tiles), dim3(kThreads), 0, stream,
+			g, b, img, capacity, vp.W, vp.H, vp.tiles_x, vp.bg, dL_dpix, dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolor);
+	} else if (pairs)
+		launch_k(blend_backward_pairs_kernel<0>, dim3(num_tiles), dim3(kThreads), 0, stream, 
 			g, b, img, capacity, vp.W, vp.H, vp.tiles_x, vp.bg, dL_dpix, dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolor);
 	else {
 		// the opt-in shared-memory size is a per-device function attribute
