@@ -716,6 +716,17 @@ __device__ __forceinline__ void red_add(float* addr, float v)
 	asm volatile("red.global.add.f32 [%0], %1;" ::"l"(addr), "f"(v) : "memory");
 }
 
+// vector forms (sm_90+): one request for two / four adjacent floats; the address must be 8- / 16-byte aligned
+__device__ __forceinline__ void red_add2(float* addr, float a, float b)
+{
+	asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(addr), "f"(a), "f"(b) : "memory");
+}
+
+__device__ __forceinline__ void red_add4(float* addr, float a, float b, float c, float d)
+{
+	asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
 // x = head + tail: head = x with the 13 low mantissa bits cleared (a TF32 value), tail exact in fp32 (the tensor core
 // reads its top 19 bits): together 21+ mantissa bits of x enter the product
 __device__ __forceinline__ void tf32_split(float x, uint32_t& head, uint32_t& tail)
@@ -1078,7 +1089,6 @@ blend_backward_mma_kernel(GeometryState g, BinningState b, ImageState img, uint3
 // 18-value butterfly of the pairs kernel (about 37 instructions per splat) this costs about 14 per splat, and nothing in it
 // sits on the alpha / T recurrence.  The survivors of the culling are paired across chunk boundaries (an odd one is carried
 // to the next chunk instead of being padded).
-constexpr int kBatchC = 128;      // records per stage
 constexpr int kSlabRowsC = 16;
 constexpr int kSlabPitchC = 66;   // floats per slab row: 32 pixels x (q, w) + 2 (rows 8 bytes apart modulo 128: conflict-free column reads)
 
@@ -1088,10 +1098,11 @@ struct WarpQueueC {
 	//   5: idA idB - -   (33 entries: up to 32 survivors of a chunk behind one carried over)
 	float v[6][17][4];
 	float slab[kSlabRowsC * kSlabPitchC];
-	float table[kSlabRowsC / 2][16];   // per parked pair: fields 0, 1, 2, 5 of its queue slot (what the flush needs)
-	float4 dlp[32];                    // dL/dpixel of the warp's 32 pixels
+	float table[kSlabRowsC / 2][17];   // per parked pair: fields 0, 1, 2, 5 of its queue slot (what the flush needs); odd pitch
+	float4 dlp[33];                    // dL/dpixel of the warp's 32 pixels, pixel p at p + (p >> 4): the two halves on different banks
 };
 
+template <int kBatchC>
 struct __align__(128) BwdSmemC {
 	float4 conic[2][kBatchC];
 	float4 xyrg[2][kBatchC];
@@ -1101,7 +1112,8 @@ struct __align__(128) BwdSmemC {
 	uint32_t warp_max[kWarps];
 };
 
-__global__ void __launch_bounds__(kThreads, 3)
+template <int kBatchC, int kMinBlocks>
+__global__ void __launch_bounds__(kThreads, kMinBlocks)
 blend_backward_cols_kernel(GeometryState g, BinningState b, ImageState img, uint32_t capacity,
                            int W, int H, int tiles_x, const float* __restrict__ bg_color,
                            const float* __restrict__ dL_dpixels,
@@ -1112,7 +1124,7 @@ blend_backward_cols_kernel(GeometryState g, BinningState b, ImageState img, uint
 {
 	pdl_sync();
 	extern __shared__ __align__(128) unsigned char smem_raw[];
-	BwdSmemC& s = *reinterpret_cast<BwdSmemC*>(smem_raw);
+	BwdSmemC<kBatchC>& s = *reinterpret_cast<BwdSmemC<kBatchC>*>(smem_raw);
 
 	const int tile = blockIdx.x;
 	const int tile_x = tile % tiles_x, tile_y = tile / tiles_x;
@@ -1164,7 +1176,7 @@ blend_backward_cols_kernel(GeometryState g, BinningState b, ImageState img, uint
 		dL_dpixel2 = dL_dpixels[2 * HW + pix_id];
 	}
 	WarpQueueC& q = s.queue[warp];
-	q.dlp[lane] = make_float4(dL_dpixel0, dL_dpixel1, dL_dpixel2, 0.0f);
+	q.dlp[lane + (lane >> 4)] = make_float4(dL_dpixel0, dL_dpixel1, dL_dpixel2, 0.0f);
 
 	// accum_rec and the pending (last_alpha * last_color, 1 - last_alpha) term of backward.cu:509-515
 	float acc0 = 0.0f, acc1 = 0.0f, acc2 = 0.0f;
@@ -1188,6 +1200,8 @@ blend_backward_cols_kernel(GeometryState g, BinningState b, ImageState img, uint
 		bulk_g2s(s.bid[buf], b.rec_bid + off, cnt4 * 8u, &s.full[buf]);
 	};
 
+	// vector REDs need 8- / 16-byte aligned gradient arrays (true for every allocation of the host side; checked, not assumed)
+	const bool vec_red = (((uintptr_t)dL_dcolors | (uintptr_t)dL_dmean2D) & 7u) == 0 && ((uintptr_t)dL_dconic2D & 15u) == 0;
 	// Shared-window addresses of everything the inner loops touch, made opaque so that they stay in registers: left to
 	// itself ptxas re-derives them from %tid and %cgaid in every iteration (S2R, a ~100-cycle instruction).
 	uint32_t q_base = smem_u32(&q);
@@ -1206,7 +1220,7 @@ blend_backward_cols_kernel(GeometryState g, BinningState b, ImageState img, uint
 		const int half = lane >> 4;
 		// row (lane & 15) of the slab, pixels 16 half .. 16 half + 15
 		const uint32_t row_addr = slab_lane + (uint32_t)(lane & 15) * (kSlabPitchC * 4u - 8u);
-		const uint32_t dl_addr = q_base + (uint32_t)offsetof(WarpQueueC, dlp) + (uint32_t)half * 256u;
+		const uint32_t dl_addr = q_base + (uint32_t)offsetof(WarpQueueC, dlp) + (uint32_t)half * 272u;
 		float Sq = 0.0f, Su = 0.0f, Sv = 0.0f, Suu = 0.0f, Suv = 0.0f, Svv = 0.0f, c0 = 0.0f, c1 = 0.0f, c2 = 0.0f;
 #pragma unroll
 		for (int r = 0; r < 2; r++) {
@@ -1246,7 +1260,7 @@ blend_backward_cols_kernel(GeometryState g, BinningState b, ImageState img, uint
 			                      __float_as_uint(Su) | __float_as_uint(Sv) | __float_as_uint(Suu) | __float_as_uint(Suv) |
 			                      __float_as_uint(Svv)) << 1;
 			if (any != 0) {
-				const uint32_t t = table_lane + (uint32_t)(lane >> 1) * 56u;   // table[lane >> 1] + (lane & 1)
+				const uint32_t t = table_lane + (uint32_t)(lane >> 1) * 60u;   // table[lane >> 1] + (lane & 1)
 				const float a = lds32(t + 16u), bb = -lds32(t + 24u), c = lds32(t + 32u), o = lds32(t + 40u);
 				const uint32_t id = __float_as_uint(lds32(t + 48u));
 				// dx = x_s - px = X - u with X = x_s - (block centre): shift the pixel-centred moments to the splat
@@ -1255,16 +1269,31 @@ blend_backward_cols_kernel(GeometryState g, BinningState b, ImageState img, uint
 				const float Sxx = fmaf(X, fmaf(X, Sq, -2.0f * Su), Suu);
 				const float Sxy = fmaf(X, fmaf(Y, Sq, -Sv), fmaf(-Y, Su, Suv));
 				const float Syy = fmaf(Y, fmaf(Y, Sq, -2.0f * Sv), Svv);
-				red_add(&dL_dcolors[3 * (size_t)id + 0], c0);
-				red_add(&dL_dcolors[3 * (size_t)id + 1], c1);
-				red_add(&dL_dcolors[3 * (size_t)id + 2], c2);
 				// dL/dG = o dL/dalpha;  dG/ddelx = -G (a dx + b dy);  dG/ddely = -G (c dy + b dx)
-				red_add(&dL_dmean2D[3 * (size_t)id + 0], -o * ddelx_dx * (a * Sx + bb * Sy));
-				red_add(&dL_dmean2D[3 * (size_t)id + 1], -o * ddely_dy * (c * Sy + bb * Sx));
+				const float gx = -o * ddelx_dx * (a * Sx + bb * Sy), gy = -o * ddely_dy * (c * Sy + bb * Sx);
 				const float hh = -0.5f * o;
-				red_add(&dL_dconic2D[4 * (size_t)id + 0], hh * Sxx);
-				red_add(&dL_dconic2D[4 * (size_t)id + 1], hh * Sxy);
-				red_add(&dL_dconic2D[4 * (size_t)id + 3], hh * Syy);
+				if (vec_red) {
+					// rows of three floats start 8-byte aligned for even ids only: the aligned pair goes out as one request,
+					// the third value alone.  dL/dmean2D.z is not written by this pass: adding 0 to it is free.
+					const bool odd = id & 1u;
+					float* const pc = dL_dcolors + 3 * (size_t)id;
+					red_add2(pc + (odd ? 1 : 0), odd ? c1 : c0, odd ? c2 : c1);
+					red_add(pc + (odd ? 0 : 2), odd ? c0 : c2);
+					float* const pm = dL_dmean2D + 3 * (size_t)id;
+					red_add2(pm + (odd ? 1 : 0), odd ? gy : gx, odd ? 0.0f : gy);
+					if (odd)
+						red_add(pm, gx);
+					red_add4(dL_dconic2D + 4 * (size_t)id, hh * Sxx, hh * Sxy, 0.0f, hh * Syy);
+				} else {
+					red_add(&dL_dcolors[3 * (size_t)id + 0], c0);
+					red_add(&dL_dcolors[3 * (size_t)id + 1], c1);
+					red_add(&dL_dcolors[3 * (size_t)id + 2], c2);
+					red_add(&dL_dmean2D[3 * (size_t)id + 0], gx);
+					red_add(&dL_dmean2D[3 * (size_t)id + 1], gy);
+					red_add(&dL_dconic2D[4 * (size_t)id + 0], hh * Sxx);
+					red_add(&dL_dconic2D[4 * (size_t)id + 1], hh * Sxy);
+					red_add(&dL_dconic2D[4 * (size_t)id + 3], hh * Syy);
+				}
 				red_add(&dL_dopacity[id], Sq);
 			}
 		}
@@ -1340,6 +1369,7 @@ blend_backward_cols_kernel(GeometryState g, BinningState b, ImageState img, uint
 				const ulonglong2 AB = lds128p(slot_addr + kField);
 				const ulonglong2 CO = lds128p(slot_addr + 2 * kField);
 				const float4 BP = lds128(slot_addr + 4 * kField);
+				const float copy_word = lds32(copy_src + (uint32_t)k * 16u);   // this lane's word of the slot for the flush table
 				// backward.cu:487-501, the forward's instruction sequence
 				const f2 dx = add2(XY.x, npx), dy = add2(XY.y, npy);
 				f2 t = mul2(dy, CO.x);
@@ -1388,7 +1418,7 @@ blend_backward_cols_kernel(GeometryState g, BinningState b, ImageState img, uint
 				const uint32_t dst = slab_lane + (uint32_t)row * (kSlabPitchC * 4u);
 				sts64(dst, lo(qq), lo(wt));
 				sts64(dst + kSlabPitchC * 4u, hi(qq), hi(wt));
-				sts32(table_lane + (uint32_t)row * 32u, lds32(copy_src + (uint32_t)k * 16u));
+				sts32(table_lane + (uint32_t)row * 34u, copy_word);
 				row += 2;
 				if (row == kSlabRowsC) {
 					flush(kSlabRowsC);
@@ -1430,21 +1460,30 @@ int launch_blend_backward(const GeometryState& g, const BinningState& b, const I
 		launch_k(blend_backward_kernel, dim3(num_tiles), dim3(kThreads), 0, stream, 
 			g, b, img, capacity, vp.W, vp.H, vp.tiles_x, vp.bg, dL_dpix, dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolor);
 	else if (cols) {
-		static bool opted_in_c[64] = {};
-		int dev = 0;
-		cudaGetDevice(&dev);
-		if (dev < 0 || dev >= 64 || !opted_in_c[dev]) {
-			const cudaError_t attr = cudaFuncSetAttribute(blend_backward_cols_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-			                                              (int)sizeof(BwdSmemC));
-			if (attr != cudaSuccess) {
-				set_last_error("blend_backward shared memory", attr);
-				return GM_ERR_CUDA;
+		const char* ev = std::getenv("GM_EXP");
+		const int e = ev ? std::atoi(ev) : 0;
+		auto go = [&](auto kern, size_t smem, int slot) -> int {
+			static bool opted_in_c[4][64] = {};
+			int dev = 0;
+			cudaGetDevice(&dev);
+			if (dev < 0 || dev >= 64 || !opted_in_c[slot][dev]) {
+				const cudaError_t attr = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+				if (attr != cudaSuccess) {
+					set_last_error("blend_backward shared memory", attr);
+					return GM_ERR_CUDA;
+				}
+				if (dev >= 0 && dev < 64)
+					opted_in_c[slot][dev] = true;
 			}
-			if (dev >= 0 && dev < 64)
-				opted_in_c[dev] = true;
-		}
-		launch_k(blend_backward_cols_kernel, dim3(num_tiles), dim3(kThreads), sizeof(BwdSmemC), stream,
-			g, b, img, capacity, vp.W, vp.H, vp.tiles_x, vp.bg, dL_dpix, dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolor);
+			launch_k(kern, dim3(num_tiles), dim3(kThreads), smem, stream,
+				g, b, img, capacity, vp.W, vp.H, vp.tiles_x, vp.bg, dL_dpix, dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolor);
+			return GM_OK;
+		};
+		if (e == 1)
+			return go(blend_backward_cols_kernel<192, 3>, sizeof(BwdSmemC<192>), 1);
+		if (e == 2)
+			return go(blend_backward_cols_kernel<256, 2>, sizeof(BwdSmemC<256>), 2);
+		return go(blend_backward_cols_kernel<128, 3>, sizeof(BwdSmemC<128>), 0);
 	} else if (pairs && std::getenv("GM_EXP") != nullptr) {
 		const int e = std::atoi(std::getenv("GM_EXP"));
 		auto kern = e == 1 ? blend_backward_pairs_kernel<1> : e == 2 ? blend_backward_pairs_kernel<2> : blend_backward_pairs_kernel<3>;
