@@ -371,7 +371,6 @@ __device__ __forceinline__ float butterfly18(const f2 (&v)[kComp], int lane)
 	return keep + __shfl_xor_sync(0xffffffffu, send, 1);
 }
 
-template <int EXP>
 __global__ void __launch_bounds__(kThreads, 4)
 blend_backward_pairs_kernel(GeometryState g, BinningState b, ImageState img, uint32_t capacity,
                             int W, int H, int tiles_x, const float* __restrict__ bg_color,
@@ -515,7 +514,7 @@ blend_backward_pairs_kernel(GeometryState g, BinningState b, ImageState img, uin
 			const int n_pairs = (n_keep + 1) >> 1;
 			uint32_t touched = 0, pair_bits = 3u;
 			float* park_at = park_lane;
-			for (int k = 0; k < (EXP == 3 ? 0 : n_pairs); k++, pair_bits <<= 2, park_at += 2 * kComp) {
+			for (int k = 0; k < n_pairs; k++, pair_bits <<= 2, park_at += 2 * kComp) {
 				const ulonglong2 XY = *reinterpret_cast<const ulonglong2*>(q.v[0][k]);
 				const ulonglong2 AB = *reinterpret_cast<const ulonglong2*>(q.v[1][k]);
 				const ulonglong2 CO = *reinterpret_cast<const ulonglong2*>(q.v[2][k]);
@@ -578,17 +577,12 @@ blend_backward_pairs_kernel(GeometryState g, BinningState b, ImageState img, uin
 				v[6] = mul2(qdx, dx);
 				v[7] = mul2(qdx, dy);
 				v[8] = mul2(qdy, dy);
-				if (EXP == 0) {
-					const float total = butterfly18(v, lane);
-					if (park_writer)
-						*park_at = total;
-				} else {
-					*reinterpret_cast<float2*>(q.park + 2 * lane) = make_float2(lo(v[3]), lo(dchannel_dcolor));
-					*reinterpret_cast<float2*>(q.park + 64 + 2 * lane) = make_float2(hi(v[3]), hi(dchannel_dcolor));
-				}
+				const float total = butterfly18(v, lane);
+				if (park_writer)
+					*park_at = total;
 			}
 			__syncwarp();
-			if (EXP < 2 && ((touched >> lane) & 1u)) {
+			if ((touched >> lane) & 1u) {
 				// this lane sends queue entry `lane` to global memory (unless no pixel accepted it)
 				const float* m = q.park + lane * kComp;
 				const float Sq = m[3], Sx = m[4], Sy = m[5], Sxx = m[6], Sxy = m[7], Syy = m[8];
@@ -1085,35 +1079,38 @@ blend_backward_mma_kernel(GeometryState g, BinningState b, ImageState img, uint3
 //     sum_p q[s, p] * (1, u, v, u^2, u v, v^2)[p]      and      sum_p w[s, p] * dL/dpixel[p, :]
 // with u, v the pixel's offset from the block centre (compile-time constants of the unrolled loop; a row of eight pixels is
 // first reduced to three partial sums).  One exchange joins the two halves, and lanes 0-15 shift the pixel-centred moments
-// to their splat (dx = X - u), apply the splat-constant factors of backward.cu:537-554 and send nine REDs.  Against the
-// 18-value butterfly of the pairs kernel (about 37 instructions per splat) this costs about 14 per splat, and nothing in it
-// sits on the alpha / T recurrence.  The survivors of the culling are paired across chunk boundaries (an odd one is carried
-// to the next chunk instead of being padded).
+// to their splat (dx = X - u), apply the splat-constant factors of backward.cu:537-554 and send the gradients (vector REDs).
+// Against the 18-value butterfly of the pairs kernel (about 37 instructions per splat) this costs about 14 per splat, and
+// nothing in it sits on the alpha / T recurrence.  The survivors of the culling are evaluated in QUADS (two pairs per
+// iteration, no branch inside: the alpha test of the second pair overlaps the recurrences of the first) formed across
+// chunk boundaries: up to three survivors are carried to the next chunk instead of being padded.
 constexpr int kSlabRowsC = 16;
 constexpr int kSlabPitchC = 66;   // floats per slab row: 32 pixels x (q, w) + 2 (rows 8 bytes apart modulo 128: conflict-free column reads)
 
 struct WarpQueueC {
 	// [field][slot][4]: slot k holds entries 2k (A, further back) and 2k+1 (B) of the compacted survivors, back to front
 	//   0: xA xB yA yB   1: aA aB -bA -bB   2: cA cB oA oB   3: rA rB gA gB   4: bA bB posA posB (0-based, as bits)
-	//   5: idA idB - -   (33 entries: up to 32 survivors of a chunk behind one carried over)
-	float v[6][17][4];
+	//   5: idA idB - -   (35 entries: up to 32 survivors of a chunk behind up to three carried over)
+	float v[6][18][4];
 	float slab[kSlabRowsC * kSlabPitchC];
 	float table[kSlabRowsC / 2][17];   // per parked pair: fields 0, 1, 2, 5 of its queue slot (what the flush needs); odd pitch
 	float4 dlp[33];                    // dL/dpixel of the warp's 32 pixels, pixel p at p + (p >> 4): the two halves on different banks
 };
 
-template <int kBatchC>
+template <int kBatchC, int kWarpsC>
 struct __align__(128) BwdSmemC {
 	float4 conic[2][kBatchC];
 	float4 xyrg[2][kBatchC];
 	float2 bid[2][kBatchC];
-	WarpQueueC queue[kWarps];
+	WarpQueueC queue[kWarpsC];
 	uint64_t full[2];
-	uint32_t warp_max[kWarps];
+	uint32_t warp_max[kWarpsC];
 };
 
-template <int kBatchC, int kMinBlocks>
-__global__ void __launch_bounds__(kThreads, kMinBlocks)
+// kWarpsC = 8: one block per 16x16 tile; kWarpsC = 4: two blocks per tile, each owning a 16x8 half (more, smaller blocks:
+// finer register / occupancy steps, a barrier among four warps instead of eight, list trimming per half tile)
+template <int kBatchC, int kMinBlocks, int kWarpsC>
+__global__ void __launch_bounds__(kWarpsC * 32, kMinBlocks)
 blend_backward_cols_kernel(GeometryState g, BinningState b, ImageState img, uint32_t capacity,
                            int W, int H, int tiles_x, const float* __restrict__ bg_color,
                            const float* __restrict__ dL_dpixels,
@@ -1124,14 +1121,16 @@ blend_backward_cols_kernel(GeometryState g, BinningState b, ImageState img, uint
 {
 	pdl_sync();
 	extern __shared__ __align__(128) unsigned char smem_raw[];
-	BwdSmemC<kBatchC>& s = *reinterpret_cast<BwdSmemC<kBatchC>*>(smem_raw);
+	BwdSmemC<kBatchC, kWarpsC>& s = *reinterpret_cast<BwdSmemC<kBatchC, kWarpsC>*>(smem_raw);
 
-	const int tile = blockIdx.x;
+	constexpr int kPerTile = kWarps / kWarpsC;          // blocks per tile
+	const int tile = blockIdx.x / kPerTile;
 	const int tile_x = tile % tiles_x, tile_y = tile / tiles_x;
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const int tw = (blockIdx.x % kPerTile) * kWarpsC + warp;   // the warp's 8x4 block inside the tile
 
-	const int bx0 = tile_x * kTile + (warp & 1) * 8;
-	const int by0 = tile_y * kTile + (warp >> 1) * 4;
+	const int bx0 = tile_x * kTile + (tw & 1) * 8;
+	const int by0 = tile_y * kTile + (tw >> 1) * 4;
 	const int px = bx0 + (lane & 7), py = by0 + (lane >> 3);
 	const bool inside = px < W && py < H;
 	const uint32_t pix_id = (uint32_t)W * py + px;
@@ -1163,7 +1162,7 @@ blend_backward_cols_kernel(GeometryState g, BinningState b, ImageState img, uint
 	__syncthreads();
 	uint32_t tile_last = 0;
 #pragma unroll
-	for (int w = 0; w < kWarps; w++)
+	for (int w = 0; w < kWarpsC; w++)
 		tile_last = max(tile_last, s.warp_max[w]);
 	if (tile_last == 0)
 		return;
@@ -1206,12 +1205,12 @@ blend_backward_cols_kernel(GeometryState g, BinningState b, ImageState img, uint
 	// itself ptxas re-derives them from %tid and %cgaid in every iteration (S2R, a ~100-cycle instruction).
 	uint32_t q_base = smem_u32(&q);
 	// this lane's word of a queue slot that is copied to the table when the slot's pair is parked (lanes 0-15: fields 0, 1, 2, 5)
-	// (lanes 16-31 duplicate lanes 0-15: same word to the same place, which spares the loop a lane predicate)
-	uint32_t copy_src = q_base + (uint32_t)((((lane >> 2) & 3) == 3 ? 5 : ((lane >> 2) & 3)) * 17 * 16 + (lane & 3) * 4);
+	// (lanes 0-15 serve the first pair of a quad, lanes 16-31 the second: next slot, next table row)
+	uint32_t copy_src = q_base + (uint32_t)((((lane >> 2) & 3) == 3 ? 5 : ((lane >> 2) & 3)) * 18 * 16 + (lane & 3) * 4 + (lane >> 4) * 16);
 	uint32_t slab_lane = q_base + (uint32_t)offsetof(WarpQueueC, slab) + (uint32_t)lane * 8u;
-	uint32_t table_lane = q_base + (uint32_t)offsetof(WarpQueueC, table) + (uint32_t)(lane & 15) * 4u;
+	uint32_t table_lane = q_base + (uint32_t)offsetof(WarpQueueC, table) + (uint32_t)(lane & 15) * 4u + (uint32_t)(lane >> 4) * 68u;
 	asm volatile("" : "+r"(q_base), "+r"(copy_src), "+r"(slab_lane), "+r"(table_lane));
-	constexpr uint32_t kField = 17 * 16;   // bytes per queue field
+	constexpr uint32_t kField = 18 * 16;   // bytes per queue field
 	const float cx = (float)bx0 + 3.5f, cy = (float)by0 + 1.5f;
 
 	// Sum the parked rows (rows 0 .. rows-1, `rows` even and warp-uniform) over the pixels and send each splat's gradients.
@@ -1304,7 +1303,70 @@ blend_backward_cols_kernel(GeometryState g, BinningState b, ImageState img, uint
 	if (tid == 0)
 		issue(batch_hi, 0);
 
-	int carry = 0;      // 1: queue entry 0 holds a survivor of an earlier chunk that has not been evaluated yet
+	// One pair of splats up to the alpha test (backward.cu:487-501, the forward's instruction sequence); independent of the
+	// T recurrence, so the two pairs of a quad overlap.
+	struct Front {
+		f2 e2, Ge;        // alpha and G of the two splats, 0 where the pixel skips the splat
+	};
+	auto front = [&](uint32_t slot_addr) -> Front {
+		const ulonglong2 XY = lds128p(slot_addr);
+		const ulonglong2 AB = lds128p(slot_addr + kField);
+		const ulonglong2 CO = lds128p(slot_addr + 2 * kField);
+		const uint2 PP = lds64u(slot_addr + 4 * kField + 8u);
+		const f2 dx = add2(XY.x, npx), dy = add2(XY.y, npy);
+		f2 t = mul2(dy, CO.x);
+		const f2 u = mul2(dx, AB.x);
+		t = mul2(dy, t);
+		const f2 sq = fma2(dx, u, t);
+		const f2 vv = mul2(dx, AB.y);
+		const f2 ww = mul2(dy, vv);
+		const f2 power = fma2(sq, neg_half, ww);
+		const f2 G = exp2x(power);
+		const f2 al = mul2(CO.y, G);
+		const float aA = fminf(lo(al), 0.99f), aB = fminf(hi(al), 0.99f);
+		const bool skipA = (PP.x >= last_contributor) | (lo(power) > 0.0f) | (aA < 1.0f / 255.0f);
+		const bool skipB = (PP.y >= last_contributor) | (hi(power) > 0.0f) | (aB < 1.0f / 255.0f);
+		Front f;
+		f.e2 = pk(skipA ? 0.0f : aA, skipB ? 0.0f : aB);
+		f.Ge = pk(skipA ? 0.0f : lo(G), skipB ? 0.0f : hi(G));
+		return f;
+	};
+	// The recurrences of backward.cu:503-534 for the pair, A then B; parks (q, w) of both splats in slab rows `at`, `at + 1`.
+	// A splat the pixel skips is carried with alpha = 0 and G = 0: T / (1 - 0) == T, the pending (last_alpha, last_color) term
+	// is folded into accum_rec one splat early, q = w = 0.
+	auto back = [&](uint32_t slot_addr, const Front& f, uint32_t dst) {
+		const f2 e2 = f.e2;
+		// backward.cu:503-507: T <- T / (1 - alpha).  MUFU.RCP: 1 ulp, far inside the 1e-3 gradient tolerance
+		const f2 om = fma2(e2, neg_one, one);
+		const float rcpA = rcp_approx_ftz(lo(om)), rcpB = rcp_approx_ftz(hi(om));
+		const float TA = T * rcpA, TB = TA * rcpB;
+		T = TB;
+		const f2 T2 = pk(TA, TB), rcp2 = pk(rcpA, rcpB);
+		// backward.cu:509-521: accum_rec, walked A then B
+		const ulonglong2 RG = lds128p(slot_addr + 3 * kField);
+		const f2 col2 = lds128p(slot_addr + 4 * kField).x;
+		const f2 col0 = RG.x, col1 = RG.y;
+		const f2 ac0 = mul2(e2, col0), ac1 = mul2(e2, col1), ac2 = mul2(e2, col2);
+		const float accA0 = fmaf(keep_prev, acc0, pend0), accA1 = fmaf(keep_prev, acc1, pend1),
+		            accA2 = fmaf(keep_prev, acc2, pend2);
+		acc0 = fmaf(lo(om), accA0, lo(ac0));
+		acc1 = fmaf(lo(om), accA1, lo(ac1));
+		acc2 = fmaf(lo(om), accA2, lo(ac2));
+		pend0 = hi(ac0); pend1 = hi(ac1); pend2 = hi(ac2);
+		keep_prev = hi(om);
+		const f2 d0 = fma2(pk(accA0, acc0), neg_one, col0);
+		const f2 d1 = fma2(pk(accA1, acc1), neg_one, col1);
+		const f2 d2 = fma2(pk(accA2, acc2), neg_one, col2);
+		f2 dL_dalpha = fma2(d2, dLp2, fma2(d1, dLp1, mul2(d0, dLp0)));
+		// backward.cu:526-534
+		dL_dalpha = fma2(dL_dalpha, T2, mul2(bg_term, rcp2));
+		// q = G dL/dalpha (backward.cu:537-554) and w = alpha T (backward.cu:523) of this pixel
+		const f2 qq = mul2(f.Ge, dL_dalpha), wt = mul2(e2, T2);
+		sts64(dst, lo(qq), lo(wt));
+		sts64(dst + kSlabPitchC * 4u, hi(qq), hi(wt));
+	};
+
+	int carry = 0;      // queue entries 0 .. carry-1 hold survivors of earlier chunks that have not been evaluated yet (< 4)
 	int row = 0;        // parked slab rows
 	for (int it = 0, batch = batch_hi; batch >= 0; it++, batch--) {
 		const int buf = it & 1;
@@ -1335,103 +1397,57 @@ blend_backward_cols_kernel(GeometryState g, BinningState b, ImageState img, uint
 			int total = carry + n_keep;
 			if (total == 0 || (n_keep == 0 && !last_chunk))
 				continue;
-			{
-				if (keep) {
-					const int at = carry + __popc(mask >> lane) - 1;   // highest list position first
-					const int slot = at >> 1, h = at & 1;
-					const float2 bi = s.bid[buf][j];
-					q.v[0][slot][h] = xr.x;
-					q.v[0][slot][2 + h] = xr.y;
-					q.v[1][slot][h] = co.x;
-					q.v[1][slot][2 + h] = -co.y;
-					q.v[2][slot][h] = co.z;
-					q.v[2][slot][2 + h] = co.w;
-					q.v[3][slot][h] = xr.z;
-					q.v[3][slot][2 + h] = xr.w;
-					q.v[4][slot][h] = bi.x;
-					q.v[4][slot][2 + h] = __uint_as_float((uint32_t)(batch_base + j));
-					q.v[5][slot][h] = bi.y;
+			if (keep) {
+				const int at = carry + __popc(mask >> lane) - 1;   // highest list position first
+				const int slot = at >> 1, h = at & 1;
+				const float2 bi = s.bid[buf][j];
+				q.v[0][slot][h] = xr.x;
+				q.v[0][slot][2 + h] = xr.y;
+				q.v[1][slot][h] = co.x;
+				q.v[1][slot][2 + h] = -co.y;
+				q.v[2][slot][h] = co.z;
+				q.v[2][slot][2 + h] = co.w;
+				q.v[3][slot][h] = xr.z;
+				q.v[3][slot][2 + h] = xr.w;
+				q.v[4][slot][h] = bi.x;
+				q.v[4][slot][2 + h] = __uint_as_float((uint32_t)(batch_base + j));
+				q.v[5][slot][h] = bi.y;
+			}
+			if (last_chunk && (total & 3)) {
+				// the list's very end is filled up to a whole quad with splats that no pixel accepts (position 2^32 - 1)
+				const int pads = (-total) & 3;
+				if (lane < 6 * pads) {
+					const int e = total + lane / 6, f = lane % 6;
+					q.v[f][e >> 1][e & 1] = 0.0f;
+					q.v[f][e >> 1][2 + (e & 1)] = f == 4 ? __uint_as_float(0xffffffffu) : 0.0f;
 				}
-				if (last_chunk && (total & 1)) {
-					// the list's very last entry, if odd, is paired with a splat that no pixel accepts (position 2^32 - 1)
-					if (lane < 6) {
-						q.v[lane][total >> 1][1] = 0.0f;
-						q.v[lane][total >> 1][3] = lane == 4 ? __uint_as_float(0xffffffffu) : 0.0f;
-					}
-					total++;
-				}
+				total += pads;
 			}
 			__syncwarp();
-			const int n_pairs = total >> 1;
+			const int n_quads = total >> 2;
 			uint32_t slot_addr = q_base;
-			for (int k = 0; k < n_pairs; k++, slot_addr += 16u) {
-				const ulonglong2 XY = lds128p(slot_addr);
-				const ulonglong2 AB = lds128p(slot_addr + kField);
-				const ulonglong2 CO = lds128p(slot_addr + 2 * kField);
-				const float4 BP = lds128(slot_addr + 4 * kField);
-				const float copy_word = lds32(copy_src + (uint32_t)k * 16u);   // this lane's word of the slot for the flush table
-				// backward.cu:487-501, the forward's instruction sequence
-				const f2 dx = add2(XY.x, npx), dy = add2(XY.y, npy);
-				f2 t = mul2(dy, CO.x);
-				const f2 u = mul2(dx, AB.x);
-				t = mul2(dy, t);
-				const f2 sq = fma2(dx, u, t);
-				const f2 vv = mul2(dx, AB.y);
-				const f2 ww = mul2(dy, vv);
-				const f2 power = fma2(sq, neg_half, ww);
-				const f2 G = exp2x(power);
-				const f2 al = mul2(CO.y, G);
-				const float aA = fminf(lo(al), 0.99f), aB = fminf(hi(al), 0.99f);
-				const bool skipA = (__float_as_uint(BP.z) >= last_contributor) | (lo(power) > 0.0f) | (aA < 1.0f / 255.0f);
-				const bool skipB = (__float_as_uint(BP.w) >= last_contributor) | (hi(power) > 0.0f) | (aB < 1.0f / 255.0f);
-				if (__all_sync(0xffffffffu, skipA & skipB))
-					continue;
-
-				const f2 e2 = pk(skipA ? 0.0f : aA, skipB ? 0.0f : aB);
-				const f2 Ge = pk(skipA ? 0.0f : lo(G), skipB ? 0.0f : hi(G));
-				// backward.cu:503-507: T <- T / (1 - alpha).  MUFU.RCP: 1 ulp, far inside the 1e-3 gradient tolerance
-				const f2 om = fma2(e2, neg_one, one);
-				const float rcpA = rcp_approx_ftz(lo(om)), rcpB = rcp_approx_ftz(hi(om));
-				const float TA = T * rcpA, TB = TA * rcpB;
-				T = TB;
-				const f2 T2 = pk(TA, TB), rcp2 = pk(rcpA, rcpB);
-				// backward.cu:509-521: accum_rec, walked A then B
-				const ulonglong2 RG = lds128p(slot_addr + 3 * kField);
-				const f2 col0 = RG.x, col1 = RG.y, col2 = pk(BP.x, BP.y);
-				const f2 ac0 = mul2(e2, col0), ac1 = mul2(e2, col1), ac2 = mul2(e2, col2);
-				const float accA0 = fmaf(keep_prev, acc0, pend0), accA1 = fmaf(keep_prev, acc1, pend1),
-				            accA2 = fmaf(keep_prev, acc2, pend2);
-				acc0 = fmaf(lo(om), accA0, lo(ac0));
-				acc1 = fmaf(lo(om), accA1, lo(ac1));
-				acc2 = fmaf(lo(om), accA2, lo(ac2));
-				pend0 = hi(ac0); pend1 = hi(ac1); pend2 = hi(ac2);
-				keep_prev = hi(om);
-				const f2 d0 = fma2(pk(accA0, acc0), neg_one, col0);
-				const f2 d1 = fma2(pk(accA1, acc1), neg_one, col1);
-				const f2 d2 = fma2(pk(accA2, acc2), neg_one, col2);
-				f2 dL_dalpha = fma2(d2, dLp2, fma2(d1, dLp1, mul2(d0, dLp0)));
-				// backward.cu:526-534
-				dL_dalpha = fma2(dL_dalpha, T2, mul2(bg_term, rcp2));
-				// q = G dL/dalpha (backward.cu:537-554) and w = alpha T (backward.cu:523) of this pixel: slab rows `row` (splat A)
-				// and row + 1 (splat B); the lanes copy what the flush needs of the queue slot, one word each
-				const f2 qq = mul2(Ge, dL_dalpha), wt = mul2(e2, T2);
+			for (int k = 0; k < n_quads; k++, slot_addr += 32u) {
+				// this lane's word of the two slots for the flush table
+				const float copy_word = lds32(copy_src + (uint32_t)k * 32u);
+				const Front f0 = front(slot_addr), f1 = front(slot_addr + 16u);
 				const uint32_t dst = slab_lane + (uint32_t)row * (kSlabPitchC * 4u);
-				sts64(dst, lo(qq), lo(wt));
-				sts64(dst + kSlabPitchC * 4u, hi(qq), hi(wt));
+				back(slot_addr, f0, dst);
+				back(slot_addr + 16u, f1, dst + 2u * kSlabPitchC * 4u);
 				sts32(table_lane + (uint32_t)row * 34u, copy_word);
-				row += 2;
+				row += 4;
 				if (row == kSlabRowsC) {
 					flush(kSlabRowsC);
 					row = 0;
 				}
 			}
 			__syncwarp();   // every lane is through with the queue
-			carry = total & 1;
-			if (carry) {
-				// the odd survivor (entry total - 1 = half A of slot n_pairs) becomes entry 0 of the next chunk's list
-				if (n_pairs > 0 && lane < 12) {
-					const int f = lane >> 1, e = (lane & 1) * 2;
-					q.v[f][0][e] = q.v[f][n_pairs][e];
+			carry = total & 3;
+			if (carry != 0 && n_quads > 0) {
+				// the survivors behind the last whole quad (slots 2 n_quads, 2 n_quads + 1) move to the front of the next chunk's list
+				if (lane < 24) {
+					const int f = lane >> 2, w = lane & 3;
+					q.v[f][0][w] = q.v[f][2 * n_quads][w];
+					q.v[f][1][w] = q.v[f][2 * n_quads + 1][w];
 				}
 				__syncwarp();
 			}
@@ -1450,48 +1466,38 @@ int launch_blend_backward(const GeometryState& g, const BinningState& b, const I
 	const int num_tiles = vp.tiles_x * vp.tiles_y;
 	if (num_tiles <= 0)
 		return GM_OK;
-	// The default is the packed-pair kernel with the shuffle butterfly.  GM_BLEND_BWD=mma selects the variant that reduces
-	// over the pixels on the tensor cores (same parity, 14 % fewer instructions, measured 2 % slower on B200: DESIGN.md 8),
-	// GM_BLEND_SCALAR=1 the one-splat-per-iteration kernel; both are kept for A/B measurements.
+	// The default is the column-sum kernel (two blocks per tile).  GM_BLEND_BWD=pairs selects the packed-pair kernel with
+	// the shuffle butterfly (the default of round 1 and most of round 2), GM_BLEND_BWD=mma the variant that reduces over the
+	// pixels on the tensor cores, GM_BLEND_SCALAR=1 the one-splat-per-iteration kernel; all kept for A/B measurements
+	// (DESIGN.md 8).
 	static const bool scalar = std::getenv("GM_BLEND_SCALAR") != nullptr && std::getenv("GM_BLEND_SCALAR")[0] == '1';
-	static const bool pairs = !(std::getenv("GM_BLEND_BWD") != nullptr && std::getenv("GM_BLEND_BWD")[0] == 'm');
-	static const bool cols = std::getenv("GM_BLEND_BWD") != nullptr && std::getenv("GM_BLEND_BWD")[0] == 'c';
+	static const char variant = std::getenv("GM_BLEND_BWD") != nullptr ? std::getenv("GM_BLEND_BWD")[0] : 'c';
 	if (scalar)
 		launch_k(blend_backward_kernel, dim3(num_tiles), dim3(kThreads), 0, stream, 
 			g, b, img, capacity, vp.W, vp.H, vp.tiles_x, vp.bg, dL_dpix, dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolor);
-	else if (cols) {
-		const char* ev = std::getenv("GM_EXP");
-		const int e = ev ? std::atoi(ev) : 0;
-		auto go = [&](auto kern, size_t smem, int slot) -> int {
-			static bool opted_in_c[4][64] = {};
-			int dev = 0;
-			cudaGetDevice(&dev);
-			if (dev < 0 || dev >= 64 || !opted_in_c[slot][dev]) {
-				const cudaError_t attr = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-				if (attr != cudaSuccess) {
-					set_last_error("blend_backward shared memory", attr);
-					return GM_ERR_CUDA;
-				}
-				if (dev >= 0 && dev < 64)
-					opted_in_c[slot][dev] = true;
+	else if (variant == 'p')
+		launch_k(blend_backward_pairs_kernel, dim3(num_tiles), dim3(kThreads), 0, stream, 
+			g, b, img, capacity, vp.W, vp.H, vp.tiles_x, vp.bg, dL_dpix, dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolor);
+	else if (variant != 'm') {
+		constexpr int kWarpsC = 4;
+		auto kern = blend_backward_cols_kernel<128, 5, kWarpsC>;
+		constexpr size_t smem = sizeof(BwdSmemC<128, kWarpsC>);
+		// the opt-in shared-memory size is a per-device function attribute
+		static bool opted_in_c[64] = {};
+		int dev = 0;
+		cudaGetDevice(&dev);
+		if (dev < 0 || dev >= 64 || !opted_in_c[dev]) {
+			const cudaError_t attr = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+			if (attr != cudaSuccess) {
+				set_last_error("blend_backward shared memory", attr);
+				return GM_ERR_CUDA;
 			}
-			launch_k(kern, dim3(num_tiles), dim3(kThreads), smem, stream,
-				g, b, img, capacity, vp.W, vp.H, vp.tiles_x, vp.bg, dL_dpix, dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolor);
-			return GM_OK;
-		};
-		if (e == 1)
-			return go(blend_backward_cols_kernel<192, 3>, sizeof(BwdSmemC<192>), 1);
-		if (e == 2)
-			return go(blend_backward_cols_kernel<256, 2>, sizeof(BwdSmemC<256>), 2);
-		return go(blend_backward_cols_kernel<128, 3>, sizeof(BwdSmemC<128>), 0);
-	} else if (pairs && std::getenv("GM_EXP") != nullptr) {
-		const int e = std::atoi(std::getenv("GM_EXP"));
-		auto kern = e == 1 ? blend_backward_pairs_kernel<1> : e == 2 ? blend_backward_pairs_kernel<2> : blend_backward_pairs_kernel<3>;
-		launch_k(kern, dim3(num_tiles), dim3(kThreads), 0, stream,
+			if (dev >= 0 && dev < 64)
+				opted_in_c[dev] = true;
+		}
+		launch_k(kern, dim3(num_tiles * (kWarps / kWarpsC)), dim3(kWarpsC * 32), smem, stream,
 			g, b, img, capacity, vp.W, vp.H, vp.tiles_x, vp.bg, dL_dpix, dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolor);
-	} else if (pairs)
-		launch_k(blend_backward_pairs_kernel<0>, dim3(num_tiles), dim3(kThreads), 0, stream, 
-			g, b, img, capacity, vp.W, vp.H, vp.tiles_x, vp.bg, dL_dpix, dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolor);
+	}
 	else {
 		// the opt-in shared-memory size is a per-device function attribute
 		static bool opted_in[64] = {};

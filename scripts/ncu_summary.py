@@ -7,7 +7,7 @@ import subprocess
 import sys
 
 STAGE_OF = {"blend_backward_kernel": "blend_backward", "blend_forward_kernel": "blend_forward",
-            "blend_backward_pairs_kernel": "blend_backward", "blend_backward_mma_kernel": "blend_backward", "blend_forward_pairs_kernel": "blend_forward", "preprocess_kernel": "preprocess",
+            "blend_backward_pairs_kernel": "blend_backward", "blend_backward_cols_kernel": "blend_backward", "blend_backward_mma_kernel": "blend_backward", "blend_forward_pairs_kernel": "blend_forward", "preprocess_kernel": "preprocess",
             "emit_kernel": "emit", "bucket_sort_pack_kernel": "sort_pack", "geometry_backward_kernel": "geometry_backward",
             "l1_kernel": "l1_loss", "tile_scan_kernel": "tile_scan"}
 WANT = [("gpu__time_duration.sum", "time"), ("dram__bytes_read.sum", "dram read"), ("dram__bytes_write.sum", "dram write"),

@@ -1169,11 +1169,12 @@ print(json.dumps(out))
 """
 
 
-@pytest.mark.parametrize("env", [{"GM_BLEND_SCALAR": "1"}, {"GM_BLEND_BWD": "mma"}, {"GM_BLEND_FWD": "ring"}, {"GM_PDL": "0"}],
-                         ids=["scalar", "bwd_mma", "fwd_ring", "no_pdl"])
+@pytest.mark.parametrize("env", [{"GM_BLEND_SCALAR": "1"}, {"GM_BLEND_BWD": "pairs"}, {"GM_BLEND_BWD": "mma"}, {"GM_BLEND_FWD": "ring"}, {"GM_PDL": "0"}],
+                         ids=["scalar", "bwd_pairs", "bwd_mma", "fwd_ring", "no_pdl"])
 def test_alternative_blend_kernels_still_match(cuda_device, tmp_path, env):
-    """GM_BLEND_SCALAR=1 selects the one-splat-per-iteration blend kernels, GM_BLEND_BWD=mma the backward that reduces
-    over the pixels on the tensor cores (TF32 mma.sync), GM_BLEND_FWD=ring the forward over a barrier-free stage ring, GM_PDL=0
+    """GM_BLEND_SCALAR=1 selects the one-splat-per-iteration blend kernels, GM_BLEND_BWD=pairs the backward with the shuffle
+    butterfly (the default before the column-sum kernel), GM_BLEND_BWD=mma the backward that reduces over the pixels on the
+    tensor cores (TF32 mma.sync), GM_BLEND_FWD=ring the forward over a barrier-free stage ring, GM_PDL=0
     plain stream-ordered launches -- all kept for A/B measurements (the library reads the variables once, hence the
     subprocess): same parity bar as the default kernels."""
     import json
