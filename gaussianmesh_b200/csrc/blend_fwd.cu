@@ -192,14 +192,15 @@ blend_forward_kernel(GeometryState g, BinningState b, ImageState img, uint32_t c
 struct WarpQueueP {
 	// [field][slot][4]: slot k holds splats 2k (A) and 2k+1 (B) of the compacted chunk
 	//   0: xA xB yA yB   1: aA aB -bA -bB   2: cA cB oA oB   3: rA rB gA gB   4: bA bB posA posB (1-based, as bits)
-	float v[5][16][4];
+	float v[5][17][4];   // 33 entries: up to 32 survivors of a chunk behind one carried over
 };
 
+template <int kWarpsF>
 struct __align__(128) FwdSmemP {
 	float4 conic[2][kBatch];
 	float4 xyrg[2][kBatch];
 	float2 bid[2][kBatch];
-	WarpQueueP queue[kThreads / 32];
+	WarpQueueP queue[kWarpsF];
 	uint64_t full[2];
 };
 
@@ -215,29 +216,34 @@ struct FwdEpilogue {
 	float inv_numel;
 };
 
-__global__ void __launch_bounds__(kThreads)
+// kWarpsF = 8: one block per 16x16 tile; kWarpsF = 4: two blocks per tile, each owning a 16x8 half (a barrier among four
+// warps instead of eight, and the block-wide early exit of forward.cu:303-306 per half tile).  kCarry: the survivors of the
+// culling are paired across the 32-splat chunks (an odd one waits for the next chunk instead of being paired with a pad).
+template <int kWarpsF, bool kCarry>
+__global__ void __launch_bounds__(kWarpsF * 32)
 blend_forward_pairs_kernel(GeometryState g, BinningState b, ImageState img, uint32_t capacity,
                            int W, int H, int tiles_x, const float* __restrict__ bg_color,
                            float* __restrict__ out_color, FwdEpilogue epi)
 {
 	pdl_sync();
-	__shared__ FwdSmemP s;
-	__shared__ float s_loss[kThreads / 32];
+	__shared__ FwdSmemP<kWarpsF> s;
+	__shared__ float s_loss[kWarpsF];
 	if (epi.zero_ptr != nullptr) {
 		// this block's slice of the buffer to clear: plain stores, issued before the blend loop and retired behind it
 		const size_t per = (epi.zero_vec4 + gridDim.x - 1) / gridDim.x;
 		const size_t z0 = (size_t)blockIdx.x * per, z1 = min(z0 + per, epi.zero_vec4);
-		for (size_t i = z0 + threadIdx.x; i < z1; i += kThreads)
+		for (size_t i = z0 + threadIdx.x; i < z1; i += kWarpsF * 32)
 			epi.zero_ptr[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
 	}
 
-	const int tile = blockIdx.x;
+	constexpr int kPerTile = (kThreads / 32) / kWarpsF;   // blocks per tile
+	const int tile = blockIdx.x / kPerTile;
 	const int tile_x = tile % tiles_x, tile_y = tile / tiles_x;
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const int tw = (blockIdx.x % kPerTile) * kWarpsF + warp;   // the warp's 8x4 pixel block inside the tile
 
-	// 8x4 pixel block per warp
-	const int bx0 = tile_x * kTile + (warp & 1) * 8;
-	const int by0 = tile_y * kTile + (warp >> 1) * 4;
+	const int bx0 = tile_x * kTile + (tw & 1) * 8;
+	const int by0 = tile_y * kTile + (tw >> 1) * 4;
 	const int px = bx0 + (lane & 7), py = by0 + (lane >> 3);
 	const bool inside = px < W && py < H;
 	const f2 npx = pk1(-(float)px), npy = pk1(-(float)py);
@@ -277,6 +283,7 @@ blend_forward_pairs_kernel(GeometryState g, BinningState b, ImageState img, uint
 	uint32_t last_contributor = 0;
 	float C0 = 0.0f, C1 = 0.0f, C2 = 0.0f;
 	const f2 neg_half = pk1(-0.5f);
+	int carry = 0;   // kCarry: queue entry 0 holds a survivor of an earlier chunk that has not been blended yet
 
 	for (int batch = 0; batch < num_batches; batch++) {
 		// forward.cu:303-306 (block-wide early exit); this barrier also frees the buffer that the
@@ -310,10 +317,40 @@ blend_forward_pairs_kernel(GeometryState g, BinningState b, ImageState img, uint
 				                               wx0, wy0, wx1, wy1);
 			}
 			const uint32_t mask = __ballot_sync(0xffffffffu, keep);
-			if (mask == 0)
-				continue;
 			const int n_keep = __popc(mask);
-			{
+			int n_pairs;
+			int total = 0;
+			if (kCarry) {
+				const bool last_chunk = batch == num_batches - 1 && base + 32 >= cnt;
+				total = carry + n_keep;
+				if (total == 0 || (n_keep == 0 && !last_chunk))
+					continue;
+				if (keep) {
+					const int pos = carry + __popc(mask & ((1u << lane) - 1u));
+					const int slot = pos >> 1, h = pos & 1;
+					q.v[0][slot][h] = xr.x;
+					q.v[0][slot][2 + h] = xr.y;
+					q.v[1][slot][h] = co.x;
+					q.v[1][slot][2 + h] = -co.y;
+					q.v[2][slot][h] = co.z;
+					q.v[2][slot][2 + h] = co.w;
+					q.v[3][slot][h] = xr.z;
+					q.v[3][slot][2 + h] = xr.w;
+					q.v[4][slot][h] = s.bid[buf][j].x;
+					q.v[4][slot][2 + h] = __uint_as_float((uint32_t)(batch * kBatch + j + 1));
+				}
+				if (last_chunk && (total & 1)) {
+					// the list's very last entry, if odd, is paired with a splat of opacity 0 (alpha == 0: skipped)
+					if (lane < 5) {
+						q.v[lane][total >> 1][1] = 0.0f;
+						q.v[lane][total >> 1][3] = 0.0f;
+					}
+					total++;
+				}
+				n_pairs = total >> 1;
+			} else {
+				if (mask == 0)
+					continue;
 				// the lane behind the last survivor pads an odd queue with a splat of opacity 0 (alpha == 0: skipped)
 				const int pos = keep ? __popc(mask & ((1u << lane) - 1u)) : n_keep;
 				const bool pad = !keep && (n_keep & 1) && lane == (__ffs(~mask) - 1);
@@ -330,9 +367,9 @@ blend_forward_pairs_kernel(GeometryState g, BinningState b, ImageState img, uint
 					q.v[4][slot][h] = keep ? s.bid[buf][j].x : 0.0f;
 					q.v[4][slot][2 + h] = __uint_as_float(keep ? (uint32_t)(batch * kBatch + j + 1) : 0u);
 				}
+				n_pairs = (n_keep + 1) >> 1;
 			}
 			__syncwarp();
-			const int n_pairs = (n_keep + 1) >> 1;
 #pragma unroll 2
 			for (int k = 0; k < n_pairs; k++) {
 				const ulonglong2 XY = *reinterpret_cast<const ulonglong2*>(q.v[0][k]);
@@ -385,6 +422,17 @@ blend_forward_pairs_kernel(GeometryState g, BinningState b, ImageState img, uint
 			__syncwarp();   // the queue is rewritten by the next chunk
 			if (__all_sync(0xffffffffu, thr == kInf))
 				break;
+			if (kCarry) {
+				carry = total & 1;
+				if (carry && n_pairs > 0) {
+					// the odd survivor (half A of slot n_pairs) becomes entry 0 of the next chunk's list
+					if (lane < 10) {
+						const int f = lane >> 1, e = (lane & 1) * 2;
+						q.v[f][0][e] = q.v[f][n_pairs][e];
+					}
+					__syncwarp();
+				}
+			}
 		}
 	}
 
@@ -423,7 +471,7 @@ blend_forward_pairs_kernel(GeometryState g, BinningState b, ImageState img, uint
 		if (tid == 0) {
 			float sum = 0.0f;
 #pragma unroll
-			for (int w = 0; w < kThreads / 32; w++)
+			for (int w = 0; w < kWarpsF; w++)
 				sum += s_loss[w];
 			atomicAdd(epi.loss, sum * epi.inv_numel);
 		}
@@ -685,7 +733,7 @@ int launch_blend_forward(const GeometryState& g, const BinningState& b, const Im
 	const int num_tiles = vp.tiles_x * vp.tiles_y;
 	if (num_tiles <= 0)
 		return GM_OK;
-	// The default is the packed-pair kernel with one block barrier per 256-record batch.  GM_BLEND_FWD=ring selects the
+	// The default is the packed-pair kernel with one block barrier per 256-record batch (two blocks per tile).  GM_BLEND_FWD=ring selects the
 	// variant over a three-stage ring without block barriers (bit-identical output, measured 5 % slower: waiting warps spin
 	// on the mbarrier and take issue slots from the working ones -- DESIGN.md 8), GM_BLEND_SCALAR=1 the one-pixel-per-thread
 	// kernel; both are kept for A/B measurements.
@@ -715,7 +763,13 @@ int launch_blend_forward(const GeometryState& g, const BinningState& b, const Im
 		if (epilogue_done != nullptr)
 			*epilogue_done = true;
 	}
-	launch_k(blend_forward_pairs_kernel, dim3(num_tiles), dim3(kThreads), 0, stream, g, b, img, capacity, vp.W, vp.H, vp.tiles_x, vp.bg, out_color, e);
+	// two 128-thread blocks per tile, survivors paired across chunks; GM_BLEND_FWD=tile selects one 256-thread block per tile
+	// with per-chunk padding (the default until late in round 2; A/B measurements)
+	static const bool whole_tile = std::getenv("GM_BLEND_FWD") != nullptr && std::getenv("GM_BLEND_FWD")[0] == 't';
+	if (whole_tile)
+		launch_k(blend_forward_pairs_kernel<8, false>, dim3(num_tiles), dim3(kThreads), 0, stream, g, b, img, capacity, vp.W, vp.H, vp.tiles_x, vp.bg, out_color, e);
+	else
+		launch_k(blend_forward_pairs_kernel<4, true>, dim3(num_tiles * 2), dim3(kThreads / 2), 0, stream, g, b, img, capacity, vp.W, vp.H, vp.tiles_x, vp.bg, out_color, e);
 	return GM_OK;
 }
 

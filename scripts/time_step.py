@@ -24,9 +24,21 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--dump", default=None, help="write the gradients of view 0 to this .npz")
+    ap.add_argument("--morton", action="store_true", help="experiment: the scene's Gaussians in 3-D Morton order")
     args = ap.parse_args()
     dev = torch.device("cuda:0")
     a = synthetic.gaussian_scene(P, seed=0)
+    if args.morton:
+        m = a["means3D"]
+        qz = ((m - m.min(0)) / (m.max(0) - m.min(0) + 1e-9) * 1023).astype(np.uint64)
+
+        def spread(v):
+            v = (v | (v << 16)) & 0x030000FF
+            v = (v | (v << 8)) & 0x0300F00F
+            v = (v | (v << 4)) & 0x030C30C3
+            return (v | (v << 2)) & 0x09249249
+        order = np.argsort(spread(qz[:, 0]) | (spread(qz[:, 1]) << 1) | (spread(qz[:, 2]) << 2), kind="stable")
+        a = {k: (np.ascontiguousarray(v[order]) if isinstance(v, np.ndarray) and v.shape[:1] == (P,) else v) for k, v in a.items()}
     sc = {k: torch.from_numpy(a[k]).to(dev) for k in ("means3D", "opacities", "shs", "scales", "rotations")}
     cams = upload_cameras(synthetic.orbit_cameras(NV, W, H), dev)
     bg = torch.zeros(3, device=dev)
@@ -52,7 +64,7 @@ def main():
     torch.cuda.synchronize()
     prof = _lib.profile_end()
     assert ts.verify() == 0
-    out = {"env": {k: v for k, v in os.environ.items() if k.startswith("GM_")}, "ms_per_step": round(ms, 4),
+    out = {"morton": args.morton, "env": {k: v for k, v in os.environ.items() if k.startswith("GM_")}, "ms_per_step": round(ms, 4),
            "stages": {k: round(t / n, 4) for k, (t, n) in prof.items()}}
     if args.dump:
         loss = ts.step(cams[0], bg, targets[0])
