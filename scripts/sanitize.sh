@@ -76,6 +76,6 @@ for tool in memcheck racecheck synccheck; do
 done
 # the selectable kernel variants (tensor-core backward, barrier-free forward ring)
 for tool in memcheck racecheck; do
-  GM_BLEND_BWD=mma GM_BLEND_FWD=ring timeout 900 compute-sanitizer --tool $tool --print-limit 20 python /tmp/san_case.py > gpurun_out/sanitize_variants_$tool.log 2>&1
+  GM_BLEND_BWD=${SAN_BWD:-mma} GM_BLEND_FWD=${SAN_FWD:-ring} timeout 900 compute-sanitizer --tool $tool --print-limit 20 python /tmp/san_case.py > gpurun_out/sanitize_variants_$tool.log 2>&1
   echo "== variants $tool exit $?"; grep -E "ERROR SUMMARY|RACECHECK SUMMARY|case " gpurun_out/sanitize_variants_$tool.log | tail -6
 done
