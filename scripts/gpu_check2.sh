@@ -25,13 +25,10 @@ echo "ncu full exit $?"
 timeout 900 ncu --set full --clock-control none --import-source on -k "regex:^(photometric|adam_kernel|densify_stats|mesh_restrict|mesh_bind)" -s 14 -c 7 -f \
     -o gpurun_out/prof_iter_${tag} python bench.py --steps 3 --warmup 2 --no-cpu-baseline --no-presize > gpurun_out/ncu_iter_${tag}.log 2>&1
 echo "ncu iteration kernels exit $?"
-GM_BLEND_BWD=mma timeout 900 ncu --set full --clock-control none --import-source on -k "regex:blend_backward" -s 2 -c 1 -f \
-    -o gpurun_out/prof_mma_${tag} python bench.py --steps 3 --warmup 2 --no-cpu-baseline --no-presize > gpurun_out/ncu_mma_${tag}.log 2>&1
-echo "ncu mma exit $?"
-GM_BLEND_FWD=ring timeout 900 ncu --set full --clock-control none --import-source on -k "regex:blend_forward" -s 2 -c 1 -f \
-    -o gpurun_out/prof_ring_${tag} python bench.py --steps 3 --warmup 2 --no-cpu-baseline --no-presize > gpurun_out/ncu_ring_${tag}.log 2>&1
-echo "ncu ring exit $?"
-for v in "GM_BLEND_BWD=mma" "GM_BLEND_FWD=ring" "GM_PDL=0"; do
+GM_BLEND_BWD=pairs GM_BLEND_FWD=tile timeout 900 ncu --set full --clock-control none --import-source on -k "regex:^blend_" -s 4 -c 2 -f \
+    -o gpurun_out/prof_prev_${tag} python bench.py --steps 3 --warmup 2 --no-cpu-baseline --no-presize > gpurun_out/ncu_prev_${tag}.log 2>&1
+echo "ncu previous default blend kernels exit $?"
+for v in "GM_BLEND_BWD=pairs" "GM_BLEND_FWD=tile" "GM_BLEND_BWD=mma" "GM_BLEND_FWD=ring" "GM_PDL=0"; do
   env $v timeout 600 python bench.py --steps 40 --warmup 5 --no-cpu-baseline > gpurun_out/bench_ours_${tag}_${v//=/_}.json 2> gpurun_out/bench_ours_${tag}_${v//=/_}.err
   echo "bench $v exit $?"
 done

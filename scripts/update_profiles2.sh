@@ -6,7 +6,7 @@ cp gpurun_out/launches_${tag}.csv profiles/r2_launches.csv
 cp gpurun_out/launches_ref_${tag}.csv profiles/r2_reference_launches.csv
 cp gpurun_out/bench_ours_${tag}.json profiles/r2_bench_ours.json
 cp gpurun_out/bench_ref_${tag}.json profiles/r2_bench_reference.json
-for v in GM_BLEND_BWD_mma GM_BLEND_FWD_ring GM_PDL_0; do cp gpurun_out/bench_ours_${tag}_$v.json profiles/r2_bench_ours_$v.json; done
+for v in GM_BLEND_BWD_pairs GM_BLEND_FWD_tile GM_BLEND_BWD_mma GM_BLEND_FWD_ring GM_PDL_0; do cp gpurun_out/bench_ours_${tag}_$v.json profiles/r2_bench_ours_$v.json; done
 [ -f gpurun_out/bench_ours_r2_n8.json ] && tail -1 gpurun_out/bench_ours_r2_n8.json > profiles/r2_bench_ours_n8.json
 [ -f gpurun_out/bench_ours_m2_n2.json ] && tail -1 gpurun_out/bench_ours_m2_n2.json > profiles/r2_bench_ours_n2.json
 python scripts/ncu_summary.py gpurun_out/prof_${tag}.ncu-rep --json profiles/dram_traffic.json > /tmp/ncu_${tag}.md
@@ -51,7 +51,7 @@ for k,v in sorted(d['stages'].items(), key=lambda kv:-kv[1]['ms_per_launch']):
 ssum=sum(v['ms_per_launch'] for v in d['stages'].values())
 print()
 print(f"step {d['ms_per_step']:.4f} ms ({d['value']:.1f} frames/s; per-step median {d['step_ms']['median_ms']:.4f}, p10 {d['step_ms']['p10_ms']:.4f}, p90 {d['step_ms']['p90_ms']:.4f}); sum of the stage times {ssum:.4f} ms; with stage events {d['ms_per_step_with_stage_events']:.4f} ms; as one CUDA graph launch {d['cuda_graph']['ms_per_step']:.4f} ms (host enqueue {d['cuda_graph']['host_enqueue_ms_per_step']*1e3:.0f} us vs {d['host_enqueue_ms_per_step']*1e3:.0f} us eager); e2e {d['e2e']['ms_per_step']:.4f} ms ({d['e2e']['value']:.1f} frames/s, {d['e2e']['h2d_bytes_per_step']/1e6:.1f} MB uploaded per step); forward {d['forward']['ms_per_frame']:.4f} ms, edit {d['edit']['ms_per_frame']:.4f} ms; clocks {d['clocks']}")
-for name in ("GM_PDL_0", "GM_BLEND_BWD_mma", "GM_BLEND_FWD_ring"):
+for name in ("GM_PDL_0", "GM_BLEND_BWD_pairs", "GM_BLEND_FWD_tile", "GM_BLEND_BWD_mma", "GM_BLEND_FWD_ring"):
     x=json.load(open(f'gpurun_out/bench_ours_${tag}_{name}.json'))
     print(f"- variant {name.replace('_', '=', 1) if name.startswith('GM_PDL') else name.replace('GM_BLEND_BWD_', 'GM_BLEND_BWD=').replace('GM_BLEND_FWD_', 'GM_BLEND_FWD=')}: step {x['ms_per_step']:.4f} ms, blend_forward {x['stages']['blend_forward']['ms_per_launch']:.4f}, blend_backward {x['stages']['blend_backward']['ms_per_launch']:.4f}, e2e {x['e2e']['ms_per_step']:.4f} ms")
 r=json.load(open('gpurun_out/bench_ref_${tag}.json'))
@@ -120,26 +120,23 @@ cat /tmp/ncu_${tag}.md
 echo "## Kernels of the full training iteration (bench section 5; \`-k regex:^(photometric|adam_kernel|densify_stats|mesh_restrict|mesh_bind) -s 14 -c 7\`)"
 echo
 python scripts/ncu_summary.py gpurun_out/prof_iter_${tag}.ncu-rep
-echo "## The two measured-and-kept-selectable variants (DESIGN.md 8)"
+echo "## The blend kernels that were the defaults until late in round 2 (DESIGN.md 8)"
 echo
-echo "\`GM_BLEND_BWD=mma\` (pixel reduction on the tensor cores) and \`GM_BLEND_FWD=ring\` (no block barrier), same capture command with the variable set:"
+echo "\`GM_BLEND_BWD=pairs GM_BLEND_FWD=tile\` (backward with the 18-value shuffle butterfly, one 256-thread block per tile in both passes), same capture command with the variables set:"
 echo
-python scripts/ncu_summary.py gpurun_out/prof_mma_${tag}.ncu-rep
-python scripts/ncu_summary.py gpurun_out/prof_ring_${tag}.ncu-rep
-echo "## Opcode mix of the blend kernels (scripts/sass_profile.py): default kernels, then the variants"
+python scripts/ncu_summary.py gpurun_out/prof_prev_${tag}.ncu-rep
+echo "## Opcode mix of the blend kernels (scripts/sass_profile.py): default kernels, then the previous ones"
 echo
 echo '```'
-python scripts/sass_profile.py gpurun_out/prof_${tag}.ncu-rep blend_backward_pairs_kernel 16
-python scripts/sass_profile.py gpurun_out/prof_mma_${tag}.ncu-rep blend_backward_mma_kernel 16
+python scripts/sass_profile.py gpurun_out/prof_${tag}.ncu-rep blend_backward_cols_kernel 16
+python scripts/sass_profile.py gpurun_out/prof_prev_${tag}.ncu-rep blend_backward_pairs_kernel 16
 python scripts/sass_profile.py gpurun_out/prof_${tag}.ncu-rep blend_forward_pairs_kernel 14
-python scripts/sass_profile.py gpurun_out/prof_ring_${tag}.ncu-rep blend_forward_ring_kernel 14
 echo '```'
 echo
 echo "## Hottest source lines (scripts/line_profile.py)"
 echo
 echo '```'
-python scripts/line_profile.py gpurun_out/prof_${tag}.ncu-rep blend_backward_pairs_kernel 12
-python scripts/line_profile.py gpurun_out/prof_mma_${tag}.ncu-rep blend_backward_mma_kernel 12
+python scripts/line_profile.py gpurun_out/prof_${tag}.ncu-rep blend_backward_cols_kernel 14
 python scripts/line_profile.py gpurun_out/prof_${tag}.ncu-rep blend_forward_pairs_kernel 10
 echo '```'
 } > profiles/r2_ncu_summary.md
