@@ -709,7 +709,9 @@ def main():
         del it_arm
         view_parallel = {"global_batch_views": world,
                          "workload": "the section-5 iteration with one view per rank per step: gradients averaged over the "
-                                     "ranks, one optimizer step per global batch"}
+                                     "ranks, one optimizer step per global batch; the densification statistics accumulate per "
+                                     "rank and are merged over the ranks when densify_and_prune consumes them "
+                                     "(ViewParallelTrainer.merge_stats), not with two collectives every step"}
         for mode in ("nccl", "p2p", "mc"):
             try:
                 vp_model = MeshGaussianModel(it_arrays, device, requires_grad=False)

@@ -63,6 +63,7 @@ def test_single_rank_fused_exchange_equals_plain_adam(cuda_device):
         assert tr.world == 1
         for i in range(3):
             tr.step(cams[i], bg, gts[i])
+        tr.merge_stats()
         results[mode] = (model, tr)
     for i in range(3):
         plain.step(cams[i], bg, gts[i])

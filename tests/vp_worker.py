@@ -39,6 +39,7 @@ def main():
         tr = ViewParallelTrainer(model, opt, W, H, mode=mode)
         for s in range(steps):
             tr.step(cams[s * world + rank], bg, gts[s * world + rank])
+        tr.merge_stats()              # the per-rank statistics are merged when they are consumed, not every step
         torch.cuda.synchronize()
         dist.barrier()
         before = ({k: getattr(model, k).detach().clone() for k in names},
