@@ -392,6 +392,61 @@ def test_row_interval_tile_walk_keeps_every_contributing_tile():
     assert kept_total <= 1.35 * exact_total
 
 
+def test_column_sum_flush_matches_the_per_pixel_sums():
+    """The backward blend's flush (csrc/blend_bwd.cu, blend_backward_cols_kernel) restated in numpy float32 with the
+    kernel's expression order: row partial sums over the eight pixels of a row with u = px - block centre, the six
+    pixel-centred moments, the join of the two 16-pixel halves, the shift to the splat (dx = X - u) -- held against the
+    sums the reference adds pixel by pixel (backward.cu:537-554: sum q dx, q dy, q dx^2, q dx dy, q dy^2 with
+    dx = x_splat - pixel) in float64.  Splats inside, beside and far from the 8x4 block."""
+    f = np.float32
+    rng = np.random.default_rng(5)
+    worst = 0.0
+    for case in range(300):
+        bx0, by0 = f(8 * rng.integers(0, 200)), f(4 * rng.integers(0, 250))
+        cx, cy = bx0 + f(3.5), by0 + f(1.5)
+        far = (0.0, 6.0, 40.0)[case % 3]
+        xs = f(cx + rng.normal(0, 3.0 + far))
+        ys = f(cy + rng.normal(0, 2.0 + far))
+        q = (rng.normal(0, 1, 32) * np.exp(rng.normal(-3, 2, 32))).astype(f)     # G dL/dalpha, any sign, wide range
+        q[rng.random(32) < 0.3] = 0                                               # pixels that skip the splat
+        Sq = Su = Sv = Suu = Suv = Svv = None
+        halves = []
+        for half in range(2):
+            acc = [f(0)] * 6
+            for r in range(2):
+                R0 = R1 = R2 = f(0)
+                for u in range(8):
+                    p = half * 16 + r * 8 + u
+                    uu = f(u) - f(3.5)
+                    R0 = f(R0 + q[p])
+                    R1 = f(np.float32(q[p]) * uu + R1)
+                    R2 = f(np.float32(q[p]) * f(uu * uu) + R2)
+                vv = f(2 * half + r) - f(1.5)
+                acc = [f(acc[0] + R0), f(acc[1] + R1), f(vv * R0 + acc[2]), f(acc[3] + R2), f(vv * R1 + acc[4]),
+                       f(f(vv * vv) * R0 + acc[5])]
+            halves.append(acc)
+        Sq, Su, Sv, Suu, Suv, Svv = (f(a + b) for a, b in zip(*halves))
+        X, Y = f(xs - cx), f(ys - cy)
+        Sx, Sy = f(X * Sq - Su), f(Y * Sq - Sv)
+        Sxx = f(X * f(X * Sq - f(2) * Su) + Suu)
+        Sxy = f(X * f(Y * Sq - Sv) + f(-Y * Su + Suv))
+        Syy = f(Y * f(Y * Sq - f(2) * Sv) + Svv)
+        # the reference's sums, float64
+        px = bx0 + (np.arange(32) % 8).astype(np.float64)
+        py = by0 + (np.arange(32) // 8).astype(np.float64)
+        dx, dy = float(xs) - px, float(ys) - py
+        q64 = q.astype(np.float64)
+        want = [q64.sum(), (q64 * dx).sum(), (q64 * dy).sum(), (q64 * dx * dx).sum(), (q64 * dx * dy).sum(), (q64 * dy * dy).sum()]
+        # the scale an fp32 accumulation of the same terms is exact to
+        mag = [np.abs(q64).sum(), (np.abs(q64) * np.abs(dx)).sum(), (np.abs(q64) * np.abs(dy)).sum(), (np.abs(q64) * dx * dx).sum(),
+               (np.abs(q64) * np.abs(dx * dy)).sum(), (np.abs(q64) * dy * dy).sum()]
+        for got, w, m in zip((Sq, Sx, Sy, Sxx, Sxy, Syy), want, mag):
+            err = abs(float(got) - w) / max(m, 1e-30)
+            worst = max(worst, err)
+            assert err <= 5e-6, (case, float(got), w, m)      # observed worst: 5.4e-7
+    assert worst > 0.0        # (the restatement is float32, not a copy of the float64 sums)
+
+
 def test_header_is_plain_c(tmp_path):
     """include/gm_rasterizer.h is the C-ABI contract: it must compile as C99 (no C++ in the signatures) and the two
     three structs passed by pointer must have the layout the ctypes mirror assumes."""
