@@ -1,3 +1,4 @@
+#include <cstdlib>
 // Tile binning without a global sort.
 //
 // The reference builds 64-bit (tile | depth) keys for every (Gaussian, tile) instance, radix-sorts
@@ -229,6 +230,7 @@ constexpr int kSortThreads = 256;
 constexpr int kSortWarps = kSortThreads / 32;
 constexpr int kSortSmem = 4096;       // keys; 32 KB -- block-wide path for oversized buckets
 constexpr int kWarpSortMax = 256;     // largest bucket one warp sorts in registers (8 keys per lane)
+constexpr int kMidKeys = 2048;        // largest bucket of the small-block class of big_bucket_sort_pack_kernel (16 KB of keys)
 
 __device__ __forceinline__ uint64_t shfl_xor_u64(uint64_t v, int lane_mask)
 {
@@ -329,7 +331,7 @@ __device__ __forceinline__ void block_bitonic(Ptr a, uint32_t n)
 	const uint32_t half = (1u << lm) >> 1;
 	for (uint32_t lk = 1; lk <= lm; lk++) {
 		const uint32_t hk_mask = (1u << (lk - 1)) - 1u;
-		for (uint32_t t = threadIdx.x; t < half; t += kSortThreads) {
+		for (uint32_t t = threadIdx.x; t < half; t += blockDim.x) {
 			const uint32_t off = t & hk_mask;
 			const uint32_t blk = (t >> (lk - 1)) << lk;
 			compare_exchange(a, blk + off, blk + ((1u << lk) - 1u - off), n);
@@ -337,7 +339,7 @@ __device__ __forceinline__ void block_bitonic(Ptr a, uint32_t n)
 		__syncthreads();
 		for (int ls = (int)lk - 2; ls >= 0; ls--) {
 			const uint32_t s_mask = (1u << ls) - 1u;
-			for (uint32_t t = threadIdx.x; t < half; t += kSortThreads) {
+			for (uint32_t t = threadIdx.x; t < half; t += blockDim.x) {
 				const uint32_t i = ((t >> ls) << (ls + 1)) + (t & s_mask);
 				compare_exchange(a, i, i + (1u << ls), n);
 			}
@@ -368,7 +370,11 @@ bucket_sort_pack_kernel(GeometryState g, BinningState b, uint32_t capacity, int 
 	else if (n <= 64) warp_sort_pack<2>(g, b, b.keys + s0, s0, n, lane);
 	else if (n <= 128) warp_sort_pack<4>(g, b, b.keys + s0, s0, n, lane);
 	else if (n <= kWarpSortMax) warp_sort_pack<8>(g, b, b.keys + s0, s0, n, lane);
-	else if (lane == 0) g.big_list[atomicAdd(&g.header->num_big, 1u)] = gw;   // left to big_bucket_sort_pack_kernel
+	else if (lane == 0) {
+		// left to big_bucket_sort_pack_kernel: two size classes, two lists in one array (the second grows from the end)
+		if (n <= (uint32_t)kMidKeys) g.big_list[atomicAdd(&g.header->num_big, 1u)] = gw;
+		else g.big_list[kMaxBucketEntries - 1 - atomicAdd(&g.header->num_huge, 1u)] = gw;
+	}
 }
 
 // The buckets the warp kernel skipped (more than kWarpSortMax instances), one BLOCK per bucket, taken from the
@@ -384,33 +390,67 @@ constexpr int kSubMax = 128;          // sub-buckets per big bucket
 constexpr int kSubTarget = 48;        // aimed-at keys per sub-bucket
 constexpr size_t kBigSmemBytes = (size_t)kSortSmem * sizeof(uint64_t);
 
-__global__ void __launch_bounds__(kSortThreads)
-big_bucket_sort_pack_kernel(GeometryState g, BinningState b, uint32_t capacity, int bucket_log2)
+// kHuge = false: the buckets of up to kMidKeys keys, 128-thread blocks with 16 KB of shared memory (twelve per SM: the
+// work is a chain of latencies per bucket, so buckets in flight are what counts); kHuge = true: the rest, 256 threads, 32 KB.
+template <int kT, int kRegKeys, bool kHuge>
+__global__ void __launch_bounds__(kT)
+big_bucket_sort_pack_kernel(GeometryState g, BinningState b, uint32_t capacity, int bucket_log2, uint32_t smem_keys)
 {
 	pdl_sync();
 	extern __shared__ __align__(16) unsigned char big_smem[];
 	uint64_t* const s_part = reinterpret_cast<uint64_t*>(big_smem);      // [kSortSmem] keys partitioned by sub-bucket
-	__shared__ uint32_t s_cnt[kSubMax], s_off[kSubMax + 1], s_lo[kSortWarps], s_hi[kSortWarps], s_fallback;
+	__shared__ uint32_t s_cnt[kSubMax], s_off[kSubMax + 1], s_lo[(kT / 32)], s_hi[(kT / 32)], s_fallback;
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	const uint32_t num_big = g.header->num_big;
-	for (uint32_t e = blockIdx.x; e < num_big; e += gridDim.x) {
-		const uint32_t gw = g.big_list[e];
+	const uint32_t num_big = kHuge ? g.header->num_huge : g.header->num_big;
+	__shared__ uint32_t s_ticket;
+	for (;;) {
+		// the blocks draw buckets from a shared ticket (sizes vary by an order of magnitude: a static stride left the
+		// grid waiting for its unluckiest block)
+		if (threadIdx.x == 0)
+			s_ticket = atomicAdd(kHuge ? &g.header->huge_ticket : &g.header->big_ticket, 1u);
+		__syncthreads();
+		const uint32_t e = s_ticket;
+		if (e >= num_big)
+			break;
+		const uint32_t gw = g.big_list[kHuge ? kMaxBucketEntries - 1 - e : e];
 		const uint32_t bk = gw & ((1u << bucket_log2) - 1u);
 		const uint32_t s0 = (bk == 0) ? g.tile_start[gw >> bucket_log2] : g.bucket_cursor[gw - 1];
 		const uint32_t n = min(g.bucket_cursor[gw], capacity) - s0;
 		uint64_t* keys = b.keys + s0;
-		if (n > kSortSmem) {
+		if (n > smem_keys) {
 			block_bitonic(keys, n);
-			for (uint32_t i = threadIdx.x; i < n; i += kSortThreads)
+			for (uint32_t i = threadIdx.x; i < n; i += kT)
 				pack_one(g, b, s0 + i, (uint32_t)keys[i]);
 			continue;
 		}
-		// depth range of the bucket (the keys were just written by emit: the three passes over them hit L2)
+		// The keys were just written by emit and sit in L2.  A bucket of up to kRegKeys keys per thread (1,024: nearly every
+		// oversized bucket of a surface scene) is read ONCE into registers, all loads in flight together; the three passes
+		// (depth range, sub-bucket histogram, scatter) then run out of registers instead of paying an L2 round trip each.
+		const bool in_regs = n <= (uint32_t)(kT * kRegKeys);
+		uint64_t kr[kRegKeys];
+		if (in_regs) {
+#pragma unroll
+			for (int u = 0; u < kRegKeys; u++) {
+				const uint32_t i = threadIdx.x + (uint32_t)u * kT;
+				kr[u] = i < n ? keys[i] : ~0ull;
+			}
+		}
 		uint32_t lo = 0xffffffffu, hi = 0u;
-		for (uint32_t i = threadIdx.x; i < n; i += kSortThreads) {
-			const uint32_t d = (uint32_t)(keys[i] >> 32);
-			lo = min(lo, d);
-			hi = max(hi, d);
+		if (in_regs) {
+#pragma unroll
+			for (int u = 0; u < kRegKeys; u++) {
+				if (threadIdx.x + (uint32_t)u * kT < n) {
+					const uint32_t d = (uint32_t)(kr[u] >> 32);
+					lo = min(lo, d);
+					hi = max(hi, d);
+				}
+			}
+		} else {
+			for (uint32_t i = threadIdx.x; i < n; i += kT) {
+				const uint32_t d = (uint32_t)(keys[i] >> 32);
+				lo = min(lo, d);
+				hi = max(hi, d);
+			}
 		}
 #pragma unroll
 		for (int o = 16; o > 0; o >>= 1) {
@@ -422,7 +462,7 @@ big_bucket_sort_pack_kernel(GeometryState g, BinningState b, uint32_t capacity, 
 		if (threadIdx.x == 0) s_fallback = 0u;
 		__syncthreads();
 #pragma unroll
-		for (int w = 0; w < kSortWarps; w++) {
+		for (int w = 0; w < (kT / 32); w++) {
 			lo = min(lo, s_lo[w]);
 			hi = max(hi, s_hi[w]);
 		}
@@ -433,8 +473,15 @@ big_bucket_sort_pack_kernel(GeometryState g, BinningState b, uint32_t capacity, 
 		auto sub_of = [&](uint64_t k) {
 			return min(S - 1u, (uint32_t)((float)((uint32_t)(k >> 32) - lo) * scale));
 		};
-		for (uint32_t i = threadIdx.x; i < n; i += kSortThreads)
-			atomicAdd(&s_cnt[sub_of(keys[i])], 1u);
+		if (in_regs) {
+#pragma unroll
+			for (int u = 0; u < kRegKeys; u++)
+				if (threadIdx.x + (uint32_t)u * kT < n)
+					atomicAdd(&s_cnt[sub_of(kr[u])], 1u);
+		} else {
+			for (uint32_t i = threadIdx.x; i < n; i += kT)
+				atomicAdd(&s_cnt[sub_of(keys[i])], 1u);
+		}
 		__syncthreads();
 		if (warp == 0) {
 			// exclusive scan of up to 128 counts, four per lane
@@ -462,12 +509,19 @@ big_bucket_sort_pack_kernel(GeometryState g, BinningState b, uint32_t capacity, 
 			if (lane == 31) s_off[S] = at;
 		}
 		__syncthreads();
-		for (uint32_t i = threadIdx.x; i < n; i += kSortThreads) {
-			const uint64_t k = keys[i];
-			s_part[atomicAdd(&s_cnt[sub_of(k)], 1u)] = k;
+		if (in_regs) {
+#pragma unroll
+			for (int u = 0; u < kRegKeys; u++)
+				if (threadIdx.x + (uint32_t)u * kT < n)
+					s_part[atomicAdd(&s_cnt[sub_of(kr[u])], 1u)] = kr[u];
+		} else {
+			for (uint32_t i = threadIdx.x; i < n; i += kT) {
+				const uint64_t k = keys[i];
+				s_part[atomicAdd(&s_cnt[sub_of(k)], 1u)] = k;
+			}
 		}
 		__syncthreads();
-		for (uint32_t sb = warp; sb < S; sb += kSortWarps) {
+		for (uint32_t sb = warp; sb < S; sb += (kT / 32)) {
 			const uint32_t o0 = s_off[sb], m = s_off[sb + 1] - o0;
 			if (m == 0) continue;
 			if (m <= 32) warp_sort_pack<1>(g, b, s_part + o0, s0 + o0, m, lane);
@@ -480,7 +534,7 @@ big_bucket_sort_pack_kernel(GeometryState g, BinningState b, uint32_t capacity, 
 		if (s_fallback) {
 			// s_part is a permutation of the bucket; the total order is unique, so re-packing is idempotent
 			block_bitonic(s_part, n);
-			for (uint32_t i = threadIdx.x; i < n; i += kSortThreads)
+			for (uint32_t i = threadIdx.x; i < n; i += kT)
 				pack_one(g, b, s0 + i, (uint32_t)s_part[i]);
 		}
 		__syncthreads();   // the shared arrays are reused by the next bucket
@@ -525,7 +579,12 @@ int launch_sort_pack(int num_tiles, const GeometryState& g, const BinningState& 
 	launch_k(bucket_sort_pack_kernel, dim3((total + kSortWarps - 1) / kSortWarps), dim3(kSortThreads), 0, stream, 
 		g, b, capacity, vp.bucket_log2, total);
 	// 32 KB of dynamic shared memory, 48 registers: six blocks per SM
-	launch_k(big_bucket_sort_pack_kernel, dim3(148 * 6), dim3(kSortThreads), kBigSmemBytes, stream, g, b, capacity, vp.bucket_log2);
+	// 16 KB of dynamic shared memory and 64 registers at 128 threads: twelve blocks per SM
+	launch_k(big_bucket_sort_pack_kernel<128, 8, false>, dim3(148 * 12), dim3(128), (size_t)kMidKeys * sizeof(uint64_t), stream, g, b, capacity,
+	         vp.bucket_log2, (uint32_t)kMidKeys);
+	// usually empty: the buckets beyond kMidKeys keys (32 KB of shared memory; beyond that, sorted in place in global memory)
+	launch_k(big_bucket_sort_pack_kernel<256, 4, true>, dim3(148 * 2), dim3(256), kBigSmemBytes, stream, g, b, capacity, vp.bucket_log2,
+	         (uint32_t)kSortSmem);
 	return GM_OK;
 }
 

@@ -46,7 +46,10 @@ struct FrameHeader {
 	uint32_t bucket_log2;
 	uint32_t num_large;      // Gaussians whose tile rectangle exceeds 64 tiles (walked by large_tiles_kernel)
 	uint32_t num_big;        // (tile, bucket) ranges too long for the register sort (big_bucket_sort_pack_kernel)
-	uint32_t pad[24];
+	uint32_t big_ticket;     // next entry of the big list to be taken by a block of big_bucket_sort_pack_kernel
+	uint32_t num_huge;       // ranges beyond the small blocks' shared memory: listed from the END of big_list downwards
+	uint32_t huge_ticket;
+	uint32_t pad[21];
 };
 static_assert(sizeof(FrameHeader) == 128, "FrameHeader must be one 128-byte line");
 

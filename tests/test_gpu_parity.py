@@ -349,12 +349,13 @@ def test_long_tile_lists_use_global_sort_path(cuda_device):
     assert float((color - ref.color).abs().max()) <= FWD_TOL
 
 
-@pytest.mark.parametrize("duplicates", [False, True])
+@pytest.mark.parametrize("duplicates", [0, 3000, 30000], ids=["none", "one_bucket_3000", "one_bucket_30000"])
 def test_surface_shell_uses_sub_bucket_sort(cuda_device, duplicates):
     """Gaussians on a thin spherical shell (what mesh-bound models look like): a tile sees two narrow depth layers,
     so most of its instances share one or two global depth buckets and go through the sub-bucket path of
-    big_bucket_sort_pack_kernel.  With `duplicates` a quarter of the Gaussians are exact copies (equal depth bits,
-    order decided by the Gaussian id) and one sub-bucket overflows into the block-wide network."""
+    big_bucket_sort_pack_kernel (its small-block class, up to 2,048 keys).  With `duplicates` that many Gaussians are exact
+    copies (equal depth bits, order decided by the Gaussian id): 3,000 land in one bucket of the large-block class (up to 4,096
+    keys) and one sub-bucket overflows into the block-wide network; 30,000 go through the in-place global-memory sort."""
     _need_ref()
     dev = cuda_device
     P, W, H = 120_000, 320, 240
@@ -364,7 +365,7 @@ def test_surface_shell_uses_sub_bucket_sort(cuda_device, duplicates):
     d = d / d.norm(dim=1, keepdim=True)
     shell = (1.5 + 0.002 * torch.randn(P, 1, generator=g)) * d
     if duplicates:
-        shell[P // 2: P // 2 + P // 4] = shell[0]          # 30K splats at one point: equal depths, > 256 per sub-bucket
+        shell[P // 2: P // 2 + duplicates] = shell[0]      # splats at one point: equal depths, > 256 per sub-bucket
     sc["means3D"] = shell.to(dev).contiguous()
     sc["opacities"] = (sc["opacities"] * 0.1).contiguous()    # keep transmittance alive through the layers
     cam = scenes.camera(dev, W, H, index=1)
