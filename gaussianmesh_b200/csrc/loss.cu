@@ -11,6 +11,7 @@
 //                        (loss, L1, SSIM), so the whole loss is two launches and no host round trip.
 //   mesh_restrict_loss   utils/loss_utils.py:84-107: sum(max(0, max_k scale_k - weight * sqrt(|(v2-v1) x (v3-v1)|)))
 #include "common.cuh"
+#include "packed.cuh"
 #include "kernels.h"
 
 namespace gm {
@@ -27,6 +28,19 @@ constexpr float kC1 = 0.01f * 0.01f, kC2 = 0.03f * 0.03f;
 // gaussian(11, 1.5) of utils/loss_utils.py:23-25, normalised
 __constant__ float c_win[11] = {0.00102838f, 0.00759876f, 0.03600077f, 0.10936069f, 0.21300554f, 0.26601172f,
                                 0.21300554f, 0.10936069f, 0.03600077f, 0.00759876f, 0.00102838f};
+
+// The same window as (tap t, tap t - 1) pairs, t = 0 .. 11 (taps -1 and 11 are zero): two ADJACENT outputs j, j + 1 read
+// input j + t through taps t and t - 1, so one packed FFMA2 (sm_100a) advances both -- 12 instead of 22 FMA
+// instructions per pair of outputs, each half rounding exactly like the scalar chain (a zero tap adds an exact zero).
+__constant__ float2 c_win2[12] = {{0.00102838f, 0.0f},        {0.00759876f, 0.00102838f}, {0.03600077f, 0.00759876f},
+                                  {0.10936069f, 0.03600077f}, {0.21300554f, 0.10936069f}, {0.26601172f, 0.21300554f},
+                                  {0.21300554f, 0.26601172f}, {0.10936069f, 0.21300554f}, {0.03600077f, 0.10936069f},
+                                  {0.00759876f, 0.03600077f}, {0.00102838f, 0.00759876f}, {0.0f, 0.00102838f}};
+
+__device__ __forceinline__ f2 win2(int t)
+{
+	return pk(c_win2[t].x, c_win2[t].y);
+}
 
 // head of the caller's scratch chunk; the three derivative maps follow at kMapsOffset
 struct PhotoSums {
@@ -104,12 +118,13 @@ __device__ __forceinline__ void vertical4(const float (*s_h)[kIn][kT + 1], int r
 		for (int k = 0; k < kSeg + 10; k++)
 			v[k] = s_h[q][row0 + k][col];
 #pragma unroll
-		for (int j = 0; j < kSeg; j++) {
-			float acc = 0.0f;
+		for (int j = 0; j < kSeg; j += 2) {
+			f2 acc = pk1(0.0f);
 #pragma unroll
-			for (int k = 0; k < 11; k++)
-				acc += c_win[k] * v[j + k];
-			out[q][j] = acc;
+			for (int t = 0; t < 12; t++)
+				acc = fma2(win2(t), pk1(v[j + t]), acc);
+			out[q][j] = lo(acc);
+			out[q][j + 1] = hi(acc);
 		}
 	}
 }
@@ -143,28 +158,32 @@ photometric_forward_kernel(int H, int W, const float* __restrict__ img1, const f
 			u[k] = s_x[ly][c0 + k];
 			v[k] = s_y[ly][c0 + k];
 		}
-		float acc[5][kSeg];
+		f2 acc[5][kSeg / 2];
 #pragma unroll
-		for (int j = 0; j < kSeg; j++)
+		for (int j = 0; j < kSeg / 2; j++)
 #pragma unroll
-			for (int q = 0; q < 5; q++) acc[q][j] = 0.0f;
+			for (int q = 0; q < 5; q++) acc[q][j] = pk1(0.0f);
 #pragma unroll
 		for (int k = 0; k < kSeg + 10; k++) {
 			const float xx = u[k] * u[k], yy = v[k] * v[k], xy = u[k] * v[k];
 #pragma unroll
-			for (int j = 0; j < kSeg; j++) {
-				const int tap = k - j;
-				if (tap >= 0 && tap < 11) {
-					const float w = c_win[tap];
-					acc[0][j] += w * u[k]; acc[1][j] += w * v[k];
-					acc[2][j] += w * xx; acc[3][j] += w * yy; acc[4][j] += w * xy;
+			for (int j = 0; j < kSeg / 2; j++) {
+				const int t = k - 2 * j;          // outputs 2j and 2j + 1 read input k through taps t and t - 1
+				if (t >= 0 && t < 12) {
+					const f2 w = win2(t);
+					acc[0][j] = fma2(w, pk1(u[k]), acc[0][j]); acc[1][j] = fma2(w, pk1(v[k]), acc[1][j]);
+					acc[2][j] = fma2(w, pk1(xx), acc[2][j]); acc[3][j] = fma2(w, pk1(yy), acc[3][j]);
+					acc[4][j] = fma2(w, pk1(xy), acc[4][j]);
 				}
 			}
 		}
 #pragma unroll
 		for (int q = 0; q < 5; q++)
 #pragma unroll
-			for (int j = 0; j < kSeg; j++) s_h[q][ly][c0 + j] = acc[q][j];
+			for (int j = 0; j < kSeg / 2; j++) {
+				s_h[q][ly][c0 + 2 * j] = lo(acc[q][j]);
+				s_h[q][ly][c0 + 2 * j + 1] = hi(acc[q][j]);
+			}
 	}
 	__syncthreads();
 	const int lx = tid & 31, ly0 = (tid >> 5) * kSeg;
@@ -241,12 +260,13 @@ photometric_backward_kernel(int H, int W, const float* __restrict__ img1, const 
 			for (int k = 0; k < kSeg + 10; k++)
 				v[k] = s_d[m][ly][c0 + k];
 #pragma unroll
-			for (int j = 0; j < kSeg; j++) {
-				float acc = 0.0f;
+			for (int j = 0; j < kSeg; j += 2) {
+				f2 acc = pk1(0.0f);
 #pragma unroll
-				for (int k = 0; k < 11; k++)
-					acc += c_win[k] * v[j + k];
-				s_h[m][ly][c0 + j] = acc;
+				for (int t = 0; t < 12; t++)
+					acc = fma2(win2(t), pk1(v[j + t]), acc);
+				s_h[m][ly][c0 + j] = lo(acc);
+				s_h[m][ly][c0 + j + 1] = hi(acc);
 			}
 		}
 	}
