@@ -1102,6 +1102,7 @@ struct __align__(128) BwdSmemC {
 	float4 conic[2][kBatchC];
 	float4 xyrg[2][kBatchC];
 	float2 bid[2][kBatchC];
+	uint32_t cmask[2][(kBatchC / 32) * 8];   // the forward's survivor masks of the staged chunks, [chunk][warp block of the tile]
 	WarpQueueC queue[kWarpsC];
 	uint64_t full[2];
 	uint32_t warp_max[kWarpsC];
@@ -1189,11 +1190,17 @@ blend_backward_cols_kernel(GeometryState g, BinningState b, ImageState img, uint
 	const f2 dLp0 = pk1(dL_dpixel0), dLp1 = pk1(dL_dpixel1), dLp2 = pk1(dL_dpixel2);
 	const f2 neg_half = pk1(-0.5f), neg_one = pk1(-1.0f), one = pk1(1.0f);
 
+	// the forward left the survivor masks of its culling in the key array (state.h: cull_mask_fits): same test, same answer
+	const bool have_masks = g.header->cull_masks != 0u;
+	const uint32_t* const cull_masks = reinterpret_cast<const uint32_t*>(b.keys) + ((size_t)(start >> 5) + (size_t)tile) * 8;
+	constexpr uint32_t kMaskBytes = (kBatchC / 32) * 8 * 4;
 	auto issue = [&](int batch, int buf) {
 		const uint32_t off = start + (uint32_t)batch * kBatchC;
 		const uint32_t cnt = min((uint32_t)kBatchC, n - (uint32_t)batch * kBatchC);
 		const uint32_t cnt4 = (cnt + 3u) & ~3u;
-		mbar_arrive_expect_tx(&s.full[buf], cnt4 * 40u);
+		mbar_arrive_expect_tx(&s.full[buf], cnt4 * 40u + (have_masks ? kMaskBytes : 0u));
+		if (have_masks)
+			bulk_g2s(s.cmask[buf], cull_masks + (size_t)batch * (kBatchC / 32) * 8, kMaskBytes, &s.full[buf]);
 		bulk_g2s(s.conic[buf], b.rec_conic + off, cnt4 * 16u, &s.full[buf]);
 		bulk_g2s(s.xyrg[buf], b.rec_xyrg + off, cnt4 * 16u, &s.full[buf]);
 		bulk_g2s(s.bid[buf], b.rec_bid + off, cnt4 * 8u, &s.full[buf]);
@@ -1385,13 +1392,25 @@ blend_backward_cols_kernel(GeometryState g, BinningState b, ImageState img, uint
 			const int j = base + lane;
 			bool keep = false;
 			float4 co, xr;
-			if (j < cnt) {
-				co = s.conic[buf][j];
-				xr = s.xyrg[buf][j];
-				keep = !rect_cannot_contribute(xr.x, xr.y, co.x, co.y, co.z, cull_threshold(co.w),
-				                               wx0, wy0, wx1, wy1);
+			uint32_t mask;
+			if (have_masks) {
+				mask = s.cmask[buf][(base >> 5) * 8 + tw];
+				if (cnt - base < 32)
+					mask &= (1u << (cnt - base)) - 1u;       // records behind this warp's last contributor
+				keep = (mask >> lane) & 1u;
+				if (keep) {
+					co = s.conic[buf][j];
+					xr = s.xyrg[buf][j];
+				}
+			} else {
+				if (j < cnt) {
+					co = s.conic[buf][j];
+					xr = s.xyrg[buf][j];
+					keep = !rect_cannot_contribute(xr.x, xr.y, co.x, co.y, co.z, cull_threshold(co.w),
+					                               wx0, wy0, wx1, wy1);
+				}
+				mask = __ballot_sync(0xffffffffu, keep);
 			}
-			const uint32_t mask = __ballot_sync(0xffffffffu, keep);
 			const bool last_chunk = (batch | base) == 0;
 			const int n_keep = __popc(mask);
 			int total = carry + n_keep;

@@ -219,8 +219,10 @@ struct FwdEpilogue {
 // kWarpsF = 8: one block per 16x16 tile; kWarpsF = 4: two blocks per tile, each owning a 16x8 half (a barrier among four
 // warps instead of eight, and the block-wide early exit of forward.cu:303-306 per half tile).  kCarry: the survivors of the
 // culling are paired across the 32-splat chunks (an odd one waits for the next chunk instead of being paired with a pad).
-template <int kWarpsF, bool kCarry>
-__global__ void __launch_bounds__(kWarpsF * 32)
+// kMinB: minimum resident blocks the register allocation is held to (the half-tile kernel measured fastest unconstrained:
+// 80 registers, six blocks per SM).
+template <int kWarpsF, bool kCarry, int kMinB = 32 / kWarpsF>
+__global__ void __launch_bounds__(kWarpsF * 32, kMinB)
 blend_forward_pairs_kernel(GeometryState g, BinningState b, ImageState img, uint32_t capacity,
                            int W, int H, int tiles_x, const float* __restrict__ bg_color,
                            float* __restrict__ out_color, FwdEpilogue epi)
@@ -255,6 +257,11 @@ blend_forward_pairs_kernel(GeometryState g, BinningState b, ImageState img, uint
 	if (start < capacity)
 		n = min(g.tile_count[tile], capacity - start);
 	const int num_batches = (int)((n + kBatch - 1) / kBatch);
+	// survivor masks of the culling for the backward pass (state.h: cull_mask_fits), in the dead key array
+	const bool leave_masks = cull_mask_fits(g.header->num_rendered, g.header->num_tiles, capacity);
+	uint32_t* const cull_masks = reinterpret_cast<uint32_t*>(b.keys) + ((size_t)(start >> 5) + (size_t)tile) * 8 + tw;
+	if (blockIdx.x == 0 && threadIdx.x == 0)
+		g.header->cull_masks = leave_masks ? 1u : 0u;
 
 	if (tid == 0) {
 		mbar_init(&s.full[0], 1);
@@ -317,6 +324,8 @@ blend_forward_pairs_kernel(GeometryState g, BinningState b, ImageState img, uint
 				                               wx0, wy0, wx1, wy1);
 			}
 			const uint32_t mask = __ballot_sync(0xffffffffu, keep);
+			if (leave_masks && lane == 0)
+				cull_masks[(size_t)(batch * (kBatch / 32) + (base >> 5)) * 8] = mask;
 			const int n_keep = __popc(mask);
 			int n_pairs;
 			int total = 0;
@@ -769,7 +778,7 @@ int launch_blend_forward(const GeometryState& g, const BinningState& b, const Im
 	if (whole_tile)
 		launch_k(blend_forward_pairs_kernel<8, false>, dim3(num_tiles), dim3(kThreads), 0, stream, g, b, img, capacity, vp.W, vp.H, vp.tiles_x, vp.bg, out_color, e);
 	else
-		launch_k(blend_forward_pairs_kernel<4, true>, dim3(num_tiles * 2), dim3(kThreads / 2), 0, stream, g, b, img, capacity, vp.W, vp.H, vp.tiles_x, vp.bg, out_color, e);
+		launch_k(blend_forward_pairs_kernel<4, true, 1>, dim3(num_tiles * 2), dim3(kThreads / 2), 0, stream, g, b, img, capacity, vp.W, vp.H, vp.tiles_x, vp.bg, out_color, e);
 	return GM_OK;
 }
 

@@ -49,7 +49,8 @@ struct FrameHeader {
 	uint32_t big_ticket;     // next entry of the big list to be taken by a block of big_bucket_sort_pack_kernel
 	uint32_t num_huge;       // ranges beyond the small blocks' shared memory: listed from the END of big_list downwards
 	uint32_t huge_ticket;
-	uint32_t pad[21];
+	uint32_t cull_masks;     // 1: the forward blend left its per-(chunk, warp block) survivor masks in the key array (cull_mask_fits)
+	uint32_t pad[20];
 };
 static_assert(sizeof(FrameHeader) == 128, "FrameHeader must be one 128-byte line");
 
@@ -154,6 +155,16 @@ inline BinningState BinningState::fromChunk(char*& chunk, size_t R)
 	obtain(chunk, b.rec_xyrg, Rp);
 	obtain(chunk, b.rec_bid, Rp);
 	return b;
+}
+
+// The forward blend leaves, per 32-record chunk of a tile's list and per 8x4 warp block of the tile, the 32-bit mask of the
+// records that survived the exact culling; the backward blend reads the mask instead of evaluating the test again.  The
+// masks live in the KEY array, which is dead once sort_pack has packed the records: chunk c of tile t is entry
+// ((start_t >> 5) + t + c) -- consecutive tiles cannot collide because start_{t+1} >= start_t + n_t -- eight words each.
+// They fit when the frame is not extremely sparse; the forward decides per frame and says so in the header.
+__host__ __device__ inline bool cull_mask_fits(uint32_t num_rendered, uint32_t num_tiles, uint32_t capacity)
+{
+	return ((size_t)(num_rendered >> 5) + num_tiles + 8) * 8 <= (size_t)capacity * 2 && num_rendered <= capacity;
 }
 
 // Per-view constants.  The four small arrays stay DEVICE pointers (the reference API hands
