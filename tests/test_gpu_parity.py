@@ -522,6 +522,34 @@ def test_train_step_matches_autograd_path(cuda_device):
         assert scenes.rel_err(ts.grads[k].view_as(a), a) <= 1e-5, k
 
 
+@pytest.mark.parametrize("sparse", [False, True], ids=["masks_shared", "frame_too_sparse_for_masks"])
+def test_backward_with_and_without_the_forward_cull_masks(cuda_device, sparse):
+    """The forward blend leaves the survivor masks of its exact culling in the (dead) key array and the backward reads them
+    (csrc/state.h: cull_mask_fits); a frame with very few instances per tile has no room for them, says so in its header,
+    and the backward evaluates the culling itself.  Both paths against the reference's gradients."""
+    _need_ref()
+    from gaussianmesh_b200.renderer import TrainStep
+    dev = cuda_device
+    P, W, H = (40, 640, 480) if sparse else (6_000, 200, 120)
+    sc = _scene(dev, P, seed=17, **({"log_scale_mean": math.log(0.02)} if sparse else {}))
+    cam = scenes.camera(dev, W, H, index=2)
+    bgt = torch.tensor([0.1, 0.0, 0.2], device=dev)
+    target = torch.rand(3, H, W, generator=torch.Generator().manual_seed(3)).to(dev)
+    ts = TrainStep(dev, sc["means3D"], sc["opacities"], sc["shs"], sc["scales"], sc["rotations"], W, H)
+    ts.step(cam, bgt, target)
+    torch.cuda.synchronize()
+    assert ts.verify() == 0
+    header = ts.arena.geom[:128].view(torch.int32)
+    assert int(header[11]) == (0 if sparse else 1), header[:12].tolist()       # FrameHeader::cull_masks
+    ref = _ref(sc, cam, bgt, 3, "sh")
+    assert float((ts.image - ref.color).abs().max()) <= FWD_TOL
+    diff = ref.color - target
+    rg = ref.backward(torch.sign(diff) / diff.numel())
+    assert int((ref.radii > 0).sum()) > 0
+    for k in ("means3D", "sh", "opacity", "scales", "rotations"):
+        scenes.assert_grad(ts.grads[k].view_as(rg[k]), rg[k], k, BWD_TOL)
+
+
 def test_forward_epilogue_matches_separate_launches(cuda_device):
     """gm_forward_ex folds the L1 loss (float or 8-bit target) and the clearing of a buffer into the blend kernel: same
     image bits, same gradient image, same loss as gm_forward + gm_l1_loss; the A/B kernel variants take the fallback."""

@@ -447,6 +447,31 @@ def test_column_sum_flush_matches_the_per_pixel_sums():
     assert worst > 0.0        # (the restatement is float32, not a copy of the float64 sums)
 
 
+def test_cull_mask_entries_of_consecutive_tiles_never_collide():
+    """csrc/state.h: the survivor masks of chunk c of tile t live at entry (start_t >> 5) + t + c of the key array.  For
+    any tile layout the binning produces (starts multiples of 4, start_{t+1} >= start_t + n_t) the entries of different
+    tiles are disjoint and stay below the bound cull_mask_fits() checks."""
+    rng = np.random.default_rng(3)
+    for trial in range(200):
+        T = int(rng.integers(1, 400))
+        counts = rng.integers(0, 200, size=T) * (rng.random(T) < 0.7)
+        if trial % 5 == 0:
+            counts[rng.integers(0, T)] = int(rng.integers(3000, 9000))
+        starts, at = [], 0
+        for n in counts:
+            starts.append(at)
+            at += (int(n) + 3) & ~3                                   # tile segments start at multiples of 4 instances
+        num_rendered = at
+        seen = {}
+        for t, (s0, n) in enumerate(zip(starts, counts)):
+            for c in range((int(n) + 31) // 32):
+                e = (s0 >> 5) + t + c
+                assert e not in seen, (trial, t, seen[e])
+                seen[e] = t
+        if seen:
+            assert max(seen) + 4 < (num_rendered >> 5) + T + 8        # the backward's 4-chunk bulk copy stays inside too
+
+
 def test_header_is_plain_c(tmp_path):
     """include/gm_rasterizer.h is the C-ABI contract: it must compile as C99 (no C++ in the signatures) and the two
     three structs passed by pointer must have the layout the ctypes mirror assumes."""
