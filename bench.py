@@ -872,7 +872,9 @@ def main():
     out["train_iteration"]["host_enqueue_ms_per_iteration"] = it_enqueue_ms / K
     out["train_iteration"]["instances_per_frame"] = it_info[0]
     out["train_iteration"]["visible_gaussians"] = it_info[1]
-    kernels_per_stage = {"depth_buckets": 2, "preprocess": 2, "emit": 2, "sort_pack": 2}    # the rest launch one kernel
+    # depth_histogram + bucket_lut; preprocess + large_tiles (count); emit + large_tiles (placement); bucket_sort_pack + the two
+    # size classes of big_bucket_sort_pack; the rest launch one kernel
+    kernels_per_stage = {"depth_buckets": 2, "preprocess": 2, "emit": 2, "sort_pack": 3}
     out["gpu_launches"] = int(sum(v[1] * kernels_per_stage.get(k, 1) for k, v in prof.items()))
     out["host_enqueue_ms_per_step"] = enqueue_ms / K
     out["ms_per_step_with_stage_events"] = ms_prof / K
