@@ -11,7 +11,7 @@ namespace gm {
 
 namespace {
 
-constexpr int kThreads = 256;
+constexpr int kThreads = 128;
 
 __device__ __forceinline__ float3 dnormvdv3(float3 v, float3 dv)   // auxiliary.h:107-117
 {
@@ -41,7 +41,7 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
 }
 
 template <bool kVecSH, bool kOverwrite, bool kCoop>
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kThreads, 5)
 geometry_backward_kernel(int P,
                          const float* __restrict__ means3D,
                          const int* __restrict__ radii,
