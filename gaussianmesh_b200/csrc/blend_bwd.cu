@@ -16,6 +16,12 @@
 //     received a contribution, instead of one per (pixel, splat).
 // Summation order differs from the reference's (which is itself non-deterministic), hence the 1e-3
 // relative tolerance of the gradient parity tests.
+//
+// Four kernels share this decomposition and differ in how the nine sums leave the warp: blend_backward_kernel (one splat
+// per iteration) and blend_backward_pairs_kernel (two, packed fp32x2) use the butterfly described above,
+// blend_backward_mma_kernel the tensor cores, and blend_backward_cols_kernel -- THE DEFAULT, at the end of the file --
+// parks two numbers per (pixel, splat) and lets lanes own splats when the sums are formed.  It also reads the survivor
+// masks the forward blend left behind instead of culling again (state.h: cull_mask_fits).
 #include <cstdlib>
 #include "common.cuh"
 #include "packed.cuh"
