@@ -11,6 +11,10 @@
 //     that block (rect_cannot_contribute, exact), so only splats that can reach the block are
 //     evaluated per pixel.  Skipped splats are exactly those for which every pixel of the block
 //     would hit one of the reference's `continue`s, so no output bit changes.
+// The default is blend_forward_pairs_kernel<4, true, 1>: two splats per iteration in packed fp32x2, two 128-thread blocks per
+// tile, survivors paired across chunks; it also leaves the survivor masks of its culling for the backward blend
+// (state.h: cull_mask_fits).  blend_forward_kernel (one splat per iteration), the <8, false> instantiation (one block per
+// tile) and blend_forward_ring_kernel (no block barrier) are kept for A/B measurements.
 #include <cstdlib>
 #include "common.cuh"
 #include "packed.cuh"
